@@ -1,0 +1,91 @@
+"""Pins oracle/ against the golden vectors recorded from the UNMODIFIED reference modules
+(oracle/make_golden.py). CPU only."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, golden_inputs
+from oracle import planesweep, costreg, pipeline, pointcloud, scenemodel
+from oracle.voxelize import voxelize
+
+CASES = ['c1_tiny', 'c1_selfedge_2scenes']
+
+
+def _params(synth, g):
+    p = synth.make_params(int(g['seed']))
+    assert synth.params_checksum(p) == pytest.approx(float(g['params_checksum']), rel=1e-12), \
+        'seeded weights drifted from the ones the golden file was recorded with'
+    return p
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_path_a_matches_reference(name, synth):
+    g = load_golden(name)
+    t, cfg, img_size = golden_inputs(g)
+    p = _params(synth, g)
+    depth, x_var, x_reg = pipeline.initial_depth(t['feats_quarter'], t['rotmats'], t['tvecs'], t['K'],
+                                                 t['ref_src_edges'], cfg, img_size, p, return_all=True)
+    np.testing.assert_allclose(x_var.numpy(), g['ref_x_var'], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(x_reg.numpy(), g['ref_x_reg'], rtol=0, atol=2e-5)
+    np.testing.assert_allclose(depth.numpy(), g['ref_depth_init'], rtol=0, atol=2e-5)
+
+
+def test_scalar_sampler_matches_grid_sample():
+    g = load_golden('c1_tiny')
+    t, cfg, img_size = golden_inputs(g)
+    v = planesweep.planesweep_var_numpy(t['feats_quarter'], t['rotmats'], t['tvecs'], t['K'], t['ref_src_edges'],
+                                        cfg['depth_start'], cfg['depth_interval'], cfg['n_intervals'], img_size,
+                                        cfg['size'])
+    np.testing.assert_allclose(v.numpy(), g['ref_x_var'], rtol=0, atol=2e-6)
+
+
+def test_voxelize_bit_exact_adversarial():
+    g = load_golden('voxelize_adversarial')
+    a_pts, a_idx, a_batch, a_edges = voxelize(g['pts'], g['batch'], float(g['edge_len']))
+    assert a_idx.dtype == np.int32 and a_batch.dtype == np.int64 and a_edges.dtype == np.int64
+    np.testing.assert_array_equal(a_idx, g['ref_anchor_idx3d'])
+    np.testing.assert_array_equal(a_batch, g['ref_anchor_batch'])
+    np.testing.assert_array_equal(a_edges, g['ref_anchor_pts_edges'])
+    np.testing.assert_array_equal(a_pts.view(np.int32), g['ref_anchor_pts'].view(np.int32))
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_path_b_matches_reference(name, synth):
+    g = load_golden(name)
+    t, cfg, img_size = golden_inputs(g)
+    p = _params(synth, g)
+    edge_len = float(g['edge_len'])
+    depth = torch.from_numpy(g['ref_depth_init']).clone()
+    ref_idx = torch.unique(t['ref_src_edges'][0])
+    depth_batch = t['images_batch'][ref_idx]
+    args = (t['feats_quarter'], t['rotmats'], t['tvecs'], t['K'], t['ref_src_edges'])
+
+    xs, mid = pipeline.model_scene(depth, depth_batch, *args, edge_len, img_size, p, return_all=True)
+    np.testing.assert_allclose(mid['pts'].numpy(), g['ref_pts'], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(mid['pts_feat'].numpy(), g['ref_pts_feat'], rtol=0, atol=1e-6)
+    np.testing.assert_array_equal(mid['pts_batch'].numpy(), g['ref_pts_batch'])
+    np.testing.assert_array_equal(mid['anchor_idx3d'].numpy(), g['ref_anchor_idx3d'])
+    np.testing.assert_array_equal(mid['anchor_batch'].numpy(), g['ref_anchor_batch'])
+    np.testing.assert_array_equal(mid['anchor_pts_edges'].numpy(), g['ref_anchor_pts_edges'])
+    np.testing.assert_array_equal(mid['anchor_pts'].numpy(), g['ref_anchor_pts'])
+    np.testing.assert_allclose(mid['pointnet'].numpy(), g['ref_pointnet'], rtol=0, atol=1e-5)
+    for li, lv in enumerate(xs):
+        np.testing.assert_array_equal(lv['idx'].numpy(), g['ref_xs%d_idx' % li])
+        np.testing.assert_array_equal(lv['batch'].numpy(), g['ref_xs%d_batch' % li])
+        np.testing.assert_allclose(lv['pts'].numpy(), g['ref_xs%d_pts' % li], rtol=0, atol=1e-6)
+        np.testing.assert_allclose(lv['feats'].numpy(), g['ref_xs%d_feats' % li], rtol=0, atol=5e-5)
+
+    off = pipeline.run_pointflow(xs, depth, depth_batch, *args, float(g['offsets'][0][0]), 3, img_size, p)
+    np.testing.assert_allclose(off.numpy(), g['ref_offset0'], rtol=0, atol=1e-5)
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_refinement_schedule_matches_reference(name, synth):
+    g = load_golden(name)
+    t, cfg, img_size = golden_inputs(g)
+    p = _params(synth, g)
+    ref_idx = torch.unique(t['ref_src_edges'][0])
+    out = pipeline.refine(torch.from_numpy(g['ref_depth_init']), t['images_batch'][ref_idx], t['feats_quarter'],
+                          t['rotmats'], t['tvecs'], t['K'], t['ref_src_edges'], float(g['edge_len']), img_size, p,
+                          offsets_list=g['offsets'].tolist())
+    np.testing.assert_allclose(out.numpy(), g['ref_depth_final'], rtol=0, atol=5e-5)
