@@ -1,0 +1,26 @@
+// Error reporting, launch accounting and ABI version of lib3dvnet_b200.
+#include <atomic>
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace dv3d {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+}  // namespace dv3d
+
+extern "C" const char* dv3d_last_error(void) { return dv3d::g_err; }
+extern "C" int dv3d_abi_version(void) { return 1; }
+extern "C" long long dv3d_launch_count(void) { return dv3d::g_launches.load(std::memory_order_relaxed); }
