@@ -36,9 +36,77 @@ void count_launch(int n = 1);
     } while (0)
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 constexpr int kNumSMs = 148;  // B200
 
 __device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
+
+// torch.linspace(start, end, steps) in fp32 (symmetric formula of ATen's linspace kernel)
+__device__ __forceinline__ float linspace_torch(float start, float end, int steps, int i) {
+    if (steps == 1) return start;
+    float step = (end - start) / (float)(steps - 1);
+    return (i < steps / 2) ? start + step * (float)i : end - step * (float)(steps - i - 1);
+}
+
+// order-preserving float <-> uint mapping for atomicMin/atomicMax on floats
+__device__ __forceinline__ unsigned f2ord(float f) {
+    unsigned b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(unsigned u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+// ---------------------------------------------------------------- sparse coordinate hash
+// A level's table maps key(b,x,y,z) -> row.  Open addressing, linear probing, capacity a
+// power of two >= 2 n.  Memory: uint64 keys[cap] then int32 rows[cap].
+constexpr unsigned long long kEmptyKey = ~0ull;
+constexpr int kCoordBias = 1 << 15;
+
+__host__ __device__ __forceinline__ unsigned long long coord_key(int b, int x, int y, int z) {
+    // ordered by (b, z, y, x): the order of the reference's voxel ids (utils.py:45-48)
+    return ((((unsigned long long)(unsigned)b << 16 | (unsigned)(z + kCoordBias)) << 16 |
+             (unsigned)(y + kCoordBias)) << 16) | (unsigned)(x + kCoordBias);
+}
+__host__ __device__ __forceinline__ bool coord_in_range(int b, int x, int y, int z) {
+    return b >= 0 && b < 65535 && x >= -kCoordBias && x < kCoordBias && y >= -kCoordBias && y < kCoordBias &&
+           z >= -kCoordBias && z < kCoordBias;
+}
+__device__ __forceinline__ unsigned hash_mix(unsigned long long k) {
+    k ^= k >> 33;
+    k *= 0xff51afd7ed558ccdull;
+    k ^= k >> 33;
+    k *= 0xc4ceb9fe1a85ec53ull;
+    k ^= k >> 33;
+    return (unsigned)k;
+}
+struct HashView {
+    unsigned long long* keys;
+    int* rows;
+    unsigned mask;  // cap - 1
+};
+static inline size_t hash_capacity_for(long long n) {
+    size_t cap = 64;
+    while (cap < (size_t)(2 * n)) cap <<= 1;
+    return cap;
+}
+static inline bool hash_view(void* table, size_t bytes, HashView* v) {
+    size_t cap = bytes / 12;
+    if (cap < 64 || (cap & (cap - 1))) return false;
+    v->keys = (unsigned long long*)table;
+    v->rows = (int*)((char*)table + cap * 8);
+    v->mask = (unsigned)(cap - 1);
+    return true;
+}
+__device__ __forceinline__ int hash_find(const HashView& t, unsigned long long key) {
+    unsigned slot = hash_mix(key) & t.mask;
+    while (true) {
+        unsigned long long k = t.keys[slot];
+        if (k == key) return t.rows[slot];
+        if (k == kEmptyKey) return -1;
+        slot = (slot + 1) & t.mask;
+    }
+}
 
 }  // namespace dv3d

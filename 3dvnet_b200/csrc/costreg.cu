@@ -218,13 +218,6 @@ conv3d_generic_kernel(const float* __restrict__ x, int Cin, int Di, int Hi, int 
 }
 
 // ------------------------------------------------------------------ prob conv + soft-argmin
-// torch.linspace(start, end, steps) in fp32 (symmetric formula of ATen's linspace kernel)
-__device__ __forceinline__ float linspace_torch(float start, float end, int steps, int i) {
-    if (steps == 1) return start;
-    float step = (end - start) / (float)(steps - 1);
-    return (i < steps / 2) ? start + step * (float)i : end - step * (float)(steps - i - 1);
-}
-
 __global__ void __launch_bounds__(128)
 prob_softargmin_kernel(const float* __restrict__ x, int Cin, int D, int H, int W, const float* __restrict__ wgt,
                        float bias, float d_start, float d_end, float* __restrict__ x_reg, float* __restrict__ depth,

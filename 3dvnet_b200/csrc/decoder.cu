@@ -1,0 +1,103 @@
+// PointFlow hypothesis decoder (refinement.py:8-13,20-25,42-44; lightningmodel.py:238-241).
+// The decoder operand is kept as [n_pts, 8, C]: the 7 hypotheses of a point plus one all-zero
+// padding row, so that the k=3 convolution over the hypothesis axis is three row-shifted GEMM
+// slices whose out-of-range taps land on a zero row (no per-row masking in the main loop).
+#include <math.h>
+
+#include "gemm.cuh"
+
+namespace dv3d {
+
+// last Conv1d (C -> 1, bias) + softmax over the hypotheses + expected offset; one warp per point
+__global__ void __launch_bounds__(256)
+decoder_head_kernel(const float* __restrict__ x, long long Np, int n_hyp, int rows_per_point, int C, int ld,
+                    const float* __restrict__ w, float bias, float offset, float* __restrict__ prob_out,
+                    float* __restrict__ offset_out) {
+    const int lane = threadIdx.x & 31;
+    const long long p = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (p >= Np) return;
+    // logit[h] = bias + sum_c sum_t w[c][t] x[h + t - 1][c]  (w is [1, C, 3])
+    float logit[8];
+#pragma unroll
+    for (int h = 0; h < 8; ++h) logit[h] = 0.f;
+    for (int c = lane; c < C; c += 32) {
+        const float w0 = __ldg(w + 3 * c), w1 = __ldg(w + 3 * c + 1), w2 = __ldg(w + 3 * c + 2);
+        float xv[8];
+#pragma unroll
+        for (int h = 0; h < 8; ++h) xv[h] = (h < n_hyp) ? __ldg(x + ((size_t)p * rows_per_point + h) * ld + c) : 0.f;
+#pragma unroll
+        for (int h = 0; h < 8; ++h) {
+            float a = w1 * xv[h];
+            if (h > 0) a = fmaf(w0, xv[h - 1], a);
+            if (h < 7) a = fmaf(w2, xv[h + 1], a);
+            logit[h] += a;
+        }
+    }
+#pragma unroll
+    for (int h = 0; h < 8; ++h) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) logit[h] += __shfl_xor_sync(0xffffffffu, logit[h], o);
+        logit[h] += bias;
+    }
+    float m = -INFINITY;
+#pragma unroll
+    for (int h = 0; h < 8; ++h)
+        if (h < n_hyp) m = fmaxf(m, logit[h]);
+    float e[8], s = 0.f;
+#pragma unroll
+    for (int h = 0; h < 8; ++h) {
+        e[h] = (h < n_hyp) ? expf(logit[h] - m) : 0.f;
+        s += e[h];
+    }
+    const int n_side = (n_hyp - 1) / 2;
+    const float lo = (float)(-(double)n_side * (double)offset), hi = (float)((double)n_side * (double)offset);
+    float acc = 0.f;
+#pragma unroll
+    for (int h = 0; h < 8; ++h) {
+        if (h < n_hyp) {
+            float pr = e[h] / s;
+            if (prob_out && lane == 0) prob_out[p * n_hyp + h] = pr;
+            acc += linspace_torch(lo, hi, n_hyp, h) * pr;
+        }
+    }
+    if (lane == 0) offset_out[p] = acc;
+}
+
+}  // namespace dv3d
+
+using namespace dv3d;
+
+extern "C" int dv3d_conv1d_bn_relu(const float* x, long long n_pts, int rows_per_point, int Cin, int ldx,
+                                   const float* weight_tkn, const float* scale, const float* shift, int Cout,
+                                   float* y, int ldy, void* stream) {
+    DV3D_REQUIRE(x && weight_tkn && scale && shift && y && n_pts >= 0, "conv1d: bad arguments");
+    DV3D_REQUIRE(rows_per_point == 8, "conv1d: the operand layout is [n_pts, 8, C] (7 hypotheses + 1 zero row)");
+    GemmDesc d = {};
+    d.n_slices = 3;
+    for (int t = 0; t < 3; ++t) d.slice[t] = GemmSlice{x, nullptr, 0, t - 1, ldx, Cin};
+    d.M = n_pts * rows_per_point;
+    d.n_src_rows = d.M;
+    d.N = Cout;
+    d.W = weight_tkn;
+    d.scale = scale;
+    d.shift = shift;
+    d.relu_out = 1;
+    d.zero_row_mod = rows_per_point;
+    d.zero_row_val = rows_per_point - 1;
+    d.out = y;
+    d.out_ld = ldy;
+    return launch_gather_gemm(d, (cudaStream_t)stream);
+}
+
+extern "C" int dv3d_decoder_head(const float* x, long long n_pts, int n_hyp, int rows_per_point, int Cin, int ldx,
+                                 const float* weight, float bias, float offset, float* prob_out, float* offset_out,
+                                 void* stream) {
+    DV3D_REQUIRE(x && weight && offset_out && n_pts >= 0 && n_hyp >= 1 && n_hyp <= 7 && (n_hyp & 1) &&
+                     rows_per_point >= n_hyp && Cin > 0 && ldx >= Cin,
+                 "decoder_head: bad arguments (n_hyp must be odd and <= 7)");
+    if (n_pts == 0) return DV3D_OK;
+    decoder_head_kernel<<<cdiv(n_pts, 8), 256, 0, (cudaStream_t)stream>>>(x, n_pts, n_hyp, rows_per_point, Cin, ldx,
+                                                                         weight, bias, offset, prob_out, offset_out);
+    DV3D_LAUNCHED();
+    return DV3D_OK;
+}

@@ -211,7 +211,8 @@ __global__ void __launch_bounds__(256, 2)
 points_var_kernel(const float4* __restrict__ feats, SampleGeom geom, const float* __restrict__ xform,
                   const int* __restrict__ rowptr, const int* __restrict__ esrc, const float* __restrict__ backproj,
                   const float* __restrict__ depth, int h, int w, int H, int W, int n_side, float offset,
-                  float* __restrict__ pts_out, float* __restrict__ feat_out, int feat_stride, int feat_off) {
+                  float* __restrict__ pts_out, float* __restrict__ feat_out, int rows_per_point, int feat_stride,
+                  int feat_off) {
     __shared__ int s_rec[EMAX][KD][TP];
     __shared__ float4 s_wt[EMAX][KD][TP];
 
@@ -282,8 +283,8 @@ points_var_kernel(const float4* __restrict__ feats, SampleGeom geom, const float
                 o.y = var_of(acc_s[k].y, acc_q[k].y, n_edges);
                 o.z = var_of(acc_s[k].z, acc_q[k].z, n_edges);
                 o.w = var_of(acc_s[k].w, acc_q[k].w, n_edges);
-                *reinterpret_cast<float4*>(feat_out + (((size_t)r * P + p) * n_hyp + k) * feat_stride + feat_off +
-                                           4 * g) = o;
+                *reinterpret_cast<float4*>(feat_out + (((size_t)r * P + p) * rows_per_point + k) * feat_stride +
+                                           feat_off + 4 * g) = o;
             }
         }
     }
@@ -438,12 +439,14 @@ extern "C" int dv3d_planesweep_var(const float* feats_nhwc, int n_imgs, int C, i
 extern "C" int dv3d_points_var(const float* feats_nhwc, int n_imgs, int C, int Hf, int Wf, const float* xform,
                                const int* edge_rowptr, const int* edge_src, const float* backproj,
                                const float* depth, int n_ref, int h, int w, int H, int W, int n_side, float offset,
-                               float* pts_out, float* feat_out, int feat_stride, int feat_off, void* stream) {
+                               float* pts_out, float* feat_out, int rows_per_point, int feat_stride, int feat_off,
+                               void* stream) {
     DV3D_REQUIRE(C == 32, "points_var: C must be 32, got %d", C);
     DV3D_REQUIRE(n_side == 0 || n_side == 3, "points_var: n_side must be 0 (point cloud) or 3 (PointFlow), got %d",
                  n_side);
     DV3D_REQUIRE(feats_nhwc && xform && edge_rowptr && edge_src && backproj && depth && pts_out && feat_out,
                  "points_var: null pointer");
+    DV3D_REQUIRE(rows_per_point >= 2 * n_side + 1, "points_var: rows_per_point < number of hypotheses");
     DV3D_REQUIRE(feat_stride % 4 == 0 && feat_off % 4 == 0 && feat_off + C <= feat_stride,
                  "points_var: feat_stride/feat_off must be multiples of 4 with room for C channels");
     DV3D_REQUIRE(n_imgs > 0 && Hf > 1 && Wf > 1 && h > 0 && w > 0 && n_ref >= 0 && n_ref <= 65535, "points_var: bad shape");
@@ -451,7 +454,7 @@ extern "C" int dv3d_points_var(const float* feats_nhwc, int n_imgs, int C, int H
     dim3 grid(cdiv(h * w, TP), n_ref);
     points_var_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const float4*>(feats_nhwc), make_geom(Hf, Wf, H, W), xform, edge_rowptr, edge_src, backproj,
-        depth, h, w, H, W, n_side, offset, pts_out, feat_out, feat_stride, feat_off);
+        depth, h, w, H, W, n_side, offset, pts_out, feat_out, rows_per_point, feat_stride, feat_off);
     DV3D_LAUNCHED();
     return DV3D_OK;
 }

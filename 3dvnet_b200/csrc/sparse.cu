@@ -1,0 +1,211 @@
+// Sparse 3D-UNet plumbing: coordinate hash, kernel maps, the sparse convolution / 1x1
+// "feature adjust" entry points (thin descriptors over the gather-GEMM) and the trilinear
+// sparse interpolation of PointFlow.  MinkowskiEngine 0.5 semantics per SURVEY.md A.4:
+// offsets enumerate x fastest (k = (dx+1) + 3(dy+1) + 9(dz+1)), no bias, strided maps are
+// floor(c / s) * s, the transposed convolution reuses the finer map with the forward kernel
+// map swapped, interpolation takes the 8 corners lower + {0,ts}^3 and missing voxels add 0.
+#include <math.h>
+
+#include "gemm.cuh"
+
+namespace dv3d {
+
+__global__ void __launch_bounds__(256)
+hash_clear_kernel(unsigned long long* keys, int* rows, size_t cap) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < cap) {
+        keys[i] = kEmptyKey;
+        rows[i] = INT_MAX;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+hash_insert_kernel(const int* __restrict__ coords, long long n, HashView t, int* __restrict__ err) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int b = coords[4 * i], x = coords[4 * i + 1], y = coords[4 * i + 2], z = coords[4 * i + 3];
+    if (!coord_in_range(b, x, y, z)) {
+        *err = 1;
+        return;
+    }
+    unsigned long long key = coord_key(b, x, y, z);
+    unsigned slot = hash_mix(key) & t.mask;
+    while (true) {
+        unsigned long long prev = atomicCAS(t.keys + slot, kEmptyKey, key);
+        if (prev == kEmptyKey || prev == key) {  // duplicate coordinates: lowest row wins deterministically
+            atomicMin(t.rows + slot, (int)i);
+            return;
+        }
+        slot = (slot + 1) & t.mask;
+    }
+}
+
+// nbr[o*27 + k] = row of (coords_out[o] + offset_k * step) in the input level, or -1
+__global__ void __launch_bounds__(256)
+kernel_map_kernel(const int* __restrict__ coords_out, long long n_out, HashView t, int step, int* __restrict__ nbr) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_out * 27) return;
+    long long o = i / 27;
+    int k = (int)(i - o * 27);
+    int dx = k % 3 - 1, dy = (k / 3) % 3 - 1, dz = k / 9 - 1;
+    int b = coords_out[4 * o], x = coords_out[4 * o + 1] + dx * step, y = coords_out[4 * o + 2] + dy * step,
+        z = coords_out[4 * o + 3] + dz * step;
+    nbr[i] = coord_in_range(b, x, y, z) ? hash_find(t, coord_key(b, x, y, z)) : -1;
+}
+
+// One warp per query point.  q = ((p - origin[b]) / res) * stride in base-voxel units
+// (refinement.py:34-35); lanes 0..7 probe the 8 corners, all lanes accumulate C channels.
+template <int C>
+__global__ void __launch_bounds__(256)
+sparse_interp_kernel(const float* __restrict__ pts, const long long* __restrict__ pts_batch, long long Nq, int n_hyp,
+                     int rows_per_point, const float* __restrict__ origin, float res, int stride, HashView t,
+                     const float* __restrict__ feat, float* __restrict__ out, int out_ld, int out_off) {
+    const int lane = threadIdx.x & 31;
+    const long long q = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= Nq) return;
+    const long long p = q / n_hyp;
+    const int hy = (int)(q - p * n_hyp);
+    const int b = (int)__ldg(pts_batch + p);
+    const float ts = (float)stride;
+    float qc[3];
+    int lo[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        float v = __fsub_rn(__ldg(pts + 3 * q + d), __ldg(origin + 3 * b + d));
+        v = __fmul_rn(__fdiv_rn(v, res), ts);
+        qc[d] = v;
+        lo[d] = (int)(floorf(__fdiv_rn(v, ts)) * ts);
+    }
+    int row = -1;
+    float wgt = 0.f;
+    if (lane < 8) {
+        int cx = lo[0] + ((lane >> 0) & 1) * stride, cy = lo[1] + ((lane >> 1) & 1) * stride,
+            cz = lo[2] + ((lane >> 2) & 1) * stride;
+        wgt = (1.f - fabsf(qc[0] - (float)cx) / ts) * (1.f - fabsf(qc[1] - (float)cy) / ts) *
+              (1.f - fabsf(qc[2] - (float)cz) / ts);
+        if (coord_in_range(b, cx, cy, cz)) row = hash_find(t, coord_key(b, cx, cy, cz));
+    }
+    constexpr int V = C / 32;  // channels per lane (2 or 4)
+    float acc[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        int r = __shfl_sync(0xffffffffu, row, c);
+        float w = __shfl_sync(0xffffffffu, wgt, c);
+        if (r >= 0) {
+            const float* f = feat + (size_t)r * C + lane * V;
+            if (V == 4) {
+                float4 v = __ldg(reinterpret_cast<const float4*>(f));
+                acc[0] = fmaf(w, v.x, acc[0]); acc[1] = fmaf(w, v.y, acc[1]);
+                acc[2] = fmaf(w, v.z, acc[2]); acc[3 % V] = fmaf(w, v.w, acc[3 % V]);
+            } else {
+                float2 v = __ldg(reinterpret_cast<const float2*>(f));
+                acc[0] = fmaf(w, v.x, acc[0]); acc[1] = fmaf(w, v.y, acc[1]);
+            }
+        }
+    }
+    float* o = out + ((size_t)p * rows_per_point + hy) * out_ld + out_off + lane * V;
+    if (V == 4)
+        *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2 % V], acc[3 % V]);
+    else
+        *reinterpret_cast<float2*>(o) = make_float2(acc[0], acc[1]);
+}
+
+}  // namespace dv3d
+
+using namespace dv3d;
+
+extern "C" size_t dv3d_hash_bytes(long long n_rows) { return n_rows < 0 ? 0 : hash_capacity_for(n_rows) * 12; }
+
+extern "C" int dv3d_hash_build(const int* coords, long long n, void* table, size_t table_bytes, int* err_flag,
+                               void* stream) {
+    HashView t;
+    DV3D_REQUIRE(coords && table && err_flag && n >= 0, "hash_build: bad arguments");
+    DV3D_REQUIRE(hash_view(table, table_bytes, &t) && (size_t)t.mask + 1 >= (size_t)(2 * n),
+                 "hash_build: table_bytes must be dv3d_hash_bytes(n)");
+    cudaStream_t st = (cudaStream_t)stream;
+    size_t cap = (size_t)t.mask + 1;
+    hash_clear_kernel<<<cdiv(cap, 256), 256, 0, st>>>(t.keys, t.rows, cap);
+    DV3D_LAUNCHED();
+    if (n == 0) return DV3D_OK;
+    hash_insert_kernel<<<cdiv(n, 256), 256, 0, st>>>(coords, n, t, err_flag);
+    DV3D_LAUNCHED();
+    return DV3D_OK;
+}
+
+extern "C" int dv3d_kernel_map(const int* coords_out, long long n_out, const void* table_in, size_t table_bytes,
+                               int step, int* nbr, void* stream) {
+    HashView t;
+    DV3D_REQUIRE(coords_out && table_in && nbr && n_out >= 0, "kernel_map: bad arguments");
+    DV3D_REQUIRE(hash_view(const_cast<void*>(table_in), table_bytes, &t), "kernel_map: bad table size");
+    if (n_out == 0) return DV3D_OK;
+    kernel_map_kernel<<<cdiv(n_out * 27, 256), 256, 0, (cudaStream_t)stream>>>(coords_out, n_out, t, step, nbr);
+    DV3D_LAUNCHED();
+    return DV3D_OK;
+}
+
+extern "C" int dv3d_sparse_conv(const float* feat, long long n_in, int Cin, const int* nbr, long long n_out,
+                                const float* W, int Cout, const float* gn_weight, const float* gn_bias,
+                                const float* residual, int relu, float* out, void* stream) {
+    DV3D_REQUIRE(feat && nbr && W && out && n_in >= 0 && n_out >= 0, "sparse_conv: bad arguments");
+    GemmDesc d = {};
+    d.n_slices = 27;
+    for (int k = 0; k < 27; ++k) d.slice[k] = GemmSlice{feat, nbr + k, 27, 0, Cin, Cin};
+    d.M = n_out;
+    d.n_src_rows = n_in;
+    d.N = Cout;
+    d.W = W;
+    d.gn_weight = gn_weight;
+    d.gn_bias = gn_bias;
+    d.residual = residual;
+    d.res_ld = Cout;
+    d.relu_out = relu;
+    d.out = out;
+    d.out_ld = Cout;
+    return launch_gather_gemm(d, (cudaStream_t)stream);
+}
+
+extern "C" int dv3d_concat_linear_gn_relu(const float* a, int Ca, const float* b, int Cb, long long n, const float* W,
+                                          int Cout, const float* gn_weight, const float* gn_bias, float* out,
+                                          void* stream) {
+    DV3D_REQUIRE(a && b && W && out && n >= 0, "concat_linear: bad arguments");
+    GemmDesc d = {};
+    d.n_slices = 2;
+    d.slice[0] = GemmSlice{a, nullptr, 0, 0, Ca, Ca};
+    d.slice[1] = GemmSlice{b, nullptr, 0, 0, Cb, Cb};
+    d.M = n;
+    d.n_src_rows = n;
+    d.N = Cout;
+    d.W = W;
+    d.gn_weight = gn_weight;
+    d.gn_bias = gn_bias;
+    d.relu_out = 1;
+    d.out = out;
+    d.out_ld = Cout;
+    return launch_gather_gemm(d, (cudaStream_t)stream);
+}
+
+extern "C" int dv3d_sparse_interp(const float* pts, const long long* pts_batch, long long n_pts, int n_hyp,
+                                  int rows_per_point, const float* origin, float res, int stride, const void* table,
+                                  size_t table_bytes, const float* feat, int C, float* out, int out_ld, int out_off,
+                                  void* stream) {
+    HashView t;
+    DV3D_REQUIRE(pts && pts_batch && origin && table && feat && out && n_pts >= 0 && n_hyp > 0 &&
+                     rows_per_point >= n_hyp && res > 0.f && stride > 0,
+                 "sparse_interp: bad arguments");
+    DV3D_REQUIRE(hash_view(const_cast<void*>(table), table_bytes, &t), "sparse_interp: bad table size");
+    DV3D_REQUIRE(C == 64 || C == 128, "sparse_interp: C must be 64 or 128, got %d", C);
+    DV3D_REQUIRE(out_ld % 4 == 0 && out_off % 4 == 0 && out_off + C <= out_ld, "sparse_interp: bad output window");
+    const long long Nq = n_pts * n_hyp;
+    if (Nq == 0) return DV3D_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (C == 64)
+        sparse_interp_kernel<64><<<cdiv(Nq, 8), 256, 0, st>>>(pts, pts_batch, Nq, n_hyp, rows_per_point, origin, res,
+                                                              stride, t, feat, out, out_ld, out_off);
+    else
+        sparse_interp_kernel<128><<<cdiv(Nq, 8), 256, 0, st>>>(pts, pts_batch, Nq, n_hyp, rows_per_point, origin, res,
+                                                               stride, t, feat, out, out_ld, out_off);
+    DV3D_LAUNCHED();
+    return DV3D_OK;
+}

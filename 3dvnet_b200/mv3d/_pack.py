@@ -1,0 +1,31 @@
+"""Derived, kernel-friendly copies of module parameters (folded BatchNorm, transposed
+weights), cached until a parameter is modified in place or re-assigned."""
+import torch
+
+
+class PackCache(object):
+    def __init__(self):
+        self._key = None
+        self._val = None
+
+    def get(self, tensors, build):
+        key = tuple((t.data_ptr(), t._version, t.device) for t in tensors)
+        if key != self._key:
+            with torch.no_grad():
+                self._val = build()
+            self._key = key
+        return self._val
+
+
+def fold_bn(bn):
+    """eval-mode BatchNorm as y = x * scale + shift."""
+    scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+    shift = bn.bias - bn.running_mean * scale
+    return scale.float().contiguous(), shift.float().contiguous()
+
+
+def require_eval(module):
+    if module.training:
+        raise NotImplementedError(
+            '%s: the B200 kernels implement the inference path (eval mode, BatchNorm running statistics); '
+            'call .eval() — the autograd/backward path is not built yet' % type(module).__name__)

@@ -1,0 +1,182 @@
+"""PL3DVNet — drop-in for /root/reference/mv3d/lightningmodel.py's inference interface:
+constructor, ``hparams``, the four methods the eval driver calls
+(/root/reference/mv3d/eval-3dvnet.py:58-59,75-76,88-98) and the sub-module names of the
+checkpoint schema. pytorch_lightning is not required: this is a plain nn.Module.
+
+The reference's inline back-projection / re-projection / variance code
+(lightningmodel.py:132-174,187-235) is replaced by csrc/planesweep.cu:points_var_kernel."""
+from argparse import Namespace
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import ops
+from . import utils
+from ._pack import require_eval
+from .subnetworks.mvsnet import MVSNet
+from .subnetworks.scenemodeling import PointNet, SparseUNet, SparseScene
+from .subnetworks.refinement import HypothesisDecoder
+from .subnetworks.upsampling import PropagationNet
+
+
+class _FeatureCache(object):
+    """channels-last copies of feature tensors, keyed on storage + version"""
+
+    def __init__(self, size=8):
+        self.size, self.items = size, []
+
+    def get(self, feats):
+        key = (feats.data_ptr(), feats._version, tuple(feats.shape))
+        for k, v in self.items:
+            if k == key:
+                return v
+        v = ops.nchw_to_nhwc(feats.detach().float().contiguous())
+        self.items = ([(key, v)] + self.items)[:self.size]
+        return v
+
+
+class PL3DVNet(nn.Module):
+    def __init__(self, depth_train, depth_test, edge_len, feat_dim=16, img_size=(256, 320), hyp_ksize=3, hyp_pad=1,
+                 lr=1e-3, lr_step=100, lr_gamma=0.1, finetune=False):
+        super().__init__()
+        self.depth_train, self.depth_test, self.edge_len = depth_train, depth_test, edge_len
+        self.feat_dim, self.img_size = feat_dim, img_size
+        self.hyp_ksize, self.hyp_pad = hyp_ksize, hyp_pad
+        self.lr, self.lr_step, self.lr_gamma, self.finetune = lr, lr_step, lr_gamma, finetune
+        self.hparams = Namespace(depth_train=depth_train, depth_test=depth_test, edge_len=edge_len,
+                                 feat_dim=feat_dim, img_size=img_size, hyp_ksize=hyp_ksize, hyp_pad=hyp_pad, lr=lr,
+                                 lr_step=lr_step, lr_gamma=lr_gamma, finetune=finetune)
+        if feat_dim != 32:
+            raise NotImplementedError('the warp kernels are specialised for IMG_FEAT_DIM = 32 '
+                                      '(/root/reference/mv3d/config.py:42), got %d' % feat_dim)
+        self.mvsnet = MVSNet(feat_dim, img_size)
+        self.pointnet = PointNet(4 * feat_dim, 2 * feat_dim, feat_dim + 3)
+        self.sparse_conv = SparseUNet(dims=(2 * feat_dim, 128, 128), n_groups=(4, 8, 8), n_res=(1, 2, 3))
+        self.decoder = HypothesisDecoder(128 + 128 + 3 * feat_dim, 128, hyp_ksize, hyp_pad)
+        self.refine_quarter = PropagationNet(in_dim=feat_dim + 1, h_dim=32)
+        self.refine_half = PropagationNet(in_dim=feat_dim + 1, h_dim=32)
+        self.refine_full = PropagationNet(in_dim=3 + 1, h_dim=32)
+        self._nhwc = _FeatureCache()
+
+    @property
+    def device(self):
+        return next(self.parameters()).device
+
+    @classmethod
+    def load_from_checkpoint(cls, path, map_location=None, **overrides):
+        """Lightning-style checkpoint: {'state_dict', 'hyper_parameters'} (lightningmodel.py:33)."""
+        ckpt = torch.load(path, map_location=map_location or 'cpu', weights_only=False)
+        hp = dict(ckpt.get('hyper_parameters', {}))
+        hp.update(overrides)
+        net = cls(**hp)
+        net.load_state_dict(ckpt['state_dict'], strict=False)
+        return net
+
+    # ------------------------------------------------------------------ hot path A
+    def make_initial_depth_predictions(self, batch, depth_config):
+        """lightningmodel.py:124-130"""
+        depth_pred, feats_half, feats_quarter, feats_eighth = self.mvsnet(
+            batch, depth_config['depth_start'], depth_config['depth_interval'], depth_config['n_intervals'],
+            depth_config['size'])
+        ref_idx = ops.edge_plan(batch.ref_src_edges, depth_pred.device).ref_idx
+        depth_batch = batch.images_batch.to(depth_pred.device)[ref_idx]
+        return depth_pred, depth_batch, feats_half, feats_quarter, feats_eighth, ref_idx
+
+    # ------------------------------------------------------------------ hot path B
+    def _geometry(self, img_feats, rotmats, tvecs, K, ref_src_edges):
+        dev = img_feats.device
+        plan = ops.edge_plan(ref_src_edges, dev)
+        R, t, Kc = rotmats.float().contiguous(), tvecs.float().contiguous(), K.float().contiguous()
+        return plan, self._nhwc.get(img_feats), ops.edge_transforms(R, t, Kc, plan), \
+            ops.ref_backprojection(R, t, Kc, plan)
+
+    def construct_feature_rich_pointcloud(self, depth_pred, depth_batch, img_feats, rotmats, tvecs, K, ref_src_edges):
+        """-> pts [n_ref*P,3], pts_feat [n_ref*P,C], pts_batch [n_ref*P] (lightningmodel.py:132-174)"""
+        plan, nhwc, xform, backproj = self._geometry(img_feats, rotmats, tvecs, K, ref_src_edges)
+        depth = depth_pred.detach().float().contiguous()
+        pts, feat = ops.points_var(nhwc, xform, plan, backproj, depth, self.hparams.img_size, 0, 0.0)
+        n, P = depth.shape[0], depth.shape[1] * depth.shape[2]
+        pts_batch = depth_batch.unsqueeze(1).expand(n, P).reshape(-1)
+        return pts.view(-1, 3), feat.view(-1, feat.shape[2]), pts_batch
+
+    def model_scene(self, depth_pred, depth_batch, img_feats, rotmats, tvecs, K, ref_src_edges, return_pts=False):
+        """lightningmodel.py:176-185"""
+        require_eval(self)
+        pts, pts_feat, pts_batch = self.construct_feature_rich_pointcloud(depth_pred, depth_batch, img_feats, rotmats,
+                                                                          tvecs, K, ref_src_edges)
+        a_pts, a_idx, a_batch, seg, grid = ops.voxelize(pts, pts_batch.contiguous(), self.edge_len)
+        x = ops.pointnet_input(pts, pts_feat, a_pts, seg, self.pointnet.in_pad)
+        x = self.pointnet.forward_padded(x, seg, a_pts.shape[0])
+        dims = (int(grid.n_cells[0]), int(grid.n_cells[1]), int(grid.n_cells[2]), int(grid.n_batch))
+        scene = SparseScene(a_idx, a_batch, self.sparse_conv.n_levels, dims)
+        xs = self.sparse_conv(x, a_pts, a_idx, a_batch, self.edge_len, scene=scene)
+        return (xs, pts) if return_pts else xs
+
+    def run_pointflow(self, xs, depth_pred, depth_batch, img_feats, rotmats, tvecs, K, ref_src_edges, offset, n,
+                      return_prob=False):
+        """expected depth offset [n_ref,h,w] over 2n+1 hypotheses (lightningmodel.py:187-242)"""
+        require_eval(self)
+        plan, nhwc, xform, backproj = self._geometry(img_feats, rotmats, tvecs, K, ref_src_edges)
+        depth = depth_pred.detach().float().contiguous()
+        n_ref, h, w = depth.shape
+        n_pts, n_hyp = n_ref * h * w, 2 * n + 1
+        operand = self.decoder.operand(n_pts, depth.device)
+        var_off = operand.shape[2] - self.hparams.feat_dim
+        pts_hyp, _ = ops.points_var(nhwc, xform, plan, backproj, depth, self.hparams.img_size, n, offset,
+                                    feat_out=operand, feat_off=var_off)
+        pts_batch = depth_batch.unsqueeze(1).expand(n_ref, h * w).reshape(-1).contiguous()
+        got = self.decoder.fill_levels(xs, pts_hyp, pts_batch, operand)
+        assert got == var_off
+        off, prob = self.decoder.run(operand, n_hyp, offset, want_prob=return_prob)
+        off = off.view(n_ref, h, w)
+        return (off, prob) if return_prob else off
+
+    # ------------------------------------------------------------------ full inference pass
+    def refine_depth(self, depth_pred, depth_batch, feats_quarter, rotmats, tvecs, K, ref_src_edges, offsets_list):
+        """eval-3dvnet.py:73-99 without the python chunking"""
+        depth = depth_pred.clone()
+        for offsets in offsets_list:
+            xs = self.model_scene(depth, depth_batch, feats_quarter, rotmats, tvecs, K, ref_src_edges)
+            for offset in offsets:
+                depth += self.run_pointflow(xs, depth, depth_batch, feats_quarter, rotmats, tvecs, K, ref_src_edges,
+                                            offset, 3)
+        return depth
+
+    def hot_path(self, feats_quarter, rotmats, tvecs, K, ref_src_edges, images_batch, depth_config, offsets_list):
+        """One pass of the hot path from quarter-resolution features: plane-sweep cost volume ->
+        CostRegNet -> soft-argmin, then the volumetric refinement schedule. -> depth [n_ref,h,w].
+        This is the benchmark "step" (BASELINE.json configs[1])."""
+        require_eval(self)
+        with torch.no_grad():
+            dev = feats_quarter.device
+            plan = ops.edge_plan(ref_src_edges, dev)
+            batch = Namespace(rotmats=rotmats, tvecs=tvecs, K=K, ref_src_edges=plan)
+            depth = self.mvsnet.depth_from_features(
+                feats_quarter, batch, depth_config['depth_start'], depth_config['depth_interval'],
+                depth_config['n_intervals'], depth_config['size'], feats_nhwc=self._nhwc.get(feats_quarter), plan=plan)
+            depth_batch = images_batch[plan.ref_idx]
+            return self.refine_depth(depth, depth_batch, feats_quarter, rotmats, tvecs, K, plan, offsets_list)
+
+    def upsample(self, depth, ref_idx, feats_quarter, feats_half, images):
+        """nearest upsampling + the three PropagationNets (lightningmodel.py:84-112)"""
+        d = F.interpolate(depth.unsqueeze(1), feats_quarter.shape[-2:], mode='nearest')
+        d = self.refine_quarter(feats_quarter[ref_idx], d)
+        d = F.interpolate(d.unsqueeze(1), feats_half.shape[-2:], mode='nearest')
+        d = self.refine_half(feats_half[ref_idx], d)
+        d = F.interpolate(d.unsqueeze(1), images.shape[-2:], mode='nearest')
+        return self.refine_full(images[ref_idx], d)
+
+    def forward(self, batch, offsets, n_iters):
+        """Inference-only counterpart of lightningmodel.py:48-122: returns the depth maps of every
+        stage instead of losses (no ground truth is consumed)."""
+        require_eval(self)
+        with torch.no_grad():
+            cfg = self.hparams.depth_test
+            depth, depth_batch, fh, fq, _, ref_idx = self.make_initial_depth_predictions(batch, cfg)
+            out = {'initial': depth}
+            refined = self.refine_depth(depth, depth_batch, fq, batch.rotmats, batch.tvecs, batch.K,
+                                        batch.ref_src_edges, [list(offsets)] * n_iters)
+            out['ref'] = refined
+            out['final'] = self.upsample(refined, ref_idx, fq, fh, batch.images)
+            return out

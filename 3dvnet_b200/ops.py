@@ -1,0 +1,340 @@
+"""torch-tensor front end of the C ABI (include/dv3d.h): checks dtypes / layouts, allocates
+outputs with torch (device memory + streams are torch's job here, nothing else) and
+enqueues the CUDA kernels of lib3dvnet_b200.so on the current stream.
+
+No function in this module has a CPU or eager-PyTorch fallback: tensors must live on a CUDA
+device and the shared library must load, otherwise the call raises.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from ._lib import lib, VoxelGrid, Dv3dError, DV3D_ENOSPC  # noqa: F401
+
+ROWS_PER_POINT = 8  # decoder operand: 7 hypotheses + 1 zero row (csrc/decoder.cu)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _chk(t, dtype, name, ndim=None):
+    if not (torch.is_tensor(t) and t.is_cuda):
+        raise RuntimeError('%s must be a CUDA tensor (3dvnet_b200 has no CPU path)' % name)
+    if t.dtype != dtype:
+        raise RuntimeError('%s must be %s, got %s' % (name, dtype, t.dtype))
+    if not t.is_contiguous():
+        raise RuntimeError('%s must be contiguous' % name)
+    if ndim is not None and t.dim() != ndim:
+        raise RuntimeError('%s must have %d dims, got shape %s' % (name, ndim, tuple(t.shape)))
+    return t
+
+
+def launch_count():
+    return int(lib().raw('dv3d_launch_count')())
+
+
+# ----------------------------------------------------------------------------- edges
+class EdgePlan(object):
+    """CSR view of ``ref_src_edges`` [2,E] (row 0 = reference image, row 1 = source image):
+    references are ``unique(row 0)`` in ascending order (mvsnet.py:179), the edges of every
+    reference are kept in their original relative order. Replaces utils.slice_edges'
+    O(E*range) compare and the gather_idx of mvsnet.py:179 / lightningmodel.py:134."""
+
+    def __init__(self, ref_src_edges, device):
+        e = ref_src_edges.detach().cpu().numpy() if torch.is_tensor(ref_src_edges) else np.asarray(ref_src_edges)
+        if e.ndim != 2 or e.shape[0] != 2:
+            raise RuntimeError('ref_src_edges must be [2, n_edges], got %s' % (e.shape,))
+        ref_idx, gather = np.unique(e[0], return_inverse=True)
+        order = np.argsort(gather, kind='stable')
+        counts = np.bincount(gather, minlength=len(ref_idx))
+        rowptr = np.zeros(len(ref_idx) + 1, dtype=np.int32)
+        np.cumsum(counts, out=rowptr[1:])
+        self.n_ref = int(len(ref_idx))
+        self.n_edges = int(e.shape[1])
+        packed = np.concatenate([rowptr, e[1][order].astype(np.int32), e[0][order].astype(np.int32),
+                                 ref_idx.astype(np.int32)])
+        dev = torch.from_numpy(packed).to(device, non_blocking=True)
+        n, E = self.n_ref, self.n_edges
+        self.rowptr, self.edge_src, self.edge_ref, self.ref_img = dev[:n + 1], dev[n + 1:n + 1 + E], \
+            dev[n + 1 + E:n + 1 + 2 * E], dev[n + 1 + 2 * E:]
+        self.ref_idx = torch.from_numpy(ref_idx.astype(np.int64)).to(device, non_blocking=True)
+        self.device = device
+
+
+_plan_cache = {}
+
+
+def edge_plan(ref_src_edges, device):
+    """Cached EdgePlan for an edge tensor (keyed on storage + version)."""
+    if isinstance(ref_src_edges, EdgePlan):
+        return ref_src_edges
+    key = (ref_src_edges.data_ptr(), ref_src_edges._version, tuple(ref_src_edges.shape), str(device))
+    plan = _plan_cache.get(key)
+    if plan is None:
+        if len(_plan_cache) > 64:
+            _plan_cache.clear()
+        plan = _plan_cache[key] = EdgePlan(ref_src_edges, device)
+    return plan
+
+
+# ----------------------------------------------------------------------------- path A
+def nchw_to_nhwc(x):
+    _chk(x, torch.float32, 'features', 4)
+    n, C, H, W = x.shape
+    out = torch.empty((n, H, W, C), dtype=torch.float32, device=x.device)
+    lib().call('dv3d_nchw_to_nhwc', _p(x), _p(out), n, C, H * W, _stream())
+    return out
+
+
+def edge_transforms(rotmats, tvecs, K, plan):
+    _chk(rotmats, torch.float32, 'rotmats', 3), _chk(tvecs, torch.float32, 'tvecs', 2), _chk(K, torch.float32, 'K', 3)
+    out = torch.empty((plan.n_edges, 12), dtype=torch.float32, device=rotmats.device)
+    lib().call('dv3d_edge_transforms', _p(rotmats), _p(tvecs), _p(K), _p(plan.edge_ref), _p(plan.edge_src),
+               plan.n_edges, _p(out), _stream())
+    return out
+
+
+def ref_backprojection(rotmats, tvecs, K, plan):
+    out = torch.empty((plan.n_ref, 12), dtype=torch.float32, device=rotmats.device)
+    lib().call('dv3d_ref_backprojection', _p(rotmats), _p(tvecs), _p(K), _p(plan.ref_img), plan.n_ref, _p(out),
+               _stream())
+    return out
+
+
+def planesweep_var(feats_nhwc, xform, plan, depth_start, depth_interval, n_planes, plane_size, img_size, out=None):
+    """x_var [n_ref,C,D,h,w] (mvsnet.py:187-216)."""
+    _chk(feats_nhwc, torch.float32, 'feats_nhwc', 4)
+    n_imgs, Hf, Wf, C = feats_nhwc.shape
+    h, w = plane_size
+    if out is None:
+        out = torch.empty((plan.n_ref, C, n_planes, h, w), dtype=torch.float32, device=feats_nhwc.device)
+    lib().call('dv3d_planesweep_var', _p(feats_nhwc), n_imgs, C, Hf, Wf, _p(xform), _p(plan.rowptr),
+               _p(plan.edge_src), plan.n_ref, float(depth_start), float(depth_interval), int(n_planes), h, w,
+               img_size[0], img_size[1], _p(out), _stream())
+    return out
+
+
+def points_var(feats_nhwc, xform, plan, backproj, depth, img_size, n_side, offset, feat_out=None, feat_off=0):
+    """World points of every pixel hypothesis + their variance feature
+    (lightningmodel.py:132-174 with n_side=0, :187-235 with n_side=3).
+    -> pts [n_ref*P, n_hyp, 3], feat [n_ref*P, rows, ld] (rows = n_hyp or the padded 8)."""
+    _chk(depth, torch.float32, 'depth', 3)
+    n_imgs, Hf, Wf, C = feats_nhwc.shape
+    n_ref, h, w = depth.shape
+    n_hyp = 2 * n_side + 1
+    Np = n_ref * h * w
+    pts = torch.empty((Np, n_hyp, 3), dtype=torch.float32, device=depth.device)
+    if feat_out is None:
+        feat_out = torch.empty((Np, n_hyp, C), dtype=torch.float32, device=depth.device)
+    rows, ld = feat_out.shape[1], feat_out.shape[2]
+    lib().call('dv3d_points_var', _p(feats_nhwc), n_imgs, C, Hf, Wf, _p(xform), _p(plan.rowptr), _p(plan.edge_src),
+               _p(backproj), _p(depth), n_ref, h, w, img_size[0], img_size[1], n_side, float(offset), _p(pts),
+               _p(feat_out), rows, ld, feat_off, _stream())
+    return pts, feat_out
+
+
+def conv3d_bn_relu(x, weight, scale, shift, stride=1, skip=None):
+    _chk(x, torch.float32, 'x', 5), _chk(weight, torch.float32, 'weight', 5)
+    n, Cin, D, H, W = x.shape
+    Cout = weight.shape[0]
+    if stride == 1:
+        oshape = (n, Cout, D, H, W)
+    else:
+        oshape = (n, Cout, (D + 1) // 2, (H + 1) // 2, (W + 1) // 2)
+    y = torch.empty(oshape, dtype=torch.float32, device=x.device)
+    lib().call('dv3d_conv3d_bn_relu', _p(x), n, Cin, D, H, W, _p(weight), _p(scale), _p(shift), Cout, stride,
+               _p(skip), _p(y), _stream())
+    return y
+
+
+def deconv3d_bn_relu(x, weight, scale, shift, skip=None):
+    n, Cin, D, H, W = x.shape
+    Cout = weight.shape[1]
+    y = torch.empty((n, Cout, 2 * D, 2 * H, 2 * W), dtype=torch.float32, device=x.device)
+    lib().call('dv3d_deconv3d_bn_relu', _p(x), n, Cin, D, H, W, _p(weight), _p(scale), _p(shift), Cout, _p(skip),
+               _p(y), _stream())
+    return y
+
+
+def prob_softargmin(x, weight, bias, depth_start, depth_end, want_reg=False):
+    n, Cin, D, H, W = x.shape
+    depth = torch.empty((n, H, W), dtype=torch.float32, device=x.device)
+    reg = torch.empty((n, D, H, W), dtype=torch.float32, device=x.device) if want_reg else None
+    lib().call('dv3d_prob_softargmin', _p(x), n, Cin, D, H, W, _p(weight), float(bias), float(depth_start),
+               float(depth_end), _p(reg), _p(depth), _stream())
+    return depth, reg
+
+
+# ----------------------------------------------------------------------------- voxelise
+def voxelize(pts, pts_batch, edge_len):
+    """utils.py:38-64 -> anchor_pts [Nv,3] f32, anchor_idx3d [Nv,3] i32, anchor_batch [Nv] i64,
+    point_anchor [N] i32 (row 0 of anchor_pts_edges), grid (VoxelGrid). Syncs twice."""
+    _chk(pts, torch.float32, 'pts', 2), _chk(pts_batch, torch.int64, 'pts_batch', 1)
+    N = pts.shape[0]
+    if N == 0:
+        raise RuntimeError('voxelize: empty point set (the reference fails on pts.min of an empty tensor)')
+    dev = pts.device
+    L = lib()
+    grid = VoxelGrid()
+    scratch = torch.empty(64, dtype=torch.uint8, device=dev)
+    L.call('dv3d_voxel_grid', _p(pts), _p(pts_batch), N, float(edge_len), ctypes.byref(grid), _p(scratch), _stream())
+    ws_bytes = L.raw('dv3d_voxelize_workspace_bytes')(ctypes.byref(grid), N)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    cap = N
+    a_pts = torch.empty((cap, 3), dtype=torch.float32, device=dev)
+    a_idx = torch.empty((cap, 3), dtype=torch.int32, device=dev)
+    a_batch = torch.empty((cap,), dtype=torch.int64, device=dev)
+    p_anchor = torch.empty((N,), dtype=torch.int32, device=dev)
+    n_anchor = ctypes.c_longlong(0)
+    L.call('dv3d_voxelize', _p(pts), _p(pts_batch), N, ctypes.byref(grid), _p(ws), ws_bytes, cap,
+           ctypes.byref(n_anchor), _p(a_pts), _p(a_idx), _p(a_batch), _p(p_anchor), _stream())
+    nv = n_anchor.value
+    return a_pts[:nv], a_idx[:nv], a_batch[:nv], p_anchor, grid
+
+
+# ----------------------------------------------------------------------------- PointNet
+def pointnet_input(pts, pts_feat, anchor_pts, seg, out_ld=48):
+    N, C = pts_feat.shape
+    out = torch.empty((N, out_ld), dtype=torch.float32, device=pts.device)
+    lib().call('dv3d_pointnet_input', _p(pts), _p(pts_feat), pts_feat.stride(0), _p(anchor_pts), _p(seg), N, C,
+               out_ld, _p(out), _stream())
+    return out
+
+
+def linear(x_a, weight_kn, bias, relu_input, pool=None, seg=None, Ca=None):
+    N, lda = x_a.shape
+    Ca = lda if Ca is None else Ca
+    Cb = 0 if pool is None else pool.shape[1]
+    Cout = weight_kn.shape[1]
+    assert weight_kn.shape[0] == Ca + Cb
+    y = torch.empty((N, Cout), dtype=torch.float32, device=x_a.device)
+    lib().call('dv3d_linear', _p(x_a), Ca, lda, _p(pool), _p(seg), Cb, N, _p(weight_kn), _p(bias), Cout,
+               int(relu_input), _p(y), _stream())
+    return y
+
+
+def segment_max(x, seg, n_seg):
+    N, C = x.shape
+    out = torch.empty((n_seg, C), dtype=torch.float32, device=x.device)
+    lib().call('dv3d_segment_max', _p(x), _p(seg), N, C, n_seg, _p(out), _stream())
+    return out
+
+
+# ----------------------------------------------------------------------------- sparse levels
+class SparseLevel(object):
+    """One coordinate level of the sparse U-Net: coords [n,4] int32 (b,x,y,z) sorted by
+    (b,z,y,x), tensor stride, hash table."""
+
+    def __init__(self, coords, stride, err_flag):
+        self.coords = coords
+        self.n = coords.shape[0]
+        self.stride = stride
+        nbytes = lib().raw('dv3d_hash_bytes')(self.n)
+        self.table = torch.empty(nbytes, dtype=torch.uint8, device=coords.device)
+        self.table_bytes = nbytes
+        lib().call('dv3d_hash_build', _p(coords), self.n, _p(self.table), nbytes, _p(err_flag), _stream())
+        self._maps = {}
+
+    def kernel_map(self, in_level, step):
+        """nbr [n,27] int32: rows of in_level at coords + offset_k * step."""
+        key = (id(in_level), step)
+        m = self._maps.get(key)
+        if m is None:
+            m = torch.empty((self.n, 27), dtype=torch.int32, device=self.coords.device)
+            lib().call('dv3d_kernel_map', _p(self.coords), self.n, _p(in_level.table), in_level.table_bytes, step,
+                       _p(m), _stream())
+            self._maps[key] = m
+        return m
+
+
+def make_coords(idx3d, batch):
+    n = idx3d.shape[0]
+    coords = torch.empty((n, 4), dtype=torch.int32, device=idx3d.device)
+    lib().call('dv3d_make_coords', _p(idx3d), _p(batch), n, _p(coords), _stream())
+    return coords
+
+
+def coarsen(level, dims, n_batch, err_flag):
+    """Output level of a stride-2 convolution on ``level`` (A.4). Syncs once."""
+    L = lib()
+    ns = level.stride * 2
+    ws_bytes = L.raw('dv3d_coarsen_workspace_bytes')(dims[0], dims[1], dims[2], n_batch, ns)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=level.coords.device)
+    out = torch.empty((level.n, 4), dtype=torch.int32, device=level.coords.device)
+    n_out = ctypes.c_longlong(0)
+    L.call('dv3d_coarsen', _p(level.coords), level.n, ns, dims[0], dims[1], dims[2], n_batch, _p(ws), ws_bytes,
+           level.n, _p(out), ctypes.byref(n_out), _stream())
+    return SparseLevel(out[:n_out.value], ns, err_flag)
+
+
+def sparse_conv(feat, nbr, W, gn_weight=None, gn_bias=None, residual=None, relu=False):
+    n_in, Cin = feat.shape
+    n_out = nbr.shape[0]
+    Cout = W.shape[2]
+    assert W.shape[0] == 27 and W.shape[1] == Cin
+    out = torch.empty((n_out, Cout), dtype=torch.float32, device=feat.device)
+    lib().call('dv3d_sparse_conv', _p(feat), n_in, Cin, _p(nbr), n_out, _p(W), Cout, _p(gn_weight), _p(gn_bias),
+               _p(residual), int(relu), _p(out), _stream())
+    return out
+
+
+def concat_linear_gn_relu(a, b, W, gn_weight, gn_bias):
+    n, Ca = a.shape
+    Cb = b.shape[1]
+    Cout = W.shape[1]
+    out = torch.empty((n, Cout), dtype=torch.float32, device=a.device)
+    lib().call('dv3d_concat_linear_gn_relu', _p(a), Ca, _p(b), Cb, n, _p(W), Cout, _p(gn_weight), _p(gn_bias), _p(out),
+               _stream())
+    return out
+
+
+def batch_origin(anchor_pts, idx3d, batch, n_batch, res):
+    origin = torch.zeros((n_batch, 3), dtype=torch.float32, device=anchor_pts.device)
+    lib().call('dv3d_batch_origin', _p(anchor_pts), _p(idx3d), _p(batch), anchor_pts.shape[0], float(res), _p(origin),
+               _stream())
+    return origin
+
+
+def level_points(level, origin, res):
+    n = level.n
+    dev = level.coords.device
+    pts = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    idx = torch.empty((n, 3), dtype=torch.int64, device=dev)
+    batch = torch.empty((n,), dtype=torch.int64, device=dev)
+    lib().call('dv3d_level_points', _p(level.coords), n, _p(origin), float(res), _p(pts), _p(idx), _p(batch),
+               _stream())
+    return pts, idx, batch
+
+
+# ----------------------------------------------------------------------------- decoder
+def sparse_interp(pts, pts_batch, n_hyp, level, origin, res, feat, out, out_off):
+    n_pts = pts.shape[0]
+    lib().call('dv3d_sparse_interp', _p(pts), _p(pts_batch), n_pts, n_hyp, out.shape[1], _p(origin), float(res),
+               level.stride, _p(level.table), level.table_bytes, _p(feat), feat.shape[1], _p(out), out.shape[2],
+               out_off, _stream())
+
+
+def conv1d_bn_relu(x, weight_tkn, scale, shift, out=None):
+    """x [n_pts, 8, Cin] -> [n_pts, 8, Cout] (refinement.py:8-13)."""
+    n_pts, rows, ldx = x.shape
+    Cin, Cout = weight_tkn.shape[1], weight_tkn.shape[2]
+    if out is None:
+        out = torch.empty((n_pts, rows, Cout), dtype=torch.float32, device=x.device)
+    lib().call('dv3d_conv1d_bn_relu', _p(x), n_pts, rows, Cin, ldx, _p(weight_tkn), _p(scale), _p(shift), Cout,
+               _p(out), out.shape[2], _stream())
+    return out
+
+
+def decoder_head(x, n_hyp, weight, bias, offset, want_prob=False):
+    n_pts, rows, ldx = x.shape
+    off = torch.empty((n_pts,), dtype=torch.float32, device=x.device)
+    prob = torch.empty((n_pts, n_hyp), dtype=torch.float32, device=x.device) if want_prob else None
+    lib().call('dv3d_decoder_head', _p(x), n_pts, n_hyp, rows, weight.shape[1], ldx, _p(weight), float(bias),
+               float(offset), _p(prob), _p(off), _stream())
+    return off, prob

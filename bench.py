@@ -1,0 +1,290 @@
+"""Benchmark of the 3DVNet hot path (BASELINE.json): ref-views/sec at 256x320, D=96, 7 source
+views, synthetic ScanNet-shape batches.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A "step" is one pass of the hot path over one batch of BASELINE.json configs[1]: 1 reference
++ 7 source views (8 images, quarter-resolution features 32x64x80), plane-sweep cost volume ->
+CostRegNet -> soft-argmin, then 2 x (scene model at 4 cm voxels + 3 PointFlow passes).
+N > 1: one process per GPU (torchrun), every rank runs its own scenes (no collective on the
+data path; weak scaling), time = max over ranks.
+
+`--impl reference` times the reference algorithm's CPU restatement (oracle/, the only other
+place this file may execute it) on the host cores for the same metric and config.
+"""
+import argparse
+import importlib
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+IMG_SIZE, PLANE, D, N_SRC = (256, 320), (56, 56), 96, 7
+DEPTH_CFG = dict(depth_start=0.5, depth_interval=0.05, n_intervals=D, size=PLANE)
+EDGE_LEN = 0.04
+OFFSETS_LIST = [[0.05, 0.05, 0.025], [0.05, 0.05, 0.025]]  # eval-3dvnet.py:23
+METRIC = 'ref-views/sec at 256x320, D=96, 7 src'
+WORKLOAD = 'C2: 1 ref + 7 src, 256x320, D=96, plane 56x56, C=32, 4cm voxels, 2x(scene model + 3 PointFlow)'
+# algorithmic bytes of the warp+variance kernel per reference view:
+# every source feature map read once + the [C,D,h,w] slab written once
+ALGO_BYTES = N_SRC * 32 * 64 * 80 * 4 + 32 * D * PLANE[0] * PLANE[1] * 4
+
+
+def synth_inputs(seed, refs_per_step):
+    synth = importlib.import_module('3dvnet_b200.synth')
+    n_imgs = refs_per_step + N_SRC
+    return synth.make_batch(1, n_imgs, IMG_SIZE, PLANE, 32, 4, 3, False, seed), synth.make_params(0)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi style clock / throttle-reason samples of one GPU during the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.samples, self.reasons, self.stop_flag, self.max_mhz, self.ok = [], set(), False, None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            pass
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: 'hw_slowdown',
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: 'hw_thermal_slowdown',
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: 'sw_thermal_slowdown',
+                 nv.nvmlClocksThrottleReasonSwPowerCap: 'sw_power_cap'}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                break
+            time.sleep(0.02)
+
+    def summary(self):
+        if not self.samples:
+            return {'sm_mhz': None, 'sm_max_mhz': self.max_mhz, 'reasons': ['unavailable']}
+        return {'sm_mhz': float(np.median(self.samples)), 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons)}
+
+
+def cpu_step(b, params):
+    """The reference algorithm's CPU restatement of one step (oracle/pipeline.py)."""
+    from oracle import pipeline
+    with torch.no_grad():
+        return pipeline.hot_path(b.feats_quarter, b.rotmats, b.tvecs, b.K, b.ref_src_edges, b.images_batch,
+                                 DEPTH_CFG, EDGE_LEN, IMG_SIZE, params)
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    b, params = synth_inputs(0, args.refs_per_step)
+    for _ in range(args.warmup):
+        cpu_step(b, params)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_step(b, params)
+    dt = time.perf_counter() - t0
+    value = args.steps * args.refs_per_step / dt
+    sample = '%d step(s) of the full workload (each %d ref view(s)), torch CPU threads=%d' % (
+        args.steps, args.refs_per_step, cores)
+    print(json.dumps({
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'ref-views/s', 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'refs_per_step': args.refs_per_step},
+        'cpu_baseline': {'value': value, 'unit': 'ref-views/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': 'ref-views/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--refs-per-step', type=int, default=1,
+                    help='reference views per step (BASELINE configs[1] = 1; larger values are a sweep, not the metric)')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+
+    if args.impl == 'reference':
+        run_reference(args, rank)
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device — the product path has no CPU fallback '
+                         '(use --impl reference for the CPU baseline)')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+
+    importlib.import_module('3dvnet_b200.build').build()
+    ops = importlib.import_module('3dvnet_b200.ops')
+    lm = importlib.import_module('3dvnet_b200.mv3d.lightningmodel')
+    warm = max(args.warmup, 3)
+
+    # every rank works on its own scenes (seed = rank): no data-path collective
+    b, params = synth_inputs(rank, args.refs_per_step)
+    net = lm.PL3DVNet(DEPTH_CFG, DEPTH_CFG, EDGE_LEN, feat_dim=32, img_size=IMG_SIZE)
+    net.load_state_dict(params, strict=False)
+    net = net.to(dev).eval()
+
+    host = {k: getattr(b, k).pin_memory() for k in ('feats_quarter', 'rotmats', 'tvecs', 'K', 'images_batch')}
+    edges = b.ref_src_edges  # host int64 [2,E]
+    resident = {k: v.to(dev) for k, v in host.items()}
+    n_ref = args.refs_per_step
+    out_host = torch.empty((n_ref,) + PLANE, dtype=torch.float32).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step_resident():
+        return net.hot_path(resident['feats_quarter'], resident['rotmats'], resident['tvecs'], resident['K'], edges,
+                            resident['images_batch'], DEPTH_CFG, OFFSETS_LIST)
+
+    def step_e2e():
+        d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        depth = net.hot_path(d['feats_quarter'], d['rotmats'], d['tvecs'], d['K'], edges, d['images_batch'],
+                             DEPTH_CFG, OFFSETS_LIST)
+        out_host.copy_(depth, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return out_host
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        """per-step CUDA events on the launching stream; L2 flushed before every step, outside the events"""
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        for s, e in ev:
+            flush.zero_()
+            s.record()
+            fn()
+            e.record()
+        barrier()
+        return sum(s.elapsed_time(e) for s, e in ev)  # ms
+
+    for _ in range(warm):
+        step_resident()
+    torch.cuda.synchronize()
+
+    # dominant-kernel timing: events around the warp+variance launch inside the timed steps
+    kernel_ms = []
+    orig = ops.planesweep_var
+
+    def timed_planesweep(*a, **k):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        r = orig(*a, **k)
+        e.record()
+        kernel_ms.append((s, e))
+        return r
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    ops.planesweep_var = timed_planesweep
+    launches0 = ops.launch_count()
+    ms = timed(step_resident, args.steps)
+    launches = ops.launch_count() - launches0
+    ops.planesweep_var = orig
+    sampler.stop_flag = True
+    sampler.join()
+    k_ms = float(np.mean([s.elapsed_time(e) for s, e in kernel_ms]))
+
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        cnt = torch.tensor([launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(cnt)
+        launches = int(cnt.item())
+    ms, ms_e2e = float(t[0]), float(t[1])
+    units = args.steps * n_ref * world
+
+    peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    else:
+        peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
+    achieved = ALGO_BYTES * n_ref / (k_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'planesweep_traffic.json')
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get('dram_bytes_per_launch')
+
+    line = {
+        'metric': METRIC, 'value': units / (ms * 1e-3), 'unit': 'ref-views/s', 'n_gpus': world,
+        'steps': args.steps, 'warmup': warm, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'refs_per_step': n_ref, 'imgs_per_step': n_ref + N_SRC,
+                   'parallelism': 'scenes sharded over %d rank(s), no collective' % world,
+                   'l2': 'flushed (256 MiB memset) before every timed step, outside the per-step events',
+                   'timing': 'sum of per-step CUDA events on the launching stream, max over ranks'},
+        'e2e': {'value': units / (ms_e2e * 1e-3), 'unit': 'ref-views/s',
+                'h2d_bytes_per_step': int(sum(v.numel() * v.element_size() for v in host.values())
+                                          + edges.numel() * 4 + 64),
+                'd2h_bytes_per_step': int(out_host.numel() * 4), 'ms_per_step': ms_e2e / args.steps},
+        'gpu_launches': launches,
+        'roofline': {'kernel': 'planesweep_var_kernel', 'bound': 'hbm', 'achieved': achieved, 'peak': peak,
+                     'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
+                     'algorithmic_bytes_per_launch': ALGO_BYTES * n_ref, 'kernel_ms': k_ms},
+        'clocks': sampler.summary(),
+    }
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        cpu_step(b, params)  # warm-up (lazy init)
+        n_cpu = 3
+        t0 = time.perf_counter()
+        for _ in range(n_cpu):
+            ref = cpu_step(b, params)
+        dt = time.perf_counter() - t0
+        got = step_resident().cpu()
+        rel = (torch.abs(got - ref) / (ref + 1e-7)).mean().item()
+        line['cpu_baseline'] = {'value': n_cpu * n_ref / dt, 'unit': 'ref-views/s', 'cores': cores, 'kind': 'port',
+                                'sample': '%d full steps of the same workload through oracle/pipeline.py '
+                                          '(torch CPU, %d threads)' % (n_cpu, cores)}
+        line['abs_rel_vs_oracle'] = rel
+    if rank == 0:
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

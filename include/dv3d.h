@@ -86,13 +86,13 @@ int dv3d_planesweep_var(const float* feats_nhwc, int n_imgs, int C, int Hf, int 
  *   depth    [n_ref,h,w];  backproj [n_ref,12] from dv3d_ref_backprojection
  *   hypothesis i (i=-n..n) has depth d + i*offset
  *   pts_out  [n_ref*h*w, n_hyp, 3]   world points
- *   feat_out [n_ref*h*w, n_hyp, feat_stride] variance feature written at channel offset
- *            feat_off (lets the caller write straight into the decoder operand)
+ *   feat_out [n_ref*h*w, rows_per_point >= n_hyp, feat_stride] variance feature written at
+ *            channel offset feat_off (lets the caller write straight into the decoder operand)
  */
 int dv3d_points_var(const float* feats_nhwc, int n_imgs, int C, int Hf, int Wf, const float* xform,
                     const int* edge_rowptr, const int* edge_src, const float* backproj, const float* depth,
                     int n_ref, int h, int w, int H, int W, int n_side, float offset, float* pts_out,
-                    float* feat_out, int feat_stride, int feat_off, void* stream);
+                    float* feat_out, int rows_per_point, int feat_stride, int feat_off, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * CostRegNet layers, inference mode (mvsnet.py:18-36,133-163).  NCDHW fp32.
@@ -114,34 +114,53 @@ int dv3d_prob_softargmin(const float* x, int n, int Cin, int D, int H, int W, co
                          float depth_start, float depth_end, float* x_reg_out, float* depth_out, void* stream);
 
 /* ------------------------------------------------------------------------------------
- * Voxelisation (utils.py:38-64 incl. torch_cluster grid_cluster; bit-exact index math).
- * SYNCS once (reads the voxel count back).
- *   pts [N,3] f32, batch [N] int64
- *   out: n_anchors_host; anchor_pts [cap,3] f32; anchor_idx3d [cap,3] int32;
- *        anchor_batch [cap] int64; point_anchor [N] int64 (row 0 of anchor_pts_edges)
- *   workspace: dv3d_voxelize_workspace_bytes(N); returns DV3D_ENOSPC if the bounding box
- *   needs more cells than the workspace bitmap holds or anchors exceed `cap`.
+ * Voxelisation (utils.py:38-64 incl. torch_geometric voxel_grid -> torch_cluster
+ * grid_cluster; bit-exact index math, anchors in ascending voxel-id order like torch.unique).
+ *
+ * Two calls, each SYNCS the stream once:
+ *   dv3d_voxel_grid   reduces the bounding box / batch count and derives the grid on the host
+ *                     (both of the reference's formulas: grid_cluster's trunc(.)+1 cells and
+ *                     voxelize's ceil(.) grid_size, utils.py:41);
+ *   dv3d_voxelize     marks occupied cells in a bitmap, ranks them with a scan, and emits
+ *                     anchors + the point->anchor map; reads the anchor count back.
  */
-size_t dv3d_voxelize_workspace_bytes(long long n_points);
-int dv3d_voxelize(const float* pts, const long long* batch, long long N, float edge_len, void* workspace,
-                  size_t workspace_bytes, long long cap, long long* n_anchors_host, float* anchor_pts,
-                  int* anchor_idx3d, long long* anchor_batch, long long* point_anchor, void* stream);
+typedef struct dv3d_voxel_grid_t {
+    float bbox_min[3];
+    float bbox_max[3];
+    float edge_len;
+    long long n_cells[3];   /* torch_cluster: trunc((max-min)/e) + 1 */
+    long long grid_size[3]; /* utils.py:41:   ceil((max-min)/e)      */
+    long long n_batch;      /* batch.max() + 1 */
+    long long total_cells;  /* prod(n_cells) * n_batch */
+} dv3d_voxel_grid_t;
+
+/* pts [N,3] f32, batch [N] int64 (device); scratch64: >= 64 bytes of device memory */
+int dv3d_voxel_grid(const float* pts, const long long* batch, long long N, float edge_len,
+                    dv3d_voxel_grid_t* grid_host, void* scratch64, void* stream);
+size_t dv3d_voxelize_workspace_bytes(const dv3d_voxel_grid_t* grid_host, long long N);
+/*   out: *n_anchors_host; anchor_pts [cap,3] f32; anchor_idx3d [cap,3] int32 (per-batch min
+ *        subtracted, utils.py:61-62); anchor_batch [cap] int64; point_anchor [N] int32
+ *        (row 0 of anchor_pts_edges; row 1 is arange(N)).
+ *   DV3D_ENOSPC if workspace or cap is too small. */
+int dv3d_voxelize(const float* pts, const long long* batch, long long N, const dv3d_voxel_grid_t* grid_host,
+                  void* workspace, size_t workspace_bytes, long long cap, long long* n_anchors_host,
+                  float* anchor_pts, int* anchor_idx3d, long long* anchor_batch, int* point_anchor, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * PointNet (scenemodeling.py:116-144).
- *   y = W x + b with optional ReLU on the INPUT (fc(relu(x))), x rows optionally the
- *   concatenation [x_a | pool[seg]] (scenemodeling.py:130-138).
- *   x_a [N,Ca]; pool [n_seg,Cb] gathered through seg [N] (may be NULL with Cb = 0);
- *   weight [Cout, Ca+Cb] (torch nn.Linear layout), bias [Cout]; y [N,Cout]
+ *   input rows [pts - anchor_pts[seg] | pts_feat | 0...] (lightningmodel.py:182): out [N,out_ld],
+ *   out_ld >= 3 + C (padded so that the GEMM K extent is a multiple of 16)
  */
-int dv3d_linear(const float* x_a, int Ca, const float* pool, const long long* seg, int Cb, long long N,
-                const float* weight, const float* bias, int Cout, int relu_input, float* y, void* stream);
+int dv3d_pointnet_input(const float* pts, const float* pts_feat, int feat_ld, const float* anchor_pts,
+                        const int* seg, long long N, int C, int out_ld, float* out, void* stream);
+/*   y = [relu](x) W + b on rows x = [x_a | pool[seg]] (scenemodeling.py:130-138).
+ *   x_a [N,lda] (first Ca columns used, Ca % 16 == 0); pool [n_seg,Cb] gathered through seg [N]
+ *   int32 (NULL with Cb = 0); weight_kn [Ca+Cb, Cout] = nn.Linear.weight transposed;
+ *   bias [Cout]; Cout in {64,128}; y [N,Cout] */
+int dv3d_linear(const float* x_a, int Ca, int lda, const float* pool, const int* seg, int Cb, long long N,
+                const float* weight_kn, const float* bias, int Cout, int relu_input, float* y, void* stream);
 /* segment max with empty segments = 0 (torch_scatter 'max'): out [n_seg,C] */
-int dv3d_segment_max(const float* x, const long long* seg, long long N, int C, long long n_seg, float* out,
-                     void* stream);
-/* PointNet input rows [pts - anchor_pts[seg] | pts_feat] (lightningmodel.py:182): out [N,3+C] */
-int dv3d_pointnet_input(const float* pts, const float* pts_feat, const float* anchor_pts, const long long* seg,
-                        long long N, int C, float* out, void* stream);
+int dv3d_segment_max(const float* x, const int* seg, long long N, int C, long long n_seg, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Sparse 3D-UNet building blocks (scenemodeling.py:16-44,78-113,147-237; MinkowskiEngine
@@ -150,51 +169,66 @@ int dv3d_pointnet_input(const float* pts, const float* pts_feat, const float* an
  * A coordinate level is: coords [n,4] int32 (batch,x,y,z) in ascending (batch,z,y,x)
  * order, its tensor stride, and an open-addressed hash table (key -> row).
  */
+/* [batch | idx3d] rows of the finest level (scenemodeling.py:192) */
+int dv3d_make_coords(const int* idx3d, const long long* batch, long long n, int* coords, void* stream);
 size_t dv3d_hash_bytes(long long n_rows);
-/* build the table of a level from its coordinates */
-int dv3d_hash_build(const int* coords, long long n, void* table, size_t table_bytes, void* stream);
-/* coarser level of a stride-2 convolution: unique(floor(c/(2 ts)) * 2 ts), sorted.  SYNCS.
- * workspace as for voxelize.  coarse_coords capacity = n rows. */
-int dv3d_coarsen(const int* coords, long long n, int new_stride, void* workspace, size_t workspace_bytes,
-                 int* coarse_coords, long long* n_coarse_host, void* stream);
-/* kernel map: for every output row o and offset k (x fastest, 27 offsets, scaled by `step`)
- * nbr[o*27+k] = row of coords_out[o] + offset_k*step in the input level, or -1. */
+/* build the table of a level; *err_flag (device int, caller-zeroed) is set on out-of-range coordinates */
+int dv3d_hash_build(const int* coords, long long n, void* table, size_t table_bytes, int* err_flag, void* stream);
+/* coarser level of a stride-2 convolution: unique(floor(c / new_stride) * new_stride) in
+ * (batch,z,y,x) order.  dim_* bound the finest-level index range (cells per axis).  SYNCS once. */
+size_t dv3d_coarsen_workspace_bytes(int dim_x, int dim_y, int dim_z, int n_batch, int new_stride);
+int dv3d_coarsen(const int* coords, long long n, int new_stride, int dim_x, int dim_y, int dim_z, int n_batch,
+                 void* workspace, size_t workspace_bytes, long long cap, int* coarse_coords,
+                 long long* n_coarse_host, void* stream);
+/* kernel map: nbr[o*27+k] = row of coords_out[o] + offset_k*step in the input level, or -1
+ * (offset_k x fastest).  k3s1: same level, step = ts.  k3s2: out = coarse, in = fine table,
+ * step = ts_fine.  transposed k3s2: out = fine, in = coarse table, step = -ts_fine
+ * (fine_j = coarse_i + offset_k*ts_fine, same W[k], no flip). */
 int dv3d_kernel_map(const int* coords_out, long long n_out, const void* table_in, size_t table_bytes, int step,
                     int* nbr, void* stream);
-/* out[o] = sum_k feat[nbr[o,k]] @ W[k]   (W [27,Cin,Cout]); optional fused per-row
- * GroupNorm (gn_weight/gn_bias [Cout], group size Cout/n_groups, eps 1e-5), optional
- * residual add (before the ReLU) and ReLU — the SparseResidual3d / down / up blocks. */
+/* out[o] = sum_k feat[nbr[o,k]] @ W[k]   (W [27,Cin,Cout], ME layout); optional fused per-row
+ * GroupNorm (gn_weight/gn_bias [Cout], 16 channels per group, eps 1e-5), optional residual
+ * add (before the ReLU) and ReLU — the SparseResidual3d / down / up blocks.  Cin % 16 == 0,
+ * Cout in {64,128}. */
 int dv3d_sparse_conv(const float* feat, long long n_in, int Cin, const int* nbr, long long n_out, const float* W,
-                     int Cout, const float* gn_weight, const float* gn_bias, int n_groups, const float* residual,
-                     int relu, float* out, void* stream);
-/* transposed map: nbrT[j*27+k] = coarse row i with fine_j = coarse_i + offset_k*ts_fine, or -1 */
-int dv3d_kernel_map_transpose(const int* coords_fine, long long n_fine, const void* table_coarse,
-                              size_t table_bytes, int ts_fine, int* nbr, void* stream);
+                     int Cout, const float* gn_weight, const float* gn_bias, const float* residual, int relu,
+                     float* out, void* stream);
 /* 1x1 "feature adjust" on the concatenation [a | b] (ME.cat + k=1 conv, scenemodeling.py:206)
  * followed by GroupNorm + ReLU: W [Ca+Cb, Cout]. */
 int dv3d_concat_linear_gn_relu(const float* a, int Ca, const float* b, int Cb, long long n, const float* W,
-                               int Cout, const float* gn_weight, const float* gn_bias, int n_groups, float* out,
-                               void* stream);
+                               int Cout, const float* gn_weight, const float* gn_bias, float* out, void* stream);
+/* voxel positions of a level (scenemodeling.py:211-226): origin[b] = anchor_pts[first voxel of b]
+ * - idx3d[first] * res; pts = coord * res + origin[batch]; optional int64 views of idx / batch */
+int dv3d_batch_origin(const float* anchor_pts, const int* idx3d, const long long* batch, long long n, float res,
+                      float* origin, void* stream);
+int dv3d_level_points(const int* coords, long long n, const float* origin, float res, float* pts,
+                      long long* idx_out, long long* batch_out, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * PointFlow hypothesis decoder (refinement.py:28-44, lightningmodel.py:238-241).
- * Trilinear sparse interpolation of one level at the query points, written into the
- * decoder operand at a channel offset (missing voxels contribute 0, no renormalisation).
- *   pts [Nq,3] world points; origin [n_batch,3] = position of index (0,0,0) per batch
- *   (scatter-min of the level's voxel positions, refinement.py:33); res = level voxel size,
- *   stride = level tensor stride; pts_batch [Nq] int64 (already unrolled per hypothesis).
+ * The decoder operand is [n_pts, rows_per_point = 8, ld]: 7 hypotheses + one all-zero row,
+ * channels [L0 64 | L1 128 | L2 128 | var 32] (refinement.py:41 prepends each level).
+ *
+ * Trilinear sparse interpolation of one level at the hypothesis points, written at channel
+ * offset out_off (missing voxels contribute 0, no renormalisation).
+ *   pts [n_pts*n_hyp,3] world points; origin [n_batch,3] from dv3d_batch_origin (equals the
+ *   scatter-min of the level's voxel positions, refinement.py:33); res = level voxel size
+ *   (stride * base edge), stride = tensor stride; pts_batch [n_pts] int64.
  */
-int dv3d_sparse_interp(const float* pts, const long long* pts_batch, long long Nq, const float* origin, float res,
-                       int stride, const void* table, size_t table_bytes, const float* feat, int C,
-                       float* out, int out_stride, int out_off, void* stream);
-/* Conv1d(k=3,pad=1,no bias)+BN(folded scale/shift)+ReLU over the hypothesis axis:
- * x [Np,n_hyp,Cin] -> y [Np,n_hyp,Cout]; weight [Cout,Cin,3] (torch layout). */
-int dv3d_conv1d_bn_relu(const float* x, long long Np, int n_hyp, int Cin, const float* weight, const float* scale,
-                        const float* shift, int Cout, float* y, void* stream);
-/* last Conv1d (Cin->1, bias) + softmax over hypotheses + expected offset
- * sum_i p_i * linspace(-n*offset, n*offset)_i; prob_out optional [Np,n_hyp]; offset_out [Np] */
-int dv3d_decoder_head(const float* x, long long Np, int n_hyp, int Cin, const float* weight, float bias,
-                      float offset, float* prob_out, float* offset_out, void* stream);
+int dv3d_sparse_interp(const float* pts, const long long* pts_batch, long long n_pts, int n_hyp, int rows_per_point,
+                       const float* origin, float res, int stride, const void* table, size_t table_bytes,
+                       const float* feat, int C, float* out, int out_ld, int out_off, void* stream);
+/* Conv1d(k=3,pad=1,no bias)+BN(folded scale/shift)+ReLU over the hypothesis axis on the padded
+ * layout: x [n_pts*8, ldx] -> y [n_pts*8, ldy] (row 7 of every point written as 0);
+ * weight_tkn [3, Cin, Cout] = torch weight [Cout,Cin,3] permuted (2,1,0). */
+int dv3d_conv1d_bn_relu(const float* x, long long n_pts, int rows_per_point, int Cin, int ldx,
+                        const float* weight_tkn, const float* scale, const float* shift, int Cout, float* y, int ldy,
+                        void* stream);
+/* last Conv1d (Cin->1, bias; weight [1,Cin,3] torch layout) + softmax over hypotheses + expected
+ * offset sum_i p_i * linspace(-n*offset, n*offset)_i; prob_out optional [n_pts,n_hyp]; offset_out [n_pts] */
+int dv3d_decoder_head(const float* x, long long n_pts, int n_hyp, int rows_per_point, int Cin, int ldx,
+                      const float* weight, float bias, float offset, float* prob_out, float* offset_out,
+                      void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,241 @@
+"""GPU parity: every kernel of lib3dvnet_b200 (through the reference-shaped modules, i.e.
+through the C ABI) against (i) the golden vectors recorded from the unmodified reference and
+(ii) the CPU oracle on fresh seeded inputs. Integer/index outputs must be bit-exact; floating
+point tolerances are stated per check (north_star: depth within 1e-3 abs-rel)."""
+import importlib
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, golden_inputs
+
+pytestmark = pytest.mark.gpu
+CASES = ['c1_tiny', 'c1_selfedge_2scenes']
+DEV = 'cuda'
+
+
+def abs_rel(pred, ref):
+    """mv3d/eval/metricfunctions.py:29-41 with `ref` as ground truth"""
+    valid = (ref >= 0.5) & (ref < 65.0)
+    n = valid.reshape(ref.shape[0], -1).sum(1).float()
+    err = (torch.abs(pred - ref) / (ref + 1e-7)) * valid
+    return (err.reshape(ref.shape[0], -1).sum(1) / (n + 1e-7)).mean().item()
+
+
+@pytest.fixture(scope='module')
+def mods():
+    importlib.import_module('3dvnet_b200.build').build()
+    return dict(lm=importlib.import_module('3dvnet_b200.mv3d.lightningmodel'),
+                ops=importlib.import_module('3dvnet_b200.ops'),
+                utils=importlib.import_module('3dvnet_b200.mv3d.utils'),
+                synth=importlib.import_module('3dvnet_b200.synth'))
+
+
+def make_net(mods, g, cfg, img_size):
+    net = mods['lm'].PL3DVNet(cfg, cfg, float(g['edge_len']), feat_dim=32, img_size=img_size)
+    p = mods['synth'].make_params(int(g['seed']))
+    assert mods['synth'].params_checksum(p) == pytest.approx(float(g['params_checksum']), rel=1e-12)
+    missing, unexpected = net.load_state_dict(p, strict=False)
+    assert not unexpected
+    return net.to(DEV).eval()
+
+
+class B(object):
+    pass
+
+
+def to_batch(t):
+    b = B()
+    for k, v in t.items():
+        setattr(b, k, v.to(DEV))
+    return b
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_path_a_golden(name, mods):
+    g = load_golden(name)
+    t, cfg, img_size = golden_inputs(g)
+    net = make_net(mods, g, cfg, img_size)
+    b = to_batch(t)
+    with torch.no_grad():
+        x_var = net.mvsnet.cost_volume(b.feats_quarter, b, cfg['depth_start'], cfg['depth_interval'],
+                                       cfg['n_intervals'], cfg['size'])
+        d_end = cfg['depth_start'] + cfg['depth_interval'] * (cfg['n_intervals'] - 1)
+        depth, x_reg = net.mvsnet.cnn_3d.depth(x_var, cfg['depth_start'], d_end, want_reg=True)
+        # interface parity: cnn_3d(x) returns x_reg [n,1,D,h,w]
+        x_reg2 = net.mvsnet.cnn_3d(x_var)
+    ref_var = torch.from_numpy(g['ref_x_var'])
+    # fp32; the projection is composed in fp64 and rounded once instead of three fp32 bmm's:
+    # sample positions differ by ~1e-5 px
+    assert (x_var.cpu() - ref_var).abs().max().item() < 2e-4
+    assert (x_var.cpu() - ref_var).abs().mean().item() < 2e-6
+    np.testing.assert_allclose(x_reg.cpu().numpy(), g['ref_x_reg'], rtol=0, atol=2e-3)
+    np.testing.assert_array_equal(x_reg2.squeeze(1).cpu().numpy(), x_reg.cpu().numpy())
+    ref_depth = torch.from_numpy(g['ref_depth_init'])
+    assert abs_rel(depth.cpu(), ref_depth) < 1e-4
+    np.testing.assert_allclose(depth.cpu().numpy(), g['ref_depth_init'], rtol=0, atol=1e-3)
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_costreg_layers_match_oracle(name, mods):
+    """CostRegNet on the reference's own x_var: isolates the conv kernels from the warp."""
+    from oracle import costreg, pipeline
+    g = load_golden(name)
+    t, cfg, img_size = golden_inputs(g)
+    net = make_net(mods, g, cfg, img_size)
+    p = pipeline.sub(mods['synth'].make_params(int(g['seed'])), 'mvsnet.cnn_3d.')
+    x_var = torch.from_numpy(g['ref_x_var'])
+    ref_out, mid = costreg.costregnet(x_var, p, return_all=True)
+    with torch.no_grad():
+        c = net.mvsnet.cnn_3d
+        xv = x_var.to(DEV)
+        conv0 = c.conv0(xv)
+        np.testing.assert_allclose(conv0.cpu().numpy(), mid['conv0'].numpy(), rtol=0, atol=1e-5)
+        x9 = c.features(xv)
+        np.testing.assert_allclose(x9.cpu().numpy(), mid['x9'].numpy(), rtol=0, atol=5e-5)
+        d_end = cfg['depth_start'] + cfg['depth_interval'] * (cfg['n_intervals'] - 1)
+        depth, x_reg = c.depth(xv, cfg['depth_start'], d_end, want_reg=True)
+    np.testing.assert_allclose(x_reg.cpu().numpy(), ref_out.squeeze(1).numpy(), rtol=0, atol=1e-4)
+    np.testing.assert_allclose(depth.cpu().numpy(), g['ref_depth_init'], rtol=0, atol=5e-5)
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_point_cloud_and_voxelize_golden(name, mods):
+    g = load_golden(name)
+    t, cfg, img_size = golden_inputs(g)
+    net = make_net(mods, g, cfg, img_size)
+    b = to_batch(t)
+    depth = torch.from_numpy(g['ref_depth_init']).to(DEV)
+    ref_idx = torch.unique(t['ref_src_edges'][0])
+    depth_batch = t['images_batch'][ref_idx].to(DEV)
+    with torch.no_grad():
+        pts, pts_feat, pts_batch = net.construct_feature_rich_pointcloud(depth, depth_batch, b.feats_quarter,
+                                                                         b.rotmats, b.tvecs, b.K, b.ref_src_edges)
+    np.testing.assert_allclose(pts.cpu().numpy(), g['ref_pts'], rtol=0, atol=2e-6)
+    assert (pts_feat.cpu() - torch.from_numpy(g['ref_pts_feat'])).abs().max().item() < 2e-4
+    np.testing.assert_array_equal(pts_batch.cpu().numpy(), g['ref_pts_batch'])
+    # voxelise the REFERENCE's points: index outputs must be bit-exact
+    a_pts, a_idx, a_batch, edges = mods['utils'].voxelize(torch.from_numpy(g['ref_pts']).to(DEV),
+                                                          torch.from_numpy(g['ref_pts_batch']).to(DEV),
+                                                          float(g['edge_len']))
+    assert a_idx.dtype == torch.int32 and a_batch.dtype == torch.int64 and edges.dtype == torch.int64
+    np.testing.assert_array_equal(a_idx.cpu().numpy(), g['ref_anchor_idx3d'])
+    np.testing.assert_array_equal(a_batch.cpu().numpy(), g['ref_anchor_batch'])
+    np.testing.assert_array_equal(edges.cpu().numpy(), g['ref_anchor_pts_edges'])
+    np.testing.assert_array_equal(a_pts.cpu().numpy().view(np.int32), g['ref_anchor_pts'].view(np.int32))
+
+
+def test_voxelize_adversarial_bit_exact(mods):
+    g = load_golden('voxelize_adversarial')
+    a_pts, a_idx, a_batch, edges = mods['utils'].voxelize(torch.from_numpy(g['pts']).to(DEV),
+                                                          torch.from_numpy(g['batch']).to(DEV), float(g['edge_len']))
+    np.testing.assert_array_equal(a_idx.cpu().numpy(), g['ref_anchor_idx3d'])
+    np.testing.assert_array_equal(a_batch.cpu().numpy(), g['ref_anchor_batch'])
+    np.testing.assert_array_equal(edges.cpu().numpy(), g['ref_anchor_pts_edges'])
+    np.testing.assert_array_equal(a_pts.cpu().numpy().view(np.int32), g['ref_anchor_pts'].view(np.int32))
+
+
+@pytest.mark.parametrize('seed,n,batches,edge', [(0, 50000, 1, 0.04), (1, 200000, 4, 0.08), (2, 7, 1, 0.5),
+                                                 (3, 1, 1, 0.04)])
+def test_voxelize_random_matches_oracle(seed, n, batches, edge, mods):
+    from oracle.voxelize import voxelize as oracle_voxelize
+    rng = np.random.RandomState(seed)
+    pts = (rng.uniform(-3, 3, size=(n, 3)) * [1.0, 0.8, 0.4]).astype(np.float32)
+    if n == 1:
+        with pytest.raises(Exception, match='degenerate'):
+            mods['utils'].voxelize(torch.from_numpy(pts).to(DEV), torch.zeros(1, dtype=torch.long, device=DEV), edge)
+        return
+    batch = np.sort(rng.randint(0, batches, size=n)).astype(np.int64)
+    ref = oracle_voxelize(pts, batch, edge)
+    got = mods['utils'].voxelize(torch.from_numpy(pts).to(DEV), torch.from_numpy(batch).to(DEV), edge)
+    np.testing.assert_array_equal(got[1].cpu().numpy(), ref[1])
+    np.testing.assert_array_equal(got[2].cpu().numpy(), ref[2])
+    np.testing.assert_array_equal(got[3].cpu().numpy(), ref[3])
+    np.testing.assert_array_equal(got[0].cpu().numpy().view(np.int32), ref[0].view(np.int32))
+    # size-independent properties: anchors sorted & unique, every point inside its voxel cube
+    a = got[0][got[3][0]]
+    assert ((torch.from_numpy(pts).to(DEV) - a).abs() <= edge / 2 + 1e-4).all()
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_scene_model_golden(name, mods):
+    g = load_golden(name)
+    t, cfg, img_size = golden_inputs(g)
+    net = make_net(mods, g, cfg, img_size)
+    b = to_batch(t)
+    depth = torch.from_numpy(g['ref_depth_init']).to(DEV)
+    ref_idx = torch.unique(t['ref_src_edges'][0])
+    depth_batch = t['images_batch'][ref_idx].to(DEV)
+    args = (b.feats_quarter, b.rotmats, b.tvecs, b.K, b.ref_src_edges)
+    with torch.no_grad():
+        # PointNet alone, on the reference's own inputs, through the reference-shaped forward()
+        pts, feat = torch.from_numpy(g['ref_pts']), torch.from_numpy(g['ref_pts_feat'])
+        a_pts, edges = torch.from_numpy(g['ref_anchor_pts']), torch.from_numpy(g['ref_anchor_pts_edges'])
+        x = torch.cat((pts[edges[1]] - a_pts[edges[0]], feat[edges[1]]), dim=1)
+        pn = net.pointnet(x.to(DEV), edges[0].to(DEV), a_pts.shape[0])
+        np.testing.assert_allclose(pn.cpu().numpy(), g['ref_pointnet'], rtol=0, atol=2e-5)
+        # SparseUNet alone through its reference signature
+        xs = net.sparse_conv(torch.from_numpy(g['ref_pointnet']).to(DEV), a_pts.to(DEV),
+                             torch.from_numpy(g['ref_anchor_idx3d']).to(DEV),
+                             torch.from_numpy(g['ref_anchor_batch']).to(DEV), float(g['edge_len']))
+        for li, lv in enumerate(xs):
+            np.testing.assert_array_equal(lv['idx'].cpu().numpy(), g['ref_xs%d_idx' % li])
+            np.testing.assert_array_equal(lv['batch'].cpu().numpy(), g['ref_xs%d_batch' % li])
+            np.testing.assert_allclose(lv['pts'].cpu().numpy(), g['ref_xs%d_pts' % li], rtol=0, atol=1e-6)
+            np.testing.assert_allclose(lv['feats'].cpu().numpy(), g['ref_xs%d_feats' % li], rtol=0, atol=2e-4)
+            assert float(lv['res']) == pytest.approx(float(g['edge_len']) * lv['stride'])
+        # whole model_scene from the reference's initial depth
+        xs2 = net.model_scene(depth, depth_batch, *args)
+        for li, lv in enumerate(xs2):
+            np.testing.assert_array_equal(lv['idx'].cpu().numpy(), g['ref_xs%d_idx' % li])
+            err = (lv['feats'].cpu() - torch.from_numpy(g['ref_xs%d_feats' % li])).abs()
+            assert err.max().item() < 5e-3 and err.mean().item() < 5e-5
+        off = net.run_pointflow(xs2, depth, depth_batch, *args, float(g['offsets'][0][0]), 3)
+    np.testing.assert_allclose(off.cpu().numpy(), g['ref_offset0'], rtol=0, atol=2e-4)
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_decoder_reference_signature(name, mods):
+    """HypothesisDecoder.forward(xs, pts, pts_feat, pts_batch) -> softmax [Np,7] vs the oracle."""
+    from oracle import pipeline, pointcloud, scenemodel
+    g = load_golden(name)
+    t, cfg, img_size = golden_inputs(g)
+    net = make_net(mods, g, cfg, img_size)
+    b = to_batch(t)
+    p = mods['synth'].make_params(int(g['seed']))
+    depth = torch.from_numpy(g['ref_depth_init'])
+    ref_idx = torch.unique(t['ref_src_edges'][0])
+    depth_batch = t['images_batch'][ref_idx]
+    cargs = (t['feats_quarter'], t['rotmats'], t['tvecs'], t['K'], t['ref_src_edges'])
+    xs_o = pipeline.model_scene(depth, depth_batch, *cargs, float(g['edge_len']), img_size, p)
+    pts_hyp, pts_feat, pts_batch = pointcloud.hypothesis_points(depth, depth_batch, *cargs, 0.05, 3, img_size)
+    prob_o = scenemodel.hypothesis_decoder(xs_o, pts_hyp, pts_feat, pts_batch, pipeline.sub(p, 'decoder.'))
+    with torch.no_grad():
+        xs = net.model_scene(depth.to(DEV), depth_batch.to(DEV), b.feats_quarter, b.rotmats, b.tvecs, b.K,
+                             b.ref_src_edges)
+        prob = net.decoder(xs, pts_hyp.to(DEV), pts_feat.to(DEV), pts_batch.to(DEV))
+    assert prob.shape == prob_o.shape
+    np.testing.assert_allclose(prob.cpu().numpy(), prob_o.numpy(), rtol=0, atol=2e-3)
+    np.testing.assert_allclose(prob.sum(1).cpu().numpy(), 1.0, atol=1e-5)
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_refinement_schedule_golden(name, mods):
+    """initial depth -> 2 x (scene model + 3 PointFlow passes): depth within 1e-3 abs-rel of the
+    reference (north_star tolerance) starting from the same feature maps."""
+    g = load_golden(name)
+    t, cfg, img_size = golden_inputs(g)
+    net = make_net(mods, g, cfg, img_size)
+    b = to_batch(t)
+    ref_idx = torch.unique(t['ref_src_edges'][0])
+    depth_batch = t['images_batch'][ref_idx].to(DEV)
+    with torch.no_grad():
+        depth0 = net.mvsnet.depth_from_features(b.feats_quarter, b, cfg['depth_start'], cfg['depth_interval'],
+                                                cfg['n_intervals'], cfg['size'])
+        out = net.refine_depth(depth0, depth_batch, b.feats_quarter, b.rotmats, b.tvecs, b.K, b.ref_src_edges,
+                               g['offsets'].tolist())
+    ref = torch.from_numpy(g['ref_depth_final'])
+    assert abs_rel(out.cpu(), ref) < 1e-3
+    assert (out.cpu() - ref).abs().max().item() < 5e-3
+    assert dict(mods)['ops'].launch_count() > 0
