@@ -68,9 +68,9 @@ decoder_head_kernel(const float* __restrict__ x, long long Np, int n_hyp, int ro
 using namespace dv3d;
 
 extern "C" int dv3d_conv1d_bn_relu(const float* x, long long n_pts, int rows_per_point, int Cin, int ldx,
-                                   const float* weight_tkn, const float* scale, const float* shift, int Cout,
-                                   float* y, int ldy, void* stream) {
-    DV3D_REQUIRE(x && weight_tkn && scale && shift && y && n_pts >= 0, "conv1d: bad arguments");
+                                   const float* weight_tkn, const void* W_packed, const float* scale,
+                                   const float* shift, int Cout, float* y, int ldy, void* stream) {
+    DV3D_REQUIRE(x && (weight_tkn || W_packed) && scale && shift && y && n_pts >= 0, "conv1d: bad arguments");
     DV3D_REQUIRE(rows_per_point == 8, "conv1d: the operand layout is [n_pts, 8, C] (7 hypotheses + 1 zero row)");
     GemmDesc d = {};
     d.n_slices = 3;
@@ -79,6 +79,7 @@ extern "C" int dv3d_conv1d_bn_relu(const float* x, long long n_pts, int rows_per
     d.n_src_rows = d.M;
     d.N = Cout;
     d.W = weight_tkn;
+    d.Wp = (const float*)W_packed;
     d.scale = scale;
     d.shift = shift;
     d.relu_out = 1;

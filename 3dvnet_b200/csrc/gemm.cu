@@ -137,23 +137,24 @@ gather_gemm_f32_kernel(const __grid_constant__ GemmDesc d) {
     }
 }
 
-static int validate(const GemmDesc& d) {
+int validate_gather_gemm(const GemmDesc& d, int k_multiple) {
     DV3D_REQUIRE(d.N == 64 || d.N == 128, "gather_gemm: N must be 64 or 128, got %d", d.N);
     DV3D_REQUIRE(d.n_slices >= 1 && d.n_slices <= kMaxSlices, "gather_gemm: bad slice count %d", d.n_slices);
-    DV3D_REQUIRE(d.W && d.out && d.M >= 0 && d.out_ld >= d.N && d.out_ld % 4 == 0, "gather_gemm: bad output");
+    DV3D_REQUIRE((d.W || d.Wp) && d.out && d.M >= 0 && d.out_ld >= d.N && d.out_ld % 4 == 0, "gather_gemm: bad output");
     DV3D_REQUIRE(!d.gn_weight || d.gn_bias, "gather_gemm: GroupNorm needs weight and bias");
     DV3D_REQUIRE(!d.residual || d.res_ld % 4 == 0, "gather_gemm: residual pitch must be a multiple of 4");
     for (int s = 0; s < d.n_slices; ++s) {
-        DV3D_REQUIRE(d.slice[s].src && d.slice[s].K > 0 && d.slice[s].K % KC == 0 && d.slice[s].ld % 4 == 0 &&
-                         d.slice[s].ld >= d.slice[s].K,
-                     "gather_gemm: slice %d needs K %% 16 == 0 and ld %% 4 == 0 (K=%d ld=%d)", s, d.slice[s].K,
-                     d.slice[s].ld);
+        DV3D_REQUIRE(d.slice[s].src && d.slice[s].K > 0 && d.slice[s].K % k_multiple == 0 && d.slice[s].ld % 4 == 0 &&
+                         d.slice[s].ld >= d.slice[s].K && ((uintptr_t)d.slice[s].src & 15) == 0,
+                     "gather_gemm: slice %d needs K %% %d == 0, ld %% 4 == 0 and a 16-byte aligned source (K=%d ld=%d)",
+                     s, k_multiple, d.slice[s].K, d.slice[s].ld);
     }
     return DV3D_OK;
 }
 
 int launch_gather_gemm(const GemmDesc& d, cudaStream_t st) {
-    int rc = validate(d);
+    if (d.Wp) return launch_gather_gemm_tc(d, st);
+    int rc = validate_gather_gemm(d, KC);
     if (rc) return rc;
     if (d.M == 0) return DV3D_OK;
     const int grid = cdiv(d.M, BM);

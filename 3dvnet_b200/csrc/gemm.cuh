@@ -34,7 +34,9 @@ struct GemmDesc {
     long long M;            // output rows
     long long n_src_rows;   // shifted (non-table) rows outside [0, n_src_rows) read as zero
     int N;                  // output channels: 64 or 128
-    const float* W;         // [sum_s K_s, N] row-major
+    const float* W;         // [sum_s K_s, N] row-major (fp32 CUDA-core kernel)
+    const float* Wp;        // packed by dv3d_gemm_pack_weights: selects the tcgen05 kernel when set
+    const int* kmap;        // set when every slice s gathers through kmap[m * n_slices + s]
     const float* scale;     // per-channel multiplier (folded BN) or nullptr
     const float* shift;     // per-channel addend (bias / folded BN) or nullptr
     const float* gn_weight; // GroupNorm affine (groups of 16 channels) or nullptr
@@ -49,7 +51,9 @@ struct GemmDesc {
     int out_ld;
 };
 
-// mode 0: fp32 CUDA-core kernel; mode 1: tcgen05 TF32 tensor-core kernel
+// d.Wp == nullptr: fp32 CUDA-core kernel (gemm.cu); otherwise the tcgen05 kernel (gemm_tc.cu),
+// 3xTF32 or TF32 according to dv3d_set_gemm_precision.
 int launch_gather_gemm(const GemmDesc& d, cudaStream_t st);
+int launch_gather_gemm_tc(const GemmDesc& d, cudaStream_t st);
 
 }  // namespace dv3d

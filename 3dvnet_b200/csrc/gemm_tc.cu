@@ -1,0 +1,419 @@
+// Gather-GEMM on the 5th-generation tensor cores (tcgen05 + TMEM), see gemm.cuh for the
+// contraction it implements.
+//
+//   CTA tile        128 output rows x N (64 | 128) channels, accumulator in TMEM
+//                   (128 lanes x N fp32 columns), UMMA shape M128 x N x K8, kind::tf32
+//   K pipeline      chunks of 32 floats (one 128-byte swizzle row per operand row), 3 stages.
+//                   A (gathered feature rows): 8 producer warps read the rows named by the
+//                   slice's row table / shift with 16-byte loads, split every value into a
+//                   TF32 "big" part and an fp32 remainder, and store both in the canonical
+//                   K-major SWIZZLE_128B layout (st.shared + fence.proxy.async).
+//                   B (weights): pre-packed once per layer (pack_weights_kernel) into the exact
+//                   shared-memory image of every chunk, big and small part, and brought in by one
+//                   bulk-copy (cp.async.bulk -> mbarrier complete_tx) per stage.
+//   precision       3xTF32: acc += A_big B_big + A_big B_small + A_small B_big  (fp32-grade,
+//                   error ~2^-21 per product), or plain TF32 (first term only) as an opt-in.
+//   MMA issue       one elected thread of warp 8; tcgen05.commit releases the stage / signals
+//                   the epilogue through mbarriers - no __syncthreads in the main loop.
+//   epilogue        4 warps, thread = output row (TMEM lane), tcgen05.ld 16 columns at a time =
+//                   one GroupNorm group: folded BN / bias, per-row GroupNorm, residual, ReLU.
+//   sparsity        kernel-map slices with no live row in the tile are skipped by producers and
+//                   issuer alike (flags computed from the staged row table).
+#include "gemm.cuh"
+
+namespace dv3d {
+
+constexpr int TC_BM = 128;
+constexpr int TC_KC = 32;                  // floats per K chunk = 128 bytes per operand row
+constexpr int TC_STAGES = 3;
+constexpr int TC_PRODUCERS = 256;          // 8 warps
+constexpr int TC_THREADS = TC_PRODUCERS + 32;
+constexpr int TC_A_BYTES = TC_BM * 128;    // one operand image (big or small part)
+
+__host__ __device__ constexpr int tc_stage_bytes(int N) { return 2 * TC_A_BYTES + 2 * N * 128; }
+__host__ __device__ constexpr size_t tc_smem_bytes(int N) {
+    return 1024 /* alignment slack */ + (size_t)TC_STAGES * tc_stage_bytes(N) + sizeof(int) * kMaxSlices * TC_BM + 256;
+}
+
+static int g_gemm_precision = 1;  // 1 = 3xTF32, 2 = TF32
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a trapped launch, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000ll) {
+            printf("dv3d gather_gemm_tc: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major operand, SWIZZLE_128B: rows of 128 bytes, 8-row groups 1024 bytes apart
+// (cute::UMMA::SmemDescriptor: start>>4 | LBO>>4 @16 | SBO>>4 @32 | version 1 @46 | layout 2 @61)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// cute::UMMA::InstrDescriptor: D fp32, A/B tf32, both K-major, N>>3 @17, M>>4 @24
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void split_tf32(float x, float& big, float& small) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    big = __uint_as_float(u);
+    small = x - big;  // exact
+}
+
+// ------------------------------------------------------------------ weight packing
+// W [Ktot, N] row-major -> per 32-row chunk the shared-memory image of B as a K-major
+// SWIZZLE_128B operand: row n (output channel) holds k = 0..31 in 16-byte units, unit j
+// stored at j ^ (n & 7).  Image of the big parts first, then of the remainders.
+__global__ void __launch_bounds__(256)
+pack_weights_kernel(const float* __restrict__ W, int Ktot, int N, float* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)Ktot * N) return;
+    const int k = (int)(i / N), n = (int)(i - (long long)k * N);
+    const int chunk = k >> 5, kk = k & 31;
+    float big, small;
+    split_tf32(__ldg(W + i), big, small);
+    const size_t img = (size_t)N * 32;  // floats per image
+    const size_t pos = (size_t)n * 32 + ((((kk >> 2) ^ (n & 7)) << 2) | (kk & 3));
+    out[(size_t)chunk * 2 * img + pos] = big;
+    out[(size_t)chunk * 2 * img + img + pos] = small;
+}
+
+// ------------------------------------------------------------------ the kernel
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gather_gemm_tc_kernel(const __grid_constant__ GemmDesc d, int precision) {
+    const float* __restrict__ Wp = d.Wp;
+    extern __shared__ unsigned char smem_raw[];
+    // SWIZZLE_128B operands need 1024-byte alignment
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    constexpr int STAGE = tc_stage_bytes(BN);
+    constexpr int B_IMG = BN * 128;
+    int* s_rows = reinterpret_cast<int*>(smem + TC_STAGES * STAGE);                 // [n_slices][128]
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_rows + kMaxSlices * TC_BM);    // full[3] empty[3] accum
+    uint32_t* s_misc = reinterpret_cast<uint32_t*>(s_bar + 2 * TC_STAGES + 1);     // [0] tmem base, [1] active mask
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long m0 = (long long)blockIdx.x * TC_BM;
+    const uint32_t bar_full = smem_u32(s_bar), bar_empty = smem_u32(s_bar + TC_STAGES),
+                   bar_accum = smem_u32(s_bar + 2 * TC_STAGES);
+
+    if (tid == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) {
+            mbar_init(bar_full + 8 * s, TC_PRODUCERS);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        mbar_init(bar_accum, 1);
+        s_misc[1] = 0;
+        fence_mbar_init();
+    }
+    if (warp == 8) tmem_alloc(smem_u32(s_misc), BN);
+    __syncthreads();
+
+    // stage the row table of the tile and flag the slices that have at least one live row
+    if (tid < TC_PRODUCERS) {
+        unsigned my_active = 0;
+        for (int i = tid; i < d.n_slices * TC_BM; i += TC_PRODUCERS) {
+            int s, r;
+            long long rr = -1;
+            if (d.kmap) {  // kernel map [M][n_slices]: the tile's block is contiguous
+                r = i / d.n_slices;
+                s = i - r * d.n_slices;
+                if (m0 + r < d.M) rr = (long long)__ldg(d.kmap + (m0 + r) * d.n_slices + s);
+            } else {
+                s = i >> 7;
+                r = i & (TC_BM - 1);
+                const GemmSlice& sl = d.slice[s];
+                const long long m = m0 + r;
+                if (m < d.M) {
+                    rr = sl.idx ? (long long)__ldg(sl.idx + m * sl.idx_stride) : m + sl.shift;
+                    if (!sl.idx && rr >= d.n_src_rows) rr = -1;
+                }
+            }
+            if (rr < 0) rr = -1;
+            s_rows[s * TC_BM + r] = (int)rr;
+            if (rr >= 0) my_active |= 1u << s;
+        }
+        my_active = __reduce_or_sync(0xffffffffu, my_active);
+        if (lane == 0 && my_active) atomicOr(&s_misc[1], my_active);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = s_misc[0];
+    const uint32_t active = s_misc[1];
+
+    if (tid < TC_PRODUCERS) {
+        // ===================== producers: gather A, split, store swizzled; thread 0 also fetches B
+        const int j = tid & 7;   // 16-byte unit within the 128-byte row
+        const int r0 = tid >> 3; // rows r0 + 32 i
+        int it = 0, wchunk = 0;
+        for (int s = 0; s < d.n_slices; ++s) {
+            const GemmSlice& sl = d.slice[s];
+            const int nk = sl.K / TC_KC;
+            if (!((active >> s) & 1u)) {
+                wchunk += nk;
+                continue;
+            }
+            const float* src[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int row = s_rows[s * TC_BM + r0 + 32 * i];
+                src[i] = row >= 0 ? sl.src + (size_t)row * sl.ld + j * 4 : nullptr;
+            }
+            for (int kc = 0; kc < nk; ++kc, ++it, ++wchunk) {
+                const int st = it % TC_STAGES;
+                const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
+                float4 v[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    v[i] = src[i] ? __ldg(reinterpret_cast<const float4*>(src[i] + kc * TC_KC)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                mbar_wait(bar_empty + 8 * st, ph ^ 1u);
+                unsigned char* stage = smem + st * STAGE;
+                if (tid == 0) {
+                    mbar_expect_tx(bar_full + 8 * st, 2 * B_IMG);
+                    bulk_g2s(smem_u32(stage + 2 * TC_A_BYTES), Wp + (size_t)wchunk * (2 * BN * 32), 2 * B_IMG,
+                             bar_full + 8 * st);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float4 a = v[i];
+                    if (d.relu_in) {
+                        a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
+                    }
+                    float4 big, small;
+                    split_tf32(a.x, big.x, small.x);
+                    split_tf32(a.y, big.y, small.y);
+                    split_tf32(a.z, big.z, small.z);
+                    split_tf32(a.w, big.w, small.w);
+                    const int r = r0 + 32 * i;
+                    const int off = r * 128 + ((j ^ (r & 7)) << 4);
+                    *reinterpret_cast<float4*>(stage + off) = big;
+                    *reinterpret_cast<float4*>(stage + TC_A_BYTES + off) = small;
+                }
+                fence_proxy_async_smem();
+                mbar_arrive(bar_full + 8 * st);
+            }
+        }
+    } else {
+      if (lane == 0 && active) {
+        // ===================== MMA issuer
+        constexpr uint32_t idesc = umma_idesc_tf32(TC_BM, BN);
+        int it = 0;
+        uint32_t acc = 0;
+        for (int s = 0; s < d.n_slices; ++s) {
+            if (!((active >> s) & 1u)) continue;
+            const int nk = d.slice[s].K / TC_KC;
+            for (int kc = 0; kc < nk; ++kc, ++it) {
+                const int st = it % TC_STAGES;
+                const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
+                mbar_wait(bar_full + 8 * st, ph);
+                tc_fence_after();
+                const uint32_t a_big = smem_u32(smem + st * STAGE), a_small = a_big + TC_A_BYTES,
+                               b_big = a_big + 2 * TC_A_BYTES, b_small = b_big + B_IMG;
+#pragma unroll
+                for (int kk = 0; kk < TC_KC / 8; ++kk) {
+                    const uint32_t ko = kk * 32;  // 8 tf32 = 32 bytes inside the swizzle row
+                    if (precision == 1) {
+                        umma_tf32(tmem_base, umma_desc_sw128(a_small + ko), umma_desc_sw128(b_big + ko), idesc, acc);
+                        acc = 1;
+                        umma_tf32(tmem_base, umma_desc_sw128(a_big + ko), umma_desc_sw128(b_small + ko), idesc, 1);
+                    }
+                    umma_tf32(tmem_base, umma_desc_sw128(a_big + ko), umma_desc_sw128(b_big + ko), idesc, acc);
+                    acc = 1;
+                }
+                umma_commit(bar_empty + 8 * st);  // frees the stage once these MMAs have read it
+            }
+        }
+        umma_commit(bar_accum);
+      }
+      __syncwarp();
+    }
+
+    // ===================== epilogue: warps 0..3, thread = output row = TMEM lane
+    if (warp < 4) {
+        if (active) mbar_wait(bar_accum, 0);
+        tc_fence_after();
+        const long long m = m0 + warp * 32 + lane;
+        const bool live = m < d.M;
+        const bool zero_row = d.zero_row_mod && (int)(m % d.zero_row_mod) == d.zero_row_val;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+            float y[16];
+            if (active) {
+                tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, y);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) y[i] = 0.f;
+            }
+            if (d.scale) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) y[i] *= __ldg(d.scale + c0 + i);
+            }
+            if (d.shift) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) y[i] += __ldg(d.shift + c0 + i);
+            }
+            if (d.gn_weight) {
+                float sum = 0.f;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) sum += y[i];
+                const float mean = sum * (1.f / 16.f);
+                float q = 0.f;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) q = fmaf(y[i] - mean, y[i] - mean, q);
+                const float rstd = 1.f / sqrtf(q * (1.f / 16.f) + 1e-5f);
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    y[i] = fmaf((y[i] - mean) * rstd, __ldg(d.gn_weight + c0 + i), __ldg(d.gn_bias + c0 + i));
+            }
+            if (live) {
+                if (d.residual) {
+                    const float4* rp = reinterpret_cast<const float4*>(d.residual + (size_t)m * d.res_ld + c0);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        float4 rv = __ldg(rp + i);
+                        y[4 * i] += rv.x; y[4 * i + 1] += rv.y; y[4 * i + 2] += rv.z; y[4 * i + 3] += rv.w;
+                    }
+                }
+                if (d.relu_out) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) y[i] = fmaxf(y[i], 0.f);
+                }
+                if (zero_row) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) y[i] = 0.f;
+                }
+                float4* op = reinterpret_cast<float4*>(d.out + (size_t)m * d.out_ld + c0);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) op[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc(tmem_base, BN);
+}
+
+int validate_gather_gemm(const GemmDesc& d, int k_multiple);
+
+int launch_gather_gemm_tc(const GemmDesc& d, cudaStream_t st) {
+    const float* Wp = d.Wp;
+    int rc = validate_gather_gemm(d, TC_KC);
+    if (rc) return rc;
+    DV3D_REQUIRE(Wp && ((uintptr_t)Wp & 15) == 0, "gather_gemm_tc: packed weights must be 16-byte aligned");
+    DV3D_REQUIRE(d.out_ld % 4 == 0 && ((uintptr_t)d.out & 15) == 0, "gather_gemm_tc: output must be 16-byte aligned");
+    if (d.M == 0) return DV3D_OK;
+    const int grid = cdiv(d.M, TC_BM);
+    if (d.N == 128) {
+        static bool attr = false;
+        if (!attr) {
+            DV3D_CUDA(cudaFuncSetAttribute(gather_gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)tc_smem_bytes(128)));
+            attr = true;
+        }
+        gather_gemm_tc_kernel<128><<<grid, TC_THREADS, tc_smem_bytes(128), st>>>(d, g_gemm_precision);
+    } else {
+        static bool attr = false;
+        if (!attr) {
+            DV3D_CUDA(cudaFuncSetAttribute(gather_gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)tc_smem_bytes(64)));
+            attr = true;
+        }
+        gather_gemm_tc_kernel<64><<<grid, TC_THREADS, tc_smem_bytes(64), st>>>(d, g_gemm_precision);
+    }
+    DV3D_LAUNCHED();
+    return DV3D_OK;
+}
+
+}  // namespace dv3d
+
+using namespace dv3d;
+
+extern "C" size_t dv3d_gemm_pack_bytes(int Ktot, int N) {
+    if (Ktot <= 0 || N <= 0 || Ktot % TC_KC) return 0;
+    return (size_t)Ktot * N * 2 * sizeof(float);
+}
+
+extern "C" int dv3d_gemm_pack_weights(const float* W, int Ktot, int N, void* packed, void* stream) {
+    DV3D_REQUIRE(W && packed && Ktot > 0 && Ktot % TC_KC == 0 && (N == 64 || N == 128),
+                 "gemm_pack_weights: need K %% 32 == 0 and N in {64,128} (K=%d N=%d)", Ktot, N);
+    pack_weights_kernel<<<cdiv((long long)Ktot * N, 256), 256, 0, (cudaStream_t)stream>>>(W, Ktot, N, (float*)packed);
+    DV3D_LAUNCHED();
+    return DV3D_OK;
+}
+
+extern "C" int dv3d_set_gemm_precision(int mode) {
+    DV3D_REQUIRE(mode == 1 || mode == 2, "set_gemm_precision: 1 = 3xTF32 (fp32-grade), 2 = TF32; got %d", mode);
+    g_gemm_precision = mode;
+    return DV3D_OK;
+}
+extern "C" int dv3d_get_gemm_precision(void) { return g_gemm_precision; }

@@ -69,9 +69,9 @@ extern "C" int dv3d_pointnet_input(const float* pts, const float* pts_feat, int 
 }
 
 extern "C" int dv3d_linear(const float* x_a, int Ca, int lda, const float* pool, const int* seg, int Cb, long long N,
-                           const float* weight_kn, const float* bias, int Cout, int relu_input, float* y,
-                           void* stream) {
-    DV3D_REQUIRE(x_a && weight_kn && y && N >= 0 && Ca > 0 && Cb >= 0, "linear: bad arguments");
+                           const float* weight_kn, const void* W_packed, const float* bias, int Cout, int relu_input,
+                           float* y, void* stream) {
+    DV3D_REQUIRE(x_a && (weight_kn || W_packed) && y && N >= 0 && Ca > 0 && Cb >= 0, "linear: bad arguments");
     DV3D_REQUIRE(Cb == 0 || (pool && seg), "linear: the pooled half needs pool and seg");
     GemmDesc d = {};
     d.n_slices = Cb ? 2 : 1;
@@ -81,6 +81,7 @@ extern "C" int dv3d_linear(const float* x_a, int Ca, int lda, const float* pool,
     d.n_src_rows = N;
     d.N = Cout;
     d.W = weight_kn;
+    d.Wp = (const float*)W_packed;
     d.shift = bias;
     d.relu_in = relu_input;
     d.out = y;

@@ -22,5 +22,5 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 }  // namespace dv3d
 
 extern "C" const char* dv3d_last_error(void) { return dv3d::g_err; }
-extern "C" int dv3d_abi_version(void) { return 1; }
+extern "C" int dv3d_abi_version(void) { return 2; }
 extern "C" long long dv3d_launch_count(void) { return dv3d::g_launches.load(std::memory_order_relaxed); }

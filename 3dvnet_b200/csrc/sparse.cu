@@ -146,12 +146,14 @@ extern "C" int dv3d_kernel_map(const int* coords_out, long long n_out, const voi
 }
 
 extern "C" int dv3d_sparse_conv(const float* feat, long long n_in, int Cin, const int* nbr, long long n_out,
-                                const float* W, int Cout, const float* gn_weight, const float* gn_bias,
-                                const float* residual, int relu, float* out, void* stream) {
-    DV3D_REQUIRE(feat && nbr && W && out && n_in >= 0 && n_out >= 0, "sparse_conv: bad arguments");
+                                const float* W, const void* W_packed, int Cout, const float* gn_weight,
+                                const float* gn_bias, const float* residual, int relu, float* out, void* stream) {
+    DV3D_REQUIRE(feat && nbr && (W || W_packed) && out && n_in >= 0 && n_out >= 0, "sparse_conv: bad arguments");
     GemmDesc d = {};
     d.n_slices = 27;
     for (int k = 0; k < 27; ++k) d.slice[k] = GemmSlice{feat, nbr + k, 27, 0, Cin, Cin};
+    d.kmap = nbr;
+    d.Wp = (const float*)W_packed;
     d.M = n_out;
     d.n_src_rows = n_in;
     d.N = Cout;
@@ -167,10 +169,11 @@ extern "C" int dv3d_sparse_conv(const float* feat, long long n_in, int Cin, cons
 }
 
 extern "C" int dv3d_concat_linear_gn_relu(const float* a, int Ca, const float* b, int Cb, long long n, const float* W,
-                                          int Cout, const float* gn_weight, const float* gn_bias, float* out,
-                                          void* stream) {
-    DV3D_REQUIRE(a && b && W && out && n >= 0, "concat_linear: bad arguments");
+                                          const void* W_packed, int Cout, const float* gn_weight,
+                                          const float* gn_bias, float* out, void* stream) {
+    DV3D_REQUIRE(a && b && (W || W_packed) && out && n >= 0, "concat_linear: bad arguments");
     GemmDesc d = {};
+    d.Wp = (const float*)W_packed;
     d.n_slices = 2;
     d.slice[0] = GemmSlice{a, nullptr, 0, 0, Ca, Ca};
     d.slice[1] = GemmSlice{b, nullptr, 0, 0, Cb, Cb};

@@ -8,8 +8,8 @@ class PackCache(object):
         self._key = None
         self._val = None
 
-    def get(self, tensors, build):
-        key = tuple((t.data_ptr(), t._version, t.device) for t in tensors)
+    def get(self, tensors, build, extra=None):
+        key = tuple((t.data_ptr(), t._version, t.device) for t in tensors) + (extra,)
         if key != self._key:
             with torch.no_grad():
                 self._val = build()

@@ -32,10 +32,10 @@ class HypothesisDecoder(nn.Module):
             layers = []
             for i in range(3):
                 w = self.net[i][0].weight.detach().float().permute(2, 1, 0).contiguous()  # [3, Cin, Cout]
-                layers.append((w,) + fold_bn(self.net[i][1]))
+                layers.append((w,) + fold_bn(self.net[i][1]) + (ops.pack_weights(w.reshape(-1, w.shape[2])),))
             head = (self.net[3].weight.detach().float().contiguous(), float(self.net[3].bias.detach().cpu()))
             return layers, head
-        return self._pack.get([p for p in self.parameters()] + [b for b in self.buffers()], build)
+        return self._pack.get([p for p in self.parameters()] + [b for b in self.buffers()], build, ops.gemm_mode())
 
     def operand(self, n_pts, device):
         """[n_pts, 8, in_dim] buffer whose padding row stays zero (reused between calls)."""
@@ -57,8 +57,8 @@ class HypothesisDecoder(nn.Module):
     def run(self, operand, n_hyp, offset=None, want_prob=True):
         layers, head = self._weights()
         x = operand
-        for w, scale, shift in layers:
-            x = ops.conv1d_bn_relu(x, w, scale, shift)
+        for w, scale, shift, packed in layers:
+            x = ops.conv1d_bn_relu(x, w, scale, shift, packed=packed)
         return ops.decoder_head(x, n_hyp, head[0], head[1], 0.0 if offset is None else offset, want_prob)
 
     def forward(self, xs, pts, pts_feat, pts_batch):

@@ -23,6 +23,14 @@ class SparseConvolution(nn.Module):
         self.kernel = nn.Parameter(torch.empty(*shape))
         n = (out_channels if transposed else in_channels) * kv
         nn.init.uniform_(self.kernel, -1.0 / math.sqrt(n), 1.0 / math.sqrt(n))
+        self._pack = PackCache()
+
+    def weights(self):
+        """(kernel fp32, packed tensor-core image or None) for ops.sparse_conv / concat_linear"""
+        k = self.kernel.detach()
+        packed = self._pack.get([self.kernel], lambda: ops.pack_weights(k.float().reshape(-1, k.shape[-1]).contiguous()),
+                                ops.gemm_mode())
+        return k, packed
 
 
 class MinkowskiGroupNorm(nn.Module):
@@ -52,10 +60,10 @@ class SparseResidual3d(nn.Module):
         self.conv2 = SparseConvolution(feat_dim, feat_dim)
 
     def forward(self, x, nbr):
-        h = ops.sparse_conv(x, nbr, self.conv1.kernel.detach(), self.n1.gn.weight.detach(), self.n1.gn.bias.detach(),
-                            None, True)
-        return ops.sparse_conv(h, nbr, self.conv2.kernel.detach(), self.n2.gn.weight.detach(),
-                               self.n2.gn.bias.detach(), x, True)
+        w1, p1 = self.conv1.weights()
+        w2, p2 = self.conv2.weights()
+        h = ops.sparse_conv(x, nbr, w1, self.n1.gn.weight.detach(), self.n1.gn.bias.detach(), None, True, packed=p1)
+        return ops.sparse_conv(h, nbr, w2, self.n2.gn.weight.detach(), self.n2.gn.bias.detach(), x, True, packed=p2)
 
 
 class PointNet(nn.Module):
@@ -70,7 +78,7 @@ class PointNet(nn.Module):
         self.fc4 = nn.Linear(2 * hidden_dim, hidden_dim)
         self.fc_out = nn.Linear(hidden_dim, out_dim)
         self.in_dim = in_dim
-        self.in_pad = (in_dim + 15) // 16 * 16
+        self.in_pad = (in_dim + 31) // 32 * 32  # K extent of the tensor-core GEMM: multiples of 32
         self._pack = PackCache()
 
     def _weights(self):
@@ -81,20 +89,24 @@ class PointNet(nn.Module):
                 w = fc.weight.detach().float().t().contiguous()  # [K, Cout]
                 if name == 'fc_pos' and w.shape[0] != self.in_pad:
                     w = torch.cat((w, w.new_zeros(self.in_pad - w.shape[0], w.shape[1])), 0).contiguous()
-                out[name] = (w, fc.bias.detach().float().contiguous())
+                out[name] = (w, fc.bias.detach().float().contiguous(), ops.pack_weights(w))
             return out
-        return self._pack.get([p for p in self.parameters()], build)
+        return self._pack.get([p for p in self.parameters()], build, ops.gemm_mode())
 
     def forward_padded(self, x_pad, seg, n_idx):
         """x_pad [N, in_pad] (zero-padded input rows), seg [N] int32"""
         w = self._weights()
-        x = ops.linear(x_pad, *w['fc_pos'], relu_input=False)
-        x = ops.linear(x, *w['fc1'], relu_input=True)
+        def fc(name, x, relu, **kw):
+            wt, b, packed = w[name]
+            return ops.linear(x, wt, b, relu_input=relu, packed=packed, **kw)
+
+        x = fc('fc_pos', x_pad, False)
+        x = fc('fc1', x, True)
         for name in ('fc2', 'fc3', 'fc4'):
             pool = ops.segment_max(x, seg, n_idx)
-            x = ops.linear(x, *w[name], relu_input=True, pool=pool, seg=seg)
+            x = fc(name, x, True, pool=pool, seg=seg)
         pool = ops.segment_max(x, seg, n_idx)
-        return ops.linear(pool, *w['fc_out'], relu_input=True)
+        return fc('fc_out', pool, True)
 
     def forward(self, pts, idx, n_idx):
         """pts [N,in_dim], idx [N] int64 -> [n_idx,out_dim]"""
@@ -172,8 +184,8 @@ class SparseUNet(nn.Module):
         xs = [x]
         for i in range(1, nl):
             conv, gn = self.down[i - 1][0], self.down[i - 1][1].gn
-            x = ops.sparse_conv(x, scene.down(i - 1), conv.kernel.detach(), gn.weight.detach(), gn.bias.detach(),
-                                None, True)
+            wk, wp = conv.weights()
+            x = ops.sparse_conv(x, scene.down(i - 1), wk, gn.weight.detach(), gn.bias.detach(), None, True, packed=wp)
             for blk in self.res_down[i]:
                 x = blk(x, scene.same(i))
             xs.append(x)
@@ -181,10 +193,11 @@ class SparseUNet(nn.Module):
         for i in range(nl - 1):
             l = nl - 2 - i  # target (finer) level
             conv, gn = self.up[i][0], self.up[i][1].gn
-            up = ops.sparse_conv(x, scene.up(l), conv.kernel.detach(), gn.weight.detach(), gn.bias.detach(), None,
-                                 True)
+            wk, wp = conv.weights()
+            up = ops.sparse_conv(x, scene.up(l), wk, gn.weight.detach(), gn.bias.detach(), None, True, packed=wp)
             adj, gn = self.feat_adj[i][0], self.feat_adj[i][1].gn
-            x = ops.concat_linear_gn_relu(up, xs[l], adj.kernel.detach(), gn.weight.detach(), gn.bias.detach())
+            wk, wp = adj.weights()
+            x = ops.concat_linear_gn_relu(up, xs[l], wk, gn.weight.detach(), gn.bias.detach(), packed=wp)
             for blk in self.res_up[i]:
                 x = blk(x, scene.same(l))
             out.append((x, l))

@@ -6,6 +6,7 @@ No function in this module has a CPU or eager-PyTorch fallback: tensors must liv
 device and the shared library must load, otherwise the call raises.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -13,6 +14,43 @@ import torch
 from ._lib import lib, VoxelGrid, Dv3dError, DV3D_ENOSPC  # noqa: F401
 
 ROWS_PER_POINT = 8  # decoder operand: 7 hypotheses + 1 zero row (csrc/decoder.cu)
+
+# Which kernel runs the dense contractions (csrc/gemm.cu / gemm_tc.cu):
+#   'tf32x3' tcgen05 tensor cores, 3xTF32 split accumulation (fp32-grade)  [default]
+#   'tf32'   tcgen05 tensor cores, plain TF32
+#   'f32'    fp32 CUDA-core kernel (verification path)
+GEMM_MODES = ('tf32x3', 'tf32', 'f32')
+_gemm_mode = None
+
+
+def set_gemm_mode(mode):
+    global _gemm_mode
+    if mode not in GEMM_MODES:
+        raise ValueError('gemm mode must be one of %s, got %r' % (GEMM_MODES, mode))
+    if mode != 'f32':
+        lib().call('dv3d_set_gemm_precision', 1 if mode == 'tf32x3' else 2)
+    _gemm_mode = mode
+
+
+def gemm_mode():
+    if _gemm_mode is None:
+        set_gemm_mode(os.environ.get('DV3D_GEMM', 'tf32x3'))
+    return _gemm_mode
+
+
+def pack_weights(w_kn):
+    """[K, N] fp32 (K % 32 == 0, N in {64,128}) -> the tcgen05 kernel's packed image, or None
+    in 'f32' mode."""
+    if gemm_mode() == 'f32':
+        return None
+    _chk(w_kn, torch.float32, 'weight', 2)
+    K, N = w_kn.shape
+    nbytes = lib().raw('dv3d_gemm_pack_bytes')(K, N)
+    if nbytes == 0:
+        raise RuntimeError('pack_weights: K must be a positive multiple of 32, got K=%d N=%d' % (K, N))
+    out = torch.empty(nbytes, dtype=torch.uint8, device=w_kn.device)
+    lib().call('dv3d_gemm_pack_weights', _p(w_kn), K, N, _p(out), _stream())
+    return out
 
 
 def _stream():
@@ -199,7 +237,7 @@ def voxelize(pts, pts_batch, edge_len):
 
 
 # ----------------------------------------------------------------------------- PointNet
-def pointnet_input(pts, pts_feat, anchor_pts, seg, out_ld=48):
+def pointnet_input(pts, pts_feat, anchor_pts, seg, out_ld=64):
     N, C = pts_feat.shape
     out = torch.empty((N, out_ld), dtype=torch.float32, device=pts.device)
     lib().call('dv3d_pointnet_input', _p(pts), _p(pts_feat), pts_feat.stride(0), _p(anchor_pts), _p(seg), N, C,
@@ -207,14 +245,14 @@ def pointnet_input(pts, pts_feat, anchor_pts, seg, out_ld=48):
     return out
 
 
-def linear(x_a, weight_kn, bias, relu_input, pool=None, seg=None, Ca=None):
+def linear(x_a, weight_kn, bias, relu_input, pool=None, seg=None, Ca=None, packed=None):
     N, lda = x_a.shape
     Ca = lda if Ca is None else Ca
     Cb = 0 if pool is None else pool.shape[1]
     Cout = weight_kn.shape[1]
     assert weight_kn.shape[0] == Ca + Cb
     y = torch.empty((N, Cout), dtype=torch.float32, device=x_a.device)
-    lib().call('dv3d_linear', _p(x_a), Ca, lda, _p(pool), _p(seg), Cb, N, _p(weight_kn), _p(bias), Cout,
+    lib().call('dv3d_linear', _p(x_a), Ca, lda, _p(pool), _p(seg), Cb, N, _p(weight_kn), _p(packed), _p(bias), Cout,
                int(relu_input), _p(y), _stream())
     return y
 
@@ -273,24 +311,24 @@ def coarsen(level, dims, n_batch, err_flag):
     return SparseLevel(out[:n_out.value], ns, err_flag)
 
 
-def sparse_conv(feat, nbr, W, gn_weight=None, gn_bias=None, residual=None, relu=False):
+def sparse_conv(feat, nbr, W, gn_weight=None, gn_bias=None, residual=None, relu=False, packed=None):
     n_in, Cin = feat.shape
     n_out = nbr.shape[0]
     Cout = W.shape[2]
     assert W.shape[0] == 27 and W.shape[1] == Cin
     out = torch.empty((n_out, Cout), dtype=torch.float32, device=feat.device)
-    lib().call('dv3d_sparse_conv', _p(feat), n_in, Cin, _p(nbr), n_out, _p(W), Cout, _p(gn_weight), _p(gn_bias),
-               _p(residual), int(relu), _p(out), _stream())
+    lib().call('dv3d_sparse_conv', _p(feat), n_in, Cin, _p(nbr), n_out, _p(W), _p(packed), Cout, _p(gn_weight),
+               _p(gn_bias), _p(residual), int(relu), _p(out), _stream())
     return out
 
 
-def concat_linear_gn_relu(a, b, W, gn_weight, gn_bias):
+def concat_linear_gn_relu(a, b, W, gn_weight, gn_bias, packed=None):
     n, Ca = a.shape
     Cb = b.shape[1]
     Cout = W.shape[1]
     out = torch.empty((n, Cout), dtype=torch.float32, device=a.device)
-    lib().call('dv3d_concat_linear_gn_relu', _p(a), Ca, _p(b), Cb, n, _p(W), Cout, _p(gn_weight), _p(gn_bias), _p(out),
-               _stream())
+    lib().call('dv3d_concat_linear_gn_relu', _p(a), Ca, _p(b), Cb, n, _p(W), _p(packed), Cout, _p(gn_weight),
+               _p(gn_bias), _p(out), _stream())
     return out
 
 
@@ -320,14 +358,14 @@ def sparse_interp(pts, pts_batch, n_hyp, level, origin, res, feat, out, out_off)
                out_off, _stream())
 
 
-def conv1d_bn_relu(x, weight_tkn, scale, shift, out=None):
+def conv1d_bn_relu(x, weight_tkn, scale, shift, out=None, packed=None):
     """x [n_pts, 8, Cin] -> [n_pts, 8, Cout] (refinement.py:8-13)."""
     n_pts, rows, ldx = x.shape
     Cin, Cout = weight_tkn.shape[1], weight_tkn.shape[2]
     if out is None:
         out = torch.empty((n_pts, rows, Cout), dtype=torch.float32, device=x.device)
-    lib().call('dv3d_conv1d_bn_relu', _p(x), n_pts, rows, Cin, ldx, _p(weight_tkn), _p(scale), _p(shift), Cout,
-               _p(out), out.shape[2], _stream())
+    lib().call('dv3d_conv1d_bn_relu', _p(x), n_pts, rows, Cin, ldx, _p(weight_tkn), _p(packed), _p(scale), _p(shift),
+               Cout, _p(out), out.shape[2], _stream())
     return out
 
 

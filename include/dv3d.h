@@ -147,9 +147,23 @@ int dv3d_voxelize(const float* pts, const long long* batch, long long N, const d
                   float* anchor_pts, int* anchor_idx3d, long long* anchor_batch, int* point_anchor, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Dense contractions of the volumetric refinement (every nn.Linear, MinkowskiConvolution and
+ * Conv1d of scenemodeling.py / refinement.py) run through one gather-GEMM.  Each entry point
+ * below takes the layer's weight twice:
+ *   W / weight_*  fp32 [K, N] row-major            -> fp32 CUDA-core kernel (verification path)
+ *   W_packed      image made by dv3d_gemm_pack_weights -> tcgen05 tensor-core kernel (TMEM
+ *                 accumulators); when non-NULL it wins and W may be NULL.  K % 32 == 0.
+ * dv3d_set_gemm_precision: 1 = 3xTF32 split accumulation (fp32-grade, default), 2 = TF32.
+ */
+size_t dv3d_gemm_pack_bytes(int Ktot, int N);
+int dv3d_gemm_pack_weights(const float* W, int Ktot, int N, void* packed, void* stream);
+int dv3d_set_gemm_precision(int mode);
+int dv3d_get_gemm_precision(void);
+
+/* ------------------------------------------------------------------------------------
  * PointNet (scenemodeling.py:116-144).
  *   input rows [pts - anchor_pts[seg] | pts_feat | 0...] (lightningmodel.py:182): out [N,out_ld],
- *   out_ld >= 3 + C (padded so that the GEMM K extent is a multiple of 16)
+ *   out_ld >= 3 + C (padded so that the GEMM K extent is a multiple of 32)
  */
 int dv3d_pointnet_input(const float* pts, const float* pts_feat, int feat_ld, const float* anchor_pts,
                         const int* seg, long long N, int C, int out_ld, float* out, void* stream);
@@ -158,7 +172,8 @@ int dv3d_pointnet_input(const float* pts, const float* pts_feat, int feat_ld, co
  *   int32 (NULL with Cb = 0); weight_kn [Ca+Cb, Cout] = nn.Linear.weight transposed;
  *   bias [Cout]; Cout in {64,128}; y [N,Cout] */
 int dv3d_linear(const float* x_a, int Ca, int lda, const float* pool, const int* seg, int Cb, long long N,
-                const float* weight_kn, const float* bias, int Cout, int relu_input, float* y, void* stream);
+                const float* weight_kn, const void* W_packed, const float* bias, int Cout, int relu_input, float* y,
+                void* stream);
 /* segment max with empty segments = 0 (torch_scatter 'max'): out [n_seg,C] */
 int dv3d_segment_max(const float* x, const int* seg, long long N, int C, long long n_seg, float* out, void* stream);
 
@@ -191,12 +206,13 @@ int dv3d_kernel_map(const int* coords_out, long long n_out, const void* table_in
  * add (before the ReLU) and ReLU — the SparseResidual3d / down / up blocks.  Cin % 16 == 0,
  * Cout in {64,128}. */
 int dv3d_sparse_conv(const float* feat, long long n_in, int Cin, const int* nbr, long long n_out, const float* W,
-                     int Cout, const float* gn_weight, const float* gn_bias, const float* residual, int relu,
-                     float* out, void* stream);
+                     const void* W_packed, int Cout, const float* gn_weight, const float* gn_bias,
+                     const float* residual, int relu, float* out, void* stream);
 /* 1x1 "feature adjust" on the concatenation [a | b] (ME.cat + k=1 conv, scenemodeling.py:206)
  * followed by GroupNorm + ReLU: W [Ca+Cb, Cout]. */
 int dv3d_concat_linear_gn_relu(const float* a, int Ca, const float* b, int Cb, long long n, const float* W,
-                               int Cout, const float* gn_weight, const float* gn_bias, float* out, void* stream);
+                               const void* W_packed, int Cout, const float* gn_weight, const float* gn_bias,
+                               float* out, void* stream);
 /* voxel positions of a level (scenemodeling.py:211-226): origin[b] = anchor_pts[first voxel of b]
  * - idx3d[first] * res; pts = coord * res + origin[batch]; optional int64 views of idx / batch */
 int dv3d_batch_origin(const float* anchor_pts, const int* idx3d, const long long* batch, long long n, float res,
@@ -222,8 +238,8 @@ int dv3d_sparse_interp(const float* pts, const long long* pts_batch, long long n
  * layout: x [n_pts*8, ldx] -> y [n_pts*8, ldy] (row 7 of every point written as 0);
  * weight_tkn [3, Cin, Cout] = torch weight [Cout,Cin,3] permuted (2,1,0). */
 int dv3d_conv1d_bn_relu(const float* x, long long n_pts, int rows_per_point, int Cin, int ldx,
-                        const float* weight_tkn, const float* scale, const float* shift, int Cout, float* y, int ldy,
-                        void* stream);
+                        const float* weight_tkn, const void* W_packed, const float* scale, const float* shift,
+                        int Cout, float* y, int ldy, void* stream);
 /* last Conv1d (Cin->1, bias; weight [1,Cin,3] torch layout) + softmax over hypotheses + expected
  * offset sum_i p_i * linspace(-n*offset, n*offset)_i; prob_out optional [n_pts,n_hyp]; offset_out [n_pts] */
 int dv3d_decoder_head(const float* x, long long n_pts, int n_hyp, int rows_per_point, int Cin, int ldx,

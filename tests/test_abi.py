@@ -22,7 +22,8 @@ def test_header_parses_and_every_symbol_is_exported(L):
                  'dv3d_prob_softargmin', 'dv3d_voxel_grid', 'dv3d_voxelize', 'dv3d_linear', 'dv3d_segment_max',
                  'dv3d_hash_build', 'dv3d_coarsen', 'dv3d_kernel_map', 'dv3d_sparse_conv',
                  'dv3d_concat_linear_gn_relu', 'dv3d_sparse_interp', 'dv3d_conv1d_bn_relu', 'dv3d_decoder_head',
-                 'dv3d_edge_transforms', 'dv3d_ref_backprojection', 'dv3d_nchw_to_nhwc', 'dv3d_launch_count'):
+                 'dv3d_edge_transforms', 'dv3d_ref_backprojection', 'dv3d_nchw_to_nhwc', 'dv3d_launch_count',
+                 'dv3d_gemm_pack_weights', 'dv3d_gemm_pack_bytes', 'dv3d_set_gemm_precision'):
         assert must in names, must
     for n in names:
         assert hasattr(L.cdll, n), 'library does not export %s' % n
@@ -30,13 +31,17 @@ def test_header_parses_and_every_symbol_is_exported(L):
 
 
 def test_abi_version_and_error_reporting(L):
-    assert L.cdll.dv3d_abi_version() == 1
+    assert L.cdll.dv3d_abi_version() == 2
     # argument validation happens before any CUDA call: safe without a GPU
     rc = L.cdll.dv3d_planesweep_var(None, 1, 16, 4, 4, None, None, None, 1, 0.5, 0.05, 8, 8, 8, 16, 16, None, None)
     assert rc == -1 and 'C must be 32' in L.last_error()
-    rc = L.cdll.dv3d_sparse_conv(None, 0, 64, None, 0, None, 64, None, None, None, 0, None, None)
+    rc = L.cdll.dv3d_sparse_conv(None, 0, 64, None, 0, None, None, 64, None, None, None, 0, None, None)
     assert rc == -1 and 'bad arguments' in L.last_error()
     assert L.cdll.dv3d_hash_bytes(1000) == 2048 * 12
+    # tensor-core weight image: big + small part of every value; K must be a multiple of 32
+    assert L.cdll.dv3d_gemm_pack_bytes(27 * 128, 128) == 27 * 128 * 128 * 8
+    assert L.cdll.dv3d_gemm_pack_bytes(48, 128) == 0
+    assert L.cdll.dv3d_set_gemm_precision(3) == -1 and L.cdll.dv3d_get_gemm_precision() == 1
 
 
 def test_struct_layout_matches_header(L):
