@@ -218,54 +218,75 @@ conv3d_generic_kernel(const float* __restrict__ x, int Cin, int Di, int Hi, int 
 }
 
 // ------------------------------------------------------------------ prob conv + soft-argmin
-__global__ void __launch_bounds__(128)
+// CTA = 16 consecutive pixels of one image row x 16 depth lanes.  A thread convolves the planes
+// d = lane, lane + 16, ... of its pixel (8 -> 1 channels, 3x3x3, bias) and folds them into an
+// online softmax(-x) state with the plane depth as value; the 16 states of a pixel are merged
+// through shared memory.  The regularised volume itself is only written on request.
+constexpr int PS_TX = 16, PS_DL = 16;
+
+__global__ void __launch_bounds__(PS_TX * PS_DL)
 prob_softargmin_kernel(const float* __restrict__ x, int Cin, int D, int H, int W, const float* __restrict__ wgt,
-                       float bias, float d_start, float d_end, float* __restrict__ x_reg, float* __restrict__ depth,
-                       long long n_pix_total) {
+                       float bias, float d_start, float d_end, float* __restrict__ x_reg, float* __restrict__ depth) {
     extern __shared__ float s_w[];  // [Cin][27]
+    __shared__ float s_m[PS_DL][PS_TX], s_s[PS_DL][PS_TX], s_t[PS_DL][PS_TX];
     for (int i = threadIdx.x; i < Cin * 27; i += blockDim.x) s_w[i] = __ldg(wgt + i);
     __syncthreads();
-    long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pix >= n_pix_total) return;
-    const int ox = (int)(pix % W);
-    const int oy = (int)((pix / W) % H);
-    const int n = (int)(pix / ((long long)W * H));
+    const int px = threadIdx.x % PS_TX, dl = threadIdx.x / PS_TX;
+    const int ox = blockIdx.x * PS_TX + px, oy = blockIdx.y, n = blockIdx.z;
     const size_t plane = (size_t)H * W, vol = plane * D;
     const float* xn = x + (size_t)n * Cin * vol;
+    const bool inside = ox < W;
 
     float m = -INFINITY, s = 0.f, t = 0.f;
-    for (int d = 0; d < D; ++d) {
-        float acc = bias;
-        for (int ci = 0; ci < Cin; ++ci) {
-            const float* xc = xn + (size_t)ci * vol;
+    if (inside) {
+        for (int d = dl; d < D; d += PS_DL) {
+            float acc = bias;
+            for (int ci = 0; ci < Cin; ++ci) {
+                const float* xc = xn + (size_t)ci * vol;
 #pragma unroll
-            for (int kd = 0; kd < 3; ++kd) {
-                int z = d + kd - 1;
-                if (z < 0 || z >= D) continue;
+                for (int kd = 0; kd < 3; ++kd) {
+                    const int z = d + kd - 1;
+                    if (z < 0 || z >= D) continue;
 #pragma unroll
-                for (int kh = 0; kh < 3; ++kh) {
-                    int yy = oy + kh - 1;
-                    if (yy < 0 || yy >= H) continue;
-                    const float* xr = xc + (size_t)z * plane + (size_t)yy * W;
+                    for (int kh = 0; kh < 3; ++kh) {
+                        const int yy = oy + kh - 1;
+                        if (yy < 0 || yy >= H) continue;
+                        const float* xr = xc + (size_t)z * plane + (size_t)yy * W;
 #pragma unroll
-                    for (int kw = 0; kw < 3; ++kw) {
-                        int xx = ox + kw - 1;
-                        if (xx < 0 || xx >= W) continue;
-                        acc = fmaf(__ldg(xr + xx), s_w[ci * 27 + (kd * 3 + kh) * 3 + kw], acc);
+                        for (int kw = 0; kw < 3; ++kw) {
+                            const int xx = ox + kw - 1;
+                            if (xx < 0 || xx >= W) continue;
+                            acc = fmaf(__ldg(xr + xx), s_w[ci * 27 + (kd * 3 + kh) * 3 + kw], acc);
+                        }
                     }
                 }
             }
+            if (x_reg) x_reg[((size_t)n * D + d) * plane + (size_t)oy * W + ox] = acc;
+            const float v = -acc;
+            const float mn = fmaxf(m, v);
+            const float corr = expf(m - mn), e = expf(v - mn);
+            s = s * corr + e;
+            t = t * corr + e * linspace_torch(d_start, d_end, D, d);
+            m = mn;
         }
-        if (x_reg) x_reg[((size_t)n * D + d) * plane + (size_t)oy * W + ox] = acc;
-        // online softmax of -acc with the plane depth as the value
-        float v = -acc;
-        float mn = fmaxf(m, v);
-        float corr = __expf(m - mn), e = __expf(v - mn);
-        s = s * corr + e;
-        t = t * corr + e * linspace_torch(d_start, d_end, D, d);
-        m = mn;
     }
-    depth[pix] = t / s;
+    s_m[dl][px] = m;
+    s_s[dl][px] = s;
+    s_t[dl][px] = t;
+    __syncthreads();
+    if (dl == 0 && inside) {
+        float M = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < PS_DL; ++i) M = fmaxf(M, s_m[i][px]);
+        float S = 0.f, T = 0.f;
+#pragma unroll
+        for (int i = 0; i < PS_DL; ++i) {
+            const float c = expf(s_m[i][px] - M);  // lanes that saw no plane carry m = -inf -> 0
+            S = fmaf(s_s[i][px], c, S);
+            T = fmaf(s_t[i][px], c, T);
+        }
+        depth[((size_t)n * H + oy) * W + ox] = T / S;
+    }
 }
 
 static int fold_check(const float* scale, const float* shift) { return scale && shift; }
@@ -348,9 +369,10 @@ extern "C" int dv3d_prob_softargmin(const float* x, int n, int Cin, int D, int H
     DV3D_REQUIRE(x && weight && depth_out, "prob_softargmin: null pointer");
     DV3D_REQUIRE(n >= 0 && Cin > 0 && Cin <= 64 && D > 0 && H > 0 && W > 0, "prob_softargmin: bad shape");
     if (n == 0) return DV3D_OK;
-    long long total = (long long)n * H * W;
-    prob_softargmin_kernel<<<cdiv(total, 128), 128, sizeof(float) * Cin * 27, (cudaStream_t)stream>>>(
-        x, Cin, D, H, W, weight, bias, depth_start, depth_end, x_reg_out, depth_out, total);
+    DV3D_REQUIRE(H <= 65535 && n <= 65535, "prob_softargmin: H or n > 65535");
+    dim3 grid(cdiv(W, PS_TX), H, n);
+    prob_softargmin_kernel<<<grid, PS_TX * PS_DL, sizeof(float) * Cin * 27, (cudaStream_t)stream>>>(
+        x, Cin, D, H, W, weight, bias, depth_start, depth_end, x_reg_out, depth_out);
     DV3D_LAUNCHED();
     return DV3D_OK;
 }

@@ -47,6 +47,9 @@ struct GemmDesc {
     int relu_out;
     int zero_row_mod;       // rows with m % zero_row_mod == zero_row_val are written as 0
     int zero_row_val;
+    float* split_ws;        // optional K-split workspace of the tcgen05 kernel (see gemm_tc.cu)
+    size_t split_ws_bytes;
+    int* split_counters;    // one int per 128-row tile, zero on entry, left zero on exit
     float* out;             // [M, out_ld]
     int out_ld;
 };
@@ -55,5 +58,6 @@ struct GemmDesc {
 // 3xTF32 or TF32 according to dv3d_set_gemm_precision.
 int launch_gather_gemm(const GemmDesc& d, cudaStream_t st);
 int launch_gather_gemm_tc(const GemmDesc& d, cudaStream_t st);
+int gather_gemm_tc_splits(long long M, int n_slices);
 
 }  // namespace dv3d

@@ -148,6 +148,92 @@ pack_weights_kernel(const float* __restrict__ W, int Ktot, int N, float* __restr
 }
 
 // ------------------------------------------------------------------ the kernel
+// Position of a producer in the CTA's sequence of K chunks (live slices of its split range).
+struct ChunkCursor {
+    int s, kc, nk, wchunk;
+    const float* src[4];
+};
+
+__device__ __forceinline__ void cursor_enter(ChunkCursor& c, const GemmDesc& d, int s_end, uint32_t active,
+                                             const int* s_rows, int r0, int j) {
+    while (c.s < s_end && !((active >> c.s) & 1u)) {
+        c.wchunk += d.slice[c.s].K / TC_KC;
+        ++c.s;
+    }
+    c.kc = 0;
+    if (c.s < s_end) {
+        const GemmSlice& sl = d.slice[c.s];
+        c.nk = sl.K / TC_KC;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int row = s_rows[c.s * TC_BM + r0 + 32 * i];
+            c.src[i] = row >= 0 ? sl.src + (size_t)row * sl.ld + j * 4 : nullptr;
+        }
+    }
+}
+__device__ __forceinline__ void cursor_next(ChunkCursor& c, const GemmDesc& d, int s_end, uint32_t active,
+                                            const int* s_rows, int r0, int j) {
+    ++c.wchunk;
+    if (++c.kc == c.nk) {
+        ++c.s;
+        cursor_enter(c, d, s_end, active, s_rows, r0, j);
+    }
+}
+__device__ __forceinline__ void cursor_load(const ChunkCursor& c, float4 (&v)[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        v[i] = c.src[i] ? __ldg(reinterpret_cast<const float4*>(c.src[i] + c.kc * TC_KC)) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// epilogue of one 16-channel group of one output row
+__device__ __forceinline__ void epilogue16(const GemmDesc& d, float (&y)[16], long long m, int c0, bool live,
+                                           bool zero_row) {
+    if (d.scale) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) y[i] *= __ldg(d.scale + c0 + i);
+    }
+    if (d.shift) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) y[i] += __ldg(d.shift + c0 + i);
+    }
+    if (d.gn_weight) {
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) sum += y[i];
+        const float mean = sum * (1.f / 16.f);
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) q = fmaf(y[i] - mean, y[i] - mean, q);
+        const float rstd = 1.f / sqrtf(q * (1.f / 16.f) + 1e-5f);
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            y[i] = fmaf((y[i] - mean) * rstd, __ldg(d.gn_weight + c0 + i), __ldg(d.gn_bias + c0 + i));
+    }
+    if (!live) return;
+    if (d.residual) {
+        const float4* rp = reinterpret_cast<const float4*>(d.residual + (size_t)m * d.res_ld + c0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float4 rv = __ldg(rp + i);
+            y[4 * i] += rv.x; y[4 * i + 1] += rv.y; y[4 * i + 2] += rv.z; y[4 * i + 3] += rv.w;
+        }
+    }
+    if (d.relu_out) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) y[i] = fmaxf(y[i], 0.f);
+    }
+    if (zero_row) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) y[i] = 0.f;
+    }
+    float4* op = reinterpret_cast<float4*>(d.out + (size_t)m * d.out_ld + c0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) op[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+}
+
+// grid = (row tiles, K splits).  With K splits > 1 every CTA contracts a contiguous range of
+// slices, parks its raw 128 x N partial in d.split_ws and bumps the tile's counter; the CTA
+// that arrives last adds the partials in split order (deterministic) and runs the epilogue.
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gather_gemm_tc_kernel(const __grid_constant__ GemmDesc d, int precision) {
@@ -159,12 +245,15 @@ gather_gemm_tc_kernel(const __grid_constant__ GemmDesc d, int precision) {
     constexpr int B_IMG = BN * 128;
     int* s_rows = reinterpret_cast<int*>(smem + TC_STAGES * STAGE);                 // [n_slices][128]
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_rows + kMaxSlices * TC_BM);    // full[3] empty[3] accum
-    uint32_t* s_misc = reinterpret_cast<uint32_t*>(s_bar + 2 * TC_STAGES + 1);     // [0] tmem base, [1] active mask
+    uint32_t* s_misc = reinterpret_cast<uint32_t*>(s_bar + 2 * TC_STAGES + 1);     // [0] tmem base, [1] active, [2] last
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long m0 = (long long)blockIdx.x * TC_BM;
     const uint32_t bar_full = smem_u32(s_bar), bar_empty = smem_u32(s_bar + TC_STAGES),
                    bar_accum = smem_u32(s_bar + 2 * TC_STAGES);
+    const int n_split = gridDim.y;
+    const int per_split = (d.n_slices + n_split - 1) / n_split;
+    const int s_begin = min((int)blockIdx.y * per_split, d.n_slices), s_end = min(s_begin + per_split, d.n_slices);
 
     if (tid == 0) {
         for (int s = 0; s < TC_STAGES; ++s) {
@@ -181,15 +270,16 @@ gather_gemm_tc_kernel(const __grid_constant__ GemmDesc d, int precision) {
     // stage the row table of the tile and flag the slices that have at least one live row
     if (tid < TC_PRODUCERS) {
         unsigned my_active = 0;
-        for (int i = tid; i < d.n_slices * TC_BM; i += TC_PRODUCERS) {
+        const int ns = s_end - s_begin;
+        for (int i = tid; i < ns * TC_BM; i += TC_PRODUCERS) {
             int s, r;
             long long rr = -1;
-            if (d.kmap) {  // kernel map [M][n_slices]: the tile's block is contiguous
-                r = i / d.n_slices;
-                s = i - r * d.n_slices;
+            if (d.kmap) {  // kernel map [M][n_slices]: consecutive threads read consecutive entries
+                r = i / ns;
+                s = s_begin + (i - r * ns);
                 if (m0 + r < d.M) rr = (long long)__ldg(d.kmap + (m0 + r) * d.n_slices + s);
             } else {
-                s = i >> 7;
+                s = s_begin + (i >> 7);
                 r = i & (TC_BM - 1);
                 const GemmSlice& sl = d.slice[s];
                 const long long m = m0 + r;
@@ -210,69 +300,90 @@ gather_gemm_tc_kernel(const __grid_constant__ GemmDesc d, int precision) {
     tc_fence_after();
     const uint32_t tmem_base = s_misc[0];
     const uint32_t active = s_misc[1];
+    int n_it = 0;
+    for (int s = s_begin; s < s_end; ++s)
+        if ((active >> s) & 1u) n_it += d.slice[s].K / TC_KC;
 
     if (tid < TC_PRODUCERS) {
-        // ===================== producers: gather A, split, store swizzled; thread 0 also fetches B
-        const int j = tid & 7;   // 16-byte unit within the 128-byte row
-        const int r0 = tid >> 3; // rows r0 + 32 i
-        int it = 0, wchunk = 0;
-        for (int s = 0; s < d.n_slices; ++s) {
-            const GemmSlice& sl = d.slice[s];
-            const int nk = sl.K / TC_KC;
-            if (!((active >> s) & 1u)) {
-                wchunk += nk;
-                continue;
+        // ===================== producers: gather A two chunks ahead, split, store swizzled;
+        // thread 0 also starts the bulk copy of the chunk's packed weights
+        const int j = tid & 7;    // 16-byte unit within the 128-byte row
+        const int r0 = tid >> 3;  // rows r0 + 32 i
+        ChunkCursor ld, stc;
+        ld.s = s_begin;
+        ld.wchunk = 0;
+        for (int s = 0; s < s_begin; ++s) ld.wchunk += d.slice[s].K / TC_KC;
+        cursor_enter(ld, d, s_end, active, s_rows, r0, j);
+        stc = ld;
+        float4 va[4], vb[4];
+        if (n_it > 0) {
+            cursor_load(ld, va);
+            cursor_next(ld, d, s_end, active, s_rows, r0, j);
+        }
+        if (n_it > 1) {
+            cursor_load(ld, vb);
+            cursor_next(ld, d, s_end, active, s_rows, r0, j);
+        }
+        auto store_chunk = [&](int it, const float4 (&v)[4]) {
+            const int st = it % TC_STAGES;
+            const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
+            mbar_wait(bar_empty + 8 * st, ph ^ 1u);
+            unsigned char* stage = smem + st * STAGE;
+            if (tid == 0) {
+                mbar_expect_tx(bar_full + 8 * st, 2 * B_IMG);
+                bulk_g2s(smem_u32(stage + 2 * TC_A_BYTES), Wp + (size_t)stc.wchunk * (2 * BN * 32), 2 * B_IMG,
+                         bar_full + 8 * st);
             }
-            const float* src[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int row = s_rows[s * TC_BM + r0 + 32 * i];
-                src[i] = row >= 0 ? sl.src + (size_t)row * sl.ld + j * 4 : nullptr;
+                float4 a = v[i];
+                if (d.relu_in) {
+                    a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
+                }
+                float4 big, small;
+                split_tf32(a.x, big.x, small.x);
+                split_tf32(a.y, big.y, small.y);
+                split_tf32(a.z, big.z, small.z);
+                split_tf32(a.w, big.w, small.w);
+                const int r = r0 + 32 * i;
+                const int off = r * 128 + ((j ^ (r & 7)) << 4);
+                *reinterpret_cast<float4*>(stage + off) = big;
+                *reinterpret_cast<float4*>(stage + TC_A_BYTES + off) = small;
             }
-            for (int kc = 0; kc < nk; ++kc, ++it, ++wchunk) {
-                const int st = it % TC_STAGES;
-                const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
-                float4 v[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    v[i] = src[i] ? __ldg(reinterpret_cast<const float4*>(src[i] + kc * TC_KC)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                mbar_wait(bar_empty + 8 * st, ph ^ 1u);
-                unsigned char* stage = smem + st * STAGE;
-                if (tid == 0) {
-                    mbar_expect_tx(bar_full + 8 * st, 2 * B_IMG);
-                    bulk_g2s(smem_u32(stage + 2 * TC_A_BYTES), Wp + (size_t)wchunk * (2 * BN * 32), 2 * B_IMG,
-                             bar_full + 8 * st);
+            fence_proxy_async_smem();
+            mbar_arrive(bar_full + 8 * st);
+            // only the weight-chunk index of the store cursor is used
+            ++stc.wchunk;
+            if (++stc.kc == stc.nk) {
+                ++stc.s;
+                while (stc.s < s_end && !((active >> stc.s) & 1u)) {
+                    stc.wchunk += d.slice[stc.s].K / TC_KC;
+                    ++stc.s;
                 }
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    float4 a = v[i];
-                    if (d.relu_in) {
-                        a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
-                    }
-                    float4 big, small;
-                    split_tf32(a.x, big.x, small.x);
-                    split_tf32(a.y, big.y, small.y);
-                    split_tf32(a.z, big.z, small.z);
-                    split_tf32(a.w, big.w, small.w);
-                    const int r = r0 + 32 * i;
-                    const int off = r * 128 + ((j ^ (r & 7)) << 4);
-                    *reinterpret_cast<float4*>(stage + off) = big;
-                    *reinterpret_cast<float4*>(stage + TC_A_BYTES + off) = small;
+                stc.kc = 0;
+                if (stc.s < s_end) stc.nk = d.slice[stc.s].K / TC_KC;
+            }
+        };
+        for (int it = 0; it < n_it; it += 2) {
+            store_chunk(it, va);
+            if (it + 2 < n_it) {
+                cursor_load(ld, va);
+                cursor_next(ld, d, s_end, active, s_rows, r0, j);
+            }
+            if (it + 1 < n_it) {
+                store_chunk(it + 1, vb);
+                if (it + 3 < n_it) {
+                    cursor_load(ld, vb);
+                    cursor_next(ld, d, s_end, active, s_rows, r0, j);
                 }
-                fence_proxy_async_smem();
-                mbar_arrive(bar_full + 8 * st);
             }
         }
     } else {
-      if (lane == 0 && active) {
-        // ===================== MMA issuer
-        constexpr uint32_t idesc = umma_idesc_tf32(TC_BM, BN);
-        int it = 0;
-        uint32_t acc = 0;
-        for (int s = 0; s < d.n_slices; ++s) {
-            if (!((active >> s) & 1u)) continue;
-            const int nk = d.slice[s].K / TC_KC;
-            for (int kc = 0; kc < nk; ++kc, ++it) {
+        if (lane == 0 && n_it > 0) {
+            // ===================== MMA issuer
+            constexpr uint32_t idesc = umma_idesc_tf32(TC_BM, BN);
+            uint32_t acc = 0;
+            for (int it = 0; it < n_it; ++it) {
                 const int st = it % TC_STAGES;
                 const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
                 mbar_wait(bar_full + 8 * st, ph);
@@ -292,69 +403,76 @@ gather_gemm_tc_kernel(const __grid_constant__ GemmDesc d, int precision) {
                 }
                 umma_commit(bar_empty + 8 * st);  // frees the stage once these MMAs have read it
             }
+            umma_commit(bar_accum);
         }
-        umma_commit(bar_accum);
-      }
-      __syncwarp();
+        __syncwarp();
     }
 
     // ===================== epilogue: warps 0..3, thread = output row = TMEM lane
     if (warp < 4) {
-        if (active) mbar_wait(bar_accum, 0);
+        if (n_it > 0) mbar_wait(bar_accum, 0);
         tc_fence_after();
-        const long long m = m0 + warp * 32 + lane;
+        const int row = warp * 32 + lane;
+        const long long m = m0 + row;
         const bool live = m < d.M;
         const bool zero_row = d.zero_row_mod && (int)(m % d.zero_row_mod) == d.zero_row_val;
+        const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+        if (n_split == 1) {
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 16) {
-            float y[16];
-            if (active) {
-                tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, y);
-            } else {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) y[i] = 0.f;
-            }
-            if (d.scale) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) y[i] *= __ldg(d.scale + c0 + i);
-            }
-            if (d.shift) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) y[i] += __ldg(d.shift + c0 + i);
-            }
-            if (d.gn_weight) {
-                float sum = 0.f;
-#pragma unroll
-                for (int i = 0; i < 16; ++i) sum += y[i];
-                const float mean = sum * (1.f / 16.f);
-                float q = 0.f;
-#pragma unroll
-                for (int i = 0; i < 16; ++i) q = fmaf(y[i] - mean, y[i] - mean, q);
-                const float rstd = 1.f / sqrtf(q * (1.f / 16.f) + 1e-5f);
-#pragma unroll
-                for (int i = 0; i < 16; ++i)
-                    y[i] = fmaf((y[i] - mean) * rstd, __ldg(d.gn_weight + c0 + i), __ldg(d.gn_bias + c0 + i));
-            }
-            if (live) {
-                if (d.residual) {
-                    const float4* rp = reinterpret_cast<const float4*>(d.residual + (size_t)m * d.res_ld + c0);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        float4 rv = __ldg(rp + i);
-                        y[4 * i] += rv.x; y[4 * i + 1] += rv.y; y[4 * i + 2] += rv.z; y[4 * i + 3] += rv.w;
-                    }
-                }
-                if (d.relu_out) {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) y[i] = fmaxf(y[i], 0.f);
-                }
-                if (zero_row) {
+            for (int c0 = 0; c0 < BN; c0 += 16) {
+                float y[16];
+                if (n_it > 0) {
+                    tmem_ld16(trow + (uint32_t)c0, y);
+                } else {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) y[i] = 0.f;
                 }
-                float4* op = reinterpret_cast<float4*>(d.out + (size_t)m * d.out_ld + c0);
+                epilogue16(d, y, m, c0, live, zero_row);
+            }
+        } else {
+            const size_t tile_floats = (size_t)TC_BM * BN;
+            float* ws_tile = d.split_ws + ((size_t)blockIdx.x * n_split) * tile_floats;  // [n_split][128][BN]
+            float* mine = ws_tile + (size_t)blockIdx.y * tile_floats + (size_t)row * BN;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 16) {
+                float y[16];
+                if (n_it > 0) {
+                    tmem_ld16(trow + (uint32_t)c0, y);
+                } else {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) op[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+                    for (int i = 0; i < 16; ++i) y[i] = 0.f;
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    reinterpret_cast<float4*>(mine + c0)[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+            }
+            __threadfence();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (tid == 0) {
+                const int prev = atomicAdd(d.split_counters + blockIdx.x, 1);
+                const bool last = prev == n_split - 1;
+                if (last) d.split_counters[blockIdx.x] = 0;  // ready for the next launch on this stream
+                s_misc[2] = last ? 1u : 0u;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (s_misc[2]) {
+                __threadfence();
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 16) {
+                    float y[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) y[i] = 0.f;
+                    for (int sp = 0; sp < n_split; ++sp) {
+                        const float4* pp = reinterpret_cast<const float4*>(ws_tile + (size_t)sp * tile_floats +
+                                                                           (size_t)row * BN + c0);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            float4 v = __ldcg(pp + i);
+                            y[4 * i] += v.x; y[4 * i + 1] += v.y; y[4 * i + 2] += v.z; y[4 * i + 3] += v.w;
+                        }
+                    }
+                    epilogue16(d, y, m, c0, live, zero_row);
+                }
             }
         }
     }
@@ -365,6 +483,15 @@ gather_gemm_tc_kernel(const __grid_constant__ GemmDesc d, int precision) {
 
 int validate_gather_gemm(const GemmDesc& d, int k_multiple);
 
+// K splits for a launch: fill the 148 SMs when the row tiles alone cannot
+int gather_gemm_tc_splits(long long M, int n_slices) {
+    const int tiles = cdiv(M, TC_BM);
+    if (tiles <= 0 || n_slices < 6) return 1;
+    int split = kNumSMs / tiles;
+    if (split > n_slices / 3) split = n_slices / 3;
+    return split < 1 ? 1 : split;
+}
+
 int launch_gather_gemm_tc(const GemmDesc& d, cudaStream_t st) {
     const float* Wp = d.Wp;
     int rc = validate_gather_gemm(d, TC_KC);
@@ -372,7 +499,15 @@ int launch_gather_gemm_tc(const GemmDesc& d, cudaStream_t st) {
     DV3D_REQUIRE(Wp && ((uintptr_t)Wp & 15) == 0, "gather_gemm_tc: packed weights must be 16-byte aligned");
     DV3D_REQUIRE(d.out_ld % 4 == 0 && ((uintptr_t)d.out & 15) == 0, "gather_gemm_tc: output must be 16-byte aligned");
     if (d.M == 0) return DV3D_OK;
-    const int grid = cdiv(d.M, TC_BM);
+    const int tiles = cdiv(d.M, TC_BM);
+    int split = 1;
+    if (d.split_ws && d.split_counters) {
+        split = gather_gemm_tc_splits(d.M, d.n_slices);
+        const size_t need = (size_t)tiles * split * TC_BM * d.N * sizeof(float);
+        DV3D_REQUIRE(split == 1 || d.split_ws_bytes >= need, "gather_gemm_tc: split workspace too small (%zu < %zu)",
+                     d.split_ws_bytes, need);
+    }
+    dim3 grid(tiles, split);
     if (d.N == 128) {
         static bool attr = false;
         if (!attr) {

@@ -59,11 +59,13 @@ class SparseResidual3d(nn.Module):
         self.conv1 = SparseConvolution(feat_dim, feat_dim)
         self.conv2 = SparseConvolution(feat_dim, feat_dim)
 
-    def forward(self, x, nbr):
+    def forward(self, x, nbr, ws=None):
         w1, p1 = self.conv1.weights()
         w2, p2 = self.conv2.weights()
-        h = ops.sparse_conv(x, nbr, w1, self.n1.gn.weight.detach(), self.n1.gn.bias.detach(), None, True, packed=p1)
-        return ops.sparse_conv(h, nbr, w2, self.n2.gn.weight.detach(), self.n2.gn.bias.detach(), x, True, packed=p2)
+        h = ops.sparse_conv(x, nbr, w1, self.n1.gn.weight.detach(), self.n1.gn.bias.detach(), None, True, packed=p1,
+                            workspace=ws)
+        return ops.sparse_conv(h, nbr, w2, self.n2.gn.weight.detach(), self.n2.gn.bias.detach(), x, True, packed=p2,
+                               workspace=ws)
 
 
 class PointNet(nn.Module):
@@ -135,6 +137,8 @@ class SparseScene(object):
         self.levels = [ops.SparseLevel(ops.make_coords(idx, batch), 1, self.err)]
         for _ in range(1, n_levels):
             self.levels.append(ops.coarsen(self.levels[-1], dims, n_batch, self.err))
+        # K-split workspace of the tensor-core sparse convolution, shared by all layers
+        self.ws = ops.sparse_conv_workspace(self.levels[0].n, 128, dev)
 
     def same(self, l):       # k3 s1 on level l
         lv = self.levels[l]
@@ -179,27 +183,30 @@ class SparseUNet(nn.Module):
             scene = SparseScene(idx, batch, self.n_levels)
         nl = self.n_levels
         x = F.float().contiguous()
+        ws = scene.ws
         for blk in self.res_down[0]:
-            x = blk(x, scene.same(0))
+            x = blk(x, scene.same(0), ws)
         xs = [x]
         for i in range(1, nl):
             conv, gn = self.down[i - 1][0], self.down[i - 1][1].gn
             wk, wp = conv.weights()
-            x = ops.sparse_conv(x, scene.down(i - 1), wk, gn.weight.detach(), gn.bias.detach(), None, True, packed=wp)
+            x = ops.sparse_conv(x, scene.down(i - 1), wk, gn.weight.detach(), gn.bias.detach(), None, True, packed=wp,
+                                workspace=ws)
             for blk in self.res_down[i]:
-                x = blk(x, scene.same(i))
+                x = blk(x, scene.same(i), ws)
             xs.append(x)
         out = [(xs[-1], nl - 1)]
         for i in range(nl - 1):
             l = nl - 2 - i  # target (finer) level
             conv, gn = self.up[i][0], self.up[i][1].gn
             wk, wp = conv.weights()
-            up = ops.sparse_conv(x, scene.up(l), wk, gn.weight.detach(), gn.bias.detach(), None, True, packed=wp)
+            up = ops.sparse_conv(x, scene.up(l), wk, gn.weight.detach(), gn.bias.detach(), None, True, packed=wp,
+                                 workspace=ws)
             adj, gn = self.feat_adj[i][0], self.feat_adj[i][1].gn
             wk, wp = adj.weights()
             x = ops.concat_linear_gn_relu(up, xs[l], wk, gn.weight.detach(), gn.bias.detach(), packed=wp)
             for blk in self.res_up[i]:
-                x = blk(x, scene.same(l))
+                x = blk(x, scene.same(l), ws)
             out.append((x, l))
 
         origin = ops.batch_origin(pts.float().contiguous(), idx.int().contiguous(), batch.long().contiguous(),

@@ -311,14 +311,26 @@ def coarsen(level, dims, n_batch, err_flag):
     return SparseLevel(out[:n_out.value], ns, err_flag)
 
 
-def sparse_conv(feat, nbr, W, gn_weight=None, gn_bias=None, residual=None, relu=False, packed=None):
+def sparse_conv_workspace(n_out, Cout, device):
+    """zeroed K-split workspace for sparse_conv on levels of up to n_out rows (None when the
+    level is large enough to fill the GPU by itself)"""
+    nbytes = lib().raw('dv3d_sparse_conv_workspace_bytes')(n_out, Cout)
+    if nbytes == 0 or gemm_mode() == 'f32':
+        return None
+    return torch.zeros(nbytes, dtype=torch.uint8, device=device)
+
+
+def sparse_conv(feat, nbr, W, gn_weight=None, gn_bias=None, residual=None, relu=False, packed=None, workspace=None):
     n_in, Cin = feat.shape
     n_out = nbr.shape[0]
     Cout = W.shape[2]
     assert W.shape[0] == 27 and W.shape[1] == Cin
     out = torch.empty((n_out, Cout), dtype=torch.float32, device=feat.device)
+    ws_bytes = 0
+    if workspace is not None:
+        ws_bytes = min(workspace.numel(), lib().raw('dv3d_sparse_conv_workspace_bytes')(n_out, Cout))
     lib().call('dv3d_sparse_conv', _p(feat), n_in, Cin, _p(nbr), n_out, _p(W), _p(packed), Cout, _p(gn_weight),
-               _p(gn_bias), _p(residual), int(relu), _p(out), _stream())
+               _p(gn_bias), _p(residual), int(relu), _p(workspace) if ws_bytes else None, ws_bytes, _p(out), _stream())
     return out
 
 

@@ -203,11 +203,18 @@ int dv3d_kernel_map(const int* coords_out, long long n_out, const void* table_in
                     int* nbr, void* stream);
 /* out[o] = sum_k feat[nbr[o,k]] @ W[k]   (W [27,Cin,Cout], ME layout); optional fused per-row
  * GroupNorm (gn_weight/gn_bias [Cout], 16 channels per group, eps 1e-5), optional residual
- * add (before the ReLU) and ReLU — the SparseResidual3d / down / up blocks.  Cin % 16 == 0,
- * Cout in {64,128}. */
+ * add (before the ReLU) and ReLU — the SparseResidual3d / down / up blocks.  Cin % 16 == 0
+ * (% 32 for the tensor-core kernel), Cout in {64,128}.
+ * workspace (optional, tensor-core kernel only): lets a small level fill the GPU by splitting
+ * the 27 offsets over several CTAs per 128-row tile; partials are added in a fixed order by the
+ * last CTA of the tile.  dv3d_sparse_conv_workspace_bytes() sizes it (0 = not useful for this
+ * n_out); it must be 256-byte aligned and ZERO before its first use - every launch leaves its
+ * counters zero again, so one buffer serves all layers of a scene on one stream. */
+size_t dv3d_sparse_conv_workspace_bytes(long long n_out, int Cout);
 int dv3d_sparse_conv(const float* feat, long long n_in, int Cin, const int* nbr, long long n_out, const float* W,
                      const void* W_packed, int Cout, const float* gn_weight, const float* gn_bias,
-                     const float* residual, int relu, float* out, void* stream);
+                     const float* residual, int relu, void* workspace, size_t workspace_bytes, float* out,
+                     void* stream);
 /* 1x1 "feature adjust" on the concatenation [a | b] (ME.cat + k=1 conv, scenemodeling.py:206)
  * followed by GroupNorm + ReLU: W [Ca+Cb, Cout]. */
 int dv3d_concat_linear_gn_relu(const float* a, int Ca, const float* b, int Cb, long long n, const float* W,

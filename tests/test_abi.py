@@ -35,7 +35,7 @@ def test_abi_version_and_error_reporting(L):
     # argument validation happens before any CUDA call: safe without a GPU
     rc = L.cdll.dv3d_planesweep_var(None, 1, 16, 4, 4, None, None, None, 1, 0.5, 0.05, 8, 8, 8, 16, 16, None, None)
     assert rc == -1 and 'C must be 32' in L.last_error()
-    rc = L.cdll.dv3d_sparse_conv(None, 0, 64, None, 0, None, None, 64, None, None, None, 0, None, None)
+    rc = L.cdll.dv3d_sparse_conv(None, 0, 64, None, 0, None, None, 64, None, None, None, 0, None, 0, None, None)
     assert rc == -1 and 'bad arguments' in L.last_error()
     assert L.cdll.dv3d_hash_bytes(1000) == 2048 * 12
     # tensor-core weight image: big + small part of every value; K must be a multiple of 32

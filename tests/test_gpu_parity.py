@@ -174,7 +174,7 @@ def test_scene_model_golden(name, mods):
         a_pts, edges = torch.from_numpy(g['ref_anchor_pts']), torch.from_numpy(g['ref_anchor_pts_edges'])
         x = torch.cat((pts[edges[1]] - a_pts[edges[0]], feat[edges[1]]), dim=1)
         pn = net.pointnet(x.to(DEV), edges[0].to(DEV), a_pts.shape[0])
-        np.testing.assert_allclose(pn.cpu().numpy(), g['ref_pointnet'], rtol=0, atol=2e-5)
+        np.testing.assert_allclose(pn.cpu().numpy(), g['ref_pointnet'], rtol=2e-5, atol=2e-5)
         # SparseUNet alone through its reference signature
         xs = net.sparse_conv(torch.from_numpy(g['ref_pointnet']).to(DEV), a_pts.to(DEV),
                              torch.from_numpy(g['ref_anchor_idx3d']).to(DEV),
