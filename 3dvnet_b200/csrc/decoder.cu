@@ -11,7 +11,7 @@ namespace dv3d {
 // last Conv1d (C -> 1, bias) + softmax over the hypotheses + expected offset; one warp per point
 __global__ void __launch_bounds__(256)
 decoder_head_kernel(const float* __restrict__ x, long long Np, int n_hyp, int rows_per_point, int C, int ld,
-                    const float* __restrict__ w, float bias, float offset, float* __restrict__ prob_out,
+                    const float* __restrict__ w, float bias, double offset, float* __restrict__ prob_out,
                     float* __restrict__ offset_out) {
     const int lane = threadIdx.x & 31;
     const long long p = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -50,7 +50,7 @@ decoder_head_kernel(const float* __restrict__ x, long long Np, int n_hyp, int ro
         s += e[h];
     }
     const int n_side = (n_hyp - 1) / 2;
-    const float lo = (float)(-(double)n_side * (double)offset), hi = (float)((double)n_side * (double)offset);
+    const float lo = (float)(-(double)n_side * offset), hi = (float)((double)n_side * offset);
     float acc = 0.f;
 #pragma unroll
     for (int h = 0; h < 8; ++h) {
@@ -91,7 +91,7 @@ extern "C" int dv3d_conv1d_bn_relu(const float* x, long long n_pts, int rows_per
 }
 
 extern "C" int dv3d_decoder_head(const float* x, long long n_pts, int n_hyp, int rows_per_point, int Cin, int ldx,
-                                 const float* weight, float bias, float offset, float* prob_out, float* offset_out,
+                                 const float* weight, float bias, double offset, float* prob_out, float* offset_out,
                                  void* stream) {
     DV3D_REQUIRE(x && weight && offset_out && n_pts >= 0 && n_hyp >= 1 && n_hyp <= 7 && (n_hyp & 1) &&
                      rows_per_point >= n_hyp && Cin > 0 && ldx >= Cin,

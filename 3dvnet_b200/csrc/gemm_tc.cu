@@ -504,8 +504,7 @@ int launch_gather_gemm_tc(const GemmDesc& d, cudaStream_t st) {
     if (d.split_ws && d.split_counters) {
         split = gather_gemm_tc_splits(d.M, d.n_slices);
         const size_t need = (size_t)tiles * split * TC_BM * d.N * sizeof(float);
-        DV3D_REQUIRE(split == 1 || d.split_ws_bytes >= need, "gather_gemm_tc: split workspace too small (%zu < %zu)",
-                     d.split_ws_bytes, need);
+        if (d.split_ws_bytes < need) split = 1;  // tiles * split <= 148 partials fit a dv3d_sparse_conv_workspace_bytes buffer
     }
     dim3 grid(tiles, split);
     if (d.N == 128) {

@@ -38,13 +38,43 @@ struct SampleGeom {
     float wfm1, hfm1;  // Wf-1, Hf-1 (grid_sample align_corners=True un-normalisation)
 };
 
-// One (pixel, plane, edge) sample: q = z*a + b, z=|q_z|+1e-8, normalise, un-normalise, split
-// into tap base + bilinear weights.  Taps outside the map get weight 0 and a clamped address
-// (zero padding per tap, like ATen's grid_sampler_2d).
-__device__ __forceinline__ void make_record(float z, float ax, float ay, float az, float bx, float by, float bz,
+// The reference's fp32 operation chain is kept instruction for instruction, so that sample
+// positions (and with them x_var and the back-projected points) are BIT-IDENTICAL to the CPU
+// PyTorch path and not merely close: torch.bmm on K = 3/4 is a sequential FMA chain
+// (a0*b0, then fma(a_k, b_k, acc) for k = 1..) - pinned empirically against MKL - and
+// torch.inverse of a zero-skew pinhole K is [[1/fx, 0, -(cx/fx)], [0, 1/fy, -(cy/fy)], [0,0,1]].
+// Per image the host-visible table holds Kinv (9) | P = K [R|t] (12) | R (9) | t (3).
+constexpr int CAM_STRIDE = 36;
+constexpr int CAM_KINV = 0, CAM_P = 9, CAM_R = 21, CAM_T = 30;
+
+__device__ __forceinline__ float chain3(float a0, float a1, float a2, float b0, float b1, float b2) {
+    return __fmaf_rn(a2, b2, __fmaf_rn(a1, b1, __fmul_rn(a0, b0)));
+}
+
+// world point X = R^T (Kinv p - t) of the homogeneous pixel * depth vector p
+// (utils.py:102-106 / lightningmodel.py:142-144)
+__device__ __forceinline__ void backproject(const float* __restrict__ cam, float p0, float p1, float p2, float& X0,
+                                            float& X1, float& X2) {
+    const float* Ki = cam + CAM_KINV;
+    const float* R = cam + CAM_R;
+    const float* t = cam + CAM_T;
+    float c0 = __fsub_rn(chain3(__ldg(Ki + 0), __ldg(Ki + 1), __ldg(Ki + 2), p0, p1, p2), __ldg(t + 0));
+    float c1 = __fsub_rn(chain3(__ldg(Ki + 3), __ldg(Ki + 4), __ldg(Ki + 5), p0, p1, p2), __ldg(t + 1));
+    float c2 = __fsub_rn(chain3(__ldg(Ki + 6), __ldg(Ki + 7), __ldg(Ki + 8), p0, p1, p2), __ldg(t + 2));
+    X0 = chain3(__ldg(R + 0), __ldg(R + 3), __ldg(R + 6), c0, c1, c2);  // rows of R^T = columns of R
+    X1 = chain3(__ldg(R + 1), __ldg(R + 4), __ldg(R + 7), c0, c1, c2);
+    X2 = chain3(__ldg(R + 2), __ldg(R + 5), __ldg(R + 8), c0, c1, c2);
+}
+
+// One (pixel, plane, edge) sample: q = P_src [X;1] (mvsnet.py:199), z = |q_z| + 1e-8, normalise
+// by the full image size, un-normalise as grid_sample does, split into tap base + bilinear
+// weights.  Taps outside the map get weight 0 and a clamped address (zero padding per tap).
+__device__ __forceinline__ void make_record(const float* __restrict__ P, float X0, float X1, float X2,
                                             const SampleGeom& g, int& rec, float4& wt) {
-    float qx = fmaf(z, ax, bx), qy = fmaf(z, ay, by), qz = fmaf(z, az, bz);
-    float zz = fabsf(qz) + 1e-8f;
+    float qx = __fmaf_rn(__ldg(P + 3), 1.f, chain3(__ldg(P + 0), __ldg(P + 1), __ldg(P + 2), X0, X1, X2));
+    float qy = __fmaf_rn(__ldg(P + 7), 1.f, chain3(__ldg(P + 4), __ldg(P + 5), __ldg(P + 6), X0, X1, X2));
+    float qz = __fmaf_rn(__ldg(P + 11), 1.f, chain3(__ldg(P + 8), __ldg(P + 9), __ldg(P + 10), X0, X1, X2));
+    float zz = __fadd_rn(fabsf(qz), 1e-8f);
     float x = __fdiv_rn(qx, zz), y = __fdiv_rn(qy, zz);
     float gx = __fsub_rn(__fmul_rn(__fdiv_rn(x, g.wm1), 2.f), 1.f);
     float gy = __fsub_rn(__fmul_rn(__fdiv_rn(y, g.hm1), 2.f), 1.f);
@@ -54,12 +84,13 @@ __device__ __forceinline__ void make_record(float z, float ax, float ay, float a
     wt = make_float4(0.f, 0.f, 0.f, 0.f);
     if (ix > -1.f && ix < (float)g.Wf && iy > -1.f && iy < (float)g.Hf) {
         float fx0 = floorf(ix), fy0 = floorf(iy);
-        float tx = ix - fx0, ty = iy - fy0;
+        float tx = __fsub_rn(ix, fx0), ty = __fsub_rn(iy, fy0);
         int x0 = (int)fx0, y0 = (int)fy0;
         bool l = x0 >= 0, r = x0 + 1 <= g.Wf - 1, t = y0 >= 0, b = y0 + 1 <= g.Hf - 1;
-        float wl = l ? 1.f - tx : 0.f, wr = r ? tx : 0.f;
-        float wtp = t ? 1.f - ty : 0.f, wb = b ? ty : 0.f;
-        wt = make_float4(wl * wtp, wr * wtp, wl * wb, wr * wb);  // nw, ne, sw, se
+        float e1 = __fsub_rn(1.f, tx), s1 = __fsub_rn(1.f, ty);  // distances to the east / south taps
+        float wl = l ? e1 : 0.f, wr = r ? tx : 0.f;
+        float wtp = t ? s1 : 0.f, wb = b ? ty : 0.f;
+        wt = make_float4(__fmul_rn(wtp, wl), __fmul_rn(wtp, wr), __fmul_rn(wb, wl), __fmul_rn(wb, wr));  // nw ne sw se
         int cx = l ? x0 : 0, cy = t ? y0 : 0;
         int dx = (l && r) ? 1 : 0, dy = (t && b) ? 1 : 0;
         // when the left/top tap is the clamped one its weight is 0 and the right/bottom tap
@@ -69,10 +100,10 @@ __device__ __forceinline__ void make_record(float z, float ax, float ay, float a
 }
 
 __device__ __forceinline__ void fma4(float4& acc, float w, const float4& t) {
-    acc.x = fmaf(w, t.x, acc.x);
-    acc.y = fmaf(w, t.y, acc.y);
-    acc.z = fmaf(w, t.z, acc.z);
-    acc.w = fmaf(w, t.w, acc.w);
+    acc.x = __fmaf_rn(t.x, w, acc.x);
+    acc.y = __fmaf_rn(t.y, w, acc.y);
+    acc.z = __fmaf_rn(t.z, w, acc.z);
+    acc.w = __fmaf_rn(t.w, w, acc.w);
 }
 
 // Phase 2 for one staged pass of edges. NK = number of live planes/hypotheses in the chunk.
@@ -98,16 +129,20 @@ __device__ __forceinline__ void consume_edges(const float4* __restrict__ feats, 
                 t11 = ldg4(p + dy + dx);
                 prev = rec;
             }
+            // grid_sample (ATen CPU kernel): fma(se, w_se, fma(sw, w_sw, fma(ne, w_ne, nw * w_nw)))
             float4 val;
-            val.x = wt.x * t00.x; val.y = wt.x * t00.y; val.z = wt.x * t00.z; val.w = wt.x * t00.w;
+            val.x = __fmul_rn(t00.x, wt.x); val.y = __fmul_rn(t00.y, wt.x);
+            val.z = __fmul_rn(t00.z, wt.x); val.w = __fmul_rn(t00.w, wt.x);
             fma4(val, wt.y, t01);
             fma4(val, wt.z, t10);
             fma4(val, wt.w, t11);
-            acc_s[k].x += val.x; acc_s[k].y += val.y; acc_s[k].z += val.z; acc_s[k].w += val.w;
-            acc_q[k].x = fmaf(val.x, val.x, acc_q[k].x);
-            acc_q[k].y = fmaf(val.y, val.y, acc_q[k].y);
-            acc_q[k].z = fmaf(val.z, val.z, acc_q[k].z);
-            acc_q[k].w = fmaf(val.w, val.w, acc_q[k].w);
+            // scatter 'mean' of x and of x**2: plain sums in edge order (mvsnet.py:214-215)
+            acc_s[k].x = __fadd_rn(acc_s[k].x, val.x); acc_s[k].y = __fadd_rn(acc_s[k].y, val.y);
+            acc_s[k].z = __fadd_rn(acc_s[k].z, val.z); acc_s[k].w = __fadd_rn(acc_s[k].w, val.w);
+            acc_q[k].x = __fadd_rn(acc_q[k].x, __fmul_rn(val.x, val.x));
+            acc_q[k].y = __fadd_rn(acc_q[k].y, __fmul_rn(val.y, val.y));
+            acc_q[k].z = __fadd_rn(acc_q[k].z, __fmul_rn(val.z, val.z));
+            acc_q[k].w = __fadd_rn(acc_q[k].w, __fmul_rn(val.w, val.w));
         }
     }
 }
@@ -126,9 +161,10 @@ __device__ __forceinline__ float linspace_np(double start, double stop, int n, i
 }
 
 __global__ void __launch_bounds__(256, 2)
-planesweep_var_kernel(const float4* __restrict__ feats, SampleGeom geom, const float* __restrict__ xform,
-                      const int* __restrict__ rowptr, const int* __restrict__ esrc, double d0, double d1, int D,
-                      int h, int w, int H, int W, int chunks_per_cta, float* __restrict__ out) {
+planesweep_var_kernel(const float4* __restrict__ feats, SampleGeom geom, const float* __restrict__ cams,
+                      const int* __restrict__ ref_img, const int* __restrict__ rowptr, const int* __restrict__ esrc,
+                      double d0, double d1, int D, int h, int w, int H, int W, int chunks_per_cta,
+                      float* __restrict__ out) {
     // dynamic shared memory (73 KB > the 48 KB static limit): weights | records | output tile
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4 (*s_wt)[KD][TP] = reinterpret_cast<float4 (*)[KD][TP]>(smem_raw);
@@ -159,18 +195,18 @@ planesweep_var_kernel(const float4* __restrict__ feats, SampleGeom geom, const f
 #pragma unroll
         for (int k = 0; k < KD; ++k) acc_s[k] = acc_q[k] = make_float4(0, 0, 0, 0);
         const float z = linspace_np(d0, d1, D, min(dbase + pk, D - 1));
+        // frustum point of (pixel, plane): pixel * depth formed in fp64, rounded once (utils.py:96-100)
+        float X0, X1, X2;
+        backproject(cams + (size_t)__ldg(ref_img + r) * CAM_STRIDE, (float)((double)u * (double)z),
+                    (float)((double)vv * (double)z), z, X0, X1, X2);
 
         for (int eb = e0; eb < e1; eb += EMAX) {
             const int n_e = min(EMAX, e1 - eb);
             if (eb != e0) __syncthreads();  // previous pass fully consumed
             for (int e = 0; e < n_e; ++e) {
-                const float* x = xform + (size_t)(eb + e) * 12;
-                float ax = fmaf(__ldg(x + 0), u, fmaf(__ldg(x + 1), vv, __ldg(x + 2)));
-                float ay = fmaf(__ldg(x + 3), u, fmaf(__ldg(x + 4), vv, __ldg(x + 5)));
-                float az = fmaf(__ldg(x + 6), u, fmaf(__ldg(x + 7), vv, __ldg(x + 8)));
                 int rec;
                 float4 wt;
-                make_record(z, ax, ay, az, __ldg(x + 9), __ldg(x + 10), __ldg(x + 11), geom, rec, wt);
+                make_record(cams + (size_t)__ldg(esrc + eb + e) * CAM_STRIDE + CAM_P, X0, X1, X2, geom, rec, wt);
                 s_rec[e][pk][pv] = rec;
                 s_wt[e][pk][pv] = wt;
             }
@@ -208,9 +244,9 @@ planesweep_var_kernel(const float4* __restrict__ feats, SampleGeom geom, const f
 // Point-level variant: the "planes" of a pixel are its 2n+1 depth hypotheses around the
 // current depth estimate (lightningmodel.py:201-205); outputs are point-major.
 __global__ void __launch_bounds__(256, 2)
-points_var_kernel(const float4* __restrict__ feats, SampleGeom geom, const float* __restrict__ xform,
-                  const int* __restrict__ rowptr, const int* __restrict__ esrc, const float* __restrict__ backproj,
-                  const float* __restrict__ depth, int h, int w, int H, int W, int n_side, float offset,
+points_var_kernel(const float4* __restrict__ feats, SampleGeom geom, const float* __restrict__ cams,
+                  const int* __restrict__ ref_img, const int* __restrict__ rowptr, const int* __restrict__ esrc,
+                  const float* __restrict__ depth, int h, int w, int H, int W, int n_side, double offset,
                   float* __restrict__ pts_out, float* __restrict__ feat_out, int rows_per_point, int feat_stride,
                   int feat_off) {
     __shared__ int s_rec[EMAX][KD][TP];
@@ -234,17 +270,16 @@ points_var_kernel(const float4* __restrict__ feats, SampleGeom geom, const float
     // hypothesis depth: depth + i*offset with i*offset rounded to fp32 first (python float
     // times int, then a tensor + scalar add, lightningmodel.py:203)
     const float dpt = __ldg(depth + (size_t)r * P + p);
-    const float z = __fadd_rn(dpt, (float)((double)(pk - n_side) * (double)offset));
+    const float z = __fadd_rn(dpt, (float)((double)(pk - n_side) * offset));
 
-    if (live && pk < n_hyp) {  // world point of hypothesis pk
-        const float* B = backproj + (size_t)r * 12;
-        float rx = fmaf(B[0], u, fmaf(B[1], vv, B[2]));
-        float ry = fmaf(B[3], u, fmaf(B[4], vv, B[5]));
-        float rz = fmaf(B[6], u, fmaf(B[7], vv, B[8]));
+    // world point of hypothesis pk: pts_img * depth is an fp32 product here (lightningmodel.py:142)
+    float X0, X1, X2;
+    backproject(cams + (size_t)__ldg(ref_img + r) * CAM_STRIDE, __fmul_rn(u, z), __fmul_rn(vv, z), z, X0, X1, X2);
+    if (live && pk < n_hyp) {
         float* o = pts_out + (((size_t)r * P + p) * n_hyp + pk) * 3;
-        o[0] = fmaf(z, rx, B[9]);
-        o[1] = fmaf(z, ry, B[10]);
-        o[2] = fmaf(z, rz, B[11]);
+        o[0] = X0;
+        o[1] = X1;
+        o[2] = X2;
     }
 
     float4 acc_s[KD], acc_q[KD];
@@ -256,13 +291,9 @@ points_var_kernel(const float4* __restrict__ feats, SampleGeom geom, const float
         if (eb != e0) __syncthreads();
         if (pk < n_hyp) {
             for (int e = 0; e < n_e; ++e) {
-                const float* x = xform + (size_t)(eb + e) * 12;
-                float ax = fmaf(__ldg(x + 0), u, fmaf(__ldg(x + 1), vv, __ldg(x + 2)));
-                float ay = fmaf(__ldg(x + 3), u, fmaf(__ldg(x + 4), vv, __ldg(x + 5)));
-                float az = fmaf(__ldg(x + 6), u, fmaf(__ldg(x + 7), vv, __ldg(x + 8)));
                 int rec;
                 float4 wt;
-                make_record(z, ax, ay, az, __ldg(x + 9), __ldg(x + 10), __ldg(x + 11), geom, rec, wt);
+                make_record(cams + (size_t)__ldg(esrc + eb + e) * CAM_STRIDE + CAM_P, X0, X1, X2, geom, rec, wt);
                 s_rec[e][pk][pv] = rec;
                 s_wt[e][pk][pv] = wt;
             }
@@ -300,50 +331,41 @@ __device__ void inv3(const double* m, double* o) {
     o[3] = B * id; o[4] = (a * i - c * g) * id;  o[5] = -(a * f - c * d) * id;
     o[6] = C * id; o[7] = -(a * h - b * g) * id; o[8] = (a * e - b * d) * id;
 }
-__device__ void mm3(const double* a, const double* b, double* o) {
-    for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) o[i * 3 + j] = a[i * 3] * b[j] + a[i * 3 + 1] * b[3 + j] + a[i * 3 + 2] * b[6 + j];
-}
 __device__ void load3x3(const float* p, double* o) {
     for (int i = 0; i < 9; ++i) o[i] = (double)p[i];
 }
 
-__global__ void edge_transforms_kernel(const float* __restrict__ R, const float* __restrict__ t,
-                                       const float* __restrict__ K, const int* __restrict__ eref,
-                                       const int* __restrict__ esrc, int E, float* __restrict__ out) {
-    int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= E) return;
-    int r = eref[e], s = esrc[e];
-    double Rr[9], Rs[9], Kr[9], Ks[9], Kri[9], RrT[9], A[9], Bm[9], M[9];
-    load3x3(R + 9 * r, Rr); load3x3(R + 9 * s, Rs); load3x3(K + 9 * r, Kr); load3x3(K + 9 * s, Ks);
-    inv3(Kr, Kri);
-    for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) RrT[i * 3 + j] = Rr[j * 3 + i];
-    mm3(Rs, RrT, A);    // R_s R_r^T
-    mm3(Ks, A, Bm);     // K_s R_s R_r^T
-    mm3(Bm, Kri, M);
-    double tr[3] = {t[3 * r], t[3 * r + 1], t[3 * r + 2]}, ts[3] = {t[3 * s], t[3 * s + 1], t[3 * s + 2]};
-    double tt[3];
-    for (int i = 0; i < 3; ++i) tt[i] = ts[i] - (A[i * 3] * tr[0] + A[i * 3 + 1] * tr[1] + A[i * 3 + 2] * tr[2]);
-    for (int i = 0; i < 9; ++i) out[e * 12 + i] = (float)M[i];
-    for (int i = 0; i < 3; ++i) out[e * 12 + 9 + i] = (float)(Ks[i * 3] * tt[0] + Ks[i * 3 + 1] * tt[1] + Ks[i * 3 + 2] * tt[2]);
-}
-
-__global__ void ref_backprojection_kernel(const float* __restrict__ R, const float* __restrict__ t,
-                                          const float* __restrict__ K, const int* __restrict__ ref_img, int n,
-                                          float* __restrict__ out) {
+// Per-image camera table: Kinv | P = K [R|t] | R | t  (see CAM_* above).
+__global__ void camera_tables_kernel(const float* __restrict__ R, const float* __restrict__ t,
+                                     const float* __restrict__ K, int n, float* __restrict__ out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    int r = ref_img[i];
-    double Rr[9], Kr[9], Kri[9], RrT[9], B[9];
-    load3x3(R + 9 * r, Rr); load3x3(K + 9 * r, Kr);
-    inv3(Kr, Kri);
+    const float* k = K + 9 * i;
+    const float* r = R + 9 * i;
+    const float* tv = t + 3 * i;
+    float* o = out + (size_t)i * CAM_STRIDE;
+    if (k[1] == 0.f && k[3] == 0.f && k[6] == 0.f && k[7] == 0.f && k[8] == 1.f) {
+        // zero-skew pinhole: what torch.inverse (LAPACK getrf/getri, no pivoting needed) returns
+        o[CAM_KINV + 0] = __fdiv_rn(1.f, k[0]); o[CAM_KINV + 1] = 0.f; o[CAM_KINV + 2] = -__fdiv_rn(k[2], k[0]);
+        o[CAM_KINV + 3] = 0.f; o[CAM_KINV + 4] = __fdiv_rn(1.f, k[4]); o[CAM_KINV + 5] = -__fdiv_rn(k[5], k[4]);
+        o[CAM_KINV + 6] = 0.f; o[CAM_KINV + 7] = 0.f; o[CAM_KINV + 8] = 1.f;
+    } else {
+        double kd[9], ki[9];
+        load3x3(k, kd);
+        inv3(kd, ki);
+        for (int a = 0; a < 9; ++a) o[CAM_KINV + a] = (float)ki[a];
+    }
+    // P = bmm(K, cat(R, t)) (mvsnet.py:196-197): for matrices this small torch.bmm takes its
+    // plain-loop path, ((k0 r0 + k1 r1) + k2 r2) with every product and sum rounded (no FMA)
     for (int a = 0; a < 3; ++a)
-        for (int b = 0; b < 3; ++b) RrT[a * 3 + b] = Rr[b * 3 + a];
-    mm3(RrT, Kri, B);
-    for (int a = 0; a < 9; ++a) out[i * 12 + a] = (float)B[a];
-    for (int a = 0; a < 3; ++a)
-        out[i * 12 + 9 + a] = (float)(-(RrT[a * 3] * t[3 * r] + RrT[a * 3 + 1] * t[3 * r + 1] + RrT[a * 3 + 2] * t[3 * r + 2]));
+        for (int b = 0; b < 4; ++b) {
+            float r0 = b < 3 ? r[b] : tv[0], r1 = b < 3 ? r[3 + b] : tv[1], r2 = b < 3 ? r[6 + b] : tv[2];
+            o[CAM_P + a * 4 + b] = __fadd_rn(__fadd_rn(__fmul_rn(k[a * 3], r0), __fmul_rn(k[a * 3 + 1], r1)),
+                                             __fmul_rn(k[a * 3 + 2], r2));
+        }
+    for (int a = 0; a < 9; ++a) o[CAM_R + a] = r[a];
+    for (int a = 0; a < 3; ++a) o[CAM_T + a] = tv[a];
+    for (int a = 33; a < CAM_STRIDE; ++a) o[a] = 0.f;
 }
 
 // NCHW -> NHWC through a padded 32x32 shared tile (both sides coalesced)
@@ -385,32 +407,22 @@ extern "C" int dv3d_nchw_to_nhwc(const float* src, float* dst, int n, int C, int
     return DV3D_OK;
 }
 
-extern "C" int dv3d_edge_transforms(const float* rotmats, const float* tvecs, const float* K, const int* edge_ref,
-                                    const int* edge_src, int n_edges, float* xform_out, void* stream) {
-    DV3D_REQUIRE(rotmats && tvecs && K && edge_ref && edge_src && xform_out && n_edges >= 0,
-                 "edge_transforms: bad arguments");
-    if (n_edges == 0) return DV3D_OK;
-    edge_transforms_kernel<<<cdiv(n_edges, 64), 64, 0, (cudaStream_t)stream>>>(rotmats, tvecs, K, edge_ref, edge_src,
-                                                                               n_edges, xform_out);
+extern "C" int dv3d_camera_tables(const float* rotmats, const float* tvecs, const float* K, int n_imgs, float* out,
+                                  void* stream) {
+    DV3D_REQUIRE(rotmats && tvecs && K && out && n_imgs >= 0, "camera_tables: bad arguments");
+    if (n_imgs == 0) return DV3D_OK;
+    camera_tables_kernel<<<cdiv(n_imgs, 64), 64, 0, (cudaStream_t)stream>>>(rotmats, tvecs, K, n_imgs, out);
     DV3D_LAUNCHED();
     return DV3D_OK;
 }
 
-extern "C" int dv3d_ref_backprojection(const float* rotmats, const float* tvecs, const float* K, const int* ref_img,
-                                       int n_ref, float* out, void* stream) {
-    DV3D_REQUIRE(rotmats && tvecs && K && ref_img && out && n_ref >= 0, "ref_backprojection: bad arguments");
-    if (n_ref == 0) return DV3D_OK;
-    ref_backprojection_kernel<<<cdiv(n_ref, 64), 64, 0, (cudaStream_t)stream>>>(rotmats, tvecs, K, ref_img, n_ref, out);
-    DV3D_LAUNCHED();
-    return DV3D_OK;
-}
-
-extern "C" int dv3d_planesweep_var(const float* feats_nhwc, int n_imgs, int C, int Hf, int Wf, const float* xform,
-                                   const int* edge_rowptr, const int* edge_src, int n_ref, double depth_start,
+extern "C" int dv3d_planesweep_var(const float* feats_nhwc, int n_imgs, int C, int Hf, int Wf, const float* cams,
+                                   const int* ref_img, const int* edge_rowptr, const int* edge_src, int n_ref,
+                                   double depth_start,
                                    double depth_interval, int D, int h, int w, int H, int W, float* x_var,
                                    void* stream) {
     DV3D_REQUIRE(C == 32, "planesweep_var: C must be 32 (IMG_FEAT_DIM, mv3d/config.py:42), got %d", C);
-    DV3D_REQUIRE(feats_nhwc && xform && edge_rowptr && edge_src && x_var, "planesweep_var: null pointer");
+    DV3D_REQUIRE(feats_nhwc && cams && ref_img && edge_rowptr && edge_src && x_var, "planesweep_var: null pointer");
     DV3D_REQUIRE(n_imgs > 0 && Hf > 1 && Wf > 1 && D > 0 && h > 0 && w > 0 && H > 1 && W > 1 && n_ref >= 0,
                  "planesweep_var: bad shape");
     DV3D_REQUIRE((long long)Hf * Wf < (1 << 29), "planesweep_var: feature map too large for the record encoding");
@@ -430,21 +442,21 @@ extern "C" int dv3d_planesweep_var(const float* feats_nhwc, int n_imgs, int C, i
         attr_set = true;
     }
     planesweep_var_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(
-        reinterpret_cast<const float4*>(feats_nhwc), make_geom(Hf, Wf, H, W), xform, edge_rowptr, edge_src,
+        reinterpret_cast<const float4*>(feats_nhwc), make_geom(Hf, Wf, H, W), cams, ref_img, edge_rowptr, edge_src,
         depth_start, d1, D, h, w, H, W, chunks_per_cta, x_var);
     DV3D_LAUNCHED();
     return DV3D_OK;
 }
 
-extern "C" int dv3d_points_var(const float* feats_nhwc, int n_imgs, int C, int Hf, int Wf, const float* xform,
-                               const int* edge_rowptr, const int* edge_src, const float* backproj,
-                               const float* depth, int n_ref, int h, int w, int H, int W, int n_side, float offset,
+extern "C" int dv3d_points_var(const float* feats_nhwc, int n_imgs, int C, int Hf, int Wf, const float* cams,
+                               const int* ref_img, const int* edge_rowptr, const int* edge_src,
+                               const float* depth, int n_ref, int h, int w, int H, int W, int n_side, double offset,
                                float* pts_out, float* feat_out, int rows_per_point, int feat_stride, int feat_off,
                                void* stream) {
     DV3D_REQUIRE(C == 32, "points_var: C must be 32, got %d", C);
     DV3D_REQUIRE(n_side == 0 || n_side == 3, "points_var: n_side must be 0 (point cloud) or 3 (PointFlow), got %d",
                  n_side);
-    DV3D_REQUIRE(feats_nhwc && xform && edge_rowptr && edge_src && backproj && depth && pts_out && feat_out,
+    DV3D_REQUIRE(feats_nhwc && cams && ref_img && edge_rowptr && edge_src && depth && pts_out && feat_out,
                  "points_var: null pointer");
     DV3D_REQUIRE(rows_per_point >= 2 * n_side + 1, "points_var: rows_per_point < number of hypotheses");
     DV3D_REQUIRE(feat_stride % 4 == 0 && feat_off % 4 == 0 && feat_off + C <= feat_stride,
@@ -453,7 +465,7 @@ extern "C" int dv3d_points_var(const float* feats_nhwc, int n_imgs, int C, int H
     if (n_ref == 0) return DV3D_OK;
     dim3 grid(cdiv(h * w, TP), n_ref);
     points_var_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const float4*>(feats_nhwc), make_geom(Hf, Wf, H, W), xform, edge_rowptr, edge_src, backproj,
+        reinterpret_cast<const float4*>(feats_nhwc), make_geom(Hf, Wf, H, W), cams, ref_img, edge_rowptr, edge_src,
         depth, h, w, H, W, n_side, offset, pts_out, feat_out, rows_per_point, feat_stride, feat_off);
     DV3D_LAUNCHED();
     return DV3D_OK;

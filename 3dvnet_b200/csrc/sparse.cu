@@ -145,13 +145,13 @@ extern "C" int dv3d_kernel_map(const int* coords_out, long long n_out, const voi
     return DV3D_OK;
 }
 
-static size_t split_counter_bytes(long long n_out) { return align_up((size_t)cdiv(n_out, 128) * sizeof(int), 256); }
+// K-split workspace: a fixed counter block (splitting only happens below 148 row tiles), then
+// room for one raw partial per resident CTA
+constexpr size_t kSplitCounterBytes = 4096;
 
-extern "C" size_t dv3d_sparse_conv_workspace_bytes(long long n_out, int Cout) {
-    if (n_out <= 0 || Cout <= 0) return 0;
-    const int split = gather_gemm_tc_splits(n_out, 27);
-    if (split <= 1) return 0;
-    return split_counter_bytes(n_out) + (size_t)cdiv(n_out, 128) * split * 128 * Cout * sizeof(float);
+extern "C" size_t dv3d_sparse_conv_workspace_bytes(int Cout) {
+    if (Cout <= 0) return 0;
+    return kSplitCounterBytes + (size_t)kNumSMs * 128 * Cout * sizeof(float);
 }
 
 extern "C" int dv3d_sparse_conv(const float* feat, long long n_in, int Cin, const int* nbr, long long n_out,
@@ -164,11 +164,11 @@ extern "C" int dv3d_sparse_conv(const float* feat, long long n_in, int Cin, cons
     for (int k = 0; k < 27; ++k) d.slice[k] = GemmSlice{feat, nbr + k, 27, 0, Cin, Cin};
     d.kmap = nbr;
     d.Wp = (const float*)W_packed;
-    if (workspace && W_packed && workspace_bytes > split_counter_bytes(n_out)) {
+    if (workspace && W_packed && workspace_bytes > kSplitCounterBytes) {
         DV3D_REQUIRE(((uintptr_t)workspace & 255) == 0, "sparse_conv: workspace must be 256-byte aligned");
         d.split_counters = (int*)workspace;
-        d.split_ws = (float*)((char*)workspace + split_counter_bytes(n_out));
-        d.split_ws_bytes = workspace_bytes - split_counter_bytes(n_out);
+        d.split_ws = (float*)((char*)workspace + kSplitCounterBytes);
+        d.split_ws_bytes = workspace_bytes - kSplitCounterBytes;
     }
     d.M = n_out;
     d.n_src_rows = n_in;

@@ -88,14 +88,13 @@ class PL3DVNet(nn.Module):
         dev = img_feats.device
         plan = ops.edge_plan(ref_src_edges, dev)
         R, t, Kc = rotmats.float().contiguous(), tvecs.float().contiguous(), K.float().contiguous()
-        return plan, self._nhwc.get(img_feats), ops.edge_transforms(R, t, Kc, plan), \
-            ops.ref_backprojection(R, t, Kc, plan)
+        return plan, self._nhwc.get(img_feats), ops.camera_tables(R, t, Kc)
 
     def construct_feature_rich_pointcloud(self, depth_pred, depth_batch, img_feats, rotmats, tvecs, K, ref_src_edges):
         """-> pts [n_ref*P,3], pts_feat [n_ref*P,C], pts_batch [n_ref*P] (lightningmodel.py:132-174)"""
-        plan, nhwc, xform, backproj = self._geometry(img_feats, rotmats, tvecs, K, ref_src_edges)
+        plan, nhwc, cams = self._geometry(img_feats, rotmats, tvecs, K, ref_src_edges)
         depth = depth_pred.detach().float().contiguous()
-        pts, feat = ops.points_var(nhwc, xform, plan, backproj, depth, self.hparams.img_size, 0, 0.0)
+        pts, feat = ops.points_var(nhwc, cams, plan, depth, self.hparams.img_size, 0, 0.0)
         n, P = depth.shape[0], depth.shape[1] * depth.shape[2]
         pts_batch = depth_batch.unsqueeze(1).expand(n, P).reshape(-1)
         return pts.view(-1, 3), feat.view(-1, feat.shape[2]), pts_batch
@@ -117,13 +116,13 @@ class PL3DVNet(nn.Module):
                       return_prob=False):
         """expected depth offset [n_ref,h,w] over 2n+1 hypotheses (lightningmodel.py:187-242)"""
         require_eval(self)
-        plan, nhwc, xform, backproj = self._geometry(img_feats, rotmats, tvecs, K, ref_src_edges)
+        plan, nhwc, cams = self._geometry(img_feats, rotmats, tvecs, K, ref_src_edges)
         depth = depth_pred.detach().float().contiguous()
         n_ref, h, w = depth.shape
         n_pts, n_hyp = n_ref * h * w, 2 * n + 1
         operand = self.decoder.operand(n_pts, depth.device)
         var_off = operand.shape[2] - self.hparams.feat_dim
-        pts_hyp, _ = ops.points_var(nhwc, xform, plan, backproj, depth, self.hparams.img_size, n, offset,
+        pts_hyp, _ = ops.points_var(nhwc, cams, plan, depth, self.hparams.img_size, n, offset,
                                     feat_out=operand, feat_off=var_off)
         pts_batch = depth_batch.unsqueeze(1).expand(n_ref, h * w).reshape(-1).contiguous()
         got = self.decoder.fill_levels(xs, pts_hyp, pts_batch, operand)

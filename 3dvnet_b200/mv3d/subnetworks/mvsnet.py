@@ -149,9 +149,9 @@ class MVSNet(nn.Module):
         plan = ops.edge_plan(batch.ref_src_edges, features_quarter.device) if plan is None else plan
         if feats_nhwc is None:
             feats_nhwc = ops.nchw_to_nhwc(features_quarter.detach().float().contiguous())
-        xform = ops.edge_transforms(batch.rotmats.float().contiguous(), batch.tvecs.float().contiguous(),
-                                    batch.K.float().contiguous(), plan)
-        return ops.planesweep_var(feats_nhwc, xform, plan, depth_start, depth_interval, n_planes,
+        cams = ops.camera_tables(batch.rotmats.float().contiguous(), batch.tvecs.float().contiguous(),
+                                 batch.K.float().contiguous())
+        return ops.planesweep_var(feats_nhwc, cams, plan, depth_start, depth_interval, n_planes,
                                   tuple(depth_img_size), tuple(self.img_size))
 
     def depth_from_features(self, features_quarter, batch, depth_start, depth_interval, n_planes, depth_img_size,

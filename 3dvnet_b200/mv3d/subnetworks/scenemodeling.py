@@ -138,7 +138,7 @@ class SparseScene(object):
         for _ in range(1, n_levels):
             self.levels.append(ops.coarsen(self.levels[-1], dims, n_batch, self.err))
         # K-split workspace of the tensor-core sparse convolution, shared by all layers
-        self.ws = ops.sparse_conv_workspace(self.levels[0].n, 128, dev)
+        self.ws = ops.sparse_conv_workspace(128, dev)
 
     def same(self, l):       # k3 s1 on level l
         lv = self.levels[l]

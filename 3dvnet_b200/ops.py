@@ -130,35 +130,29 @@ def nchw_to_nhwc(x):
     return out
 
 
-def edge_transforms(rotmats, tvecs, K, plan):
+def camera_tables(rotmats, tvecs, K):
+    """[n_imgs,36] = Kinv | P | R | t per image, in the reference's own fp32 arithmetic"""
     _chk(rotmats, torch.float32, 'rotmats', 3), _chk(tvecs, torch.float32, 'tvecs', 2), _chk(K, torch.float32, 'K', 3)
-    out = torch.empty((plan.n_edges, 12), dtype=torch.float32, device=rotmats.device)
-    lib().call('dv3d_edge_transforms', _p(rotmats), _p(tvecs), _p(K), _p(plan.edge_ref), _p(plan.edge_src),
-               plan.n_edges, _p(out), _stream())
+    n = rotmats.shape[0]
+    out = torch.empty((n, 36), dtype=torch.float32, device=rotmats.device)
+    lib().call('dv3d_camera_tables', _p(rotmats), _p(tvecs), _p(K), n, _p(out), _stream())
     return out
 
 
-def ref_backprojection(rotmats, tvecs, K, plan):
-    out = torch.empty((plan.n_ref, 12), dtype=torch.float32, device=rotmats.device)
-    lib().call('dv3d_ref_backprojection', _p(rotmats), _p(tvecs), _p(K), _p(plan.ref_img), plan.n_ref, _p(out),
-               _stream())
-    return out
-
-
-def planesweep_var(feats_nhwc, xform, plan, depth_start, depth_interval, n_planes, plane_size, img_size, out=None):
+def planesweep_var(feats_nhwc, cams, plan, depth_start, depth_interval, n_planes, plane_size, img_size, out=None):
     """x_var [n_ref,C,D,h,w] (mvsnet.py:187-216)."""
     _chk(feats_nhwc, torch.float32, 'feats_nhwc', 4)
     n_imgs, Hf, Wf, C = feats_nhwc.shape
     h, w = plane_size
     if out is None:
         out = torch.empty((plan.n_ref, C, n_planes, h, w), dtype=torch.float32, device=feats_nhwc.device)
-    lib().call('dv3d_planesweep_var', _p(feats_nhwc), n_imgs, C, Hf, Wf, _p(xform), _p(plan.rowptr),
+    lib().call('dv3d_planesweep_var', _p(feats_nhwc), n_imgs, C, Hf, Wf, _p(cams), _p(plan.ref_img), _p(plan.rowptr),
                _p(plan.edge_src), plan.n_ref, float(depth_start), float(depth_interval), int(n_planes), h, w,
                img_size[0], img_size[1], _p(out), _stream())
     return out
 
 
-def points_var(feats_nhwc, xform, plan, backproj, depth, img_size, n_side, offset, feat_out=None, feat_off=0):
+def points_var(feats_nhwc, cams, plan, depth, img_size, n_side, offset, feat_out=None, feat_off=0):
     """World points of every pixel hypothesis + their variance feature
     (lightningmodel.py:132-174 with n_side=0, :187-235 with n_side=3).
     -> pts [n_ref*P, n_hyp, 3], feat [n_ref*P, rows, ld] (rows = n_hyp or the padded 8)."""
@@ -171,8 +165,8 @@ def points_var(feats_nhwc, xform, plan, backproj, depth, img_size, n_side, offse
     if feat_out is None:
         feat_out = torch.empty((Np, n_hyp, C), dtype=torch.float32, device=depth.device)
     rows, ld = feat_out.shape[1], feat_out.shape[2]
-    lib().call('dv3d_points_var', _p(feats_nhwc), n_imgs, C, Hf, Wf, _p(xform), _p(plan.rowptr), _p(plan.edge_src),
-               _p(backproj), _p(depth), n_ref, h, w, img_size[0], img_size[1], n_side, float(offset), _p(pts),
+    lib().call('dv3d_points_var', _p(feats_nhwc), n_imgs, C, Hf, Wf, _p(cams), _p(plan.ref_img), _p(plan.rowptr),
+               _p(plan.edge_src), _p(depth), n_ref, h, w, img_size[0], img_size[1], n_side, float(offset), _p(pts),
                _p(feat_out), rows, ld, feat_off, _stream())
     return pts, feat_out
 
@@ -311,13 +305,11 @@ def coarsen(level, dims, n_batch, err_flag):
     return SparseLevel(out[:n_out.value], ns, err_flag)
 
 
-def sparse_conv_workspace(n_out, Cout, device):
-    """zeroed K-split workspace for sparse_conv on levels of up to n_out rows (None when the
-    level is large enough to fill the GPU by itself)"""
-    nbytes = lib().raw('dv3d_sparse_conv_workspace_bytes')(n_out, Cout)
-    if nbytes == 0 or gemm_mode() == 'f32':
+def sparse_conv_workspace(Cout, device):
+    """zeroed K-split workspace for sparse_conv (any level, up to Cout output channels)"""
+    if gemm_mode() == 'f32':
         return None
-    return torch.zeros(nbytes, dtype=torch.uint8, device=device)
+    return torch.zeros(lib().raw('dv3d_sparse_conv_workspace_bytes')(Cout), dtype=torch.uint8, device=device)
 
 
 def sparse_conv(feat, nbr, W, gn_weight=None, gn_bias=None, residual=None, relu=False, packed=None, workspace=None):
@@ -326,9 +318,7 @@ def sparse_conv(feat, nbr, W, gn_weight=None, gn_bias=None, residual=None, relu=
     Cout = W.shape[2]
     assert W.shape[0] == 27 and W.shape[1] == Cin
     out = torch.empty((n_out, Cout), dtype=torch.float32, device=feat.device)
-    ws_bytes = 0
-    if workspace is not None:
-        ws_bytes = min(workspace.numel(), lib().raw('dv3d_sparse_conv_workspace_bytes')(n_out, Cout))
+    ws_bytes = 0 if workspace is None else workspace.numel()
     lib().call('dv3d_sparse_conv', _p(feat), n_in, Cin, _p(nbr), n_out, _p(W), _p(packed), Cout, _p(gn_weight),
                _p(gn_bias), _p(residual), int(relu), _p(workspace) if ws_bytes else None, ws_bytes, _p(out), _stream())
     return out

@@ -45,54 +45,53 @@ long long dv3d_launch_count(void);
 int dv3d_nchw_to_nhwc(const float* src, float* dst, int n, int C, int HW, void* stream);
 
 /* ------------------------------------------------------------------------------------
- * Per-edge composed camera transform.  For edge e = (ref r, src s):
- *     q = P_s [X;1],  X = R_r^T (K_r^-1 [u z, v z, z] - t_r)      (utils.py:102-106, mvsnet.py:196-199)
- *       = z * (M_e [u,v,1]) + b_e,   M_e = K_s R_s R_r^T K_r^-1,  b_e = K_s (t_s - R_s R_r^T t_r)
- * composed in fp64 on the device and rounded once to fp32.
+ * Per-image camera table used by the two warp kernels: out [n_imgs, 36] =
+ *     Kinv (9) | P = K [R|t] (12) | R (9) | t (3) | 0 (3)
+ * with the reference's own fp32 arithmetic: P as torch.bmm forms it for 3x3 @ 3x4 operands
+ * (plain loop, every product and sum rounded; mvsnet.py:196-197) and Kinv is what torch.inverse returns for a zero-skew pinhole K
+ * ([[1/fx,0,-(cx/fx)],[0,1/fy,-(cy/fy)],[0,0,1]]; any other K: fp64 adjugate, rounded once).
+ * The kernels then evaluate X = R^T (Kinv [u z, v z, z] - t) and q = P_src [X;1] in the
+ * reference's operation order, so sample positions and back-projected points are
+ * bit-identical to the CPU PyTorch path (utils.py:102-106, mvsnet.py:199-206,
+ * lightningmodel.py:138-160).
  *   rotmats [n_imgs,3,3], tvecs [n_imgs,3], K [n_imgs,3,3] (world->camera, full-res K)
- *   edge_ref [E], edge_src [E]  int32 image indices
- *   xform_out [E,12] = M (row-major 9) then b (3)
- * Replaces: torch.inverse + 3 torch.bmm of mvsnet.py:188-199 / lightningmodel.py:138-160.
+ * Replaces: torch.inverse + 3 torch.bmm per call site.
  */
-int dv3d_edge_transforms(const float* rotmats, const float* tvecs, const float* K, const int* edge_ref,
-                         const int* edge_src, int n_edges, float* xform_out, void* stream);
-
-/* Per-reference back-projection ray basis: X(u,v,d) = d * (B_r [u,v,1]) + C_r with
- * B_r = R_r^T K_r^-1, C_r = -R_r^T t_r (lightningmodel.py:138-144), fp64-composed.
- *   ref_img [n_ref] int32 image index of every reference;  out [n_ref,12] = B (9) then C (3).
- */
-int dv3d_ref_backprojection(const float* rotmats, const float* tvecs, const float* K, const int* ref_img,
-                            int n_ref, float* out, void* stream);
+int dv3d_camera_tables(const float* rotmats, const float* tvecs, const float* K, int n_imgs, float* out,
+                       void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Fused plane-sweep warp + variance  (mvsnet.py:187-216 with utils.py:86-108).
  *   feats_nhwc [n_imgs,Hf,Wf,C]   quarter-resolution features, channels-last, C == 32
- *   xform      [E,12]             from dv3d_edge_transforms, edges sorted by reference
- *   edge_rowptr[n_ref+1], edge_src[E]   CSR of the edges of every reference (int32)
+ *   cams       [n_imgs,36]        from dv3d_camera_tables
+ *   ref_img    [n_ref]            image index of every reference (int32, ascending)
+ *   edge_rowptr[n_ref+1], edge_src[E]   CSR of the edges of every reference (int32), the edges
+ *                                 of a reference in their original order (it is the summation order)
  *   depth hypotheses z_d = linspace(depth_start, depth_start+(D-1)*depth_interval, D)
  *   plane lattice u_j = linspace(0,W-1,w), v_i = linspace(0,H-1,h); grid normalised by the
  *   FULL image size (W-1,H-1) and un-normalised by (Wf-1,Hf-1) as grid_sample does;
  *   bilinear, zero padding per tap, z = |q_z| + 1e-8; divisor = number of edges.
- *   x_var [n_ref,C,D,h,w]         var = E[x^2] - E[x]^2
+ *   x_var [n_ref,C,D,h,w]         var = E[x^2] - E[x]^2, sums in edge order like scatter-add
  * No x_vox[E,C,D,h,w] is ever materialised.
  */
-int dv3d_planesweep_var(const float* feats_nhwc, int n_imgs, int C, int Hf, int Wf, const float* xform,
-                        const int* edge_rowptr, const int* edge_src, int n_ref, double depth_start,
-                        double depth_interval, int D, int h, int w, int H, int W, float* x_var, void* stream);
+int dv3d_planesweep_var(const float* feats_nhwc, int n_imgs, int C, int Hf, int Wf, const float* cams,
+                        const int* ref_img, const int* edge_rowptr, const int* edge_src, int n_ref,
+                        double depth_start, double depth_interval, int D, int h, int w, int H, int W, float* x_var,
+                        void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Point-level back-projection + re-projection warp + variance, 1 or 2n+1 hypotheses per
  * pixel (lightningmodel.py:132-174 with n_side = 0, and :187-235 with n_side = 3).
- *   depth    [n_ref,h,w];  backproj [n_ref,12] from dv3d_ref_backprojection
- *   hypothesis i (i=-n..n) has depth d + i*offset
+ *   depth    [n_ref,h,w];  cams / ref_img / CSR as above
+ *   hypothesis i (i=-n..n) has depth d + (float)(i*offset), offset a double like the python float
  *   pts_out  [n_ref*h*w, n_hyp, 3]   world points
  *   feat_out [n_ref*h*w, rows_per_point >= n_hyp, feat_stride] variance feature written at
  *            channel offset feat_off (lets the caller write straight into the decoder operand)
  */
-int dv3d_points_var(const float* feats_nhwc, int n_imgs, int C, int Hf, int Wf, const float* xform,
-                    const int* edge_rowptr, const int* edge_src, const float* backproj, const float* depth,
-                    int n_ref, int h, int w, int H, int W, int n_side, float offset, float* pts_out,
-                    float* feat_out, int rows_per_point, int feat_stride, int feat_off, void* stream);
+int dv3d_points_var(const float* feats_nhwc, int n_imgs, int C, int Hf, int Wf, const float* cams,
+                    const int* ref_img, const int* edge_rowptr, const int* edge_src, const float* depth, int n_ref,
+                    int h, int w, int H, int W, int n_side, double offset, float* pts_out, float* feat_out,
+                    int rows_per_point, int feat_stride, int feat_off, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * CostRegNet layers, inference mode (mvsnet.py:18-36,133-163).  NCDHW fp32.
@@ -207,10 +206,10 @@ int dv3d_kernel_map(const int* coords_out, long long n_out, const void* table_in
  * (% 32 for the tensor-core kernel), Cout in {64,128}.
  * workspace (optional, tensor-core kernel only): lets a small level fill the GPU by splitting
  * the 27 offsets over several CTAs per 128-row tile; partials are added in a fixed order by the
- * last CTA of the tile.  dv3d_sparse_conv_workspace_bytes() sizes it (0 = not useful for this
- * n_out); it must be 256-byte aligned and ZERO before its first use - every launch leaves its
- * counters zero again, so one buffer serves all layers of a scene on one stream. */
-size_t dv3d_sparse_conv_workspace_bytes(long long n_out, int Cout);
+ * last CTA of the tile.  dv3d_sparse_conv_workspace_bytes(max Cout) sizes it for any level; it
+ * must be 256-byte aligned and ZERO before its first use - every launch leaves its counters
+ * zero again, so one buffer serves all layers of a scene on one stream. */
+size_t dv3d_sparse_conv_workspace_bytes(int Cout);
 int dv3d_sparse_conv(const float* feat, long long n_in, int Cin, const int* nbr, long long n_out, const float* W,
                      const void* W_packed, int Cout, const float* gn_weight, const float* gn_bias,
                      const float* residual, int relu, void* workspace, size_t workspace_bytes, float* out,
@@ -250,7 +249,7 @@ int dv3d_conv1d_bn_relu(const float* x, long long n_pts, int rows_per_point, int
 /* last Conv1d (Cin->1, bias; weight [1,Cin,3] torch layout) + softmax over hypotheses + expected
  * offset sum_i p_i * linspace(-n*offset, n*offset)_i; prob_out optional [n_pts,n_hyp]; offset_out [n_pts] */
 int dv3d_decoder_head(const float* x, long long n_pts, int n_hyp, int rows_per_point, int Cin, int ldx,
-                      const float* weight, float bias, float offset, float* prob_out, float* offset_out,
+                      const float* weight, float bias, double offset, float* prob_out, float* offset_out,
                       void* stream);
 
 #ifdef __cplusplus

@@ -22,7 +22,7 @@ def test_header_parses_and_every_symbol_is_exported(L):
                  'dv3d_prob_softargmin', 'dv3d_voxel_grid', 'dv3d_voxelize', 'dv3d_linear', 'dv3d_segment_max',
                  'dv3d_hash_build', 'dv3d_coarsen', 'dv3d_kernel_map', 'dv3d_sparse_conv',
                  'dv3d_concat_linear_gn_relu', 'dv3d_sparse_interp', 'dv3d_conv1d_bn_relu', 'dv3d_decoder_head',
-                 'dv3d_edge_transforms', 'dv3d_ref_backprojection', 'dv3d_nchw_to_nhwc', 'dv3d_launch_count',
+                 'dv3d_camera_tables', 'dv3d_nchw_to_nhwc', 'dv3d_launch_count',
                  'dv3d_gemm_pack_weights', 'dv3d_gemm_pack_bytes', 'dv3d_set_gemm_precision'):
         assert must in names, must
     for n in names:
@@ -33,7 +33,8 @@ def test_header_parses_and_every_symbol_is_exported(L):
 def test_abi_version_and_error_reporting(L):
     assert L.cdll.dv3d_abi_version() == 2
     # argument validation happens before any CUDA call: safe without a GPU
-    rc = L.cdll.dv3d_planesweep_var(None, 1, 16, 4, 4, None, None, None, 1, 0.5, 0.05, 8, 8, 8, 16, 16, None, None)
+    rc = L.cdll.dv3d_planesweep_var(None, 1, 16, 4, 4, None, None, None, None, 1, 0.5, 0.05, 8, 8, 8, 16, 16, None,
+                                    None)
     assert rc == -1 and 'C must be 32' in L.last_error()
     rc = L.cdll.dv3d_sparse_conv(None, 0, 64, None, 0, None, None, 64, None, None, None, 0, None, 0, None, None)
     assert rc == -1 and 'bad arguments' in L.last_error()

@@ -101,13 +101,13 @@ def test_sparse_conv(ops, mode, n_in, n_out, Cin, Cout, density):
     ref = sparse_ref(feat, nbr, W, gw, gb, residual, True)
     check(y, ref, mode)
     # K-split over CTAs (small levels): same result, bit-identical from launch to launch
-    ws = ops.sparse_conv_workspace(n_out, Cout, DEV)
+    ws = ops.sparse_conv_workspace(Cout, DEV)
     if ws is not None:
         y_s = ops.sparse_conv(feat, nbr, W, gw, gb, residual, True, packed=packed, workspace=ws)
         check(y_s, ref, mode)
         y_s2 = ops.sparse_conv(feat, nbr, W, gw, gb, residual, True, packed=packed, workspace=ws)
         assert torch.equal(y_s, y_s2)
-        assert int(ws[:4096].max()) == 0 or True
+        assert int(ws[:4096].max()) == 0  # counters left zero
     # no normalisation, no residual, no ReLU: the raw contraction
     y2 = ops.sparse_conv(feat, nbr, W, None, None, None, False, packed=packed)
     check(y2, sparse_ref(feat, nbr, W, None, None, None, False), mode)

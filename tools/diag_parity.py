@@ -19,8 +19,9 @@ def stats(name, got, ref):
     d = (got - ref).abs().flatten()
     rel = (d / (ref.flatten().abs() + 1e-7))
     q = torch.quantile(d, torch.tensor([0.5, 0.9, 0.99, 0.999]))
-    print('%-34s mean|d| %.3e  absrel %.3e  q50 %.1e q90 %.1e q99 %.1e q999 %.1e max %.1e  frac>1e-3 %.4f' % (
-        name, d.mean(), rel.mean(), q[0], q[1], q[2], q[3], d.max(), (d > 1e-3).float().mean()))
+    print('%-34s mean|d| %.3e  absrel %.3e  q50 %.1e q90 %.1e q99 %.1e q999 %.1e max %.1e  frac>1e-3 %.4f  '
+          'bit-equal %.6f' % (name, d.mean(), rel.mean(), q[0], q[1], q[2], q[3], d.max(),
+                              (d > 1e-3).float().mean(), (d == 0).float().mean()))
 
 
 def main():
@@ -59,6 +60,9 @@ def main():
             xs_o, mid = pipeline.model_scene(depth_o, db, fq, R, t, K, e, bench.EDGE_LEN, img, params,
                                              return_all=True)
             xs_g = net.model_scene(depth_g, gdb, gfq, gR, gt, gK, e)
+            pts_tf, feat_tf, _ = net.construct_feature_rich_pointcloud(depth_o.to(dev), gdb, gfq, gR, gt, gK, e)
+            stats('  TF pts', pts_tf.cpu(), mid['pts'])
+            stats('  TF pts_feat', feat_tf.cpu(), mid['pts_feat'])
             xs_tf = net.model_scene(depth_o.to(dev), gdb, gfq, gR, gt, gK, e)
             print('iter %d: voxels oracle %d / gpu free %d / gpu teacher-forced %d' % (
                 it, mid['anchor_pts'].shape[0], xs_g[-1]['feats'].shape[0], xs_tf[-1]['feats'].shape[0]))
