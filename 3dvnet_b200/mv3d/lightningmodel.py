@@ -104,13 +104,19 @@ class PL3DVNet(nn.Module):
         require_eval(self)
         pts, pts_feat, pts_batch = self.construct_feature_rich_pointcloud(depth_pred, depth_batch, img_feats, rotmats,
                                                                           tvecs, K, ref_src_edges)
-        a_pts, a_idx, a_batch, seg, grid = ops.voxelize(pts, pts_batch.contiguous(), self.edge_len)
+        xs = self.scene_from_points(pts, pts_feat, pts_batch.contiguous())
+        return (xs, pts) if return_pts else xs
+
+    def scene_from_points(self, pts, pts_feat, pts_batch):
+        """voxelise -> PointNet -> sparse U-Net on a feature-rich point cloud (lightningmodel.py:180-184).
+        Also the entry of the multi-GPU path after its all-gather (3dvnet_b200/parallel.py)."""
+        require_eval(self)
+        a_pts, a_idx, a_batch, seg, grid = ops.voxelize(pts, pts_batch, self.edge_len)
         x = ops.pointnet_input(pts, pts_feat, a_pts, seg, self.pointnet.in_pad)
         x = self.pointnet.forward_padded(x, seg, a_pts.shape[0])
         dims = (int(grid.n_cells[0]), int(grid.n_cells[1]), int(grid.n_cells[2]), int(grid.n_batch))
         scene = SparseScene(a_idx, a_batch, self.sparse_conv.n_levels, dims)
-        xs = self.sparse_conv(x, a_pts, a_idx, a_batch, self.edge_len, scene=scene)
-        return (xs, pts) if return_pts else xs
+        return self.sparse_conv(x, a_pts, a_idx, a_batch, self.edge_len, scene=scene)
 
     def run_pointflow(self, xs, depth_pred, depth_batch, img_feats, rotmats, tvecs, K, ref_src_edges, offset, n,
                       return_prob=False):

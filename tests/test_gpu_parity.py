@@ -65,11 +65,9 @@ def test_path_a_golden(name, mods):
         depth, x_reg = net.mvsnet.cnn_3d.depth(x_var, cfg['depth_start'], d_end, want_reg=True)
         # interface parity: cnn_3d(x) returns x_reg [n,1,D,h,w]
         x_reg2 = net.mvsnet.cnn_3d(x_var)
-    ref_var = torch.from_numpy(g['ref_x_var'])
-    # fp32; the projection is composed in fp64 and rounded once instead of three fp32 bmm's:
-    # sample positions differ by ~1e-5 px
-    assert (x_var.cpu() - ref_var).abs().max().item() < 2e-4
-    assert (x_var.cpu() - ref_var).abs().mean().item() < 2e-6
+    # the warp kernel follows the reference's fp32 operation chain instruction for instruction
+    # (csrc/planesweep.cu): the variance slab is BIT-IDENTICAL to the reference's CPU path
+    np.testing.assert_array_equal(x_var.cpu().numpy().view(np.int32), g['ref_x_var'].view(np.int32))
     np.testing.assert_allclose(x_reg.cpu().numpy(), g['ref_x_reg'], rtol=0, atol=2e-3)
     np.testing.assert_array_equal(x_reg2.squeeze(1).cpu().numpy(), x_reg.cpu().numpy())
     ref_depth = torch.from_numpy(g['ref_depth_init'])
@@ -112,8 +110,10 @@ def test_point_cloud_and_voxelize_golden(name, mods):
     with torch.no_grad():
         pts, pts_feat, pts_batch = net.construct_feature_rich_pointcloud(depth, depth_batch, b.feats_quarter,
                                                                          b.rotmats, b.tvecs, b.K, b.ref_src_edges)
-    np.testing.assert_allclose(pts.cpu().numpy(), g['ref_pts'], rtol=0, atol=2e-6)
-    assert (pts_feat.cpu() - torch.from_numpy(g['ref_pts_feat'])).abs().max().item() < 2e-4
+    # back-projected points and their variance features: bit-identical, hence the voxel
+    # indices of the whole pipeline are bit-exact whenever the depth map is
+    np.testing.assert_array_equal(pts.cpu().numpy().view(np.int32), g['ref_pts'].view(np.int32))
+    np.testing.assert_array_equal(pts_feat.cpu().numpy().view(np.int32), g['ref_pts_feat'].view(np.int32))
     np.testing.assert_array_equal(pts_batch.cpu().numpy(), g['ref_pts_batch'])
     # voxelise the REFERENCE's points: index outputs must be bit-exact
     a_pts, a_idx, a_batch, edges = mods['utils'].voxelize(torch.from_numpy(g['ref_pts']).to(DEV),
@@ -237,12 +237,44 @@ def test_refinement_schedule_golden(name, mods):
                                g['offsets'].tolist())
     ref = torch.from_numpy(g['ref_depth_final'])
     assert abs_rel(out.cpu(), ref) < 1e-3
-    # The schedule is not a smooth map: a point that crosses a voxel face between two passes
-    # changes the occupancy pattern (PointNet max-pool, kernel maps) discretely, so fp32
-    # rounding noise in the depth of a few pixels is amplified into offset changes of the
-    # order of the hypothesis spacing for those pixels (tools/diag_parity.py: teacher-forced
-    # stages agree to ~1e-6). The bulk of the pixels must still agree tightly.
+    # The schedule is not a smooth map: the initial depth differs from the reference's by fp32
+    # summation-order noise of the 3D convolutions (~2e-6), and a point that this noise moves
+    # across a voxel face changes the occupancy pattern discretely (one voxel more or less,
+    # tools/diag_parity.py), which moves the offsets of the pixels in that voxel's receptive
+    # field. The bulk must agree tightly; test_refinement_schedule_teacher_forced pins every
+    # pass on identical inputs.
     d = (out.cpu() - ref).abs().flatten()
     assert torch.quantile(d, 0.5).item() < 1e-4
-    assert torch.quantile(d, 0.99).item() < 5e-3
+    assert torch.quantile(d, 0.9).item() < 5e-3
     assert dict(mods)['ops'].launch_count() > 0
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_refinement_schedule_teacher_forced(name, mods):
+    """every model_scene / PointFlow pass of the schedule, each started from the ORACLE's depth of
+    that pass: voxel tables bit-exact, sparse features and offsets at fp32 rounding level."""
+    from oracle import pipeline
+    g = load_golden(name)
+    t, cfg, img_size = golden_inputs(g)
+    net = make_net(mods, g, cfg, img_size)
+    b = to_batch(t)
+    p = mods['synth'].make_params(int(g['seed']))
+    ref_idx = torch.unique(t['ref_src_edges'][0])
+    db = t['images_batch'][ref_idx]
+    cargs = (t['feats_quarter'], t['rotmats'], t['tvecs'], t['K'], t['ref_src_edges'])
+    gargs = (b.feats_quarter, b.rotmats, b.tvecs, b.K, b.ref_src_edges)
+    edge_len = float(g['edge_len'])
+    depth = torch.from_numpy(g['ref_depth_init']).clone()
+    with torch.no_grad():
+        for offsets in g['offsets'].tolist():
+            xs_o, mid = pipeline.model_scene(depth, db, *cargs, edge_len, img_size, p, return_all=True)
+            xs = net.model_scene(depth.to(DEV), db.to(DEV), *gargs)
+            for lo, lg in zip(xs_o, xs):
+                np.testing.assert_array_equal(lg['idx'].cpu().numpy(), lo['idx'].numpy())
+                np.testing.assert_allclose(lg['feats'].cpu().numpy(), lo['feats'].numpy(), rtol=0, atol=2e-4)
+            for offset in offsets:
+                off_o = pipeline.run_pointflow(xs_o, depth, db, *cargs, offset, 3, img_size, p)
+                off = net.run_pointflow(xs, depth.to(DEV), db.to(DEV), *gargs, offset, 3)
+                np.testing.assert_allclose(off.cpu().numpy(), off_o.numpy(), rtol=0, atol=2e-5)
+                depth += off_o
+    np.testing.assert_allclose(depth.numpy(), g['ref_depth_final'], rtol=0, atol=1e-5)

@@ -25,11 +25,24 @@ def stats(name, got, ref):
 
 
 def main():
-    seed = int(sys.argv[1]) if len(sys.argv) > 1 else 0
     torch.set_num_threads(os.cpu_count())
     lm = importlib.import_module('3dvnet_b200.mv3d.lightningmodel')
-    b, params = bench.synth_inputs(seed, 1)
-    cfg, img = bench.DEPTH_CFG, bench.IMG_SIZE
+    synth = importlib.import_module('3dvnet_b200.synth')
+    arg = sys.argv[1] if len(sys.argv) > 1 else '0'
+    if arg.isdigit():
+        b, params = bench.synth_inputs(int(arg), 1)
+        cfg, img, edge_len, offsets_list = bench.DEPTH_CFG, bench.IMG_SIZE, bench.EDGE_LEN, bench.OFFSETS_LIST
+    else:  # a golden case name, e.g. c1_selfedge_2scenes
+        import numpy as np
+        g = np.load(os.path.join(ROOT, 'tests', 'golden', arg + '.npz'))
+        b = type('B', (), {k: torch.from_numpy(g[k]) for k in ('feats_quarter', 'rotmats', 'tvecs', 'K',
+                                                                'ref_src_edges', 'images_batch')})
+        cfg = dict(depth_start=float(g['depth_start']), depth_interval=float(g['depth_interval']),
+                   n_intervals=int(g['D']), size=tuple(int(v) for v in g['plane']))
+        img = tuple(int(v) for v in g['img_size'])
+        edge_len, offsets_list = float(g['edge_len']), g['offsets'].tolist()
+        params = synth.make_params(int(g['seed']))
+    bench.EDGE_LEN, bench.OFFSETS_LIST = edge_len, offsets_list
     net = lm.PL3DVNet(cfg, cfg, bench.EDGE_LEN, feat_dim=32, img_size=img)
     net.load_state_dict(params, strict=False)
     net = net.cuda().eval()
