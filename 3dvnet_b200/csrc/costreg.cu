@@ -4,28 +4,35 @@
 // mvsnet.py:18-36,133-163,219-227.  NCDHW fp32, fp32 accumulation on the CUDA cores.
 //
 // Two kernels:
-//  * conv3d_s1_tiled: stride-1 layers on large volumes (conv0 = 68 % of the FLOPs, conv2).
-//    CTA tile 4x14x28 outputs x 8 output channels; the haloed input tile of 8 input channels
+//  * conv3d_s1_tiled: stride-1 layers on large volumes (conv0 = 68 % of the FLOPs).
+//    CTA tile TZ x14x28 outputs x 8 output channels; the haloed input tile of 8 input channels
 //    and the matching weights are staged in shared memory; each thread owns a 4(x) x 2(y)
-//    x 8(co) register tile = 64 accumulators, 576 FMAs per 26 shared loads.
-//  * conv3d_generic: stride-2, transposed and small-volume layers: one thread per output
-//    voxel x CO_T output channels, weights of the channel group in shared memory.
+//    x 8(co) register tile = 64 accumulators, 576 FMAs per 26 shared loads.  TZ is chosen
+//    per launch so that the CTAs fill the 148 SMs (2 CTAs each) in whole rounds.
+//  * conv3d_direct: every other layer (stride-2, transposed, small volumes): thread = output
+//    voxel x CO_T output channels x a slice of the input channels (K split, reduced through
+//    shared memory), weights of the channel group in shared memory.
 #include "common.cuh"
 
 namespace dv3d {
 
 // ------------------------------------------------------------------ tiled stride-1 conv
-constexpr int TZ = 4, TY = 14, TX = 28;            // output tile
-constexpr int IZ = TZ + 2, IY = TY + 2, IXP = 32;  // haloed input tile, row pitch padded 30 -> 32
-constexpr int CIC = 8;                             // input channels staged per pass
-constexpr int COT = 8;                             // output channels per CTA
-constexpr int S1_THREADS = (TX / 4) * (TY / 2) * TZ;  // 7 * 7 * 4 = 196
-constexpr size_t S1_SMEM = sizeof(float) * (CIC * IZ * IY * IXP + CIC * 27 * COT);
+constexpr int TY = 14, TX = 28;       // output tile in y, x (TZ is a template parameter)
+constexpr int IY = TY + 2, IXP = 32;  // haloed input tile, row pitch padded 30 -> 32
+constexpr int CIC = 8;                // input channels staged per pass
+constexpr int COT = 8;                // output channels per CTA
+__host__ __device__ constexpr int s1_threads(int TZ) { return (TX / 4) * (TY / 2) * TZ; }  // 49 per plane
+__host__ __device__ constexpr size_t s1_smem(int TZ) {
+    return sizeof(float) * (CIC * (TZ + 2) * IY * IXP + CIC * 27 * COT);
+}
 
-__global__ void __launch_bounds__(S1_THREADS, 2)
+template <int TZ>
+__global__ void __launch_bounds__(s1_threads(TZ), 2)
 conv3d_s1_tiled_kernel(const float* __restrict__ x, int Cin, int D, int H, int W, const float* __restrict__ wgt,
                        const float* __restrict__ scale, const float* __restrict__ shift, int Cout,
                        const float* __restrict__ skip, float* __restrict__ y, int tiles_x, int tiles_y) {
+    constexpr int IZ = TZ + 2;
+    constexpr int S1_THREADS = s1_threads(TZ);
     extern __shared__ __align__(16) float smem[];
     float* s_in = smem;                          // [CIC][IZ][IY][IXP]
     float* s_w = smem + CIC * IZ * IY * IXP;     // [CIC][27][COT]
@@ -38,13 +45,15 @@ conv3d_s1_tiled_kernel(const float* __restrict__ x, int Cin, int D, int H, int W
     const size_t plane = (size_t)H * W, vol = plane * D;
     const float* xn = x + (size_t)n * Cin * vol;
 
-    float acc[2][4][COT];
+    // accumulators as channel pairs: FFMA2 (packed fp32, scalar-broadcast input operand) does
+    // two output channels per issue slot
+    float2 acc[2][4][COT / 2];
 #pragma unroll
     for (int a = 0; a < 2; ++a)
 #pragma unroll
         for (int b = 0; b < 4; ++b)
 #pragma unroll
-            for (int c = 0; c < COT; ++c) acc[a][b][c] = 0.f;
+            for (int c = 0; c < COT / 2; ++c) acc[a][b][c] = make_float2(0.f, 0.f);
 
     for (int c0 = 0; c0 < Cin; c0 += CIC) {
         __syncthreads();  // previous pass consumed
@@ -86,14 +95,16 @@ conv3d_s1_tiled_kernel(const float* __restrict__ x, int Cin, int D, int H, int W
                     for (int kw = 0; kw < 3; ++kw) {
                         float4 w0 = *reinterpret_cast<const float4*>(wp + (kh * 3 + kw) * COT);
                         float4 w1 = *reinterpret_cast<const float4*>(wp + (kh * 3 + kw) * COT + 4);
-                        float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+                        const float2 wv[4] = {make_float2(w0.x, w0.y), make_float2(w0.z, w0.w),
+                                              make_float2(w1.x, w1.y), make_float2(w1.z, w1.w)};
 #pragma unroll
                         for (int a = 0; a < 2; ++a)
 #pragma unroll
                             for (int b = 0; b < 4; ++b) {
-                                float v = in[a + kh][b + kw];
+                                const float v = in[a + kh][b + kw];
+                                const float2 vv = make_float2(v, v);
 #pragma unroll
-                                for (int c = 0; c < COT; ++c) acc[a][b][c] = fmaf(v, wv[c], acc[a][b][c]);
+                                for (int c = 0; c < COT / 2; ++c) acc[a][b][c] = __ffma2_rn(vv, wv[c], acc[a][b][c]);
                             }
                     }
                 }
@@ -119,7 +130,8 @@ conv3d_s1_tiled_kernel(const float* __restrict__ x, int Cin, int D, int H, int W
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
                 if (x0 + 4 * tx + b < W) {
-                    float v = fmaxf(fmaf(acc[a][b][c], sc, sh), 0.f);
+                    const float2 pr = acc[a][b][c >> 1];
+                    float v = fmaxf(fmaf((c & 1) ? pr.y : pr.x, sc, sh), 0.f);
                     if (sn) v += __ldg(sn + base + b);
                     yn[base + b] = v;
                 }
@@ -128,85 +140,110 @@ conv3d_s1_tiled_kernel(const float* __restrict__ x, int Cin, int D, int H, int W
     }
 }
 
-// ------------------------------------------------------------------ generic kernel
+// ------------------------------------------------------------------ direct kernel, optional K split
 enum ConvMode { kConvS1 = 0, kConvS2 = 1, kDeconvS2 = 2 };
 
-// weights in shared memory as [ci][tap][co_t]; x is [n,Cin,Di,Hi,Wi]; y is [n,Cout,Do,Ho,Wo]
+constexpr int DC_THREADS = 256;
+
+// input index of tap k for output index o along one dimension, or -1
+template <int MODE>
+__device__ __forceinline__ int tap_src(int o, int k, int n_in) {
+    if (MODE == kDeconvS2) {
+        const int t = o + 1 - k;  // o = 2 i - 1 + k
+        return (t >= 0 && !(t & 1) && (t >> 1) < n_in) ? (t >> 1) : -1;
+    }
+    const int t = o * (MODE == kConvS2 ? 2 : 1) + k - 1;
+    return (t >= 0 && t < n_in) ? t : -1;
+}
+
+// thread = (output voxel v, input-channel slice s); CTA = (256 / n_slices) voxels x n_slices.
+// A slice contracts Cin / n_slices input channels over the valid taps of its voxel (tap loop
+// outside, channel loop inside: the tap's validity and address are computed once); the
+// partial sums of the slices are added in slice order through shared memory.  The K split
+// gives the small levels of the U-Net (588 .. 4704 voxels) enough threads to fill 148 SMs.
+// weights in shared memory as [ci][tap][CO_T]; x is [n,Cin,Di,Hi,Wi]; y is [n,Cout,Do,Ho,Wo]
 template <int MODE, int CO_T>
-__global__ void __launch_bounds__(128)
-conv3d_generic_kernel(const float* __restrict__ x, int Cin, int Di, int Hi, int Wi, const float* __restrict__ wgt,
-                      const float* __restrict__ scale, const float* __restrict__ shift, int Cout, int Do, int Ho,
-                      int Wo, const float* __restrict__ skip, float* __restrict__ y, long long n_vox_total) {
-    extern __shared__ __align__(16) float s_w[];
+__global__ void __launch_bounds__(DC_THREADS)
+conv3d_direct_kernel(const float* __restrict__ x, int Cin, int Di, int Hi, int Wi, const float* __restrict__ wgt,
+                     const float* __restrict__ scale, const float* __restrict__ shift, int Cout, int Do, int Ho,
+                     int Wo, const float* __restrict__ skip, float* __restrict__ y, long long n_vox_total,
+                     int n_slices) {
+    extern __shared__ __align__(16) float smem[];
+    float* s_w = smem;                      // [Cin][27][CO_T]
+    float* s_red = smem + Cin * 27 * CO_T;  // [n_slices][CO_T][vox]
+    const int tid = threadIdx.x;
     const int cog = blockIdx.y;
-    for (int i = threadIdx.x; i < Cin * 27 * CO_T; i += blockDim.x) {
-        int co = i % CO_T, tap = (i / CO_T) % 27, ci = i / (CO_T * 27);
-        size_t src = (MODE == kDeconvS2) ? ((size_t)ci * Cout + cog * CO_T + co) * 27 + tap
-                                         : ((size_t)(cog * CO_T + co) * Cin + ci) * 27 + tap;
-        s_w[i] = __ldg(wgt + src);
+    // weights: read in global order (contiguous runs), store transposed
+    for (int i = tid; i < Cin * 27 * CO_T; i += DC_THREADS) {
+        const int tap = i % 27;
+        int ci, co;
+        size_t src;
+        if (MODE == kDeconvS2) {  // [Cin][Cout][27]
+            co = (i / 27) % CO_T;
+            ci = i / (27 * CO_T);
+            src = ((size_t)ci * Cout + cog * CO_T + co) * 27 + tap;
+        } else {  // [Cout][Cin][27]
+            ci = (i / 27) % Cin;
+            co = i / (27 * Cin);
+            src = ((size_t)(cog * CO_T + co) * Cin + ci) * 27 + tap;
+        }
+        s_w[(ci * 27 + tap) * CO_T + co] = __ldg(wgt + src);
     }
     __syncthreads();
 
+    const int vox = DC_THREADS / n_slices;
+    const int v = tid % vox, s = tid / vox;
+    const int cps = Cin / n_slices;
     const size_t ivol = (size_t)Di * Hi * Wi, iplane = (size_t)Hi * Wi;
     const size_t ovol = (size_t)Do * Ho * Wo;
-    for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < n_vox_total;
-         v += (long long)gridDim.x * blockDim.x) {
-        int ox = (int)(v % Wo);
-        long long r = v / Wo;
-        int oy = (int)(r % Ho);
-        r /= Ho;
-        int oz = (int)(r % Do);
-        int n = (int)(r / Do);
-        const float* xn = x + (size_t)n * Cin * ivol;
+    const long long gv = (long long)blockIdx.x * vox + v;
 
-        // per-dimension tap -> input index (or -1)
-        int iz[3], iy[3], ixx[3];
+    float2 acc2[CO_T / 2];  // channel pairs for FFMA2
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            if (MODE == kDeconvS2) {
-                int tz = oz + 1 - k, ty = oy + 1 - k, tx = ox + 1 - k;  // o = 2 i - 1 + k
-                iz[k] = (tz >= 0 && !(tz & 1) && (tz >> 1) < Di) ? (tz >> 1) : -1;
-                iy[k] = (ty >= 0 && !(ty & 1) && (ty >> 1) < Hi) ? (ty >> 1) : -1;
-                ixx[k] = (tx >= 0 && !(tx & 1) && (tx >> 1) < Wi) ? (tx >> 1) : -1;
-            } else {
-                const int s = (MODE == kConvS2) ? 2 : 1;
-                int tz = oz * s + k - 1, ty = oy * s + k - 1, tx = ox * s + k - 1;
-                iz[k] = (tz >= 0 && tz < Di) ? tz : -1;
-                iy[k] = (ty >= 0 && ty < Hi) ? ty : -1;
-                ixx[k] = (tx >= 0 && tx < Wi) ? tx : -1;
-            }
-        }
-        float acc[CO_T];
+    for (int c = 0; c < CO_T / 2; ++c) acc2[c] = make_float2(0.f, 0.f);
+    if (gv < n_vox_total) {
+        const int n = (int)(gv / (long long)ovol);
+        const int sp = (int)(gv - (long long)n * ovol);
+        const int ox = sp % Wo, oy = (sp / Wo) % Ho, oz = sp / (Wo * Ho);
+        const float* xs = x + ((size_t)n * Cin + (size_t)s * cps) * ivol;
+        const float* ws = s_w + (size_t)s * cps * 27 * CO_T;
 #pragma unroll
-        for (int c = 0; c < CO_T; ++c) acc[c] = 0.f;
-        for (int ci = 0; ci < Cin; ++ci) {
-            const float* xc = xn + (size_t)ci * ivol;
-            const float* wc = s_w + ci * 27 * CO_T;
+        for (int kd = 0; kd < 3; ++kd) {
+            const int iz = tap_src<MODE>(oz, kd, Di);
+            if (iz < 0) continue;
 #pragma unroll
-            for (int kd = 0; kd < 3; ++kd) {
-                if (iz[kd] < 0) continue;
+            for (int kh = 0; kh < 3; ++kh) {
+                const int iy = tap_src<MODE>(oy, kh, Hi);
+                if (iy < 0) continue;
 #pragma unroll
-                for (int kh = 0; kh < 3; ++kh) {
-                    if (iy[kh] < 0) continue;
-                    const float* xr = xc + (size_t)iz[kd] * iplane + (size_t)iy[kh] * Wi;
-#pragma unroll
-                    for (int kw = 0; kw < 3; ++kw) {
-                        if (ixx[kw] < 0) continue;
-                        float in = __ldg(xr + ixx[kw]);
-                        const float* wp = wc + ((kd * 3 + kh) * 3 + kw) * CO_T;
+                for (int kw = 0; kw < 3; ++kw) {
+                    const int ix = tap_src<MODE>(ox, kw, Wi);
+                    if (ix < 0) continue;
+                    const float* xp = xs + (size_t)iz * iplane + (size_t)iy * Wi + ix;
+                    const float* wp = ws + ((kd * 3 + kh) * 3 + kw) * CO_T;
+#pragma unroll 4
+                    for (int ci = 0; ci < cps; ++ci) {
+                        const float in = __ldg(xp + (size_t)ci * ivol);
+                        const float2 in2 = make_float2(in, in);
+                        const float* wc = wp + ci * 27 * CO_T;
 #pragma unroll
                         for (int c4 = 0; c4 < CO_T; c4 += 4) {
-                            float4 w = *reinterpret_cast<const float4*>(wp + c4);
-                            acc[c4] = fmaf(in, w.x, acc[c4]);
-                            acc[c4 + 1] = fmaf(in, w.y, acc[c4 + 1]);
-                            acc[c4 + 2] = fmaf(in, w.z, acc[c4 + 2]);
-                            acc[c4 + 3] = fmaf(in, w.w, acc[c4 + 3]);
+                            const float4 w = *reinterpret_cast<const float4*>(wc + c4);
+                            acc2[c4 / 2] = __ffma2_rn(in2, make_float2(w.x, w.y), acc2[c4 / 2]);
+                            acc2[c4 / 2 + 1] = __ffma2_rn(in2, make_float2(w.z, w.w), acc2[c4 / 2 + 1]);
                         }
                     }
                 }
             }
         }
-        const size_t o = ((size_t)n * Cout + cog * CO_T) * ovol + ((size_t)oz * Ho + oy) * Wo + ox;
+    }
+    float acc[CO_T];
+#pragma unroll
+    for (int c = 0; c < CO_T / 2; ++c) acc[2 * c] = acc2[c].x, acc[2 * c + 1] = acc2[c].y;
+    if (n_slices == 1) {
+        if (gv >= n_vox_total) return;
+        const int n = (int)(gv / (long long)ovol);
+        const size_t o = ((size_t)n * Cout + cog * CO_T) * ovol + (size_t)(gv - (long long)n * ovol);
 #pragma unroll
         for (int c = 0; c < CO_T; ++c) {
             const int co = cog * CO_T + c;
@@ -214,22 +251,40 @@ conv3d_generic_kernel(const float* __restrict__ x, int Cin, int Di, int Hi, int 
             if (skip) val += __ldg(skip + o + (size_t)c * ovol);
             y[o + (size_t)c * ovol] = val;
         }
+        return;
+    }
+#pragma unroll
+    for (int c = 0; c < CO_T; ++c) s_red[(s * CO_T + c) * vox + v] = acc[c];
+    __syncthreads();
+    for (int o = tid; o < vox * CO_T; o += DC_THREADS) {
+        const int vv = o % vox, c = o / vox;
+        const long long g = (long long)blockIdx.x * vox + vv;
+        if (g >= n_vox_total) continue;
+        float sum = 0.f;
+        for (int ss = 0; ss < n_slices; ++ss) sum += s_red[(ss * CO_T + c) * vox + vv];
+        const int n = (int)(g / (long long)ovol);
+        const int co = cog * CO_T + c;
+        const size_t idx = ((size_t)n * Cout + co) * ovol + (size_t)(g - (long long)n * ovol);
+        float val = fmaxf(fmaf(sum, __ldg(scale + co), __ldg(shift + co)), 0.f);
+        if (skip) val += __ldg(skip + idx);
+        y[idx] = val;
     }
 }
 
 // ------------------------------------------------------------------ prob conv + soft-argmin
-// CTA = 16 consecutive pixels of one image row x 16 depth lanes.  A thread convolves the planes
-// d = lane, lane + 16, ... of its pixel (8 -> 1 channels, 3x3x3, bias) and folds them into an
-// online softmax(-x) state with the plane depth as value; the 16 states of a pixel are merged
-// through shared memory.  The regularised volume itself is only written on request.
-constexpr int PS_TX = 16, PS_DL = 16;
+// CTA = 8 consecutive pixels of one image row x 32 depth lanes.  A thread convolves the planes
+// d = lane, lane + 32, ... of its pixel (Cin -> 1 channels, 3x3x3, bias; a warp reads four
+// 32-byte row segments per tap) and folds them into an online softmax(-x) state with the plane
+// depth as value; the 32 states of a pixel are merged through shared memory.  The regularised
+// volume itself is only written on request.
+constexpr int PS_TX = 8, PS_DL = 32;
 
 __global__ void __launch_bounds__(PS_TX * PS_DL)
 prob_softargmin_kernel(const float* __restrict__ x, int Cin, int D, int H, int W, const float* __restrict__ wgt,
                        float bias, float d_start, float d_end, float* __restrict__ x_reg, float* __restrict__ depth) {
-    extern __shared__ float s_w[];  // [Cin][27]
+    extern __shared__ float s_w[];  // [27][Cin]
     __shared__ float s_m[PS_DL][PS_TX], s_s[PS_DL][PS_TX], s_t[PS_DL][PS_TX];
-    for (int i = threadIdx.x; i < Cin * 27; i += blockDim.x) s_w[i] = __ldg(wgt + i);
+    for (int i = threadIdx.x; i < Cin * 27; i += blockDim.x) s_w[(i % 27) * Cin + i / 27] = __ldg(wgt + i);
     __syncthreads();
     const int px = threadIdx.x % PS_TX, dl = threadIdx.x / PS_TX;
     const int ox = blockIdx.x * PS_TX + px, oy = blockIdx.y, n = blockIdx.z;
@@ -240,27 +295,27 @@ prob_softargmin_kernel(const float* __restrict__ x, int Cin, int D, int H, int W
     float m = -INFINITY, s = 0.f, t = 0.f;
     if (inside) {
         for (int d = dl; d < D; d += PS_DL) {
-            float acc = bias;
-            for (int ci = 0; ci < Cin; ++ci) {
-                const float* xc = xn + (size_t)ci * vol;
+            float part[3] = {0.f, 0.f, 0.f};  // one chain per kd: three independent FMA chains
 #pragma unroll
-                for (int kd = 0; kd < 3; ++kd) {
-                    const int z = d + kd - 1;
-                    if (z < 0 || z >= D) continue;
+            for (int kd = 0; kd < 3; ++kd) {
+                const int z = d + kd - 1;
+                if (z < 0 || z >= D) continue;
 #pragma unroll
-                    for (int kh = 0; kh < 3; ++kh) {
-                        const int yy = oy + kh - 1;
-                        if (yy < 0 || yy >= H) continue;
-                        const float* xr = xc + (size_t)z * plane + (size_t)yy * W;
+                for (int kh = 0; kh < 3; ++kh) {
+                    const int yy = oy + kh - 1;
+                    if (yy < 0 || yy >= H) continue;
 #pragma unroll
-                        for (int kw = 0; kw < 3; ++kw) {
-                            const int xx = ox + kw - 1;
-                            if (xx < 0 || xx >= W) continue;
-                            acc = fmaf(__ldg(xr + xx), s_w[ci * 27 + (kd * 3 + kh) * 3 + kw], acc);
-                        }
+                    for (int kw = 0; kw < 3; ++kw) {
+                        const int xx = ox + kw - 1;
+                        if (xx < 0 || xx >= W) continue;
+                        const float* xp = xn + (size_t)z * plane + (size_t)yy * W + xx;
+                        const float* wp = s_w + ((kd * 3 + kh) * 3 + kw) * Cin;
+#pragma unroll 8
+                        for (int ci = 0; ci < Cin; ++ci) part[kd] = fmaf(__ldg(xp + (size_t)ci * vol), wp[ci], part[kd]);
                     }
                 }
             }
+            const float acc = bias + ((part[0] + part[1]) + part[2]);
             if (x_reg) x_reg[((size_t)n * D + d) * plane + (size_t)oy * W + ox] = acc;
             const float v = -acc;
             const float mn = fmaxf(m, v);
@@ -296,19 +351,55 @@ static int fold_check(const float* scale, const float* shift) { return scale && 
 using namespace dv3d;
 
 template <int MODE, int CO_T>
-static int launch_generic(const float* x, int n, int Cin, int Di, int Hi, int Wi, const float* w, const float* scale,
-                          const float* shift, int Cout, int Do, int Ho, int Wo, const float* skip, float* y,
-                          cudaStream_t st) {
-    const size_t smem = sizeof(float) * Cin * 27 * CO_T;
-    DV3D_CUDA(cudaFuncSetAttribute(conv3d_generic_kernel<MODE, CO_T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)smem));
-    long long total = (long long)n * Do * Ho * Wo;
-    int blocks = cdiv(total, 128);
-    int cap = kNumSMs * 16;
-    if (blocks > cap) blocks = cap;
-    dim3 grid(blocks, Cout / CO_T);
-    conv3d_generic_kernel<MODE, CO_T><<<grid, 128, smem, st>>>(x, Cin, Di, Hi, Wi, w, scale, shift, Cout, Do, Ho, Wo,
-                                                               skip, y, total);
+static int launch_direct(const float* x, int n, int Cin, int Di, int Hi, int Wi, const float* w, const float* scale,
+                         const float* shift, int Cout, int Do, int Ho, int Wo, const float* skip, float* y,
+                         cudaStream_t st) {
+    const long long total = (long long)n * Do * Ho * Wo;
+    const int cogs = Cout / CO_T;
+    // K split: the smallest power of two that gives every SM two CTAs (or 8)
+    int ns = 1;
+    while (ns < 8 && Cin % (2 * ns) == 0 && (long long)cdiv(total, DC_THREADS / ns) * cogs < 2 * kNumSMs) ns *= 2;
+    const size_t smem = sizeof(float) * ((size_t)Cin * 27 * CO_T + (ns > 1 ? DC_THREADS * CO_T : 0));
+    DV3D_REQUIRE(smem <= 200 * 1024, "conv3d: weights of one channel group (%zu bytes) do not fit shared memory", smem);
+    static size_t attr = 0;  // per instantiation
+    if (smem > attr) {
+        DV3D_CUDA(cudaFuncSetAttribute(conv3d_direct_kernel<MODE, CO_T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+        attr = smem;
+    }
+    dim3 grid(cdiv(total, DC_THREADS / ns), cogs);
+    DV3D_REQUIRE(grid.y <= 65535, "conv3d: too many channel groups");
+    conv3d_direct_kernel<MODE, CO_T><<<grid, DC_THREADS, smem, st>>>(x, Cin, Di, Hi, Wi, w, scale, shift, Cout, Do, Ho,
+                                                                   Wo, skip, y, total, ns);
+    DV3D_LAUNCHED();
+    return DV3D_OK;
+}
+
+// 16 output channels per thread halve the input loads per FMA; the weights of the group must
+// leave room for several CTAs per SM
+template <int MODE>
+static int launch_direct_any(const float* x, int n, int Cin, int Di, int Hi, int Wi, const float* w, const float* scale,
+                             const float* shift, int Cout, int Do, int Ho, int Wo, const float* skip, float* y,
+                             cudaStream_t st) {
+    if (Cout % 16 == 0 && Cin <= 32)
+        return launch_direct<MODE, 16>(x, n, Cin, Di, Hi, Wi, w, scale, shift, Cout, Do, Ho, Wo, skip, y, st);
+    return launch_direct<MODE, 8>(x, n, Cin, Di, Hi, Wi, w, scale, shift, Cout, Do, Ho, Wo, skip, y, st);
+}
+
+template <int TZ>
+static int launch_s1_tiled(const float* x, int n, int Cin, int D, int H, int W, const float* weight, const float* scale,
+                           const float* shift, int Cout, const float* skip, float* y, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) {
+        DV3D_CUDA(cudaFuncSetAttribute(conv3d_s1_tiled_kernel<TZ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)s1_smem(TZ)));
+        attr = true;
+    }
+    const int tiles_x = cdiv(W, TX), tiles_y = cdiv(H, TY);
+    dim3 grid(tiles_x * tiles_y, cdiv(D, TZ), n * (Cout / COT));
+    DV3D_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "conv3d: grid too large");
+    conv3d_s1_tiled_kernel<TZ><<<grid, s1_threads(TZ), s1_smem(TZ), st>>>(x, Cin, D, H, W, weight, scale, shift, Cout,
+                                                                        skip, y, tiles_x, tiles_y);
     DV3D_LAUNCHED();
     return DV3D_OK;
 }
@@ -322,30 +413,24 @@ extern "C" int dv3d_conv3d_bn_relu(const float* x, int n, int Cin, int D, int H,
     DV3D_REQUIRE(Cin <= 128, "conv3d: Cin > 128 unsupported");
     if (n == 0) return DV3D_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    if (stride == 1 && Cin % CIC == 0 && (long long)D * H * W >= 16384) {
-        static bool attr = false;
-        if (!attr) {
-            DV3D_CUDA(cudaFuncSetAttribute(conv3d_s1_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)S1_SMEM));
-            attr = true;
+    if (stride == 1 && Cin % CIC == 0 && (long long)D * H * W >= 100000) {
+        // depth of the CTA tile: fewest rounds of 2 CTAs per SM, weighted by the planes per CTA
+        const long long per_plane = (long long)cdiv(W, TX) * cdiv(H, TY) * n * (Cout / COT);
+        int best = 4;
+        long long best_cost = -1;
+        for (int tz = 4; tz >= 2; --tz) {
+            const long long ctas = per_plane * cdiv(D, tz);
+            const long long cost = ((ctas + 2 * kNumSMs - 1) / (2 * kNumSMs)) * (tz + 1);
+            if (best_cost < 0 || cost < best_cost) best = tz, best_cost = cost;
         }
-        int tiles_x = cdiv(W, TX), tiles_y = cdiv(H, TY);
-        dim3 grid(tiles_x * tiles_y, cdiv(D, TZ), n * (Cout / COT));
-        DV3D_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "conv3d: grid too large");
-        conv3d_s1_tiled_kernel<<<grid, S1_THREADS, S1_SMEM, st>>>(x, Cin, D, H, W, weight, scale, shift, Cout, skip, y,
-                                                                  tiles_x, tiles_y);
-        DV3D_LAUNCHED();
-        return DV3D_OK;
+        if (best == 2) return launch_s1_tiled<2>(x, n, Cin, D, H, W, weight, scale, shift, Cout, skip, y, st);
+        if (best == 3) return launch_s1_tiled<3>(x, n, Cin, D, H, W, weight, scale, shift, Cout, skip, y, st);
+        return launch_s1_tiled<4>(x, n, Cin, D, H, W, weight, scale, shift, Cout, skip, y, st);
     }
-    if (stride == 1) {
-        if (Cout % 16 == 0)
-            return launch_generic<kConvS1, 16>(x, n, Cin, D, H, W, weight, scale, shift, Cout, D, H, W, skip, y, st);
-        return launch_generic<kConvS1, 8>(x, n, Cin, D, H, W, weight, scale, shift, Cout, D, H, W, skip, y, st);
-    }
+    if (stride == 1)
+        return launch_direct_any<kConvS1>(x, n, Cin, D, H, W, weight, scale, shift, Cout, D, H, W, skip, y, st);
     const int Do = (D + 1) / 2, Ho = (H + 1) / 2, Wo = (W + 1) / 2;  // floor((D + 2 - 3)/2) + 1
-    if (Cout % 16 == 0)
-        return launch_generic<kConvS2, 16>(x, n, Cin, D, H, W, weight, scale, shift, Cout, Do, Ho, Wo, skip, y, st);
-    return launch_generic<kConvS2, 8>(x, n, Cin, D, H, W, weight, scale, shift, Cout, Do, Ho, Wo, skip, y, st);
+    return launch_direct_any<kConvS2>(x, n, Cin, D, H, W, weight, scale, shift, Cout, Do, Ho, Wo, skip, y, st);
 }
 
 extern "C" int dv3d_deconv3d_bn_relu(const float* x, int n, int Cin, int D, int H, int W, const float* weight,
@@ -355,12 +440,8 @@ extern "C" int dv3d_deconv3d_bn_relu(const float* x, int n, int Cin, int D, int 
     DV3D_REQUIRE(n >= 0 && Cin > 0 && Cin <= 128 && Cout > 0 && Cout % 8 == 0 && D > 0 && H > 0 && W > 0,
                  "deconv3d: bad shape");
     if (n == 0) return DV3D_OK;
-    cudaStream_t st = (cudaStream_t)stream;
-    if (Cout % 16 == 0)
-        return launch_generic<kDeconvS2, 16>(x, n, Cin, D, H, W, weight, scale, shift, Cout, 2 * D, 2 * H, 2 * W, skip,
-                                             y, st);
-    return launch_generic<kDeconvS2, 8>(x, n, Cin, D, H, W, weight, scale, shift, Cout, 2 * D, 2 * H, 2 * W, skip, y,
-                                        st);
+    return launch_direct_any<kDeconvS2>(x, n, Cin, D, H, W, weight, scale, shift, Cout, 2 * D, 2 * H, 2 * W, skip, y,
+                                        (cudaStream_t)stream);
 }
 
 extern "C" int dv3d_prob_softargmin(const float* x, int n, int Cin, int D, int H, int W, const float* weight,

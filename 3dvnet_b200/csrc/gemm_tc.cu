@@ -5,18 +5,24 @@
 //                   (128 lanes x N fp32 columns), UMMA shape M128 x N x K8, kind::tf32
 //   K pipeline      chunks of 32 floats (one 128-byte swizzle row per operand row), 3 stages.
 //                   A (gathered feature rows): 8 producer warps read the rows named by the
-//                   slice's row table / shift with 16-byte loads, split every value into a
+//                   slice's row table / shift with 16-byte loads FOUR chunks ahead (the register
+//                   ring covers the L2 / HBM latency of a gather), split every value into a
 //                   TF32 "big" part and an fp32 remainder, and store both in the canonical
 //                   K-major SWIZZLE_128B layout (st.shared + fence.proxy.async).
 //                   B (weights): pre-packed once per layer (pack_weights_kernel) into the exact
 //                   shared-memory image of every chunk, big and small part, and brought in by one
-//                   bulk-copy (cp.async.bulk -> mbarrier complete_tx) per stage.
+//                   bulk-copy (cp.async.bulk -> mbarrier complete_tx) per stage, issued by a
+//                   dedicated copy thread (warp 9) as soon as the stage is free - the first
+//                   copies are in flight while the producers still wait for their first rows.
 //   precision       3xTF32: acc += A_big B_big + A_big B_small + A_small B_big  (fp32-grade,
 //                   error ~2^-21 per product), or plain TF32 (first term only) as an opt-in.
 //   MMA issue       one elected thread of warp 8; tcgen05.commit releases the stage / signals
 //                   the epilogue through mbarriers - no __syncthreads in the main loop.
-//   epilogue        4 warps, thread = output row (TMEM lane), tcgen05.ld 16 columns at a time =
-//                   one GroupNorm group: folded BN / bias, per-row GroupNorm, residual, ReLU.
+//   epilogue        warps 0-3 move the accumulator tile TMEM -> shared memory (tcgen05.ld, thread =
+//                   row); then ALL warps run the epilogue on 16-byte units (thread = row x 4
+//                   channels, GroupNorm statistics by shuffles over the 4 lanes of a 16-channel
+//                   group): folded BN / bias, per-row GroupNorm, residual, ReLU - residual reads
+//                   and output stores are fully coalesced.
 //   sparsity        kernel-map slices with no live row in the tile are skipped by producers and
 //                   issuer alike (flags computed from the staged row table).
 #include "gemm.cuh"
@@ -27,7 +33,9 @@ constexpr int TC_BM = 128;
 constexpr int TC_KC = 32;                  // floats per K chunk = 128 bytes per operand row
 constexpr int TC_STAGES = 3;
 constexpr int TC_PRODUCERS = 256;          // 8 warps
-constexpr int TC_THREADS = TC_PRODUCERS + 32;
+constexpr int TC_THREADS = TC_PRODUCERS + 64;  // + warp 8: MMA issuer, warp 9: weight copies
+constexpr int TC_PREFETCH = 4;             // chunks of A rows in flight per producer thread
+constexpr int TC_MAX_SPLIT = 9;
 constexpr int TC_A_BYTES = TC_BM * 128;    // one operand image (big or small part)
 
 __host__ __device__ constexpr int tc_stage_bytes(int N) { return 2 * TC_A_BYTES + 2 * N * 128; }
@@ -46,8 +54,8 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
@@ -185,50 +193,58 @@ __device__ __forceinline__ void cursor_load(const ChunkCursor& c, float4 (&v)[4]
         v[i] = c.src[i] ? __ldg(reinterpret_cast<const float4*>(c.src[i] + c.kc * TC_KC)) : make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
-// epilogue of one 16-channel group of one output row
-__device__ __forceinline__ void epilogue16(const GemmDesc& d, float (&y)[16], long long m, int c0, bool live,
-                                           bool zero_row) {
+// Epilogue of one 16-byte unit (4 channels c0..c0+3 of output row m).  The 4 lanes that hold
+// the 16 channels of a GroupNorm group are consecutive and aligned, so the group statistics are
+// two xor-shuffles; every lane of the warp must call this (live = false rows only skip the store).
+__device__ __forceinline__ void epilogue4(const GemmDesc& d, float4 y, long long m, int c0, bool live, bool zero_row) {
     if (d.scale) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) y[i] *= __ldg(d.scale + c0 + i);
+        const float4 s = __ldg(reinterpret_cast<const float4*>(d.scale + c0));
+        y.x *= s.x; y.y *= s.y; y.z *= s.z; y.w *= s.w;
     }
     if (d.shift) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) y[i] += __ldg(d.shift + c0 + i);
+        const float4 s = __ldg(reinterpret_cast<const float4*>(d.shift + c0));
+        y.x += s.x; y.y += s.y; y.z += s.z; y.w += s.w;
     }
     if (d.gn_weight) {
-        float sum = 0.f;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) sum += y[i];
+        float sum = (y.x + y.y) + (y.z + y.w);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
         const float mean = sum * (1.f / 16.f);
-        float q = 0.f;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) q = fmaf(y[i] - mean, y[i] - mean, q);
+        const float dx = y.x - mean, dy = y.y - mean, dz = y.z - mean, dw = y.w - mean;
+        float q = fmaf(dx, dx, dy * dy) + fmaf(dz, dz, dw * dw);
+        q += __shfl_xor_sync(0xffffffffu, q, 1);
+        q += __shfl_xor_sync(0xffffffffu, q, 2);
         const float rstd = 1.f / sqrtf(q * (1.f / 16.f) + 1e-5f);
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-            y[i] = fmaf((y[i] - mean) * rstd, __ldg(d.gn_weight + c0 + i), __ldg(d.gn_bias + c0 + i));
+        const float4 gw = __ldg(reinterpret_cast<const float4*>(d.gn_weight + c0));
+        const float4 gb = __ldg(reinterpret_cast<const float4*>(d.gn_bias + c0));
+        y.x = fmaf(dx * rstd, gw.x, gb.x);
+        y.y = fmaf(dy * rstd, gw.y, gb.y);
+        y.z = fmaf(dz * rstd, gw.z, gb.z);
+        y.w = fmaf(dw * rstd, gw.w, gb.w);
     }
     if (!live) return;
     if (d.residual) {
-        const float4* rp = reinterpret_cast<const float4*>(d.residual + (size_t)m * d.res_ld + c0);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            float4 rv = __ldg(rp + i);
-            y[4 * i] += rv.x; y[4 * i + 1] += rv.y; y[4 * i + 2] += rv.z; y[4 * i + 3] += rv.w;
-        }
+        const float4 rv = __ldg(reinterpret_cast<const float4*>(d.residual + (size_t)m * d.res_ld + c0));
+        y.x += rv.x; y.y += rv.y; y.z += rv.z; y.w += rv.w;
     }
     if (d.relu_out) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) y[i] = fmaxf(y[i], 0.f);
+        y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f);
     }
-    if (zero_row) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) y[i] = 0.f;
+    if (zero_row) y = make_float4(0.f, 0.f, 0.f, 0.f);
+    *reinterpret_cast<float4*>(d.out + (size_t)m * d.out_ld + c0) = y;
+}
+
+// advance (s, kc, wchunk) over the live slices of a split range
+struct ChunkWalk {
+    int s, kc, nk, wchunk;
+};
+__device__ __forceinline__ void walk_enter(ChunkWalk& c, const GemmDesc& d, int s_end, uint32_t active) {
+    while (c.s < s_end && !((active >> c.s) & 1u)) {
+        c.wchunk += d.slice[c.s].K / TC_KC;
+        ++c.s;
     }
-    float4* op = reinterpret_cast<float4*>(d.out + (size_t)m * d.out_ld + c0);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) op[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+    c.kc = 0;
+    c.nk = c.s < s_end ? d.slice[c.s].K / TC_KC : 0;
 }
 
 // grid = (row tiles, K splits).  With K splits > 1 every CTA contracts a contiguous range of
@@ -243,9 +259,12 @@ gather_gemm_tc_kernel(const __grid_constant__ GemmDesc d, int precision) {
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     constexpr int STAGE = tc_stage_bytes(BN);
     constexpr int B_IMG = BN * 128;
+    constexpr int TILE_LD = BN + 4;  // padded row pitch of the epilogue tile (conflict-free both ways)
+    static_assert((size_t)TC_BM * TILE_LD * sizeof(float) <= (size_t)TC_STAGES * STAGE, "epilogue tile must fit the stages");
     int* s_rows = reinterpret_cast<int*>(smem + TC_STAGES * STAGE);                 // [n_slices][128]
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_rows + kMaxSlices * TC_BM);    // full[3] empty[3] accum
     uint32_t* s_misc = reinterpret_cast<uint32_t*>(s_bar + 2 * TC_STAGES + 1);     // [0] tmem base, [1] active, [2] last
+    float* s_tile = reinterpret_cast<float*>(smem);                                 // reuses the stages after the last MMA
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long m0 = (long long)blockIdx.x * TC_BM;
@@ -257,7 +276,7 @@ gather_gemm_tc_kernel(const __grid_constant__ GemmDesc d, int precision) {
 
     if (tid == 0) {
         for (int s = 0; s < TC_STAGES; ++s) {
-            mbar_init(bar_full + 8 * s, TC_PRODUCERS);
+            mbar_init(bar_full + 8 * s, TC_PRODUCERS + 1);  // 256 producers + the copy thread's arrive.expect_tx
             mbar_init(bar_empty + 8 * s, 1);
         }
         mbar_init(bar_accum, 1);
@@ -305,35 +324,26 @@ gather_gemm_tc_kernel(const __grid_constant__ GemmDesc d, int precision) {
         if ((active >> s) & 1u) n_it += d.slice[s].K / TC_KC;
 
     if (tid < TC_PRODUCERS) {
-        // ===================== producers: gather A two chunks ahead, split, store swizzled;
-        // thread 0 also starts the bulk copy of the chunk's packed weights
+        // ===================== producers: gather A TC_PREFETCH chunks ahead, split, store swizzled
         const int j = tid & 7;    // 16-byte unit within the 128-byte row
         const int r0 = tid >> 3;  // rows r0 + 32 i
-        ChunkCursor ld, stc;
+        ChunkCursor ld;
         ld.s = s_begin;
         ld.wchunk = 0;
-        for (int s = 0; s < s_begin; ++s) ld.wchunk += d.slice[s].K / TC_KC;
         cursor_enter(ld, d, s_end, active, s_rows, r0, j);
-        stc = ld;
-        float4 va[4], vb[4];
-        if (n_it > 0) {
-            cursor_load(ld, va);
-            cursor_next(ld, d, s_end, active, s_rows, r0, j);
-        }
-        if (n_it > 1) {
-            cursor_load(ld, vb);
-            cursor_next(ld, d, s_end, active, s_rows, r0, j);
+        float4 buf[TC_PREFETCH][4];
+#pragma unroll
+        for (int p = 0; p < TC_PREFETCH; ++p) {
+            if (p < n_it) {
+                cursor_load(ld, buf[p]);
+                cursor_next(ld, d, s_end, active, s_rows, r0, j);
+            }
         }
         auto store_chunk = [&](int it, const float4 (&v)[4]) {
             const int st = it % TC_STAGES;
             const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
             mbar_wait(bar_empty + 8 * st, ph ^ 1u);
             unsigned char* stage = smem + st * STAGE;
-            if (tid == 0) {
-                mbar_expect_tx(bar_full + 8 * st, 2 * B_IMG);
-                bulk_g2s(smem_u32(stage + 2 * TC_A_BYTES), Wp + (size_t)stc.wchunk * (2 * BN * 32), 2 * B_IMG,
-                         bar_full + 8 * st);
-            }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 float4 a = v[i];
@@ -352,33 +362,21 @@ gather_gemm_tc_kernel(const __grid_constant__ GemmDesc d, int precision) {
             }
             fence_proxy_async_smem();
             mbar_arrive(bar_full + 8 * st);
-            // only the weight-chunk index of the store cursor is used
-            ++stc.wchunk;
-            if (++stc.kc == stc.nk) {
-                ++stc.s;
-                while (stc.s < s_end && !((active >> stc.s) & 1u)) {
-                    stc.wchunk += d.slice[stc.s].K / TC_KC;
-                    ++stc.s;
-                }
-                stc.kc = 0;
-                if (stc.s < s_end) stc.nk = d.slice[stc.s].K / TC_KC;
-            }
         };
-        for (int it = 0; it < n_it; it += 2) {
-            store_chunk(it, va);
-            if (it + 2 < n_it) {
-                cursor_load(ld, va);
-                cursor_next(ld, d, s_end, active, s_rows, r0, j);
-            }
-            if (it + 1 < n_it) {
-                store_chunk(it + 1, vb);
-                if (it + 3 < n_it) {
-                    cursor_load(ld, vb);
-                    cursor_next(ld, d, s_end, active, s_rows, r0, j);
+        for (int it0 = 0; it0 < n_it; it0 += TC_PREFETCH) {
+#pragma unroll
+            for (int p = 0; p < TC_PREFETCH; ++p) {
+                const int it = it0 + p;
+                if (it < n_it) {
+                    store_chunk(it, buf[p]);
+                    if (it + TC_PREFETCH < n_it) {
+                        cursor_load(ld, buf[p]);
+                        cursor_next(ld, d, s_end, active, s_rows, r0, j);
+                    }
                 }
             }
         }
-    } else {
+    } else if (warp == 8) {
         if (lane == 0 && n_it > 0) {
             // ===================== MMA issuer
             constexpr uint32_t idesc = umma_idesc_tf32(TC_BM, BN);
@@ -406,79 +404,98 @@ gather_gemm_tc_kernel(const __grid_constant__ GemmDesc d, int precision) {
             umma_commit(bar_accum);
         }
         __syncwarp();
+    } else {
+        if (lane == 0 && n_it > 0) {
+            // ===================== weight copies: one bulk copy per chunk as soon as its stage is free
+            ChunkWalk w;
+            w.s = s_begin;
+            w.wchunk = 0;
+            for (int s = 0; s < s_begin; ++s) w.wchunk += d.slice[s].K / TC_KC;
+            walk_enter(w, d, s_end, active);
+            for (int it = 0; it < n_it; ++it) {
+                const int st = it % TC_STAGES;
+                const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
+                mbar_wait(bar_empty + 8 * st, ph ^ 1u);
+                mbar_arrive_expect_tx(bar_full + 8 * st, 2 * B_IMG);
+                bulk_g2s(smem_u32(smem + st * STAGE + 2 * TC_A_BYTES), Wp + (size_t)w.wchunk * (2 * BN * 32), 2 * B_IMG,
+                         bar_full + 8 * st);
+                ++w.wchunk;
+                if (++w.kc == w.nk) {
+                    ++w.s;
+                    walk_enter(w, d, s_end, active);
+                }
+            }
+        }
+        __syncwarp();
     }
 
-    // ===================== epilogue: warps 0..3, thread = output row = TMEM lane
+    // ===================== accumulator tile TMEM -> shared memory: warps 0..3, thread = row = TMEM lane
     if (warp < 4) {
-        if (n_it > 0) mbar_wait(bar_accum, 0);
+        if (n_it > 0) mbar_wait(bar_accum, 0);  // all MMAs done: the stages are free to be overwritten
         tc_fence_after();
         const int row = warp * 32 + lane;
-        const long long m = m0 + row;
-        const bool live = m < d.M;
-        const bool zero_row = d.zero_row_mod && (int)(m % d.zero_row_mod) == d.zero_row_val;
         const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
-        if (n_split == 1) {
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 16) {
-                float y[16];
-                if (n_it > 0) {
-                    tmem_ld16(trow + (uint32_t)c0, y);
-                } else {
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+            float y[16];
+            if (n_it > 0) {
+                tmem_ld16(trow + (uint32_t)c0, y);
+            } else {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) y[i] = 0.f;
-                }
-                epilogue16(d, y, m, c0, live, zero_row);
+                for (int i = 0; i < 16; ++i) y[i] = 0.f;
             }
-        } else {
-            const size_t tile_floats = (size_t)TC_BM * BN;
-            float* ws_tile = d.split_ws + ((size_t)blockIdx.x * n_split) * tile_floats;  // [n_split][128][BN]
-            float* mine = ws_tile + (size_t)blockIdx.y * tile_floats + (size_t)row * BN;
-#pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 16) {
-                float y[16];
-                if (n_it > 0) {
-                    tmem_ld16(trow + (uint32_t)c0, y);
-                } else {
+            float4* tp = reinterpret_cast<float4*>(s_tile + row * TILE_LD + c0);
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) y[i] = 0.f;
-                }
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    reinterpret_cast<float4*>(mine + c0)[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
-            }
-            __threadfence();
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (tid == 0) {
-                const int prev = atomicAdd(d.split_counters + blockIdx.x, 1);
-                const bool last = prev == n_split - 1;
-                if (last) d.split_counters[blockIdx.x] = 0;  // ready for the next launch on this stream
-                s_misc[2] = last ? 1u : 0u;
-            }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (s_misc[2]) {
-                __threadfence();
-#pragma unroll 1
-                for (int c0 = 0; c0 < BN; c0 += 16) {
-                    float y[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) y[i] = 0.f;
-                    for (int sp = 0; sp < n_split; ++sp) {
-                        const float4* pp = reinterpret_cast<const float4*>(ws_tile + (size_t)sp * tile_floats +
-                                                                           (size_t)row * BN + c0);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            float4 v = __ldcg(pp + i);
-                            y[4 * i] += v.x; y[4 * i + 1] += v.y; y[4 * i + 2] += v.z; y[4 * i + 3] += v.w;
-                        }
-                    }
-                    epilogue16(d, y, m, c0, live, zero_row);
-                }
-            }
+            for (int i = 0; i < 4; ++i) tp[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 8) tmem_dealloc(tmem_base, BN);
+
+    // ===================== epilogue on 16-byte units, all warps
+    constexpr int UNITS = BN / 4;          // per row
+    constexpr int ITEMS = TC_BM * UNITS;   // per tile; a multiple of 32, so warps stay converged
+    const float4* ws_tile4 = nullptr;
+    if (n_split > 1) {
+        float4* ws_base = reinterpret_cast<float4*>(d.split_ws) + (size_t)blockIdx.x * n_split * ITEMS;  // [n_split][ITEMS]
+        float4* mine = ws_base + (size_t)blockIdx.y * ITEMS;
+        for (int i = tid; i < ITEMS; i += TC_THREADS)
+            mine[i] = *reinterpret_cast<const float4*>(s_tile + (i / UNITS) * TILE_LD + (i % UNITS) * 4);
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            const int prev = atomicAdd(d.split_counters + blockIdx.x, 1);
+            const bool last = prev == n_split - 1;
+            if (last) d.split_counters[blockIdx.x] = 0;  // ready for the next launch on this stream
+            s_misc[2] = last ? 1u : 0u;
+        }
+        __syncthreads();
+        if (!s_misc[2]) return;
+        __threadfence();
+        ws_tile4 = ws_base;
+    }
+    for (int i = tid; i < ITEMS; i += TC_THREADS) {
+        const int row = i / UNITS, c0 = (i % UNITS) * 4;
+        float4 y;
+        if (ws_tile4) {
+            // partials in split order; every load is issued before the first add
+            float4 v[TC_MAX_SPLIT];
+#pragma unroll
+            for (int sp = 0; sp < TC_MAX_SPLIT; ++sp)
+                v[sp] = sp < n_split ? __ldcg(ws_tile4 + (size_t)sp * ITEMS + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            y = v[0];
+#pragma unroll
+            for (int sp = 1; sp < TC_MAX_SPLIT; ++sp) {
+                y.x += v[sp].x; y.y += v[sp].y; y.z += v[sp].z; y.w += v[sp].w;
+            }
+        } else {
+            y = *reinterpret_cast<const float4*>(s_tile + row * TILE_LD + c0);
+        }
+        const long long m = m0 + row;
+        const bool zero_row = d.zero_row_mod && (int)(m % d.zero_row_mod) == d.zero_row_val;
+        epilogue4(d, y, m, c0, m < d.M, zero_row);
+    }
 }
 
 int validate_gather_gemm(const GemmDesc& d, int k_multiple);
@@ -489,6 +506,7 @@ int gather_gemm_tc_splits(long long M, int n_slices) {
     if (tiles <= 0 || n_slices < 6) return 1;
     int split = kNumSMs / tiles;
     if (split > n_slices / 3) split = n_slices / 3;
+    if (split > TC_MAX_SPLIT) split = TC_MAX_SPLIT;
     return split < 1 ? 1 : split;
 }
 

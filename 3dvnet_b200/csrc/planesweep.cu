@@ -99,19 +99,22 @@ __device__ __forceinline__ void make_record(const float* __restrict__ P, float X
     }
 }
 
-__device__ __forceinline__ void fma4(float4& acc, float w, const float4& t) {
-    acc.x = __fmaf_rn(t.x, w, acc.x);
-    acc.y = __fmaf_rn(t.y, w, acc.y);
-    acc.z = __fmaf_rn(t.z, w, acc.z);
-    acc.w = __fmaf_rn(t.w, w, acc.w);
-}
+// Packed fp32 (FFMA2 / FMUL2 / FADD2, sm_100): two channels per issue slot, every lane rounded
+// to nearest exactly like the scalar instruction, so bit-exactness is unaffected.
+// x * x with its own rounding.  ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2
+// (even with --fmad=false and explicit .rn), which would skip the rounding of the square the
+// reference performs before its scatter-add; scalar FMULs are never contracted.
+__device__ __forceinline__ float2 sq2_rn(const float2& a) { return make_float2(__fmul_rn(a.x, a.x), __fmul_rn(a.y, a.y)); }
+__device__ __forceinline__ float2 lo2(const float4& t) { return make_float2(t.x, t.y); }
+__device__ __forceinline__ float2 hi2(const float4& t) { return make_float2(t.z, t.w); }
 
 // Phase 2 for one staged pass of edges. NK = number of live planes/hypotheses in the chunk.
+// Accumulators are channel pairs: acc_s[k][0] = channels (0,1), [1] = (2,3) of the thread's group.
 template <int NK>
 __device__ __forceinline__ void consume_edges(const float4* __restrict__ feats, const int* __restrict__ esrc,
                                               int e_begin, int n_e, int img_stride4, int Wf, int v, int g,
                                               const int (*s_rec)[KD][TP], const float4 (*s_wt)[KD][TP],
-                                              float4 (&acc_s)[KD], float4 (&acc_q)[KD]) {
+                                              float2 (&acc_s)[KD][2], float2 (&acc_q)[KD][2]) {
     for (int e = 0; e < n_e; ++e) {
         const float4* base = feats + (size_t)__ldg(esrc + e_begin + e) * img_stride4 + g;
         int prev = -1;
@@ -130,19 +133,17 @@ __device__ __forceinline__ void consume_edges(const float4* __restrict__ feats, 
                 prev = rec;
             }
             // grid_sample (ATen CPU kernel): fma(se, w_se, fma(sw, w_sw, fma(ne, w_ne, nw * w_nw)))
-            float4 val;
-            val.x = __fmul_rn(t00.x, wt.x); val.y = __fmul_rn(t00.y, wt.x);
-            val.z = __fmul_rn(t00.z, wt.x); val.w = __fmul_rn(t00.w, wt.x);
-            fma4(val, wt.y, t01);
-            fma4(val, wt.z, t10);
-            fma4(val, wt.w, t11);
+            const float2 wx = make_float2(wt.x, wt.x), wy = make_float2(wt.y, wt.y), wz = make_float2(wt.z, wt.z),
+                         ww = make_float2(wt.w, wt.w);
+            float2 va = __fmul2_rn(lo2(t00), wx), vb = __fmul2_rn(hi2(t00), wx);
+            va = __ffma2_rn(lo2(t01), wy, va); vb = __ffma2_rn(hi2(t01), wy, vb);
+            va = __ffma2_rn(lo2(t10), wz, va); vb = __ffma2_rn(hi2(t10), wz, vb);
+            va = __ffma2_rn(lo2(t11), ww, va); vb = __ffma2_rn(hi2(t11), ww, vb);
             // scatter 'mean' of x and of x**2: plain sums in edge order (mvsnet.py:214-215)
-            acc_s[k].x = __fadd_rn(acc_s[k].x, val.x); acc_s[k].y = __fadd_rn(acc_s[k].y, val.y);
-            acc_s[k].z = __fadd_rn(acc_s[k].z, val.z); acc_s[k].w = __fadd_rn(acc_s[k].w, val.w);
-            acc_q[k].x = __fadd_rn(acc_q[k].x, __fmul_rn(val.x, val.x));
-            acc_q[k].y = __fadd_rn(acc_q[k].y, __fmul_rn(val.y, val.y));
-            acc_q[k].z = __fadd_rn(acc_q[k].z, __fmul_rn(val.z, val.z));
-            acc_q[k].w = __fadd_rn(acc_q[k].w, __fmul_rn(val.w, val.w));
+            acc_s[k][0] = __fadd2_rn(acc_s[k][0], va);
+            acc_s[k][1] = __fadd2_rn(acc_s[k][1], vb);
+            acc_q[k][0] = __fadd2_rn(acc_q[k][0], sq2_rn(va));
+            acc_q[k][1] = __fadd2_rn(acc_q[k][1], sq2_rn(vb));
         }
     }
 }
@@ -191,9 +192,9 @@ planesweep_var_kernel(const float4* __restrict__ feats, SampleGeom geom, const f
     const int n_chunks = (D + KD - 1) / KD;
     for (int ch = chunk_begin; ch < min(chunk_begin + chunks_per_cta, n_chunks); ++ch) {
         const int dbase = ch * KD;
-        float4 acc_s[KD], acc_q[KD];
+        float2 acc_s[KD][2], acc_q[KD][2];
 #pragma unroll
-        for (int k = 0; k < KD; ++k) acc_s[k] = acc_q[k] = make_float4(0, 0, 0, 0);
+        for (int k = 0; k < KD; ++k) acc_s[k][0] = acc_s[k][1] = acc_q[k][0] = acc_q[k][1] = make_float2(0, 0);
         const float z = linspace_np(d0, d1, D, min(dbase + pk, D - 1));
         // frustum point of (pixel, plane): pixel * depth formed in fp64, rounded once (utils.py:96-100)
         float X0, X1, X2;
@@ -218,10 +219,10 @@ planesweep_var_kernel(const float4* __restrict__ feats, SampleGeom geom, const f
 #pragma unroll
         for (int k = 0; k < KD; ++k) {
             float* o = s_out + (4 * g) * CS + k * TP + v;
-            o[0] = var_of(acc_s[k].x, acc_q[k].x, n_edges);
-            o[CS] = var_of(acc_s[k].y, acc_q[k].y, n_edges);
-            o[2 * CS] = var_of(acc_s[k].z, acc_q[k].z, n_edges);
-            o[3 * CS] = var_of(acc_s[k].w, acc_q[k].w, n_edges);
+            o[0] = var_of(acc_s[k][0].x, acc_q[k][0].x, n_edges);
+            o[CS] = var_of(acc_s[k][0].y, acc_q[k][0].y, n_edges);
+            o[2 * CS] = var_of(acc_s[k][1].x, acc_q[k][1].x, n_edges);
+            o[3 * CS] = var_of(acc_s[k][1].y, acc_q[k][1].y, n_edges);
         }
         __syncthreads();
         {
@@ -282,9 +283,9 @@ points_var_kernel(const float4* __restrict__ feats, SampleGeom geom, const float
         o[2] = X2;
     }
 
-    float4 acc_s[KD], acc_q[KD];
+    float2 acc_s[KD][2], acc_q[KD][2];
 #pragma unroll
-    for (int k = 0; k < KD; ++k) acc_s[k] = acc_q[k] = make_float4(0, 0, 0, 0);
+    for (int k = 0; k < KD; ++k) acc_s[k][0] = acc_s[k][1] = acc_q[k][0] = acc_q[k][1] = make_float2(0, 0);
 
     for (int eb = e0; eb < e1; eb += EMAX) {
         const int n_e = min(EMAX, e1 - eb);
@@ -310,10 +311,10 @@ points_var_kernel(const float4* __restrict__ feats, SampleGeom geom, const float
         for (int k = 0; k < 7; ++k) {
             if (k < n_hyp) {
                 float4 o;
-                o.x = var_of(acc_s[k].x, acc_q[k].x, n_edges);
-                o.y = var_of(acc_s[k].y, acc_q[k].y, n_edges);
-                o.z = var_of(acc_s[k].z, acc_q[k].z, n_edges);
-                o.w = var_of(acc_s[k].w, acc_q[k].w, n_edges);
+                o.x = var_of(acc_s[k][0].x, acc_q[k][0].x, n_edges);
+                o.y = var_of(acc_s[k][0].y, acc_q[k][0].y, n_edges);
+                o.z = var_of(acc_s[k][1].x, acc_q[k][1].x, n_edges);
+                o.w = var_of(acc_s[k][1].y, acc_q[k][1].y, n_edges);
                 *reinterpret_cast<float4*>(feat_out + (((size_t)r * P + p) * rows_per_point + k) * feat_stride +
                                            feat_off + 4 * g) = o;
             }
