@@ -13,7 +13,7 @@ import torch.nn.functional as F
 
 from .. import ops
 from . import utils
-from ._pack import require_eval
+from ._pack import PackCache, fold_bn, require_eval
 from .subnetworks.mvsnet import MVSNet
 from .subnetworks.scenemodeling import PointNet, SparseUNet, SparseScene
 from .subnetworks.refinement import HypothesisDecoder
@@ -58,6 +58,7 @@ class PL3DVNet(nn.Module):
         self.refine_half = PropagationNet(in_dim=feat_dim + 1, h_dim=32)
         self.refine_full = PropagationNet(in_dim=3 + 1, h_dim=32)
         self._nhwc = _FeatureCache()
+        self._engine_pack = PackCache()
 
     @property
     def device(self):
@@ -148,10 +149,89 @@ class PL3DVNet(nn.Module):
                                             offset, 3)
         return depth
 
-    def hot_path(self, feats_quarter, rotmats, tvecs, K, ref_src_edges, images_batch, depth_config, offsets_list):
+    def engine_params(self):
+        """dv3d_net_params_t for csrc/engine.cu: device pointers of the parameters and of their
+        kernel-friendly derived copies (folded BN, transposed / packed weights), cached until a
+        parameter changes. The tensors behind the pointers are kept alive in the returned holder."""
+        def build():
+            keep = []
+
+            def dense(W, Wp, a, b):
+                keep.extend((W, Wp, a, b))
+                return ops.dense_params(W, Wp, a, b)
+
+            P = ops.NetParams()
+            c3 = self.mvsnet.cnn_3d
+            layers = [c3.conv0, c3.conv1, c3.conv2, c3.conv3, c3.conv4, c3.conv5, c3.conv6, c3.conv7, c3.conv8, c3.conv9]
+            for i, m in enumerate(layers):
+                deconv = hasattr(m, 'deconv')
+                wt = (m.deconv if deconv else m.conv).weight.detach().float().contiguous()
+                scale, shift = (t.to(wt.device) for t in fold_bn(m.bn))
+                keep.extend((wt, scale, shift))
+                e = P.costreg[i]
+                e.weight, e.scale, e.shift = wt.data_ptr(), scale.data_ptr(), shift.data_ptr()
+                e.Cin, e.Cout = (wt.shape[0], wt.shape[1]) if deconv else (wt.shape[1], wt.shape[0])
+                e.kind = 2 if deconv else (1 if m.stride == 2 else 0)
+            pw = c3.prob.weight.detach().float().contiguous()
+            keep.append(pw)
+            P.prob_weight, P.prob_bias = pw.data_ptr(), float(c3.prob.bias.detach().float().cpu())
+            pn = self.pointnet._weights()
+            P.pointnet_in_pad = self.pointnet.in_pad
+            for i, name in enumerate(('fc_pos', 'fc1', 'fc2', 'fc3', 'fc4', 'fc_out')):
+                w, b, packed = pn[name]
+                P.pointnet[i] = dense(w, packed, None, b)
+            u = self.sparse_conv
+
+            def sconv(conv, gn):
+                k, packed = conv.weights()
+                W = k.float().reshape(-1, k.shape[-1]).contiguous()
+                return dense(W, packed, gn.weight.detach().float().contiguous(), gn.bias.detach().float().contiguous())
+
+            nl = u.n_levels
+            if nl > ops.MAX_LEVELS or max(len(seq) for seq in u.res_down) > ops.MAX_RES:
+                raise NotImplementedError('engine supports up to %d levels x %d residual blocks' % (ops.MAX_LEVELS, ops.MAX_RES))
+            P.n_levels = nl
+            for l in range(nl):
+                P.n_res[l] = len(u.res_down[l])
+                for b, blk in enumerate(u.res_down[l]):
+                    P.res_down[l][b][0] = sconv(blk.conv1, blk.n1.gn)
+                    P.res_down[l][b][1] = sconv(blk.conv2, blk.n2.gn)
+            for i in range(nl - 1):
+                P.down[i] = sconv(u.down[i][0], u.down[i][1].gn)
+                P.up[i] = sconv(u.up[i][0], u.up[i][1].gn)
+                P.feat_adj[i] = sconv(u.feat_adj[i][0], u.feat_adj[i][1].gn)
+                for b, blk in enumerate(u.res_up[i]):
+                    P.res_up[i][b][0] = sconv(blk.conv1, blk.n1.gn)
+                    P.res_up[i][b][1] = sconv(blk.conv2, blk.n2.gn)
+            layers, head = self.decoder._weights()
+            for i, (w, scale, shift, packed) in enumerate(layers):
+                P.dec[i] = dense(w.reshape(-1, w.shape[2]), packed, scale, shift)
+            keep.append(head[0])
+            P.dec_head_weight, P.dec_head_bias = head[0].data_ptr(), head[1]
+            return P, keep
+        tensors = [p for p in self.parameters()] + [b for b in self.buffers()]
+        return self._engine_pack.get(tensors, build, ops.gemm_mode())[0]
+
+    def hot_path(self, feats_quarter, rotmats, tvecs, K, ref_src_edges, images_batch, depth_config, offsets_list,
+                 return_init=False):
         """One pass of the hot path from quarter-resolution features: plane-sweep cost volume ->
         CostRegNet -> soft-argmin, then the volumetric refinement schedule. -> depth [n_ref,h,w].
-        This is the benchmark "step" (BASELINE.json configs[1])."""
+        This is the benchmark "step" (BASELINE.json configs[1]). The whole pass is enqueued by one
+        native call (csrc/engine.cu); hot_path_composed is the same pass composed op by op."""
+        require_eval(self)
+        dev = feats_quarter.device
+        plan = ops.edge_plan(ref_src_edges, dev)
+        depth_batch = images_batch[plan.ref_idx].long().contiguous()
+        # the channels-last copy is made on every call (one small kernel): the storage-keyed cache
+        # of the composed path must not be trusted for freshly uploaded tensors
+        nhwc = ops.nchw_to_nhwc(feats_quarter.detach().float().contiguous())
+        return ops.hot_path_engine(self.engine_params(), nhwc, rotmats.float().contiguous(),
+                                   tvecs.float().contiguous(), K.float().contiguous(), plan, depth_batch, depth_config,
+                                   self.hparams.img_size, self.edge_len, offsets_list, want_init=return_init)
+
+    def hot_path_composed(self, feats_quarter, rotmats, tvecs, K, ref_src_edges, images_batch, depth_config,
+                          offsets_list):
+        """hot_path through the reference-shaped modules, one C-ABI call per op (cross-check of the engine)."""
         require_eval(self)
         with torch.no_grad():
             dev = feats_quarter.device

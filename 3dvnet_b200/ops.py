@@ -378,3 +378,93 @@ def decoder_head(x, n_hyp, weight, bias, offset, want_prob=False):
     lib().call('dv3d_decoder_head', _p(x), n_pts, n_hyp, rows, weight.shape[1], ldx, _p(weight), float(bias),
                float(offset), _p(prob), _p(off), _stream())
     return off, prob
+
+
+# ----------------------------------------------------------------------------- engine
+class Conv3dParams(ctypes.Structure):
+    """dv3d_conv3d_params_t"""
+    _fields_ = [('weight', ctypes.c_void_p), ('scale', ctypes.c_void_p), ('shift', ctypes.c_void_p),
+                ('Cin', ctypes.c_int), ('Cout', ctypes.c_int), ('kind', ctypes.c_int), ('reserved', ctypes.c_int)]
+
+
+class DenseParams(ctypes.Structure):
+    """dv3d_dense_params_t"""
+    _fields_ = [('W', ctypes.c_void_p), ('Wp', ctypes.c_void_p), ('a', ctypes.c_void_p), ('b', ctypes.c_void_p),
+                ('K', ctypes.c_int), ('N', ctypes.c_int)]
+
+
+MAX_LEVELS, MAX_RES = 3, 4
+
+
+class NetParams(ctypes.Structure):
+    """dv3d_net_params_t"""
+    _fields_ = [('costreg', Conv3dParams * 10), ('prob_weight', ctypes.c_void_p), ('prob_bias', ctypes.c_float),
+                ('pointnet_in_pad', ctypes.c_int), ('pointnet', DenseParams * 6),
+                ('n_levels', ctypes.c_int), ('n_res', ctypes.c_int * MAX_LEVELS),
+                ('res_down', ((DenseParams * 2) * MAX_RES) * MAX_LEVELS),
+                ('down', DenseParams * (MAX_LEVELS - 1)), ('up', DenseParams * (MAX_LEVELS - 1)),
+                ('feat_adj', DenseParams * (MAX_LEVELS - 1)),
+                ('res_up', ((DenseParams * 2) * MAX_RES) * (MAX_LEVELS - 1)),
+                ('dec', DenseParams * 3), ('dec_head_weight', ctypes.c_void_p), ('dec_head_bias', ctypes.c_float)]
+
+
+def dense_params(W, Wp, a, b):
+    """W [K,N] fp32 (kept alive by the caller), Wp packed image or None, a / b per-channel vectors or None"""
+    d = DenseParams()
+    d.W, d.Wp = W.data_ptr(), (Wp.data_ptr() if Wp is not None else None)
+    d.a, d.b = (a.data_ptr() if a is not None else None), (b.data_ptr() if b is not None else None)
+    d.K, d.N = W.shape[0], W.shape[1]
+    return d
+
+
+_arena = {}
+
+
+def hot_path_engine(net_params, feats_nhwc, rotmats, tvecs, K, plan, depth_batch, depth_cfg, img_size, edge_len,
+                    offsets_list, want_init=False):
+    """The whole hot path from one native call (csrc/engine.cu) -> depth [n_ref,h,w] (and the
+    initial soft-argmin depth when want_init)."""
+    _chk(feats_nhwc, torch.float32, 'feats_nhwc', 4), _chk(depth_batch, torch.int64, 'depth_batch', 1)
+    _chk(rotmats, torch.float32, 'rotmats', 3), _chk(tvecs, torch.float32, 'tvecs', 2), _chk(K, torch.float32, 'K', 3)
+    n_imgs, Hf, Wf, C = feats_nhwc.shape
+    h, w = depth_cfg['size']
+    D = int(depth_cfg['n_intervals'])
+    dev = feats_nhwc.device
+    L = lib()
+    need = L.raw('dv3d_hot_path_workspace_bytes')(ctypes.byref(net_params), n_imgs, plan.n_ref, D, h, w)
+    arena = _arena.get(dev)
+    if arena is None or arena.numel() < need:
+        arena = _arena[dev] = torch.empty(need, dtype=torch.uint8, device=dev)
+    n_outer = len(offsets_list)
+    n_inner = len(offsets_list[0]) if n_outer else 0
+    if any(len(o) != n_inner for o in offsets_list):
+        raise RuntimeError('hot_path: every refinement iteration must have the same number of PointFlow passes')
+    offs = (ctypes.c_double * max(1, n_outer * n_inner))(*[float(v) for o in offsets_list for v in o])
+    depth = torch.empty((plan.n_ref, h, w), dtype=torch.float32, device=dev)
+    init = torch.empty_like(depth) if want_init else None
+    L.call('dv3d_hot_path', ctypes.byref(net_params), _p(feats_nhwc), n_imgs, Hf, Wf, _p(rotmats), _p(tvecs), _p(K),
+           _p(plan.ref_img), _p(plan.rowptr), _p(plan.edge_src), plan.n_ref, _p(depth_batch),
+           float(depth_cfg['depth_start']), float(depth_cfg['depth_interval']), D, h, w, img_size[0], img_size[1],
+           float(edge_len), offs, n_outer, n_inner, _p(arena), arena.numel(), _p(init), _p(depth), _stream())
+    return (depth, init) if want_init else depth
+
+
+(STAGE_PLANESWEEP, STAGE_COSTREG, STAGE_SOFTARGMIN, STAGE_POINTCLOUD, STAGE_VOXELIZE, STAGE_POINTNET, STAGE_LEVELS,
+ STAGE_UNET, STAGE_FLOW_WARP, STAGE_FLOW_INTERP, STAGE_DEC_GEMM0, STAGE_DEC_REST) = range(12)
+STAGE_NAMES = ('planesweep_var', 'costreg', 'softargmin', 'pointcloud', 'voxelize', 'pointnet', 'levels', 'unet',
+               'flow_warp', 'flow_interp', 'dec_gemm0', 'dec_rest')
+
+
+def engine_profile(enable):
+    """record CUDA events around the stages of dv3d_hot_path (clears earlier records)"""
+    lib().call('dv3d_engine_profile', int(bool(enable)))
+
+
+def engine_profile_read(cap=1 << 16):
+    """[(stage id, ms), ...] in launch order; synchronise the stream first"""
+    ids = (ctypes.c_int * cap)()
+    ms = (ctypes.c_float * cap)()
+    n = lib().raw('dv3d_engine_profile_read')(ids, ms, cap)
+    if n < 0:
+        raise Dv3dError(n, 'dv3d_engine_profile_read', lib().last_error())
+    return [(ids[i], ms[i]) for i in range(n)]

@@ -198,28 +198,24 @@ def main():
         step_resident()
     torch.cuda.synchronize()
 
-    # dominant-kernel timing: events around the warp+variance launch inside the timed steps
-    kernel_ms = []
-    orig = ops.planesweep_var
-
-    def timed_planesweep(*a, **k):
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        r = orig(*a, **k)
-        e.record()
-        kernel_ms.append((s, e))
-        return r
-
+    # kernel / stage timing inside the timed steps: the engine records CUDA events on the launching
+    # stream around its stages (include/dv3d.h: dv3d_engine_profile)
     sampler = ClockSampler(local)
     sampler.start()
-    ops.planesweep_var = timed_planesweep
+    ops.engine_profile(True)
     launches0 = ops.launch_count()
     ms = timed(step_resident, args.steps)
     launches = ops.launch_count() - launches0
-    ops.planesweep_var = orig
+    recs = ops.engine_profile_read()
+    ops.engine_profile(False)
     sampler.stop_flag = True
     sampler.join()
-    k_ms = float(np.mean([s.elapsed_time(e) for s, e in kernel_ms]))
+    stage_ms = {}
+    for sid, t in recs:
+        stage_ms.setdefault(sid, []).append(t)
+    k_ms = float(np.mean(stage_ms[ops.STAGE_PLANESWEEP]))
+    g_ms = float(np.mean(stage_ms[ops.STAGE_DEC_GEMM0]))
+    stages_per_step = {ops.STAGE_NAMES[sid]: float(np.sum(v)) / args.steps for sid, v in sorted(stage_ms.items())}
 
     for _ in range(2):
         step_e2e()
@@ -236,14 +232,22 @@ def main():
 
     peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+        pk = json.load(open(peaks_path))
+        peak, peak_src = float(pk['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+        tpeak, tpeak_src = float(pk.get('bf16_tflops_sustained', pk['bf16_tflops'])), \
+            'measured (MEASURED_PEAKS.json bf16_tflops_sustained: kernel timed inside a long step)'
     else:
         peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
+        tpeak, tpeak_src = 1400.0, 'fallback (B200_PROFILING.md, sustained)'
     achieved = ALGO_BYTES * n_ref / (k_ms * 1e-3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, 'profiles', 'planesweep_traffic.json')
+    traffic = {}
+    tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get('dram_bytes_per_launch')
+        traffic = json.load(open(tpath))
+    # first decoder Conv1d as one launch of the dominant kernel (tcgen05 gather-GEMM): useful FLOPs
+    # 2 M K N with M = n_ref * 3136 points * 8 rows, K = 3 * 352, N = 128
+    gemm_flops = 2.0 * (n_ref * PLANE[0] * PLANE[1] * 8) * (3 * 352) * 128
+    g_achieved = gemm_flops / (g_ms * 1e-3) / 1e12
 
     line = {
         'metric': METRIC, 'value': units / (ms * 1e-3), 'unit': 'ref-views/s', 'n_gpus': world,
@@ -258,9 +262,17 @@ def main():
                                           + edges.numel() * 4 + 64),
                 'd2h_bytes_per_step': int(out_host.numel() * 4), 'ms_per_step': ms_e2e / args.steps},
         'gpu_launches': launches,
-        'roofline': {'kernel': 'planesweep_var_kernel', 'bound': 'hbm', 'achieved': achieved, 'peak': peak,
-                     'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
-                     'algorithmic_bytes_per_launch': ALGO_BYTES * n_ref, 'kernel_ms': k_ms},
+        'roofline': {'kernel': 'gather_gemm_tc_kernel<128> (first decoder Conv1d, M=%d K=1056 N=128)' % (n_ref * 25088),
+                     'bound': 'tensor', 'achieved': g_achieved, 'peak': tpeak, 'unit': 'TFLOP/s',
+                     'frac': g_achieved / tpeak, 'traffic': traffic.get('gather_gemm_tc_decoder0'),
+                     'peak_source': tpeak_src, 'algorithmic_flops_per_launch': gemm_flops, 'kernel_ms': g_ms,
+                     'note': 'useful fp32-grade FLOPs; the kernel issues 3 TF32 MMAs per useful one (3xTF32 split) and '
+                             'TF32 runs at half the bf16 rate, so 1/6 of the bf16 peak is its ceiling'},
+        'roofline_warp': {'kernel': 'planesweep_var_kernel', 'bound': 'hbm', 'achieved': achieved, 'peak': peak,
+                          'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic.get('planesweep_var_kernel'),
+                          'peak_source': peak_src, 'algorithmic_bytes_per_launch': ALGO_BYTES * n_ref,
+                          'kernel_ms': k_ms},
+        'stages_ms_per_step': stages_per_step,
         'clocks': sampler.summary(),
     }
 

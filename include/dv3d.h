@@ -252,6 +252,100 @@ int dv3d_decoder_head(const float* x, long long n_pts, int n_hyp, int rows_per_p
                       const float* weight, float bias, double offset, float* prob_out, float* offset_out,
                       void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * Engine: the whole hot path enqueued by ONE call from native code.
+ *
+ * The reference drives its hot path from Python, one library call per tensor op
+ * (eval-3dvnet.py:58-99 -> lightningmodel.py:124-242); at B200 kernel durations (5-50 us) a
+ * per-op interpreter round trip would bound the step.  dv3d_hot_path runs
+ *   plane-sweep cost volume -> CostRegNet -> soft-argmin                    (mvsnet.py:176-229)
+ *   n_outer x { feature-rich point cloud -> voxelise -> PointNet -> sparse 3D-UNet
+ *               (lightningmodel.py:132-185), n_inner x PointFlow pass (:187-242), depth += offset
+ *               (eval-3dvnet.py:73-99) }
+ * with exactly the kernels and the order of the per-op entry points above (results are
+ * bit-identical to composing them), temporaries bump-allocated from a caller-provided arena.
+ * It SYNCS the stream 4 times per outer iteration (voxel grid, anchor count, two coarse-level
+ * counts: the sizes of the sparse levels are data dependent).
+ *
+ * Parameters are passed as a table of device pointers the caller has prepared once: folded
+ * BatchNorm (scale, shift), nn.Linear / Conv1d weights transposed to [K, N], tensor-core
+ * images from dv3d_gemm_pack_weights (Wp; NULL selects the fp32 CUDA-core GEMM).
+ */
+typedef struct dv3d_conv3d_params_t {
+    const float* weight;  /* torch layout: conv [Cout,Cin,3,3,3], deconv [Cin,Cout,3,3,3] */
+    const float* scale;   /* folded BatchNorm3d */
+    const float* shift;
+    int Cin, Cout;
+    int kind;             /* 0 = conv stride 1, 1 = conv stride 2, 2 = transposed conv stride 2 */
+    int reserved;
+} dv3d_conv3d_params_t;
+
+typedef struct dv3d_dense_params_t {
+    const float* W;       /* fp32 [K, N] row-major (sparse conv: [27*Cin, Cout]; conv1d: [3*Cin, Cout]) */
+    const void* Wp;       /* dv3d_gemm_pack_weights image or NULL */
+    const float* a;       /* Linear: unused; Conv1d: folded BN scale; sparse conv / 1x1: GroupNorm weight */
+    const float* b;       /* Linear: bias;   Conv1d: folded BN shift; sparse conv / 1x1: GroupNorm bias */
+    int K, N;
+} dv3d_dense_params_t;
+
+#define DV3D_MAX_LEVELS 3
+#define DV3D_MAX_RES 4
+typedef struct dv3d_net_params_t {
+    /* CostRegNet conv0..conv6, conv7..conv9 (mvsnet.py:133-150), then the prob conv */
+    dv3d_conv3d_params_t costreg[10];
+    const float* prob_weight;  /* [1,8,3,3,3] */
+    float prob_bias;
+    /* PointNet fc_pos (input rows zero-padded to pointnet_in_pad), fc1, fc2, fc3, fc4, fc_out */
+    int pointnet_in_pad;
+    dv3d_dense_params_t pointnet[6];
+    /* SparseUNet (scenemodeling.py:147-237): res blocks are [level][block][conv1|conv2] */
+    int n_levels;
+    int n_res[DV3D_MAX_LEVELS];
+    dv3d_dense_params_t res_down[DV3D_MAX_LEVELS][DV3D_MAX_RES][2];
+    dv3d_dense_params_t down[DV3D_MAX_LEVELS - 1];      /* k3 s2, level i -> i+1 */
+    dv3d_dense_params_t up[DV3D_MAX_LEVELS - 1];        /* transposed k3 s2; up[i] produces level n_levels-2-i */
+    dv3d_dense_params_t feat_adj[DV3D_MAX_LEVELS - 1];  /* 1x1 on [up | skip] */
+    dv3d_dense_params_t res_up[DV3D_MAX_LEVELS - 1][DV3D_MAX_RES][2];  /* res_up[i] on level n_levels-2-i */
+    /* HypothesisDecoder: three Conv1d+BN+ReLU, then the 1-channel head (refinement.py:17-26) */
+    dv3d_dense_params_t dec[3];
+    const float* dec_head_weight;  /* [1,Cin,3] torch layout */
+    float dec_head_bias;
+} dv3d_net_params_t;
+
+/* Optional stage timing of dv3d_hot_path: CUDA events recorded on the launching stream around
+ * the stages below.  dv3d_engine_profile(1) clears the records and enables recording (0 disables);
+ * after synchronising the stream, dv3d_engine_profile_read fills ids[] / ms[] with one record per
+ * stage execution in launch order and returns their number (or a negative error). */
+#define DV3D_STAGE_PLANESWEEP 0   /* planesweep_var_kernel alone */
+#define DV3D_STAGE_COSTREG 1      /* the ten CostRegNet layers */
+#define DV3D_STAGE_SOFTARGMIN 2
+#define DV3D_STAGE_POINTCLOUD 3   /* points_var_kernel, 1 hypothesis */
+#define DV3D_STAGE_VOXELIZE 4
+#define DV3D_STAGE_POINTNET 5
+#define DV3D_STAGE_LEVELS 6       /* coordinate levels + hash tables */
+#define DV3D_STAGE_UNET 7         /* kernel maps + sparse convolutions */
+#define DV3D_STAGE_FLOW_WARP 8    /* points_var_kernel, 7 hypotheses */
+#define DV3D_STAGE_FLOW_INTERP 9
+#define DV3D_STAGE_DEC_GEMM0 10   /* first decoder Conv1d (K = 3*352) as one gather-GEMM launch */
+#define DV3D_STAGE_DEC_REST 11    /* two more Conv1d GEMMs + head + depth update */
+int dv3d_engine_profile(int enable);
+int dv3d_engine_profile_read(int* ids, float* ms, int cap);
+
+/* arena size that dv3d_hot_path needs for these shapes (the voxel bitmaps get a fixed 64 MiB
+ * share; DV3D_ENOSPC from dv3d_hot_path means the scene's bounding box needs more) */
+size_t dv3d_hot_path_workspace_bytes(const dv3d_net_params_t* net, int n_imgs, int n_ref, int D, int h, int w);
+/*   feats_nhwc [n_imgs,Hf,Wf,32]; rotmats/tvecs/K as dv3d_camera_tables; ref_img/edge CSR as
+ *   dv3d_planesweep_var; depth_batch [n_ref] int64 (scene id of every reference view);
+ *   offsets_host [n_outer*n_inner] doubles (HOST memory; eval-3dvnet.py:23), n_side = 3;
+ *   workspace: 256-byte aligned device arena; depth_out [n_ref,h,w];
+ *   depth_init_out optional [n_ref,h,w] (the soft-argmin depth before refinement) */
+int dv3d_hot_path(const dv3d_net_params_t* net, const float* feats_nhwc, int n_imgs, int Hf, int Wf,
+                  const float* rotmats, const float* tvecs, const float* K, const int* ref_img,
+                  const int* edge_rowptr, const int* edge_src, int n_ref, const long long* depth_batch,
+                  double depth_start, double depth_interval, int D, int h, int w, int H, int W, double edge_len,
+                  const double* offsets_host, int n_outer, int n_inner, void* workspace, size_t workspace_bytes,
+                  float* depth_init_out, float* depth_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

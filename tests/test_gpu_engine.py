@@ -1,0 +1,79 @@
+"""The native engine (csrc/engine.cu: the whole hot path from one C-ABI call) against the same
+pass composed op by op through the reference-shaped modules, and against the CPU oracle."""
+import importlib
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, golden_inputs
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+@pytest.fixture(scope='module')
+def mods():
+    importlib.import_module('3dvnet_b200.build').build()
+    return dict(lm=importlib.import_module('3dvnet_b200.mv3d.lightningmodel'),
+                ops=importlib.import_module('3dvnet_b200.ops'), synth=importlib.import_module('3dvnet_b200.synth'))
+
+
+def _net(mods, cfg, edge_len, img_size, seed=0):
+    net = mods['lm'].PL3DVNet(cfg, cfg, edge_len, feat_dim=32, img_size=img_size)
+    net.load_state_dict(mods['synth'].make_params(seed), strict=False)
+    return net.to(DEV).eval()
+
+
+@pytest.mark.parametrize('n_scenes,n_imgs,offsets', [(1, 3, [[0.05, 0.05, 0.025]]), (2, 5, [[0.05, 0.025], [0.05, 0.025]]),
+                                                      (1, 4, [])])
+def test_engine_equals_composed_path(mods, n_scenes, n_imgs, offsets):
+    """same kernels, same order: the depth maps must be bit-identical"""
+    img_size, plane, D = (64, 80), (16, 24), 16
+    cfg = dict(depth_start=0.5, depth_interval=0.3, n_intervals=D, size=plane)
+    b = mods['synth'].make_batch(n_scenes, n_imgs, img_size, plane, 32, 1, 1, False, 3)
+    net = _net(mods, cfg, 0.3, img_size)
+    args = (b.feats_quarter.to(DEV), b.rotmats.to(DEV), b.tvecs.to(DEV), b.K.to(DEV), b.ref_src_edges,
+            b.images_batch.to(DEV), cfg, offsets)
+    got, init = net.hot_path(*args, return_init=True)
+    ref = net.hot_path_composed(*args)
+    np.testing.assert_array_equal(got.cpu().numpy().view(np.int32), ref.cpu().numpy().view(np.int32))
+    if not offsets:
+        np.testing.assert_array_equal(got.cpu().numpy(), init.cpu().numpy())
+    again = net.hot_path(*args)   # arena reuse: a second pass over the same arena gives the same bits
+    np.testing.assert_array_equal(got.cpu().numpy().view(np.int32), again.cpu().numpy().view(np.int32))
+
+
+def test_engine_c2_size_and_stage_profile(mods):
+    """BASELINE configs[1] shape through the engine, with the stage timing hooks bench.py uses"""
+    import ctypes
+    bench = importlib.import_module('bench')
+    ops = mods['ops']
+    b, params = bench.synth_inputs(1, 1)
+    net = mods['lm'].PL3DVNet(bench.DEPTH_CFG, bench.DEPTH_CFG, bench.EDGE_LEN, feat_dim=32, img_size=bench.IMG_SIZE)
+    net.load_state_dict(params, strict=False)
+    net = net.to(DEV).eval()
+    args = (b.feats_quarter.to(DEV), b.rotmats.to(DEV), b.tvecs.to(DEV), b.K.to(DEV), b.ref_src_edges,
+            b.images_batch.to(DEV), bench.DEPTH_CFG, bench.OFFSETS_LIST)
+    ref = net.hot_path_composed(*args)
+    ops.engine_profile(True)
+    got = net.hot_path(*args)
+    torch.cuda.synchronize()
+    recs = ops.engine_profile_read()
+    ops.engine_profile(False)
+    np.testing.assert_array_equal(got.cpu().numpy().view(np.int32), ref.cpu().numpy().view(np.int32))
+    ids = [i for i, _ in recs]
+    assert ids.count(ops.STAGE_PLANESWEEP) == 1 and ids.count(ops.STAGE_UNET) == 2 and ids.count(ops.STAGE_DEC_GEMM0) == 6
+    assert all(ms > 0 for _, ms in recs)
+
+
+def test_engine_rejects_bad_arguments(mods):
+    img_size, plane = (64, 80), (16, 20)   # w = 20 is not a multiple of 8
+    cfg = dict(depth_start=0.5, depth_interval=0.3, n_intervals=16, size=plane)
+    b = mods['synth'].make_batch(1, 3, img_size, (16, 16), 32, 1, 1, False, 0)
+    net = _net(mods, cfg, 0.3, img_size)
+    with pytest.raises(mods['ops'].Dv3dError, match='multiples of 8'):
+        net.hot_path(b.feats_quarter.to(DEV), b.rotmats.to(DEV), b.tvecs.to(DEV), b.K.to(DEV), b.ref_src_edges,
+                     b.images_batch.to(DEV), cfg, [[0.05]])
+    with pytest.raises(RuntimeError, match='CUDA tensor'):
+        net.hot_path(b.feats_quarter, b.rotmats, b.tvecs, b.K, b.ref_src_edges, b.images_batch, cfg, [[0.05]])
