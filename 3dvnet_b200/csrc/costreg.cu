@@ -329,7 +329,7 @@ conv3d_direct_kernel(const float* __restrict__ x, int Cin, int Di, int Hi, int W
 __device__ __forceinline__ constexpr int deconv_tap(int a, int d) { return a == 0 ? (d == 0 ? 1 : -1) : (d == 0 ? 2 : 0); }
 
 template <int CO_T>
-__global__ void __launch_bounds__(DC_THREADS)
+__global__ void __launch_bounds__(DC_THREADS, 2)
 deconv3d_block_kernel(const float* __restrict__ x, int Cin, int Di, int Hi, int Wi, const float* __restrict__ wgt,
                       const float* __restrict__ scale, const float* __restrict__ shift, int Cout,
                       const float* __restrict__ skip, float* __restrict__ y, long long n_vox_total, int n_slices) {
@@ -514,10 +514,10 @@ static int fold_check(const float* scale, const float* shift) { return scale && 
 
 using namespace dv3d;
 
-// K split: the smallest power of two that gives every SM two CTAs (or 8)
-static int pick_slices(long long threads_voxels, int Cin, int cogs) {
+// K split: the smallest power of two that gives the 148 SMs `min_ctas` CTAs (or 8)
+static int pick_slices(long long threads_voxels, int Cin, int cogs, int min_ctas) {
     int ns = 1;
-    while (ns < 8 && Cin % (2 * ns) == 0 && (long long)cdiv(threads_voxels, DC_THREADS / ns) * cogs < 2 * kNumSMs) ns *= 2;
+    while (ns < 8 && Cin % (2 * ns) == 0 && (long long)cdiv(threads_voxels, DC_THREADS / ns) * cogs < min_ctas) ns *= 2;
     return ns;
 }
 
@@ -527,7 +527,7 @@ static int launch_direct(const float* x, int n, int Cin, int Di, int Hi, int Wi,
                          cudaStream_t st) {
     const long long total = (long long)n * Do * Ho * Wo;
     const int cogs = Cout / CO_T;
-    const int ns = pick_slices(total, Cin, cogs);
+    const int ns = pick_slices(total, Cin, cogs, 2 * kNumSMs);
     const size_t smem = sizeof(float) * ((size_t)Cin * 27 * CO_T + (ns > 1 ? DC_THREADS * CO_T : 0));
     DV3D_REQUIRE(smem <= 200 * 1024, "conv3d: weights of one channel group (%zu bytes) do not fit shared memory", smem);
     static size_t attr = 0;  // per instantiation
@@ -560,7 +560,8 @@ static int launch_deconv(const float* x, int n, int Cin, int Di, int Hi, int Wi,
     constexpr int CO_T = 8;
     const long long total = (long long)n * Di * Hi * Wi;  // threads are INPUT voxels
     const int cogs = Cout / CO_T;
-    const int ns = pick_slices(total, Cin, cogs);
+    // a thread produces 8 output voxels x 8 channels: one CTA per SM is already a full round
+    const int ns = pick_slices(total, Cin, cogs, kNumSMs - 8);
     const size_t smem = sizeof(float) * ((size_t)Cin * 27 * CO_T + (ns > 1 ? DC_THREADS * CO_T : 0));
     DV3D_REQUIRE(smem <= 200 * 1024, "deconv3d: weights of one channel group (%zu bytes) do not fit shared memory", smem);
     static size_t attr = 0;

@@ -95,6 +95,7 @@ __global__ void add_inplace_kernel(float* __restrict__ x, const float* __restric
     if (i < n) x[i] = x[i] + y[i];
 }
 
+
 struct Level {
     int* coords;
     long long n;
@@ -103,12 +104,27 @@ struct Level {
     size_t table_bytes;
 };
 
+// kernel map + its pair-major plan (csrc/sparse_pairs.cu)
+struct KMap {
+    int* nbr;
+    long long n_out;
+    void* plan;
+    size_t plan_bytes;
+    long long n_tiles;
+    bool use_pairs;
+    const struct Level* out_lv;
+    const struct Level* in_lv;
+    int step;
+};
+
 struct Scene {
     Level lv[DV3D_MAX_LEVELS];
     int n_levels;
-    int* same[DV3D_MAX_LEVELS];      // k3 s1 kernel map of level l
-    int* down[DV3D_MAX_LEVELS - 1];  // rows of level l+1 <- level l
-    int* up[DV3D_MAX_LEVELS - 1];    // rows of level l   <- level l+1
+    KMap same[DV3D_MAX_LEVELS];      // k3 s1 kernel map of level l
+    KMap down[DV3D_MAX_LEVELS - 1];  // rows of level l+1 <- level l
+    KMap up[DV3D_MAX_LEVELS - 1];    // rows of level l   <- level l+1
+    void* pair_ws;                   // P buffer of the pair-major convolutions
+    size_t pair_ws_bytes;
     float* feats[DV3D_MAX_LEVELS];   // decoder inputs (output of the U-Net per level)
     int dims[DV3D_MAX_LEVELS];
     float* origin;                   // [n_batch,3]
@@ -116,14 +132,17 @@ struct Scene {
     size_t split_ws_bytes;
 };
 
-static int sparse_conv(const dv3d_dense_params_t& p, const float* feat, long long n_in, const int* nbr, long long n_out,
+static int sparse_conv(const dv3d_dense_params_t& p, const float* feat, long long n_in, const KMap& km, long long n_out,
                        const float* residual, Scene& sc, float* out, void* st) {
-    return dv3d_sparse_conv(feat, n_in, p.K / 27, nbr, n_out, p.W, p.Wp, p.N, p.a, p.b, residual, 1, sc.split_ws,
+    if (km.use_pairs && p.Wp)
+        return dv3d_sparse_conv_pairs(feat, n_in, p.K / 27, km.plan, km.n_tiles, n_out, p.Wp, p.N, p.a, p.b, residual, 1,
+                                      sc.pair_ws, sc.pair_ws_bytes, out, st);
+    return dv3d_sparse_conv(feat, n_in, p.K / 27, km.nbr, n_out, p.W, p.Wp, p.N, p.a, p.b, residual, 1, sc.split_ws,
                             sc.split_ws_bytes, out, st);
 }
 
 // relu(x + GN2(conv2(relu(GN1(conv1(x))))))  (scenemodeling.py:16-44)
-static int res_block(const dv3d_dense_params_t (&p)[2], const float* x, long long n, const int* nbr, Scene& sc, Arena& ar,
+static int res_block(const dv3d_dense_params_t (&p)[2], const float* x, long long n, const KMap& nbr, Scene& sc, Arena& ar,
                      float** out, void* st) {
     const int C = p[0].N;
     float* h = ar.get<float>((size_t)n * C);
@@ -142,10 +161,22 @@ static int build_level(Level& L, int* err_flag, Arena& ar, void* st) {
     return dv3d_hash_build(L.coords, L.n, L.table, L.table_bytes, err_flag, st);
 }
 
-static int kernel_map(const Level& out_lv, const Level& in_lv, int step, Arena& ar, int** nbr, void* st) {
-    *nbr = ar.get<int>((size_t)out_lv.n * 27);
+// kernel map and, on the tensor-core path, its pair-major plan (counts are read back later, once)
+static int kernel_map(const Level& out_lv, const Level& in_lv, int step, bool want_plan, Arena& ar, KMap* km, void* st) {
+    km->n_out = out_lv.n;
+    km->nbr = ar.get<int>((size_t)out_lv.n * 27);
+    km->plan = nullptr;
+    km->n_tiles = 0;
+    km->use_pairs = false;
+    const size_t pb = want_plan ? dv3d_pair_plan_bytes(out_lv.n) : 0;
+    if (want_plan) km->plan = ar.get<char>(pb);
     ARENA_CHECK(ar);
-    return dv3d_kernel_map(out_lv.coords, out_lv.n, in_lv.table, in_lv.table_bytes, step, *nbr, st);
+    km->plan_bytes = pb;
+    km->out_lv = &out_lv;
+    km->in_lv = &in_lv;
+    km->step = step;
+    (void)st;  // the maps of a scene are filled by one batched launch (model_scene)
+    return DV3D_OK;
 }
 
 // voxelise -> PointNet -> sparse 3D-UNet on the feature-rich point cloud (lightningmodel.py:176-185)
@@ -231,21 +262,79 @@ static int model_scene(const dv3d_net_params_t& net, const float* pts, const flo
         TRY(build_level(sc.lv[l], err_flag, ar, st));
     }
 
-    // ---- sparse U-Net (scenemodeling.py:191-237); kernel maps are built where first needed,
-    // in the order the Python-composed path builds them
+    // every kernel map of the U-Net and its pair-major plan, then ONE sync for the counts
+    {
+        const bool want_plan = net.res_down[0][0][0].Wp != nullptr;
+        KMap* maps[3 * DV3D_MAX_LEVELS];
+        int n_maps = 0;
+        for (int l = 0; l < nl; ++l) {
+            TRY(kernel_map(sc.lv[l], sc.lv[l], sc.lv[l].stride, want_plan, ar, &sc.same[l], st));
+            maps[n_maps++] = &sc.same[l];
+        }
+        for (int l = 0; l + 1 < nl; ++l) {
+            TRY(kernel_map(sc.lv[l + 1], sc.lv[l], sc.lv[l].stride, want_plan, ar, &sc.down[l], st));
+            maps[n_maps++] = &sc.down[l];
+        }
+        for (int l = 0; l + 1 < nl; ++l) {
+            TRY(kernel_map(sc.lv[l], sc.lv[l + 1], -sc.lv[l].stride, want_plan, ar, &sc.up[l], st));
+            maps[n_maps++] = &sc.up[l];
+        }
+        {
+            const int* co[3 * DV3D_MAX_LEVELS];
+            long long no[3 * DV3D_MAX_LEVELS];
+            const void* tb[3 * DV3D_MAX_LEVELS];
+            size_t tbb[3 * DV3D_MAX_LEVELS];
+            int stp[3 * DV3D_MAX_LEVELS];
+            int* nb[3 * DV3D_MAX_LEVELS];
+            for (int i = 0; i < n_maps; ++i) {
+                co[i] = maps[i]->out_lv->coords;
+                no[i] = maps[i]->out_lv->n;
+                tb[i] = maps[i]->in_lv->table;
+                tbb[i] = maps[i]->in_lv->table_bytes;
+                stp[i] = maps[i]->step;
+                nb[i] = maps[i]->nbr;
+            }
+            TRY(dv3d_kernel_map_batch(co, no, tb, tbb, stp, nb, n_maps, st));
+        }
+        sc.pair_ws = nullptr;
+        sc.pair_ws_bytes = 0;
+        if (want_plan) {
+            const void* plans[3 * DV3D_MAX_LEVELS];
+            void* plans_w[3 * DV3D_MAX_LEVELS];
+            const int* nbrs[3 * DV3D_MAX_LEVELS];
+            long long n_outs[3 * DV3D_MAX_LEVELS], tiles[3 * DV3D_MAX_LEVELS];
+            size_t pbytes[3 * DV3D_MAX_LEVELS];
+            for (int i = 0; i < n_maps; ++i) {
+                plans[i] = plans_w[i] = maps[i]->plan;
+                nbrs[i] = maps[i]->nbr;
+                n_outs[i] = maps[i]->n_out;
+                pbytes[i] = maps[i]->plan_bytes;
+            }
+            TRY(dv3d_pair_plan_build(nbrs, n_outs, plans_w, pbytes, n_maps, st));
+            TRY(dv3d_pair_plan_counts(plans, n_maps, tiles, nullptr, st));
+            long long max_tiles = 0;
+            for (int i = 0; i < n_maps; ++i) {
+                maps[i]->n_tiles = tiles[i];
+                maps[i]->use_pairs = dv3d_sparse_conv_prefers_pairs(maps[i]->n_out, tiles[i]) != 0;
+                if (maps[i]->use_pairs && tiles[i] > max_tiles) max_tiles = tiles[i];
+            }
+            sc.pair_ws_bytes = dv3d_sparse_conv_pairs_workspace_bytes(max_tiles, 128);
+            sc.pair_ws = ar.get<char>(sc.pair_ws_bytes + 256);
+            ARENA_CHECK(ar);
+        }
+    }
+
+    // ---- sparse U-Net (scenemodeling.py:191-237)
     next_stage(DV3D_STAGE_UNET);
     float* xs[DV3D_MAX_LEVELS];
     float* x = F;
-    TRY(kernel_map(sc.lv[0], sc.lv[0], sc.lv[0].stride, ar, &sc.same[0], st));
     for (int b = 0; b < net.n_res[0]; ++b) TRY(res_block(net.res_down[0][b], x, sc.lv[0].n, sc.same[0], sc, ar, &x, st));
     xs[0] = x;
     for (int i = 1; i < nl; ++i) {
-        TRY(kernel_map(sc.lv[i], sc.lv[i - 1], sc.lv[i - 1].stride, ar, &sc.down[i - 1], st));
         float* y = ar.get<float>((size_t)sc.lv[i].n * net.down[i - 1].N);
         ARENA_CHECK(ar);
         TRY(sparse_conv(net.down[i - 1], x, sc.lv[i - 1].n, sc.down[i - 1], sc.lv[i].n, nullptr, sc, y, st));
         x = y;
-        TRY(kernel_map(sc.lv[i], sc.lv[i], sc.lv[i].stride, ar, &sc.same[i], st));
         for (int b = 0; b < net.n_res[i]; ++b) TRY(res_block(net.res_down[i][b], x, sc.lv[i].n, sc.same[i], sc, ar, &x, st));
         xs[i] = x;
     }
@@ -253,7 +342,6 @@ static int model_scene(const dv3d_net_params_t& net, const float* pts, const flo
     sc.dims[nl - 1] = net.res_down[nl - 1][0][0].N;
     for (int i = 0; i < nl - 1; ++i) {
         const int l = nl - 2 - i;  // target (finer) level
-        TRY(kernel_map(sc.lv[l], sc.lv[l + 1], -sc.lv[l].stride, ar, &sc.up[l], st));
         const int Cu = net.up[i].N;
         float* up = ar.get<float>((size_t)sc.lv[l].n * Cu);
         float* adj = ar.get<float>((size_t)sc.lv[l].n * net.feat_adj[i].N);
@@ -319,6 +407,9 @@ extern "C" size_t dv3d_hot_path_workspace_bytes(const dv3d_net_params_t* net, in
     per_outer += Np * (net->pointnet_in_pad + 3 * 128 + 64);      // PointNet
     // levels: coords 4, table <= 12 * 4 n + 768, kernel maps 27 x (3 same + 2 down + 2 up) per voxel
     per_outer += Np * 3 * (4 + 12) + Np * 27 * 7 + 3 * 1024;
+    // pair-major plans (7 maps: pair_in <= 27 n + 27*128, pair_slot 27 n, tile ids) and the P buffer of
+    // the largest map that takes the pair path (at most 0.6 * 27 * n rows of 128 channels)
+    per_outer += 7 * (Np * 27 * 2 + Np * 27 / 128 + 27 * 130 + 256) + (Np * 27 * 6 / 10 + 27 * 128) * 128;
     // U-Net features: 2 outputs per residual block + down / up / adj, at most 128 channels each
     int blocks = 0;
     for (int l = 0; l < net->n_levels; ++l) blocks += net->n_res[l] * (l == net->n_levels - 1 ? 1 : 2);

@@ -37,6 +37,9 @@ struct GemmDesc {
     const float* W;         // [sum_s K_s, N] row-major (fp32 CUDA-core kernel)
     const float* Wp;        // packed by dv3d_gemm_pack_weights: selects the tcgen05 kernel when set
     const int* kmap;        // set when every slice s gathers through kmap[m * n_slices + s]
+    const int* tile_wslice; // tcgen05 kernel, n_slices == 1: 128-row tile t contracts with the weight block
+                            // W[tile_wslice[t] * K : (tile_wslice[t] + 1) * K, :] (pair-major sparse convolution)
+    const int* m_tiles_dev; // optional device count of live 128-row tiles: CTAs beyond it exit at once
     const float* scale;     // per-channel multiplier (folded BN) or nullptr
     const float* shift;     // per-channel addend (bias / folded BN) or nullptr
     const float* gn_weight; // GroupNorm affine (groups of 16 channels) or nullptr
@@ -53,6 +56,47 @@ struct GemmDesc {
     float* out;             // [M, out_ld]
     int out_ld;
 };
+
+// Epilogue of one 16-byte unit (4 channels c0..c0+3 of output row m).  The 4 lanes that hold
+// the 16 channels of a GroupNorm group are consecutive and aligned, so the group statistics are
+// two xor-shuffles; every lane of the warp must call this (live = false rows only skip the store).
+__device__ __forceinline__ void epilogue4(const GemmDesc& d, float4 y, long long m, int c0, bool live, bool zero_row) {
+    if (d.scale) {
+        const float4 s = __ldg(reinterpret_cast<const float4*>(d.scale + c0));
+        y.x *= s.x; y.y *= s.y; y.z *= s.z; y.w *= s.w;
+    }
+    if (d.shift) {
+        const float4 s = __ldg(reinterpret_cast<const float4*>(d.shift + c0));
+        y.x += s.x; y.y += s.y; y.z += s.z; y.w += s.w;
+    }
+    if (d.gn_weight) {
+        float sum = (y.x + y.y) + (y.z + y.w);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+        const float mean = sum * (1.f / 16.f);
+        const float dx = y.x - mean, dy = y.y - mean, dz = y.z - mean, dw = y.w - mean;
+        float q = fmaf(dx, dx, dy * dy) + fmaf(dz, dz, dw * dw);
+        q += __shfl_xor_sync(0xffffffffu, q, 1);
+        q += __shfl_xor_sync(0xffffffffu, q, 2);
+        const float rstd = 1.f / sqrtf(q * (1.f / 16.f) + 1e-5f);
+        const float4 gw = __ldg(reinterpret_cast<const float4*>(d.gn_weight + c0));
+        const float4 gb = __ldg(reinterpret_cast<const float4*>(d.gn_bias + c0));
+        y.x = fmaf(dx * rstd, gw.x, gb.x);
+        y.y = fmaf(dy * rstd, gw.y, gb.y);
+        y.z = fmaf(dz * rstd, gw.z, gb.z);
+        y.w = fmaf(dw * rstd, gw.w, gb.w);
+    }
+    if (!live) return;
+    if (d.residual) {
+        const float4 rv = __ldg(reinterpret_cast<const float4*>(d.residual + (size_t)m * d.res_ld + c0));
+        y.x += rv.x; y.y += rv.y; y.z += rv.z; y.w += rv.w;
+    }
+    if (d.relu_out) {
+        y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f);
+    }
+    if (zero_row) y = make_float4(0.f, 0.f, 0.f, 0.f);
+    *reinterpret_cast<float4*>(d.out + (size_t)m * d.out_ld + c0) = y;
+}
 
 // d.Wp == nullptr: fp32 CUDA-core kernel (gemm.cu); otherwise the tcgen05 kernel (gemm_tc.cu),
 // 3xTF32 or TF32 according to dv3d_set_gemm_precision.

@@ -193,47 +193,6 @@ __device__ __forceinline__ void cursor_load(const ChunkCursor& c, float4 (&v)[4]
         v[i] = c.src[i] ? __ldg(reinterpret_cast<const float4*>(c.src[i] + c.kc * TC_KC)) : make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
-// Epilogue of one 16-byte unit (4 channels c0..c0+3 of output row m).  The 4 lanes that hold
-// the 16 channels of a GroupNorm group are consecutive and aligned, so the group statistics are
-// two xor-shuffles; every lane of the warp must call this (live = false rows only skip the store).
-__device__ __forceinline__ void epilogue4(const GemmDesc& d, float4 y, long long m, int c0, bool live, bool zero_row) {
-    if (d.scale) {
-        const float4 s = __ldg(reinterpret_cast<const float4*>(d.scale + c0));
-        y.x *= s.x; y.y *= s.y; y.z *= s.z; y.w *= s.w;
-    }
-    if (d.shift) {
-        const float4 s = __ldg(reinterpret_cast<const float4*>(d.shift + c0));
-        y.x += s.x; y.y += s.y; y.z += s.z; y.w += s.w;
-    }
-    if (d.gn_weight) {
-        float sum = (y.x + y.y) + (y.z + y.w);
-        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-        const float mean = sum * (1.f / 16.f);
-        const float dx = y.x - mean, dy = y.y - mean, dz = y.z - mean, dw = y.w - mean;
-        float q = fmaf(dx, dx, dy * dy) + fmaf(dz, dz, dw * dw);
-        q += __shfl_xor_sync(0xffffffffu, q, 1);
-        q += __shfl_xor_sync(0xffffffffu, q, 2);
-        const float rstd = 1.f / sqrtf(q * (1.f / 16.f) + 1e-5f);
-        const float4 gw = __ldg(reinterpret_cast<const float4*>(d.gn_weight + c0));
-        const float4 gb = __ldg(reinterpret_cast<const float4*>(d.gn_bias + c0));
-        y.x = fmaf(dx * rstd, gw.x, gb.x);
-        y.y = fmaf(dy * rstd, gw.y, gb.y);
-        y.z = fmaf(dz * rstd, gw.z, gb.z);
-        y.w = fmaf(dw * rstd, gw.w, gb.w);
-    }
-    if (!live) return;
-    if (d.residual) {
-        const float4 rv = __ldg(reinterpret_cast<const float4*>(d.residual + (size_t)m * d.res_ld + c0));
-        y.x += rv.x; y.y += rv.y; y.z += rv.z; y.w += rv.w;
-    }
-    if (d.relu_out) {
-        y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f);
-    }
-    if (zero_row) y = make_float4(0.f, 0.f, 0.f, 0.f);
-    *reinterpret_cast<float4*>(d.out + (size_t)m * d.out_ld + c0) = y;
-}
-
 // advance (s, kc, wchunk) over the live slices of a split range
 struct ChunkWalk {
     int s, kc, nk, wchunk;
@@ -252,7 +211,12 @@ __device__ __forceinline__ void walk_enter(ChunkWalk& c, const GemmDesc& d, int 
 // that arrives last adds the partials in split order (deterministic) and runs the epilogue.
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-gather_gemm_tc_kernel(const __grid_constant__ GemmDesc d, int precision) {
+gather_gemm_tc_kernel(const __grid_constant__ GemmDesc d, int precision_and_flags) {
+    // bits 8.. of the precision word are TIMING EXPERIMENT switches (tools/bench_gemm.py): they
+    // remove one pipeline stage's work at a time and make the result meaningless
+    const int precision = precision_and_flags & 0xff;
+    const bool dbg_no_a_store = (precision_and_flags >> 8) & 1, dbg_no_a_load = (precision_and_flags >> 9) & 1,
+               dbg_no_b_copy = (precision_and_flags >> 10) & 1, dbg_no_mma = (precision_and_flags >> 11) & 1;
     const float* __restrict__ Wp = d.Wp;
     extern __shared__ unsigned char smem_raw[];
     // SWIZZLE_128B operands need 1024-byte alignment
@@ -267,6 +231,7 @@ gather_gemm_tc_kernel(const __grid_constant__ GemmDesc d, int precision) {
     float* s_tile = reinterpret_cast<float*>(smem);                                 // reuses the stages after the last MMA
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (d.m_tiles_dev && (int)blockIdx.x >= __ldg(d.m_tiles_dev)) return;  // uniform per CTA
     const long long m0 = (long long)blockIdx.x * TC_BM;
     const uint32_t bar_full = smem_u32(s_bar), bar_empty = smem_u32(s_bar + TC_STAGES),
                    bar_accum = smem_u32(s_bar + 2 * TC_STAGES);
@@ -344,6 +309,10 @@ gather_gemm_tc_kernel(const __grid_constant__ GemmDesc d, int precision) {
             const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
             mbar_wait(bar_empty + 8 * st, ph ^ 1u);
             unsigned char* stage = smem + st * STAGE;
+            if (dbg_no_a_store) {
+                mbar_arrive(bar_full + 8 * st);
+                return;
+            }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 float4 a = v[i];
@@ -370,7 +339,7 @@ gather_gemm_tc_kernel(const __grid_constant__ GemmDesc d, int precision) {
                 if (it < n_it) {
                     store_chunk(it, buf[p]);
                     if (it + TC_PREFETCH < n_it) {
-                        cursor_load(ld, buf[p]);
+                        if (!dbg_no_a_load) cursor_load(ld, buf[p]);
                         cursor_next(ld, d, s_end, active, s_rows, r0, j);
                     }
                 }
@@ -391,6 +360,7 @@ gather_gemm_tc_kernel(const __grid_constant__ GemmDesc d, int precision) {
 #pragma unroll
                 for (int kk = 0; kk < TC_KC / 8; ++kk) {
                     const uint32_t ko = kk * 32;  // 8 tf32 = 32 bytes inside the swizzle row
+                    if (dbg_no_mma) continue;
                     if (precision == 1) {
                         umma_tf32(tmem_base, umma_desc_sw128(a_small + ko), umma_desc_sw128(b_big + ko), idesc, acc);
                         acc = 1;
@@ -409,13 +379,22 @@ gather_gemm_tc_kernel(const __grid_constant__ GemmDesc d, int precision) {
             // ===================== weight copies: one bulk copy per chunk as soon as its stage is free
             ChunkWalk w;
             w.s = s_begin;
-            w.wchunk = 0;
+            w.wchunk = d.tile_wslice ? __ldg(d.tile_wslice + blockIdx.x) * (d.slice[0].K / TC_KC) : 0;
             for (int s = 0; s < s_begin; ++s) w.wchunk += d.slice[s].K / TC_KC;
             walk_enter(w, d, s_end, active);
             for (int it = 0; it < n_it; ++it) {
                 const int st = it % TC_STAGES;
                 const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
                 mbar_wait(bar_empty + 8 * st, ph ^ 1u);
+                if (dbg_no_b_copy) {
+                    mbar_arrive(bar_full + 8 * st);
+                    ++w.wchunk;
+                    if (++w.kc == w.nk) {
+                        ++w.s;
+                        walk_enter(w, d, s_end, active);
+                    }
+                    continue;
+                }
                 mbar_arrive_expect_tx(bar_full + 8 * st, 2 * B_IMG);
                 bulk_g2s(smem_u32(smem + st * STAGE + 2 * TC_A_BYTES), Wp + (size_t)w.wchunk * (2 * BN * 32), 2 * B_IMG,
                          bar_full + 8 * st);
@@ -515,11 +494,12 @@ int launch_gather_gemm_tc(const GemmDesc& d, cudaStream_t st) {
     int rc = validate_gather_gemm(d, TC_KC);
     if (rc) return rc;
     DV3D_REQUIRE(Wp && ((uintptr_t)Wp & 15) == 0, "gather_gemm_tc: packed weights must be 16-byte aligned");
+    DV3D_REQUIRE(!d.tile_wslice || (d.n_slices == 1 && !d.kmap), "gather_gemm_tc: tile_wslice needs exactly one slice");
     DV3D_REQUIRE(d.out_ld % 4 == 0 && ((uintptr_t)d.out & 15) == 0, "gather_gemm_tc: output must be 16-byte aligned");
     if (d.M == 0) return DV3D_OK;
     const int tiles = cdiv(d.M, TC_BM);
     int split = 1;
-    if (d.split_ws && d.split_counters) {
+    if (d.split_ws && d.split_counters && !d.tile_wslice) {
         split = gather_gemm_tc_splits(d.M, d.n_slices);
         const size_t need = (size_t)tiles * split * TC_BM * d.N * sizeof(float);
         if (d.split_ws_bytes < need) split = 1;  // tiles * split <= 148 partials fit a dv3d_sparse_conv_workspace_bytes buffer
@@ -564,7 +544,8 @@ extern "C" int dv3d_gemm_pack_weights(const float* W, int Ktot, int N, void* pac
 }
 
 extern "C" int dv3d_set_gemm_precision(int mode) {
-    DV3D_REQUIRE(mode == 1 || mode == 2, "set_gemm_precision: 1 = 3xTF32 (fp32-grade), 2 = TF32; got %d", mode);
+    DV3D_REQUIRE((mode & 0xff) == 1 || (mode & 0xff) == 2, "set_gemm_precision: 1 = 3xTF32 (fp32-grade), 2 = TF32; got %d",
+                 mode);  // bits 8..11: timing-experiment switches, see gather_gemm_tc_kernel
     g_gemm_precision = mode;
     return DV3D_OK;
 }

@@ -53,6 +53,31 @@ kernel_map_kernel(const int* __restrict__ coords_out, long long n_out, HashView 
     nbr[i] = coord_in_range(b, x, y, z) ? hash_find(t, coord_key(b, x, y, z)) : -1;
 }
 
+// all kernel maps of a scene in one launch: blockIdx.y selects the map
+constexpr int KM_MAX_MAPS = 16;
+struct KernelMapBatch {
+    const int* coords_out[KM_MAX_MAPS];
+    long long n_out[KM_MAX_MAPS];
+    HashView table[KM_MAX_MAPS];
+    int step[KM_MAX_MAPS];
+    int* nbr[KM_MAX_MAPS];
+};
+__global__ void __launch_bounds__(256)
+kernel_map_batch_kernel(const __grid_constant__ KernelMapBatch b) {
+    const int j = blockIdx.y;
+    const long long n_out = b.n_out[j];
+    const int* __restrict__ coords_out = b.coords_out[j];
+    const int step = b.step[j];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_out * 27; i += (long long)gridDim.x * blockDim.x) {
+        long long o = i / 27;
+        int k = (int)(i - o * 27);
+        int dx = k % 3 - 1, dy = (k / 3) % 3 - 1, dz = k / 9 - 1;
+        int bb = coords_out[4 * o], x = coords_out[4 * o + 1] + dx * step, y = coords_out[4 * o + 2] + dy * step,
+            z = coords_out[4 * o + 3] + dz * step;
+        b.nbr[j][i] = coord_in_range(bb, x, y, z) ? hash_find(b.table[j], coord_key(bb, x, y, z)) : -1;
+    }
+}
+
 // One warp per query point.  q = ((p - origin[b]) / res) * stride in base-voxel units
 // (refinement.py:34-35); lanes 0..7 probe the 8 corners, all lanes accumulate C channels.
 template <int C>
@@ -148,6 +173,29 @@ extern "C" int dv3d_kernel_map(const int* coords_out, long long n_out, const voi
 // K-split workspace: a fixed counter block (splitting only happens below 148 row tiles), then
 // room for one raw partial per resident CTA
 constexpr size_t kSplitCounterBytes = 4096;
+
+extern "C" int dv3d_kernel_map_batch(const int* const* coords_out, const long long* n_out, const void* const* table_in,
+                                     const size_t* table_bytes, const int* step, int* const* nbr, int n_maps, void* stream) {
+    DV3D_REQUIRE(coords_out && n_out && table_in && table_bytes && step && nbr && n_maps >= 0 && n_maps <= KM_MAX_MAPS,
+                 "kernel_map_batch: bad arguments (at most %d maps per call)", KM_MAX_MAPS);
+    KernelMapBatch b = {};
+    long long max_n = 0;
+    for (int i = 0; i < n_maps; ++i) {
+        DV3D_REQUIRE(coords_out[i] && table_in[i] && nbr[i] && n_out[i] >= 0, "kernel_map_batch: bad map %d", i);
+        DV3D_REQUIRE(hash_view(const_cast<void*>(table_in[i]), table_bytes[i], &b.table[i]), "kernel_map_batch: bad table size");
+        b.coords_out[i] = coords_out[i];
+        b.n_out[i] = n_out[i];
+        b.step[i] = step[i];
+        b.nbr[i] = nbr[i];
+        if (n_out[i] > max_n) max_n = n_out[i];
+    }
+    if (n_maps == 0 || max_n == 0) return DV3D_OK;
+    int gx = cdiv(max_n * 27, 256);
+    if (gx > 8 * kNumSMs) gx = 8 * kNumSMs;
+    kernel_map_batch_kernel<<<dim3(gx, n_maps), 256, 0, (cudaStream_t)stream>>>(b);
+    DV3D_LAUNCHED();
+    return DV3D_OK;
+}
 
 extern "C" size_t dv3d_sparse_conv_workspace_bytes(int Cout) {
     if (Cout <= 0) return 0;

@@ -139,6 +139,11 @@ class SparseScene(object):
             self.levels.append(ops.coarsen(self.levels[-1], dims, n_batch, self.err))
         # K-split workspace of the tensor-core sparse convolution, shared by all layers
         self.ws = ops.sparse_conv_workspace(128, dev)
+        # every kernel map of the U-Net and its pair-major plan, then one sync for the counts
+        n = len(self.levels)
+        maps = [self.same(l) for l in range(n)] + [self.down(l) for l in range(n - 1)] + [self.up(l) for l in range(n - 1)]
+        ops.build_plans(maps)
+        ops.finish_plans(maps)
 
     def same(self, l):       # k3 s1 on level l
         lv = self.levels[l]

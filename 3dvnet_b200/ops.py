@@ -274,15 +274,70 @@ class SparseLevel(object):
         self._maps = {}
 
     def kernel_map(self, in_level, step):
-        """nbr [n,27] int32: rows of in_level at coords + offset_k * step."""
+        """KernelMap of this level's rows onto in_level at coords + offset_k * step."""
         key = (id(in_level), step)
         m = self._maps.get(key)
         if m is None:
-            m = torch.empty((self.n, 27), dtype=torch.int32, device=self.coords.device)
+            nbr = torch.empty((self.n, 27), dtype=torch.int32, device=self.coords.device)
             lib().call('dv3d_kernel_map', _p(self.coords), self.n, _p(in_level.table), in_level.table_bytes, step,
-                       _p(m), _stream())
-            self._maps[key] = m
+                       _p(nbr), _stream())
+            m = self._maps[key] = KernelMap(nbr)
         return m
+
+
+class KernelMap(object):
+    """nbr [n_out,27] int32 (-1 = absent) plus, for the tensor-core path, the pair-major plan of
+    csrc/sparse_pairs.cu and the library's choice between the two sparse-convolution variants."""
+
+    def __init__(self, nbr):
+        self.nbr = nbr
+        self.n_out = nbr.shape[0]
+        self.plan = None
+        self.n_tiles = self.n_pairs = 0
+        self.use_pairs = False
+        self._P = None
+
+    def build_plan(self):
+        build_plans([self])
+        return self
+
+    def workspace(self, Cout):
+        need = lib().raw('dv3d_sparse_conv_pairs_workspace_bytes')(self.n_tiles, Cout)
+        if self._P is None or self._P.numel() < need:
+            self._P = torch.empty(max(need, 16), dtype=torch.uint8, device=self.nbr.device)
+        return self._P
+
+
+def build_plans(maps):
+    """enqueue the plan kernels of several KernelMaps (two launches per 16 maps, no sync);
+    finish_plans() reads the counts back"""
+    if gemm_mode() == 'f32':
+        return
+    todo = [m for m in maps if m.plan is None]
+    for i in range(0, len(todo), 16):
+        grp = todo[i:i + 16]
+        n = len(grp)
+        sizes = [lib().raw('dv3d_pair_plan_bytes')(m.n_out) for m in grp]
+        for m, nb in zip(grp, sizes):
+            m.plan = torch.empty(nb, dtype=torch.uint8, device=m.nbr.device)
+        lib().call('dv3d_pair_plan_build', (ctypes.c_void_p * n)(*[m.nbr.data_ptr() for m in grp]),
+                   (ctypes.c_longlong * n)(*[m.n_out for m in grp]),
+                   (ctypes.c_void_p * n)(*[m.plan.data_ptr() for m in grp]), (ctypes.c_size_t * n)(*sizes), n, _stream())
+
+
+def finish_plans(maps):
+    """one sync for the tile / pair counts of several KernelMaps"""
+    maps = [m for m in maps if m.plan is not None]
+    if not maps:
+        return
+    n = len(maps)
+    ptrs = (ctypes.c_void_p * n)(*[m.plan.data_ptr() for m in maps])
+    tiles = (ctypes.c_longlong * n)()
+    pairs = (ctypes.c_longlong * n)()
+    lib().call('dv3d_pair_plan_counts', ptrs, n, tiles, pairs, _stream())
+    for i, m in enumerate(maps):
+        m.n_tiles, m.n_pairs = int(tiles[i]), int(pairs[i])
+        m.use_pairs = bool(lib().raw('dv3d_sparse_conv_prefers_pairs')(m.n_out, m.n_tiles))
 
 
 def make_coords(idx3d, batch):
@@ -313,10 +368,19 @@ def sparse_conv_workspace(Cout, device):
 
 
 def sparse_conv(feat, nbr, W, gn_weight=None, gn_bias=None, residual=None, relu=False, packed=None, workspace=None):
+    """nbr: [n_out,27] int32 tensor, or a KernelMap (which may route to the pair-major variant)"""
     n_in, Cin = feat.shape
-    n_out = nbr.shape[0]
     Cout = W.shape[2]
     assert W.shape[0] == 27 and W.shape[1] == Cin
+    if isinstance(nbr, KernelMap):
+        km, nbr = nbr, nbr.nbr
+        if km.use_pairs and packed is not None:
+            out = torch.empty((km.n_out, Cout), dtype=torch.float32, device=feat.device)
+            P = km.workspace(Cout)
+            lib().call('dv3d_sparse_conv_pairs', _p(feat), n_in, Cin, _p(km.plan), km.n_tiles, km.n_out, _p(packed), Cout,
+                       _p(gn_weight), _p(gn_bias), _p(residual), int(relu), _p(P), P.numel(), _p(out), _stream())
+            return out
+    n_out = nbr.shape[0]
     out = torch.empty((n_out, Cout), dtype=torch.float32, device=feat.device)
     ws_bytes = 0 if workspace is None else workspace.numel()
     lib().call('dv3d_sparse_conv', _p(feat), n_in, Cin, _p(nbr), n_out, _p(W), _p(packed), Cout, _p(gn_weight),

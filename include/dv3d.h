@@ -200,6 +200,9 @@ int dv3d_coarsen(const int* coords, long long n, int new_stride, int dim_x, int 
  * (fine_j = coarse_i + offset_k*ts_fine, same W[k], no flip). */
 int dv3d_kernel_map(const int* coords_out, long long n_out, const void* table_in, size_t table_bytes, int step,
                     int* nbr, void* stream);
+/* up to 16 kernel maps (all the maps of a scene) with one launch; HOST arrays of device pointers / sizes */
+int dv3d_kernel_map_batch(const int* const* coords_out, const long long* n_out, const void* const* table_in,
+                          const size_t* table_bytes, const int* step, int* const* nbr, int n_maps, void* stream);
 /* out[o] = sum_k feat[nbr[o,k]] @ W[k]   (W [27,Cin,Cout], ME layout); optional fused per-row
  * GroupNorm (gn_weight/gn_bias [Cout], 16 channels per group, eps 1e-5), optional residual
  * add (before the ReLU) and ReLU — the SparseResidual3d / down / up blocks.  Cin % 16 == 0
@@ -214,6 +217,29 @@ int dv3d_sparse_conv(const float* feat, long long n_in, int Cin, const int* nbr,
                      const void* W_packed, int Cout, const float* gn_weight, const float* gn_bias,
                      const float* residual, int relu, void* workspace, size_t workspace_bytes, float* out,
                      void* stream);
+/* Pair-major variant for SPARSELY connected levels (csrc/sparse_pairs.cu): the rows of the GEMM
+ * are the existing (output row, offset) pairs grouped by offset - what MinkowskiEngine's in/out
+ * kernel maps are - so no tensor-core work is spent on absent neighbours:
+ *   plan    built once per kernel map (no sync; the maps of a scene in one call): pairs of every offset in ascending output row,
+ *           padded to 128-row tiles;
+ *   GEMM    P[slot,:] = feat[in_row(slot),:] @ W[offset(tile)]  (tcgen05 kernel, weight block per tile);
+ *   reduce  out[m,:] = epilogue(sum over offsets ascending of P[slot(m,k),:]) - fixed order, bit-reproducible.
+ * dv3d_pair_plan_counts reads the tile / pair counts of several plans back with ONE sync;
+ * dv3d_sparse_conv_prefers_pairs is the library's choice between the two variants (callers that
+ * must agree bit for bit - the engine and the composed path - both ask it). */
+size_t dv3d_pair_plan_bytes(long long n_out);
+/* plans n_maps (<= 16) kernel maps with two launches; arrays are HOST arrays of device pointers / sizes */
+int dv3d_pair_plan_build(const int* const* nbrs, const long long* n_outs, void* const* plans, const size_t* plan_bytes,
+                         int n_maps, void* stream);
+int dv3d_pair_plan_counts(const void* const* plans, int n_plans, long long* n_tiles_host, long long* n_pairs_host,
+                          void* stream);
+int dv3d_sparse_conv_prefers_pairs(long long n_out, long long n_tiles);
+size_t dv3d_sparse_conv_pairs_workspace_bytes(long long n_tiles, int Cout);
+/* W_packed: dv3d_gemm_pack_weights image of W [27*Cin, Cout] (required: tensor-core path only) */
+int dv3d_sparse_conv_pairs(const float* feat, long long n_in, int Cin, const void* plan, long long n_tiles,
+                           long long n_out, const void* W_packed, int Cout, const float* gn_weight,
+                           const float* gn_bias, const float* residual, int relu, void* workspace,
+                           size_t workspace_bytes, float* out, void* stream);
 /* 1x1 "feature adjust" on the concatenation [a | b] (ME.cat + k=1 conv, scenemodeling.py:206)
  * followed by GroupNorm + ReLU: W [Ca+Cb, Cout]. */
 int dv3d_concat_linear_gn_relu(const float* a, int Ca, const float* b, int Cb, long long n, const float* W,

@@ -151,3 +151,50 @@ def test_tc_matches_f32_kernel_bitwise_shape_and_close(ops):
     ops.set_gemm_mode('f32')
     y_f32 = ops.linear(x, w, b, relu_input=False, packed=None)
     assert (y_tc - y_f32).abs().max().item() < 2e-5 * y_f32.abs().max().item()
+
+
+@pytest.mark.parametrize('mode', ['tf32x3', 'tf32'])
+@pytest.mark.parametrize('n_in,n_out,Cin,Cout,density', [(3134, 3134, 64, 64, 0.045), (3045, 3045, 128, 128, 0.10),
+                                                         (2408, 2408, 128, 128, 0.38), (900, 3000, 128, 64, 0.2),
+                                                         (3000, 700, 64, 128, 0.3), (100, 100, 64, 64, 0.0),
+                                                         (40000, 40000, 128, 128, 0.05)])
+def test_sparse_conv_pair_major(ops, mode, n_in, n_out, Cin, Cout, density):
+    """pair-major sparse convolution (csrc/sparse_pairs.cu: plan -> gather-GEMM on existing pairs
+    -> ordered reduce + epilogue) against the float64 restatement and the output-stationary kernel"""
+    ops.set_gemm_mode(mode)
+    g = torch.Generator().manual_seed(n_in + 7 * n_out)
+    nbr = torch.randint(0, n_in, (n_out, 27), generator=g)
+    nbr[torch.rand(n_out, 27, generator=g) >= density] = -1
+    if n_out >= 512:
+        nbr[300:420] = -1          # rows with no neighbour at all
+        nbr[:, 5] = -1             # an offset with no pair at all
+    nbr = nbr.int().to(DEV)
+    feat = rnd(n_in, Cin, seed=31)
+    W = rnd(27, Cin, Cout, seed=32, scale=(9 * Cin) ** -0.5)
+    gw, gb = rnd(Cout, seed=33) * 0.3 + 1.0, rnd(Cout, seed=34) * 0.1
+    residual = rnd(n_out, Cout, seed=35) if Cin == Cout and n_in == n_out else None
+    packed = ops.pack_weights(W.reshape(-1, Cout).contiguous())
+    km = ops.KernelMap(nbr).build_plan()
+    ops.finish_plans([km])
+    live = (nbr >= 0)
+    assert km.n_pairs == int(live.sum())
+    assert km.n_tiles == int(((live.sum(0) + 127) // 128).sum())
+    km.use_pairs = True   # force the variant under test whatever the library would choose
+    y = ops.sparse_conv(feat, km, W, gw, gb, residual, True, packed=packed)
+    ref = sparse_ref(feat, nbr, W, gw, gb, residual, True)
+    check(y, ref, mode)
+    y_again = ops.sparse_conv(feat, km, W, gw, gb, residual, True, packed=packed)
+    assert torch.equal(y, y_again)     # fixed summation order: bit-reproducible
+    y_dense = ops.sparse_conv(feat, nbr, W, gw, gb, residual, True, packed=packed)
+    check(y, y_dense.double(), mode)
+    # raw contraction, no epilogue
+    y2 = ops.sparse_conv(feat, km, W, None, None, None, False, packed=packed)
+    check(y2, sparse_ref(feat, nbr, W, None, None, None, False), mode)
+
+
+def test_pair_major_choice_is_a_pure_function_of_counts(ops):
+    L = importlib.import_module('3dvnet_b200._lib').lib()
+    f = L.raw('dv3d_sparse_conv_prefers_pairs')
+    assert f(3134, 51) == 1 and f(2408, 203) == 1     # C2 levels 0 and 2 (SURVEY sizes)
+    assert f(9765, 1459) == 0                          # dense level of an 8-view scene
+    assert f(100, 0) == 0
