@@ -35,6 +35,34 @@ void count_launch(int n = 1);
         DV3D_CUDA(cudaGetLastError());       \
     } while (0)
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// The hot path is a chain of ~250 short dependent kernels per reference view.  Every kernel is
+// launched with cudaLaunchAttributeProgrammaticStreamSerialization and starts with
+// griddepcontrol.wait: the next launch is set up and its CTAs scheduled while the previous
+// kernel drains, and the wait returns once that kernel has completed and flushed its writes.
+// DV3D_PDL=0 in the environment launches without the attribute (A/B measurements).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+// kernel names with template commas are passed in parentheses
+#define DV3D_LAUNCH(kernel, grid, block, smem, stream, ...) \
+    (void)dv3d::launch_pdl(kernel, grid, block, smem, stream, __VA_ARGS__)
+
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 

@@ -41,6 +41,7 @@ __global__ void __launch_bounds__(s1_threads(TZ), 2)
 conv3d_s1_tiled_kernel(const float* __restrict__ x, int Cin, int D, int H, int W, const float* __restrict__ wgt,
                        const float* __restrict__ scale, const float* __restrict__ shift, int Cout,
                        const float* __restrict__ skip, float* __restrict__ y, int tiles_x, int tiles_y) {
+    pdl_wait();
     constexpr int IZ = TZ + 2;
     constexpr int S1_THREADS = s1_threads(TZ);
     constexpr int IN_F = CIC * IZ * IY * IXP, W_F = CIC * 27 * COT;  // floats per buffer
@@ -223,6 +224,7 @@ conv3d_direct_kernel(const float* __restrict__ x, int Cin, int Di, int Hi, int W
                      const float* __restrict__ scale, const float* __restrict__ shift, int Cout, int Do, int Ho,
                      int Wo, const float* __restrict__ skip, float* __restrict__ y, long long n_vox_total,
                      int n_slices) {
+    pdl_wait();
     extern __shared__ __align__(16) float smem[];
     float* s_w = smem;                      // [Cin][27][CO_T]
     float* s_red = smem + Cin * 27 * CO_T;  // [n_slices][CO_T][vox]
@@ -333,6 +335,7 @@ __global__ void __launch_bounds__(DC_THREADS, 2)
 deconv3d_block_kernel(const float* __restrict__ x, int Cin, int Di, int Hi, int Wi, const float* __restrict__ wgt,
                       const float* __restrict__ scale, const float* __restrict__ shift, int Cout,
                       const float* __restrict__ skip, float* __restrict__ y, long long n_vox_total, int n_slices) {
+    pdl_wait();
     extern __shared__ __align__(16) float smem[];
     float* s_w = smem;                      // [Cin][27][CO_T]
     float* s_red = smem + Cin * 27 * CO_T;  // [n_slices][CO_T][vox] per output parity
@@ -446,6 +449,7 @@ constexpr int PS_TX = 8, PS_DL = 32;
 __global__ void __launch_bounds__(PS_TX * PS_DL)
 prob_softargmin_kernel(const float* __restrict__ x, int Cin, int D, int H, int W, const float* __restrict__ wgt,
                        float bias, float d_start, float d_end, float* __restrict__ x_reg, float* __restrict__ depth) {
+    pdl_wait();
     extern __shared__ float s_w[];  // [27][Cin]
     __shared__ float s_m[PS_DL][PS_TX], s_s[PS_DL][PS_TX], s_t[PS_DL][PS_TX];
     for (int i = threadIdx.x; i < Cin * 27; i += blockDim.x) s_w[(i % 27) * Cin + i / 27] = __ldg(wgt + i);
@@ -538,8 +542,7 @@ static int launch_direct(const float* x, int n, int Cin, int Di, int Hi, int Wi,
     }
     dim3 grid(cdiv(total, DC_THREADS / ns), cogs);
     DV3D_REQUIRE(grid.y <= 65535, "conv3d: too many channel groups");
-    conv3d_direct_kernel<STRIDE, CO_T><<<grid, DC_THREADS, smem, st>>>(x, Cin, Di, Hi, Wi, w, scale, shift, Cout, Do, Ho,
-                                                                     Wo, skip, y, total, ns);
+    DV3D_LAUNCH((conv3d_direct_kernel<STRIDE, CO_T>), grid, DC_THREADS, smem, st, x, Cin, Di, Hi, Wi, w, scale, shift, Cout, Do, Ho, Wo, skip, y, total, ns);
     DV3D_LAUNCHED();
     return DV3D_OK;
 }
@@ -571,7 +574,7 @@ static int launch_deconv(const float* x, int n, int Cin, int Di, int Hi, int Wi,
     }
     dim3 grid(cdiv(total, DC_THREADS / ns), cogs);
     DV3D_REQUIRE(grid.y <= 65535, "deconv3d: too many channel groups");
-    deconv3d_block_kernel<CO_T><<<grid, DC_THREADS, smem, st>>>(x, Cin, Di, Hi, Wi, w, scale, shift, Cout, skip, y, total, ns);
+    DV3D_LAUNCH((deconv3d_block_kernel<CO_T>), grid, DC_THREADS, smem, st, x, Cin, Di, Hi, Wi, w, scale, shift, Cout, skip, y, total, ns);
     DV3D_LAUNCHED();
     return DV3D_OK;
 }
@@ -588,8 +591,7 @@ static int launch_s1_tiled(const float* x, int n, int Cin, int D, int H, int W, 
     const int tiles_x = cdiv(W, TX), tiles_y = cdiv(H, TY);
     dim3 grid(tiles_x * tiles_y, cdiv(D, TZ), n * (Cout / COT));
     DV3D_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "conv3d: grid too large");
-    conv3d_s1_tiled_kernel<TZ><<<grid, s1_threads(TZ), s1_smem(TZ), st>>>(x, Cin, D, H, W, weight, scale, shift, Cout,
-                                                                        skip, y, tiles_x, tiles_y);
+    DV3D_LAUNCH((conv3d_s1_tiled_kernel<TZ>), grid, s1_threads(TZ), s1_smem(TZ), st, x, Cin, D, H, W, weight, scale, shift, Cout, skip, y, tiles_x, tiles_y);
     DV3D_LAUNCHED();
     return DV3D_OK;
 }
@@ -641,8 +643,7 @@ extern "C" int dv3d_prob_softargmin(const float* x, int n, int Cin, int D, int H
     if (n == 0) return DV3D_OK;
     DV3D_REQUIRE(H <= 65535 && n <= 65535, "prob_softargmin: H or n > 65535");
     dim3 grid(cdiv(W, PS_TX), H, n);
-    prob_softargmin_kernel<<<grid, PS_TX * PS_DL, sizeof(float) * Cin * 27, (cudaStream_t)stream>>>(
-        x, Cin, D, H, W, weight, bias, depth_start, depth_end, x_reg_out, depth_out);
+    DV3D_LAUNCH((prob_softargmin_kernel), grid, PS_TX * PS_DL, sizeof(float) * Cin * 27, (cudaStream_t)stream, x, Cin, D, H, W, weight, bias, depth_start, depth_end, x_reg_out, depth_out);
     DV3D_LAUNCHED();
     return DV3D_OK;
 }

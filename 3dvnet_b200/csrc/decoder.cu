@@ -13,6 +13,7 @@ __global__ void __launch_bounds__(256)
 decoder_head_kernel(const float* __restrict__ x, long long Np, int n_hyp, int rows_per_point, int C, int ld,
                     const float* __restrict__ w, float bias, double offset, float* __restrict__ prob_out,
                     float* __restrict__ offset_out) {
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const long long p = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (p >= Np) return;
@@ -97,8 +98,7 @@ extern "C" int dv3d_decoder_head(const float* x, long long n_pts, int n_hyp, int
                      rows_per_point >= n_hyp && Cin > 0 && ldx >= Cin,
                  "decoder_head: bad arguments (n_hyp must be odd and <= 7)");
     if (n_pts == 0) return DV3D_OK;
-    decoder_head_kernel<<<cdiv(n_pts, 8), 256, 0, (cudaStream_t)stream>>>(x, n_pts, n_hyp, rows_per_point, Cin, ldx,
-                                                                         weight, bias, offset, prob_out, offset_out);
+    DV3D_LAUNCH((decoder_head_kernel), cdiv(n_pts, 8), 256, 0, (cudaStream_t)stream, x, n_pts, n_hyp, rows_per_point, Cin, ldx, weight, bias, offset, prob_out, offset_out);
     DV3D_LAUNCHED();
     return DV3D_OK;
 }

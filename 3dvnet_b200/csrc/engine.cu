@@ -86,11 +86,13 @@ constexpr size_t kBitmapShare = 64ull << 20;  // voxelize / coarsen bitmaps and 
 
 // pts_batch[r*P + p] = depth_batch[r]  (lightningmodel.py:171-172)
 __global__ void expand_batch_kernel(const long long* __restrict__ depth_batch, int P, long long n, long long* __restrict__ out) {
+    pdl_wait();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = depth_batch[i / P];
 }
 // depth += offset  (eval-3dvnet.py:99)
 __global__ void add_inplace_kernel(float* __restrict__ x, const float* __restrict__ y, long long n) {
+    pdl_wait();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) x[i] = x[i] + y[i];
 }
@@ -506,7 +508,7 @@ extern "C" int dv3d_hot_path(const dv3d_net_params_t* netp, const float* feats_n
         ARENA_CHECK(ar);
         DV3D_CUDA(cudaMemsetAsync(operand, 0, sizeof(float) * Np * 8 * in_dim, cs));
         DV3D_CUDA(cudaMemsetAsync(split_ws, 0, dv3d_sparse_conv_workspace_bytes(128), cs));
-        expand_batch_kernel<<<cdiv(Np, 256), 256, 0, cs>>>(depth_batch, (int)P, Np, pts_batch);
+        DV3D_LAUNCH((expand_batch_kernel), cdiv(Np, 256), 256, 0, cs, depth_batch, (int)P, Np, pts_batch);
         DV3D_LAUNCHED();
         const size_t mark = ar.off;
         for (int o = 0; o < n_outer; ++o) {
@@ -557,7 +559,7 @@ extern "C" int dv3d_hot_path(const dv3d_net_params_t* netp, const float* feats_n
                                             net.dec[2].a, net.dec[2].b, net.dec[2].N, dec_a, net.dec[2].N, stream));
                     TRY(dv3d_decoder_head(dec_a, Np, 7, 8, net.dec[2].N, net.dec[2].N, net.dec_head_weight, net.dec_head_bias,
                                           offset, nullptr, offs, stream));
-                    add_inplace_kernel<<<cdiv(Np, 256), 256, 0, cs>>>(depth, offs, Np);
+                    DV3D_LAUNCH((add_inplace_kernel), cdiv(Np, 256), 256, 0, cs, depth, offs, Np);
                     DV3D_LAUNCHED();
                 }
             }

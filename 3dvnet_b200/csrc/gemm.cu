@@ -11,6 +11,7 @@ constexpr int BM = 64, KC = 16, AS_LD = BM + 4;
 template <int BN>
 __global__ void __launch_bounds__(256)
 gather_gemm_f32_kernel(const __grid_constant__ GemmDesc d) {
+    pdl_wait();
     __shared__ __align__(16) float As[KC][AS_LD];
     __shared__ __align__(16) float Ws[KC][BN];
     __shared__ int s_row[BM];
@@ -159,9 +160,9 @@ int launch_gather_gemm(const GemmDesc& d, cudaStream_t st) {
     if (d.M == 0) return DV3D_OK;
     const int grid = cdiv(d.M, BM);
     if (d.N == 128)
-        gather_gemm_f32_kernel<128><<<grid, 256, 0, st>>>(d);
+        DV3D_LAUNCH((gather_gemm_f32_kernel<128>), grid, 256, 0, st, d);
     else
-        gather_gemm_f32_kernel<64><<<grid, 256, 0, st>>>(d);
+        DV3D_LAUNCH((gather_gemm_f32_kernel<64>), grid, 256, 0, st, d);
     DV3D_LAUNCHED();
     return DV3D_OK;
 }

@@ -143,6 +143,7 @@ __device__ __forceinline__ void split_tf32(float x, float& big, float& small) {
 // stored at j ^ (n & 7).  Image of the big parts first, then of the remainders.
 __global__ void __launch_bounds__(256)
 pack_weights_kernel(const float* __restrict__ W, int Ktot, int N, float* __restrict__ out) {
+    pdl_wait();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)Ktot * N) return;
     const int k = (int)(i / N), n = (int)(i - (long long)k * N);
@@ -212,6 +213,7 @@ __device__ __forceinline__ void walk_enter(ChunkWalk& c, const GemmDesc& d, int 
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gather_gemm_tc_kernel(const __grid_constant__ GemmDesc d, int precision_and_flags) {
+    pdl_wait();
     // bits 8.. of the precision word are TIMING EXPERIMENT switches (tools/bench_gemm.py): they
     // remove one pipeline stage's work at a time and make the result meaningless
     const int precision = precision_and_flags & 0xff;
@@ -512,7 +514,7 @@ int launch_gather_gemm_tc(const GemmDesc& d, cudaStream_t st) {
                                            (int)tc_smem_bytes(128)));
             attr = true;
         }
-        gather_gemm_tc_kernel<128><<<grid, TC_THREADS, tc_smem_bytes(128), st>>>(d, g_gemm_precision);
+        DV3D_LAUNCH((gather_gemm_tc_kernel<128>), grid, TC_THREADS, tc_smem_bytes(128), st, d, g_gemm_precision);
     } else {
         static bool attr = false;
         if (!attr) {
@@ -520,7 +522,7 @@ int launch_gather_gemm_tc(const GemmDesc& d, cudaStream_t st) {
                                            (int)tc_smem_bytes(64)));
             attr = true;
         }
-        gather_gemm_tc_kernel<64><<<grid, TC_THREADS, tc_smem_bytes(64), st>>>(d, g_gemm_precision);
+        DV3D_LAUNCH((gather_gemm_tc_kernel<64>), grid, TC_THREADS, tc_smem_bytes(64), st, d, g_gemm_precision);
     }
     DV3D_LAUNCHED();
     return DV3D_OK;
@@ -538,7 +540,7 @@ extern "C" size_t dv3d_gemm_pack_bytes(int Ktot, int N) {
 extern "C" int dv3d_gemm_pack_weights(const float* W, int Ktot, int N, void* packed, void* stream) {
     DV3D_REQUIRE(W && packed && Ktot > 0 && Ktot % TC_KC == 0 && (N == 64 || N == 128),
                  "gemm_pack_weights: need K %% 32 == 0 and N in {64,128} (K=%d N=%d)", Ktot, N);
-    pack_weights_kernel<<<cdiv((long long)Ktot * N, 256), 256, 0, (cudaStream_t)stream>>>(W, Ktot, N, (float*)packed);
+    DV3D_LAUNCH((pack_weights_kernel), cdiv((long long)Ktot * N, 256), 256, 0, (cudaStream_t)stream, W, Ktot, N, (float*)packed);
     DV3D_LAUNCHED();
     return DV3D_OK;
 }

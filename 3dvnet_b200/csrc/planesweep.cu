@@ -166,6 +166,7 @@ planesweep_var_kernel(const float4* __restrict__ feats, SampleGeom geom, const f
                       const int* __restrict__ ref_img, const int* __restrict__ rowptr, const int* __restrict__ esrc,
                       double d0, double d1, int D, int h, int w, int H, int W, int chunks_per_cta,
                       float* __restrict__ out) {
+    pdl_wait();
     // dynamic shared memory (73 KB > the 48 KB static limit): weights | records | output tile
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4 (*s_wt)[KD][TP] = reinterpret_cast<float4 (*)[KD][TP]>(smem_raw);
@@ -250,6 +251,7 @@ points_var_kernel(const float4* __restrict__ feats, SampleGeom geom, const float
                   const float* __restrict__ depth, int h, int w, int H, int W, int n_side, double offset,
                   float* __restrict__ pts_out, float* __restrict__ feat_out, int rows_per_point, int feat_stride,
                   int feat_off) {
+    pdl_wait();
     __shared__ int s_rec[EMAX][KD][TP];
     __shared__ float4 s_wt[EMAX][KD][TP];
 
@@ -339,6 +341,7 @@ __device__ void load3x3(const float* p, double* o) {
 // Per-image camera table: Kinv | P = K [R|t] | R | t  (see CAM_* above).
 __global__ void camera_tables_kernel(const float* __restrict__ R, const float* __restrict__ t,
                                      const float* __restrict__ K, int n, float* __restrict__ out) {
+    pdl_wait();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float* k = K + 9 * i;
@@ -371,6 +374,7 @@ __global__ void camera_tables_kernel(const float* __restrict__ R, const float* _
 
 // NCHW -> NHWC through a padded 32x32 shared tile (both sides coalesced)
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int HW) {
+    pdl_wait();
     __shared__ float tile[32][33];
     int n = blockIdx.z;
     int hw0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -403,7 +407,7 @@ extern "C" int dv3d_nchw_to_nhwc(const float* src, float* dst, int n, int C, int
     DV3D_REQUIRE(src && dst && n >= 0 && C > 0 && HW > 0, "nchw_to_nhwc: bad arguments");
     if (n == 0) return DV3D_OK;
     dim3 grid(cdiv(HW, 32), cdiv(C, 32), n), block(32, 8);
-    nchw_to_nhwc_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(src, dst, C, HW);
+    DV3D_LAUNCH((nchw_to_nhwc_kernel), grid, block, 0, (cudaStream_t)stream, src, dst, C, HW);
     DV3D_LAUNCHED();
     return DV3D_OK;
 }
@@ -412,7 +416,7 @@ extern "C" int dv3d_camera_tables(const float* rotmats, const float* tvecs, cons
                                   void* stream) {
     DV3D_REQUIRE(rotmats && tvecs && K && out && n_imgs >= 0, "camera_tables: bad arguments");
     if (n_imgs == 0) return DV3D_OK;
-    camera_tables_kernel<<<cdiv(n_imgs, 64), 64, 0, (cudaStream_t)stream>>>(rotmats, tvecs, K, n_imgs, out);
+    DV3D_LAUNCH((camera_tables_kernel), cdiv(n_imgs, 64), 64, 0, (cudaStream_t)stream, rotmats, tvecs, K, n_imgs, out);
     DV3D_LAUNCHED();
     return DV3D_OK;
 }
@@ -442,9 +446,7 @@ extern "C" int dv3d_planesweep_var(const float* feats_nhwc, int n_imgs, int C, i
         DV3D_CUDA(cudaFuncSetAttribute(planesweep_var_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    planesweep_var_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(
-        reinterpret_cast<const float4*>(feats_nhwc), make_geom(Hf, Wf, H, W), cams, ref_img, edge_rowptr, edge_src,
-        depth_start, d1, D, h, w, H, W, chunks_per_cta, x_var);
+    DV3D_LAUNCH((planesweep_var_kernel), grid, 256, smem, (cudaStream_t)stream, reinterpret_cast<const float4*>(feats_nhwc), make_geom(Hf, Wf, H, W), cams, ref_img, edge_rowptr, edge_src, depth_start, d1, D, h, w, H, W, chunks_per_cta, x_var);
     DV3D_LAUNCHED();
     return DV3D_OK;
 }
@@ -465,9 +467,7 @@ extern "C" int dv3d_points_var(const float* feats_nhwc, int n_imgs, int C, int H
     DV3D_REQUIRE(n_imgs > 0 && Hf > 1 && Wf > 1 && h > 0 && w > 0 && n_ref >= 0 && n_ref <= 65535, "points_var: bad shape");
     if (n_ref == 0) return DV3D_OK;
     dim3 grid(cdiv(h * w, TP), n_ref);
-    points_var_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const float4*>(feats_nhwc), make_geom(Hf, Wf, H, W), cams, ref_img, edge_rowptr, edge_src,
-        depth, h, w, H, W, n_side, offset, pts_out, feat_out, rows_per_point, feat_stride, feat_off);
+    DV3D_LAUNCH((points_var_kernel), grid, 256, 0, (cudaStream_t)stream, reinterpret_cast<const float4*>(feats_nhwc), make_geom(Hf, Wf, H, W), cams, ref_img, edge_rowptr, edge_src, depth, h, w, H, W, n_side, offset, pts_out, feat_out, rows_per_point, feat_stride, feat_off);
     DV3D_LAUNCHED();
     return DV3D_OK;
 }

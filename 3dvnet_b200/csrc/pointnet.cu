@@ -11,6 +11,7 @@ __global__ void __launch_bounds__(256)
 pointnet_input_kernel(const float* __restrict__ pts, const float* __restrict__ pts_feat, int feat_ld,
                       const float* __restrict__ anchor_pts, const int* __restrict__ seg, long long N, int C, int ld,
                       float* __restrict__ out) {
+    pdl_wait();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N * ld) return;
     long long p = i / ld;
@@ -25,6 +26,7 @@ pointnet_input_kernel(const float* __restrict__ pts, const float* __restrict__ p
 
 __global__ void __launch_bounds__(256)
 fill_kernel(unsigned* p, long long n, unsigned v) {
+    pdl_wait();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
 }
@@ -33,6 +35,7 @@ fill_kernel(unsigned* p, long long n, unsigned v) {
 __global__ void __launch_bounds__(256)
 segment_max_kernel(const float* __restrict__ x, const int* __restrict__ seg, long long N, int C,
                    unsigned* __restrict__ out) {
+    pdl_wait();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N * (C / 4)) return;
     long long p = i / (C / 4);
@@ -47,6 +50,7 @@ segment_max_kernel(const float* __restrict__ x, const int* __restrict__ seg, lon
 
 __global__ void __launch_bounds__(256)
 segment_max_decode_kernel(unsigned* __restrict__ out, long long n) {
+    pdl_wait();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     unsigned u = out[i];
@@ -62,8 +66,7 @@ extern "C" int dv3d_pointnet_input(const float* pts, const float* pts_feat, int 
     DV3D_REQUIRE(pts && pts_feat && anchor_pts && seg && out && N >= 0 && C > 0 && out_ld >= 3 + C && feat_ld >= C,
                  "pointnet_input: bad arguments");
     if (N == 0) return DV3D_OK;
-    pointnet_input_kernel<<<cdiv(N * out_ld, 256), 256, 0, (cudaStream_t)stream>>>(pts, pts_feat, feat_ld, anchor_pts,
-                                                                                  seg, N, C, out_ld, out);
+    DV3D_LAUNCH((pointnet_input_kernel), cdiv(N * out_ld, 256), 256, 0, (cudaStream_t)stream, pts, pts_feat, feat_ld, anchor_pts, seg, N, C, out_ld, out);
     DV3D_LAUNCHED();
     return DV3D_OK;
 }
@@ -96,10 +99,10 @@ extern "C" int dv3d_segment_max(const float* x, const int* seg, long long N, int
     cudaStream_t st = (cudaStream_t)stream;
     DV3D_CUDA(cudaMemsetAsync(out, 0, (size_t)n_seg * C * 4, st));  // 0 orders below every encoded float
     if (N > 0) {
-        segment_max_kernel<<<cdiv(N * (C / 4), 256), 256, 0, st>>>(x, seg, N, C, reinterpret_cast<unsigned*>(out));
+        DV3D_LAUNCH((segment_max_kernel), cdiv(N * (C / 4), 256), 256, 0, st, x, seg, N, C, reinterpret_cast<unsigned*>(out));
         DV3D_LAUNCHED();
     }
-    segment_max_decode_kernel<<<cdiv(n_seg * C, 256), 256, 0, st>>>(reinterpret_cast<unsigned*>(out), n_seg * C);
+    DV3D_LAUNCH((segment_max_decode_kernel), cdiv(n_seg * C, 256), 256, 0, st, reinterpret_cast<unsigned*>(out), n_seg * C);
     DV3D_LAUNCHED();
     return DV3D_OK;
 }

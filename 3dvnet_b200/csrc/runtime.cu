@@ -1,6 +1,7 @@
 // Error reporting, launch accounting and ABI version of lib3dvnet_b200.
 #include <atomic>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -18,6 +19,14 @@ void set_error(const char* fmt, ...) {
 }
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+bool pdl_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("DV3D_PDL");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
 
 }  // namespace dv3d
 

@@ -12,6 +12,7 @@ namespace dv3d {
 
 __global__ void __launch_bounds__(256)
 hash_clear_kernel(unsigned long long* keys, int* rows, size_t cap) {
+    pdl_wait();
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < cap) {
         keys[i] = kEmptyKey;
@@ -21,6 +22,7 @@ hash_clear_kernel(unsigned long long* keys, int* rows, size_t cap) {
 
 __global__ void __launch_bounds__(256)
 hash_insert_kernel(const int* __restrict__ coords, long long n, HashView t, int* __restrict__ err) {
+    pdl_wait();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int b = coords[4 * i], x = coords[4 * i + 1], y = coords[4 * i + 2], z = coords[4 * i + 3];
@@ -43,6 +45,7 @@ hash_insert_kernel(const int* __restrict__ coords, long long n, HashView t, int*
 // nbr[o*27 + k] = row of (coords_out[o] + offset_k * step) in the input level, or -1
 __global__ void __launch_bounds__(256)
 kernel_map_kernel(const int* __restrict__ coords_out, long long n_out, HashView t, int step, int* __restrict__ nbr) {
+    pdl_wait();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_out * 27) return;
     long long o = i / 27;
@@ -64,6 +67,7 @@ struct KernelMapBatch {
 };
 __global__ void __launch_bounds__(256)
 kernel_map_batch_kernel(const __grid_constant__ KernelMapBatch b) {
+    pdl_wait();
     const int j = blockIdx.y;
     const long long n_out = b.n_out[j];
     const int* __restrict__ coords_out = b.coords_out[j];
@@ -85,6 +89,7 @@ __global__ void __launch_bounds__(256)
 sparse_interp_kernel(const float* __restrict__ pts, const long long* __restrict__ pts_batch, long long Nq, int n_hyp,
                      int rows_per_point, const float* __restrict__ origin, float res, int stride, HashView t,
                      const float* __restrict__ feat, float* __restrict__ out, int out_ld, int out_off) {
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const long long q = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (q >= Nq) return;
@@ -151,10 +156,10 @@ extern "C" int dv3d_hash_build(const int* coords, long long n, void* table, size
                  "hash_build: table_bytes must be dv3d_hash_bytes(n)");
     cudaStream_t st = (cudaStream_t)stream;
     size_t cap = (size_t)t.mask + 1;
-    hash_clear_kernel<<<cdiv(cap, 256), 256, 0, st>>>(t.keys, t.rows, cap);
+    DV3D_LAUNCH((hash_clear_kernel), cdiv(cap, 256), 256, 0, st, t.keys, t.rows, cap);
     DV3D_LAUNCHED();
     if (n == 0) return DV3D_OK;
-    hash_insert_kernel<<<cdiv(n, 256), 256, 0, st>>>(coords, n, t, err_flag);
+    DV3D_LAUNCH((hash_insert_kernel), cdiv(n, 256), 256, 0, st, coords, n, t, err_flag);
     DV3D_LAUNCHED();
     return DV3D_OK;
 }
@@ -165,7 +170,7 @@ extern "C" int dv3d_kernel_map(const int* coords_out, long long n_out, const voi
     DV3D_REQUIRE(coords_out && table_in && nbr && n_out >= 0, "kernel_map: bad arguments");
     DV3D_REQUIRE(hash_view(const_cast<void*>(table_in), table_bytes, &t), "kernel_map: bad table size");
     if (n_out == 0) return DV3D_OK;
-    kernel_map_kernel<<<cdiv(n_out * 27, 256), 256, 0, (cudaStream_t)stream>>>(coords_out, n_out, t, step, nbr);
+    DV3D_LAUNCH((kernel_map_kernel), cdiv(n_out * 27, 256), 256, 0, (cudaStream_t)stream, coords_out, n_out, t, step, nbr);
     DV3D_LAUNCHED();
     return DV3D_OK;
 }
@@ -192,7 +197,7 @@ extern "C" int dv3d_kernel_map_batch(const int* const* coords_out, const long lo
     if (n_maps == 0 || max_n == 0) return DV3D_OK;
     int gx = cdiv(max_n * 27, 256);
     if (gx > 8 * kNumSMs) gx = 8 * kNumSMs;
-    kernel_map_batch_kernel<<<dim3(gx, n_maps), 256, 0, (cudaStream_t)stream>>>(b);
+    DV3D_LAUNCH((kernel_map_batch_kernel), dim3(gx, n_maps), 256, 0, (cudaStream_t)stream, b);
     DV3D_LAUNCHED();
     return DV3D_OK;
 }
@@ -268,11 +273,9 @@ extern "C" int dv3d_sparse_interp(const float* pts, const long long* pts_batch, 
     if (Nq == 0) return DV3D_OK;
     cudaStream_t st = (cudaStream_t)stream;
     if (C == 64)
-        sparse_interp_kernel<64><<<cdiv(Nq, 8), 256, 0, st>>>(pts, pts_batch, Nq, n_hyp, rows_per_point, origin, res,
-                                                              stride, t, feat, out, out_ld, out_off);
+        DV3D_LAUNCH((sparse_interp_kernel<64>), cdiv(Nq, 8), 256, 0, st, pts, pts_batch, Nq, n_hyp, rows_per_point, origin, res, stride, t, feat, out, out_ld, out_off);
     else
-        sparse_interp_kernel<128><<<cdiv(Nq, 8), 256, 0, st>>>(pts, pts_batch, Nq, n_hyp, rows_per_point, origin, res,
-                                                               stride, t, feat, out, out_ld, out_off);
+        DV3D_LAUNCH((sparse_interp_kernel<128>), cdiv(Nq, 8), 256, 0, st, pts, pts_batch, Nq, n_hyp, rows_per_point, origin, res, stride, t, feat, out, out_ld, out_off);
     DV3D_LAUNCHED();
     return DV3D_OK;
 }

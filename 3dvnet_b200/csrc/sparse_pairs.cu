@@ -72,6 +72,7 @@ struct PlanBatch {
 //   pair_fill          CTA (row block, map): rank inside the block (ballots) + block offset -> slots
 __global__ void __launch_bounds__(PP_RB)
 pair_block_count_kernel(const __grid_constant__ PlanBatch pb) {
+    pdl_wait();
     const int j = blockIdx.y;
     const long long n_out = pb.n_out[j], r0 = (long long)blockIdx.x * PP_RB;
     if (r0 >= n_out) return;
@@ -88,6 +89,7 @@ pair_block_count_kernel(const __grid_constant__ PlanBatch pb) {
 
 __global__ void __launch_bounds__(256)
 pair_block_scan_kernel(const __grid_constant__ PlanBatch pb) {
+    pdl_wait();
     const int k = blockIdx.x, j = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const PlanView pv = pb.pv[j];
     const int n_rb = (int)((pb.n_out[j] + PP_RB - 1) / PP_RB);
@@ -122,6 +124,7 @@ pair_block_scan_kernel(const __grid_constant__ PlanBatch pb) {
 
 __global__ void __launch_bounds__(PP_RB)
 pair_fill_kernel(const __grid_constant__ PlanBatch pb) {
+    pdl_wait();
     const int j = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long n_out = pb.n_out[j], r0 = (long long)blockIdx.x * PP_RB;
     if (r0 >= n_out && blockIdx.x != 0) return;
@@ -185,6 +188,7 @@ pair_fill_kernel(const __grid_constant__ PlanBatch pb) {
 template <int N>
 __global__ void __launch_bounds__(256)
 pair_reduce_kernel(const __grid_constant__ GemmDesc d, const float* __restrict__ P, const int* __restrict__ pair_slot) {
+    pdl_wait();
     constexpr int UNITS = N / 4, ROWS = 256 / UNITS;
     const int u = threadIdx.x % UNITS;
     const long long m = (long long)blockIdx.x * ROWS + threadIdx.x / UNITS;
@@ -230,11 +234,11 @@ extern "C" int dv3d_pair_plan_build(const int* const* nbrs, const long long* n_o
     for (int i = 0; i < n_maps; ++i)
         if (plan_row_blocks(n_outs[i]) > max_rb) max_rb = plan_row_blocks(n_outs[i]);
     DV3D_REQUIRE(max_rb <= 0x7fffffff, "pair_plan_build: level too large");
-    pair_block_count_kernel<<<dim3((unsigned)max_rb, n_maps), PP_RB, 0, st>>>(pb);
+    DV3D_LAUNCH((pair_block_count_kernel), dim3((unsigned)max_rb, n_maps), PP_RB, 0, st, pb);
     DV3D_LAUNCHED();
-    pair_block_scan_kernel<<<dim3(27, n_maps), 256, 0, st>>>(pb);
+    DV3D_LAUNCH((pair_block_scan_kernel), dim3(27, n_maps), 256, 0, st, pb);
     DV3D_LAUNCHED();
-    pair_fill_kernel<<<dim3((unsigned)max_rb, n_maps), PP_RB, 0, st>>>(pb);
+    DV3D_LAUNCH((pair_fill_kernel), dim3((unsigned)max_rb, n_maps), PP_RB, 0, st, pb);
     DV3D_LAUNCHED();
     return DV3D_OK;
 }
@@ -304,9 +308,9 @@ extern "C" int dv3d_sparse_conv_pairs(const float* feat, long long n_in, int Cin
     e.out_ld = Cout;
     DV3D_REQUIRE(!gn_weight || gn_bias, "sparse_conv_pairs: GroupNorm needs weight and bias");
     if (Cout == 128)
-        pair_reduce_kernel<128><<<cdiv(n_out, 8), 256, 0, st>>>(e, P, pv.pair_slot);
+        DV3D_LAUNCH((pair_reduce_kernel<128>), cdiv(n_out, 8), 256, 0, st, e, P, pv.pair_slot);
     else
-        pair_reduce_kernel<64><<<cdiv(n_out, 16), 256, 0, st>>>(e, P, pv.pair_slot);
+        DV3D_LAUNCH((pair_reduce_kernel<64>), cdiv(n_out, 16), 256, 0, st, e, P, pv.pair_slot);
     DV3D_LAUNCHED();
     return DV3D_OK;
 }

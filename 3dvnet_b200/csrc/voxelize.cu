@@ -25,6 +25,7 @@ struct BBoxHeader {  // device-side reduction target
 };
 
 __global__ void bbox_init_kernel(BBoxHeader* h) {
+    pdl_wait();
     if (threadIdx.x < 3) {
         h->mn[threadIdx.x] = 0xffffffffu;
         h->mx[threadIdx.x] = 0u;
@@ -34,6 +35,7 @@ __global__ void bbox_init_kernel(BBoxHeader* h) {
 
 __global__ void __launch_bounds__(256)
 bbox_kernel(const float* __restrict__ pts, const long long* __restrict__ batch, long long N, BBoxHeader* h) {
+    pdl_wait();
     float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
     long long bm = 0;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
@@ -67,6 +69,7 @@ bbox_kernel(const float* __restrict__ pts, const long long* __restrict__ batch, 
 }
 
 __global__ void bbox_decode_kernel(const BBoxHeader* h, float* out8) {
+    pdl_wait();
     if (threadIdx.x < 3) {
         out8[threadIdx.x] = ord2f(h->mn[threadIdx.x]);
         out8[3 + threadIdx.x] = ord2f(h->mx[threadIdx.x]);
@@ -97,6 +100,7 @@ __global__ void __launch_bounds__(256)
 mark_points_kernel(const float* __restrict__ pts, const long long* __restrict__ batch, long long N, GridDev G,
                    long long total_cells, long long* __restrict__ point_id, unsigned* __restrict__ bitmap,
                    int* __restrict__ err) {
+    pdl_wait();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     float p[3] = {__ldg(pts + 3 * i), __ldg(pts + 3 * i + 1), __ldg(pts + 3 * i + 2)};
@@ -113,6 +117,7 @@ mark_points_kernel(const float* __restrict__ pts, const long long* __restrict__ 
 __global__ void __launch_bounds__(SCAN_T)
 scan_words_kernel(const unsigned* __restrict__ bitmap, long long n_words, unsigned* __restrict__ prefix,
                   unsigned* __restrict__ block_sums) {
+    pdl_wait();
     __shared__ unsigned s_warp[SCAN_T / 32];
     const long long base = (long long)blockIdx.x * SCAN_BLK + (long long)threadIdx.x * SCAN_W;
     unsigned c[SCAN_W], tot = 0;
@@ -143,6 +148,7 @@ scan_words_kernel(const unsigned* __restrict__ bitmap, long long n_words, unsign
 // stage 2: one block turns block_sums into exclusive offsets and writes the grand total
 __global__ void __launch_bounds__(1024)
 scan_blocks_kernel(unsigned* __restrict__ block_sums, int n_blocks, long long* __restrict__ total) {
+    pdl_wait();
     __shared__ unsigned s_warp[32];
     __shared__ unsigned s_carry;
     if (threadIdx.x == 0) s_carry = 0;
@@ -182,6 +188,7 @@ emit_anchors_kernel(const unsigned* __restrict__ bitmap, const unsigned* __restr
                     const unsigned* __restrict__ block_offs, long long n_words, GridDev G, float half_e,
                     long long cap, float* __restrict__ anchor_pts, int* __restrict__ anchor_idx3d,
                     long long* __restrict__ anchor_batch, int* __restrict__ min_idx) {
+    pdl_wait();
     long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= n_words) return;
     unsigned bits = bitmap[w];
@@ -224,6 +231,7 @@ finish_voxelize_kernel(long long n_anchors, long long N, const long long* __rest
                        const long long* __restrict__ point_id, const unsigned* __restrict__ bitmap,
                        const unsigned* __restrict__ prefix, const unsigned* __restrict__ block_offs,
                        int* __restrict__ point_anchor) {
+    pdl_wait();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n_anchors) {
         long long b = anchor_batch[i];
@@ -245,6 +253,7 @@ struct LevelDims {
 __global__ void __launch_bounds__(256)
 mark_coarse_kernel(const int* __restrict__ coords, long long n, LevelDims L, int n_batch,
                    unsigned* __restrict__ bitmap, int* __restrict__ err) {
+    pdl_wait();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int b = coords[4 * i], x = coords[4 * i + 1], y = coords[4 * i + 2], z = coords[4 * i + 3];
@@ -262,6 +271,7 @@ __global__ void __launch_bounds__(256)
 emit_coarse_kernel(const unsigned* __restrict__ bitmap, const unsigned* __restrict__ prefix,
                    const unsigned* __restrict__ block_offs, long long n_words, LevelDims L, long long cap,
                    int* __restrict__ coarse) {
+    pdl_wait();
     long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= n_words) return;
     unsigned bits = bitmap[w];
@@ -292,6 +302,7 @@ emit_coarse_kernel(const unsigned* __restrict__ bitmap, const unsigned* __restri
 __global__ void batch_origin_kernel(const float* __restrict__ anchor_pts, const int* __restrict__ idx3d,
                                     const long long* __restrict__ batch, long long n, float res,
                                     float* __restrict__ origin) {
+    pdl_wait();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     long long b = batch[i];
@@ -305,6 +316,7 @@ __global__ void batch_origin_kernel(const float* __restrict__ anchor_pts, const 
 __global__ void __launch_bounds__(256)
 level_points_kernel(const int* __restrict__ coords, long long n, const float* __restrict__ origin, float res,
                     float* __restrict__ pts, long long* __restrict__ idx_out, long long* __restrict__ batch_out) {
+    pdl_wait();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int b = coords[4 * i];
@@ -320,6 +332,7 @@ level_points_kernel(const int* __restrict__ coords, long long n, const float* __
 __global__ void __launch_bounds__(256)
 make_coords_kernel(const int* __restrict__ idx3d, const long long* __restrict__ batch, long long n,
                    int* __restrict__ coords) {
+    pdl_wait();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     coords[4 * i] = (int)batch[i];
@@ -362,9 +375,9 @@ static ScanSpace carve(void* ws, long long n_words) {
 
 static int run_scan(const ScanSpace& s, long long n_words, cudaStream_t st) {
     int nb = cdiv(n_words, SCAN_BLK);
-    scan_words_kernel<<<nb, SCAN_T, 0, st>>>(s.bitmap, n_words, s.prefix, s.block_sums);
+    DV3D_LAUNCH((scan_words_kernel), nb, SCAN_T, 0, st, s.bitmap, n_words, s.prefix, s.block_sums);
     DV3D_LAUNCHED();
-    scan_blocks_kernel<<<1, 1024, 0, st>>>(s.block_sums, nb, s.total);
+    DV3D_LAUNCH((scan_blocks_kernel), 1, 1024, 0, st, s.block_sums, nb, s.total);
     DV3D_LAUNCHED();
     return DV3D_OK;
 }
@@ -379,13 +392,13 @@ extern "C" int dv3d_voxel_grid(const float* pts, const long long* batch, long lo
     cudaStream_t st = (cudaStream_t)stream;
     BBoxHeader* h = (BBoxHeader*)scratch64;
     float* out8 = (float*)((char*)scratch64 + 32);
-    bbox_init_kernel<<<1, 32, 0, st>>>(h);
+    DV3D_LAUNCH((bbox_init_kernel), 1, 32, 0, st, h);
     DV3D_LAUNCHED();
     int blocks = cdiv(N, 256 * 4);
     if (blocks > kNumSMs * 4) blocks = kNumSMs * 4;
-    bbox_kernel<<<blocks, 256, 0, st>>>(pts, batch, N, h);
+    DV3D_LAUNCH((bbox_kernel), blocks, 256, 0, st, pts, batch, N, h);
     DV3D_LAUNCHED();
-    bbox_decode_kernel<<<1, 32, 0, st>>>(h, out8);
+    DV3D_LAUNCH((bbox_decode_kernel), 1, 32, 0, st, h, out8);
     DV3D_LAUNCHED();
     float host8[8];
     DV3D_CUDA(cudaMemcpyAsync(host8, out8, sizeof(host8), cudaMemcpyDeviceToHost, st));
@@ -450,13 +463,11 @@ extern "C" int dv3d_voxelize(const float* pts, const long long* batch, long long
 
     DV3D_CUDA(cudaMemsetAsync(workspace, 0, s.extra_off, st));                         // bitmap, sums, total, err
     DV3D_CUDA(cudaMemsetAsync(min_idx, 0x7f, (size_t)grid->n_batch * 12, st));        // > any index
-    mark_points_kernel<<<cdiv(N, 256), 256, 0, st>>>(pts, batch, N, G, grid->total_cells, point_id, s.bitmap, s.err);
+    DV3D_LAUNCH((mark_points_kernel), cdiv(N, 256), 256, 0, st, pts, batch, N, G, grid->total_cells, point_id, s.bitmap, s.err);
     DV3D_LAUNCHED();
     int rc = run_scan(s, n_words, st);
     if (rc) return rc;
-    emit_anchors_kernel<<<cdiv(n_words, 256), 256, 0, st>>>(s.bitmap, s.prefix, s.block_sums, n_words, G,
-                                                           (float)(grid->edge_len / 2.0), cap, anchor_pts,
-                                                           anchor_idx3d, anchor_batch, min_idx);
+    DV3D_LAUNCH((emit_anchors_kernel), cdiv(n_words, 256), 256, 0, st, s.bitmap, s.prefix, s.block_sums, n_words, G, (float)(grid->edge_len / 2.0), cap, anchor_pts, anchor_idx3d, anchor_batch, min_idx);
     DV3D_LAUNCHED();
     long long host[2] = {0, 0};
     DV3D_CUDA(cudaMemcpyAsync(host, s.total, 16, cudaMemcpyDeviceToHost, st));
@@ -468,8 +479,7 @@ extern "C" int dv3d_voxelize(const float* pts, const long long* batch, long long
         return DV3D_ENOSPC;
     }
     long long m = host[0] > N ? host[0] : N;
-    finish_voxelize_kernel<<<cdiv(m, 256), 256, 0, st>>>(host[0], N, anchor_batch, min_idx, anchor_idx3d, point_id,
-                                                        s.bitmap, s.prefix, s.block_sums, point_anchor);
+    DV3D_LAUNCH((finish_voxelize_kernel), cdiv(m, 256), 256, 0, st, host[0], N, anchor_batch, min_idx, anchor_idx3d, point_id, s.bitmap, s.prefix, s.block_sums, point_anchor);
     DV3D_LAUNCHED();
     return DV3D_OK;
 }
@@ -477,7 +487,7 @@ extern "C" int dv3d_voxelize(const float* pts, const long long* batch, long long
 extern "C" int dv3d_make_coords(const int* idx3d, const long long* batch, long long n, int* coords, void* stream) {
     DV3D_REQUIRE(idx3d && batch && coords && n >= 0, "make_coords: bad arguments");
     if (n == 0) return DV3D_OK;
-    make_coords_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(idx3d, batch, n, coords);
+    DV3D_LAUNCH((make_coords_kernel), cdiv(n, 256), 256, 0, (cudaStream_t)stream, idx3d, batch, n, coords);
     DV3D_LAUNCHED();
     return DV3D_OK;
 }
@@ -505,12 +515,11 @@ extern "C" int dv3d_coarsen(const int* coords, long long n, int new_stride, int 
     const long long n_words = ((long long)L.X * L.Y * L.Z * n_batch + 31) / 32;
     ScanSpace s = carve(workspace, n_words);
     DV3D_CUDA(cudaMemsetAsync(workspace, 0, s.extra_off, st));
-    mark_coarse_kernel<<<cdiv(n, 256), 256, 0, st>>>(coords, n, L, n_batch, s.bitmap, s.err);
+    DV3D_LAUNCH((mark_coarse_kernel), cdiv(n, 256), 256, 0, st, coords, n, L, n_batch, s.bitmap, s.err);
     DV3D_LAUNCHED();
     int rc = run_scan(s, n_words, st);
     if (rc) return rc;
-    emit_coarse_kernel<<<cdiv(n_words, 256), 256, 0, st>>>(s.bitmap, s.prefix, s.block_sums, n_words, L, cap,
-                                                          coarse_coords);
+    DV3D_LAUNCH((emit_coarse_kernel), cdiv(n_words, 256), 256, 0, st, s.bitmap, s.prefix, s.block_sums, n_words, L, cap, coarse_coords);
     DV3D_LAUNCHED();
     long long host[2] = {0, 0};
     DV3D_CUDA(cudaMemcpyAsync(host, s.total, 16, cudaMemcpyDeviceToHost, st));
@@ -527,7 +536,7 @@ extern "C" int dv3d_coarsen(const int* coords, long long n, int new_stride, int 
 extern "C" int dv3d_batch_origin(const float* anchor_pts, const int* idx3d, const long long* batch, long long n,
                                  float res, float* origin, void* stream) {
     DV3D_REQUIRE(anchor_pts && idx3d && batch && origin && n > 0, "batch_origin: bad arguments");
-    batch_origin_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(anchor_pts, idx3d, batch, n, res, origin);
+    DV3D_LAUNCH((batch_origin_kernel), cdiv(n, 256), 256, 0, (cudaStream_t)stream, anchor_pts, idx3d, batch, n, res, origin);
     DV3D_LAUNCHED();
     return DV3D_OK;
 }
@@ -536,8 +545,7 @@ extern "C" int dv3d_level_points(const int* coords, long long n, const float* or
                                  long long* idx_out, long long* batch_out, void* stream) {
     DV3D_REQUIRE(coords && origin && pts && n >= 0, "level_points: bad arguments");
     if (n == 0) return DV3D_OK;
-    level_points_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(coords, n, origin, res, pts, idx_out,
-                                                                        batch_out);
+    DV3D_LAUNCH((level_points_kernel), cdiv(n, 256), 256, 0, (cudaStream_t)stream, coords, n, origin, res, pts, idx_out, batch_out);
     DV3D_LAUNCHED();
     return DV3D_OK;
 }
