@@ -41,6 +41,8 @@ void count_launch(int n = 1);
 // griddepcontrol.wait: the next launch is set up and its CTAs scheduled while the previous
 // kernel drains, and the wait returns once that kernel has completed and flushed its writes.
 // DV3D_PDL=0 in the environment launches without the attribute (A/B measurements).
+// (An explicit griddepcontrol.launch_dependents at kernel entry was measured and is not used: the
+// dependents' CTAs then spin next to the running kernel and the step got 1.5 % slower.)
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 bool pdl_enabled();
 

@@ -39,7 +39,6 @@ struct GemmDesc {
     const int* kmap;        // set when every slice s gathers through kmap[m * n_slices + s]
     const int* tile_wslice; // tcgen05 kernel, n_slices == 1: 128-row tile t contracts with the weight block
                             // W[tile_wslice[t] * K : (tile_wslice[t] + 1) * K, :] (pair-major sparse convolution)
-    const int* m_tiles_dev; // optional device count of live 128-row tiles: CTAs beyond it exit at once
     const float* scale;     // per-channel multiplier (folded BN) or nullptr
     const float* shift;     // per-channel addend (bias / folded BN) or nullptr
     const float* gn_weight; // GroupNorm affine (groups of 16 channels) or nullptr

@@ -213,7 +213,6 @@ __device__ __forceinline__ void walk_enter(ChunkWalk& c, const GemmDesc& d, int 
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gather_gemm_tc_kernel(const __grid_constant__ GemmDesc d, int precision_and_flags) {
-    pdl_wait();
     // bits 8.. of the precision word are TIMING EXPERIMENT switches (tools/bench_gemm.py): they
     // remove one pipeline stage's work at a time and make the result meaningless
     const int precision = precision_and_flags & 0xff;
@@ -233,7 +232,6 @@ gather_gemm_tc_kernel(const __grid_constant__ GemmDesc d, int precision_and_flag
     float* s_tile = reinterpret_cast<float*>(smem);                                 // reuses the stages after the last MMA
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (d.m_tiles_dev && (int)blockIdx.x >= __ldg(d.m_tiles_dev)) return;  // uniform per CTA
     const long long m0 = (long long)blockIdx.x * TC_BM;
     const uint32_t bar_full = smem_u32(s_bar), bar_empty = smem_u32(s_bar + TC_STAGES),
                    bar_accum = smem_u32(s_bar + 2 * TC_STAGES);
@@ -251,6 +249,8 @@ gather_gemm_tc_kernel(const __grid_constant__ GemmDesc d, int precision_and_flag
         fence_mbar_init();
     }
     if (warp == 8) tmem_alloc(smem_u32(s_misc), BN);
+    // everything above is independent of the previous kernel in the stream (PDL prologue)
+    pdl_wait();
     __syncthreads();
 
     // stage the row table of the tile and flag the slices that have at least one live row

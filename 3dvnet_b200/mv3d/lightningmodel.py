@@ -59,6 +59,7 @@ class PL3DVNet(nn.Module):
         self.refine_full = PropagationNet(in_dim=3 + 1, h_dim=32)
         self._nhwc = _FeatureCache()
         self._engine_pack = PackCache()
+        self._engine_tensors = None
 
     @property
     def device(self):
@@ -209,8 +210,12 @@ class PL3DVNet(nn.Module):
             keep.append(head[0])
             P.dec_head_weight, P.dec_head_bias = head[0].data_ptr(), head[1]
             return P, keep
-        tensors = [p for p in self.parameters()] + [b for b in self.buffers()]
-        return self._engine_pack.get(tensors, build, ops.gemm_mode())[0]
+        # invalidation key: storage + version of the hot-path parameters only (the module tree is
+        # static; walking all ~560 tensors incl. the 2D backbone costs more than a PointFlow pass)
+        if self._engine_tensors is None:
+            mods = (self.mvsnet.cnn_3d, self.pointnet, self.sparse_conv, self.decoder)
+            self._engine_tensors = [t for m in mods for t in list(m.parameters()) + list(m.buffers())]
+        return self._engine_pack.get(self._engine_tensors, build, ops.gemm_mode())[0]
 
     def hot_path(self, feats_quarter, rotmats, tvecs, K, ref_src_edges, images_batch, depth_config, offsets_list,
                  return_init=False):
