@@ -51,6 +51,27 @@ struct Prof {
     }
 };
 
+// ------------------------------------------------------------------ side stream
+// PointNet (per point) and the coordinate levels / kernel maps / pair plans (per voxel) both
+// depend only on the voxelisation: they run concurrently, the latter on a per-device side stream
+// (it contains the host read-backs of the level sizes, which then overlap PointNet's kernels).
+struct SideStream {
+    cudaStream_t stream;
+    cudaEvent_t fork, join;
+};
+static SideStream* side_stream() {
+    static SideStream per_dev[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    SideStream& s = per_dev[dev];
+    if (!s.stream) {
+        if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming);
+    }
+    return &s;
+}
+
 // ------------------------------------------------------------------ arena
 struct Arena {
     char* base;
@@ -185,15 +206,17 @@ static int kernel_map(const Level& out_lv, const Level& in_lv, int step, bool wa
 static int model_scene(const dv3d_net_params_t& net, const float* pts, const float* pts_feat, const long long* pts_batch,
                        long long N, double edge_len, Scene& sc, Arena& ar, void* st) {
     cudaStream_t cs = (cudaStream_t)st;
+    SideStream* side = side_stream();
+    DV3D_REQUIRE(side, "hot_path: cannot create the side stream");
     // ---- voxelise (utils.py:38-64)
     Prof* pr = new Prof(DV3D_STAGE_VOXELIZE, cs);
     struct ProfGuard {  // closes the open stage on every return path
         Prof*& p;
         ~ProfGuard() { delete p; }
     } guard{pr};
-    auto next_stage = [&](int id) {
+    auto next_stage = [&](int id, cudaStream_t on) {
         delete pr;
-        pr = new Prof(id, cs);
+        pr = new Prof(id, on);
     };
     dv3d_voxel_grid_t grid;
     void* scratch = ar.get<char>(256);
@@ -209,8 +232,12 @@ static int model_scene(const dv3d_net_params_t& net, const float* pts, const flo
     long long nv = 0;
     TRY(dv3d_voxelize(pts, pts_batch, N, &grid, vws, vws_bytes, N, &nv, a_pts, a_idx, a_batch, seg, st));
 
-    // ---- PointNet (scenemodeling.py:127-144)
-    next_stage(DV3D_STAGE_POINTNET);
+    // fork: the side stream sees the voxelisation
+    DV3D_CUDA(cudaEventRecord(side->fork, cs));
+    DV3D_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+
+    // ---- PointNet (scenemodeling.py:127-144), main stream
+    next_stage(DV3D_STAGE_POINTNET, cs);
     const int in_pad = net.pointnet_in_pad, Hd = net.pointnet[0].N;
     float* x0 = ar.get<float>((size_t)N * in_pad);
     float* xa = ar.get<float>((size_t)N * Hd);
@@ -237,18 +264,19 @@ static int model_scene(const dv3d_net_params_t& net, const float* pts, const flo
                     net.pointnet[5].N, 1, F, st));
 
     // ---- coordinate levels, hash tables, kernel maps (what ME keeps in its coordinate manager)
-    next_stage(DV3D_STAGE_LEVELS);
+    next_stage(DV3D_STAGE_LEVELS, side->stream);
+    void* const sst = (void*)side->stream;
     const int nl = net.n_levels;
     sc.n_levels = nl;
     int* err_flag = ar.get<int>(1);
     ARENA_CHECK(ar);
-    DV3D_CUDA(cudaMemsetAsync(err_flag, 0, sizeof(int), cs));
+    DV3D_CUDA(cudaMemsetAsync(err_flag, 0, sizeof(int), side->stream));
     sc.lv[0].n = nv;
     sc.lv[0].stride = 1;
     sc.lv[0].coords = ar.get<int>((size_t)nv * 4);
     ARENA_CHECK(ar);
-    TRY(dv3d_make_coords(a_idx, a_batch, nv, sc.lv[0].coords, st));
-    TRY(build_level(sc.lv[0], err_flag, ar, st));
+    TRY(dv3d_make_coords(a_idx, a_batch, nv, sc.lv[0].coords, sst));
+    TRY(build_level(sc.lv[0], err_flag, ar, sst));
     for (int l = 1; l < nl; ++l) {
         const int ns = sc.lv[l - 1].stride * 2;
         const size_t cws_bytes = dv3d_coarsen_workspace_bytes((int)grid.n_cells[0], (int)grid.n_cells[1], (int)grid.n_cells[2],
@@ -258,10 +286,10 @@ static int model_scene(const dv3d_net_params_t& net, const float* pts, const flo
         ARENA_CHECK(ar);
         long long n_out = 0;
         TRY(dv3d_coarsen(sc.lv[l - 1].coords, sc.lv[l - 1].n, ns, (int)grid.n_cells[0], (int)grid.n_cells[1],
-                         (int)grid.n_cells[2], (int)grid.n_batch, cws, cws_bytes, sc.lv[l - 1].n, sc.lv[l].coords, &n_out, st));
+                         (int)grid.n_cells[2], (int)grid.n_batch, cws, cws_bytes, sc.lv[l - 1].n, sc.lv[l].coords, &n_out, sst));
         sc.lv[l].n = n_out;
         sc.lv[l].stride = ns;
-        TRY(build_level(sc.lv[l], err_flag, ar, st));
+        TRY(build_level(sc.lv[l], err_flag, ar, sst));
     }
 
     // every kernel map of the U-Net and its pair-major plan, then ONE sync for the counts
@@ -270,15 +298,15 @@ static int model_scene(const dv3d_net_params_t& net, const float* pts, const flo
         KMap* maps[3 * DV3D_MAX_LEVELS];
         int n_maps = 0;
         for (int l = 0; l < nl; ++l) {
-            TRY(kernel_map(sc.lv[l], sc.lv[l], sc.lv[l].stride, want_plan, ar, &sc.same[l], st));
+            TRY(kernel_map(sc.lv[l], sc.lv[l], sc.lv[l].stride, want_plan, ar, &sc.same[l], sst));
             maps[n_maps++] = &sc.same[l];
         }
         for (int l = 0; l + 1 < nl; ++l) {
-            TRY(kernel_map(sc.lv[l + 1], sc.lv[l], sc.lv[l].stride, want_plan, ar, &sc.down[l], st));
+            TRY(kernel_map(sc.lv[l + 1], sc.lv[l], sc.lv[l].stride, want_plan, ar, &sc.down[l], sst));
             maps[n_maps++] = &sc.down[l];
         }
         for (int l = 0; l + 1 < nl; ++l) {
-            TRY(kernel_map(sc.lv[l], sc.lv[l + 1], -sc.lv[l].stride, want_plan, ar, &sc.up[l], st));
+            TRY(kernel_map(sc.lv[l], sc.lv[l + 1], -sc.lv[l].stride, want_plan, ar, &sc.up[l], sst));
             maps[n_maps++] = &sc.up[l];
         }
         {
@@ -296,7 +324,7 @@ static int model_scene(const dv3d_net_params_t& net, const float* pts, const flo
                 stp[i] = maps[i]->step;
                 nb[i] = maps[i]->nbr;
             }
-            TRY(dv3d_kernel_map_batch(co, no, tb, tbb, stp, nb, n_maps, st));
+            TRY(dv3d_kernel_map_batch(co, no, tb, tbb, stp, nb, n_maps, sst));
         }
         sc.pair_ws = nullptr;
         sc.pair_ws_bytes = 0;
@@ -312,8 +340,8 @@ static int model_scene(const dv3d_net_params_t& net, const float* pts, const flo
                 n_outs[i] = maps[i]->n_out;
                 pbytes[i] = maps[i]->plan_bytes;
             }
-            TRY(dv3d_pair_plan_build(nbrs, n_outs, plans_w, pbytes, n_maps, st));
-            TRY(dv3d_pair_plan_counts(plans, n_maps, tiles, nullptr, st));
+            TRY(dv3d_pair_plan_build(nbrs, n_outs, plans_w, pbytes, n_maps, sst));
+            TRY(dv3d_pair_plan_counts(plans, n_maps, tiles, nullptr, sst));
             long long max_tiles = 0;
             for (int i = 0; i < n_maps; ++i) {
                 maps[i]->n_tiles = tiles[i];
@@ -326,8 +354,12 @@ static int model_scene(const dv3d_net_params_t& net, const float* pts, const flo
         }
     }
 
+    // join: the U-Net needs PointNet's features (main stream) and the maps / plans (side stream)
+    DV3D_CUDA(cudaEventRecord(side->join, side->stream));
+    DV3D_CUDA(cudaStreamWaitEvent(cs, side->join, 0));
+
     // ---- sparse U-Net (scenemodeling.py:191-237)
-    next_stage(DV3D_STAGE_UNET);
+    next_stage(DV3D_STAGE_UNET, cs);
     float* xs[DV3D_MAX_LEVELS];
     float* x = F;
     for (int b = 0; b < net.n_res[0]; ++b) TRY(res_block(net.res_down[0][b], x, sc.lv[0].n, sc.same[0], sc, ar, &x, st));
@@ -538,12 +570,24 @@ extern "C" int dv3d_hot_path(const dv3d_net_params_t* netp, const float* feats_n
                 int off_c = 0;
                 {
                     Prof pr(DV3D_STAGE_FLOW_INTERP, cs);
-                    for (int l = 0; l < sc.n_levels; ++l) {  // finest level first (refinement.py:41 prepends)
-                        TRY(dv3d_sparse_interp(pts_hyp, pts_batch, Np, 7, 8, sc.origin, (float)(sc.lv[l].stride * edge_len),
-                                               sc.lv[l].stride, sc.lv[l].table, sc.lv[l].table_bytes, sc.feats[l], sc.dims[l],
-                                               operand, in_dim, off_c, stream));
+                    // all levels with one launch, finest level first in the operand (refinement.py:41 prepends)
+                    float res_l[DV3D_MAX_LEVELS];
+                    int stride_l[DV3D_MAX_LEVELS], C_l[DV3D_MAX_LEVELS], off_l[DV3D_MAX_LEVELS];
+                    const void* tab_l[DV3D_MAX_LEVELS];
+                    size_t tabb_l[DV3D_MAX_LEVELS];
+                    const float* feat_l[DV3D_MAX_LEVELS];
+                    for (int l = 0; l < sc.n_levels; ++l) {
+                        res_l[l] = (float)(sc.lv[l].stride * edge_len);
+                        stride_l[l] = sc.lv[l].stride;
+                        tab_l[l] = sc.lv[l].table;
+                        tabb_l[l] = sc.lv[l].table_bytes;
+                        feat_l[l] = sc.feats[l];
+                        C_l[l] = sc.dims[l];
+                        off_l[l] = off_c;
                         off_c += sc.dims[l];
                     }
+                    TRY(dv3d_sparse_interp_batch(pts_hyp, pts_batch, Np, 7, 8, sc.origin, sc.n_levels, res_l, stride_l, tab_l,
+                                                 tabb_l, feat_l, C_l, off_l, operand, in_dim, stream));
                 }
                 DV3D_REQUIRE(off_c == var_off, "hot_path: decoder input width %d != level widths %d + 32", in_dim, off_c);
                 {

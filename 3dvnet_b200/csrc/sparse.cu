@@ -85,11 +85,11 @@ kernel_map_batch_kernel(const __grid_constant__ KernelMapBatch b) {
 // One warp per query point.  q = ((p - origin[b]) / res) * stride in base-voxel units
 // (refinement.py:34-35); lanes 0..7 probe the 8 corners, all lanes accumulate C channels.
 template <int C>
-__global__ void __launch_bounds__(256)
-sparse_interp_kernel(const float* __restrict__ pts, const long long* __restrict__ pts_batch, long long Nq, int n_hyp,
-                     int rows_per_point, const float* __restrict__ origin, float res, int stride, HashView t,
-                     const float* __restrict__ feat, float* __restrict__ out, int out_ld, int out_off) {
-    pdl_wait();
+__device__ __forceinline__ void sparse_interp_body(const float* __restrict__ pts, const long long* __restrict__ pts_batch,
+                                                   long long Nq, int n_hyp, int rows_per_point,
+                                                   const float* __restrict__ origin, float res, int stride, HashView t,
+                                                   const float* __restrict__ feat, float* __restrict__ out, int out_ld,
+                                                   int out_off) {
     const int lane = threadIdx.x & 31;
     const long long q = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (q >= Nq) return;
@@ -140,6 +140,39 @@ sparse_interp_kernel(const float* __restrict__ pts, const long long* __restrict_
         *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2 % V], acc[3 % V]);
     else
         *reinterpret_cast<float2*>(o) = make_float2(acc[0], acc[1]);
+}
+
+template <int C>
+__global__ void __launch_bounds__(256)
+sparse_interp_kernel(const float* __restrict__ pts, const long long* __restrict__ pts_batch, long long Nq, int n_hyp,
+                     int rows_per_point, const float* __restrict__ origin, float res, int stride, HashView t,
+                     const float* __restrict__ feat, float* __restrict__ out, int out_ld, int out_off) {
+    pdl_wait();
+    sparse_interp_body<C>(pts, pts_batch, Nq, n_hyp, rows_per_point, origin, res, stride, t, feat, out, out_ld, out_off);
+}
+
+// every level of the U-Net in one launch: blockIdx.y selects the level
+constexpr int SI_MAX_LEVELS = 4;
+struct InterpBatch {
+    float res[SI_MAX_LEVELS];
+    int stride[SI_MAX_LEVELS];
+    HashView table[SI_MAX_LEVELS];
+    const float* feat[SI_MAX_LEVELS];
+    int C[SI_MAX_LEVELS];
+    int out_off[SI_MAX_LEVELS];
+};
+__global__ void __launch_bounds__(256)
+sparse_interp_batch_kernel(const float* __restrict__ pts, const long long* __restrict__ pts_batch, long long Nq, int n_hyp,
+                           int rows_per_point, const float* __restrict__ origin, const __grid_constant__ InterpBatch b,
+                           float* __restrict__ out, int out_ld) {
+    pdl_wait();
+    const int l = blockIdx.y;
+    if (b.C[l] == 64)
+        sparse_interp_body<64>(pts, pts_batch, Nq, n_hyp, rows_per_point, origin, b.res[l], b.stride[l], b.table[l], b.feat[l],
+                               out, out_ld, b.out_off[l]);
+    else
+        sparse_interp_body<128>(pts, pts_batch, Nq, n_hyp, rows_per_point, origin, b.res[l], b.stride[l], b.table[l],
+                                b.feat[l], out, out_ld, b.out_off[l]);
 }
 
 }  // namespace dv3d
@@ -198,6 +231,34 @@ extern "C" int dv3d_kernel_map_batch(const int* const* coords_out, const long lo
     int gx = cdiv(max_n * 27, 256);
     if (gx > 8 * kNumSMs) gx = 8 * kNumSMs;
     DV3D_LAUNCH((kernel_map_batch_kernel), dim3(gx, n_maps), 256, 0, (cudaStream_t)stream, b);
+    DV3D_LAUNCHED();
+    return DV3D_OK;
+}
+
+extern "C" int dv3d_sparse_interp_batch(const float* pts, const long long* pts_batch, long long n_pts, int n_hyp,
+                                        int rows_per_point, const float* origin, int n_levels, const float* res,
+                                        const int* stride, const void* const* table, const size_t* table_bytes,
+                                        const float* const* feat, const int* C, const int* out_off, float* out, int out_ld,
+                                        void* stream) {
+    DV3D_REQUIRE(pts && pts_batch && origin && res && stride && table && table_bytes && feat && C && out_off && out &&
+                     n_pts >= 0 && n_hyp > 0 && rows_per_point >= n_hyp && n_levels >= 1 && n_levels <= SI_MAX_LEVELS,
+                 "sparse_interp_batch: bad arguments (1..%d levels)", SI_MAX_LEVELS);
+    InterpBatch b = {};
+    for (int l = 0; l < n_levels; ++l) {
+        DV3D_REQUIRE(table[l] && feat[l] && res[l] > 0.f && stride[l] > 0, "sparse_interp_batch: bad level %d", l);
+        DV3D_REQUIRE(hash_view(const_cast<void*>(table[l]), table_bytes[l], &b.table[l]), "sparse_interp_batch: bad table size");
+        DV3D_REQUIRE(C[l] == 64 || C[l] == 128, "sparse_interp_batch: C must be 64 or 128, got %d", C[l]);
+        DV3D_REQUIRE(out_ld % 4 == 0 && out_off[l] % 4 == 0 && out_off[l] + C[l] <= out_ld, "sparse_interp_batch: bad output window");
+        b.res[l] = res[l];
+        b.stride[l] = stride[l];
+        b.feat[l] = feat[l];
+        b.C[l] = C[l];
+        b.out_off[l] = out_off[l];
+    }
+    const long long Nq = n_pts * n_hyp;
+    if (Nq == 0) return DV3D_OK;
+    DV3D_LAUNCH((sparse_interp_batch_kernel), dim3(cdiv(Nq, 8), n_levels), 256, 0, (cudaStream_t)stream, pts, pts_batch, Nq, n_hyp,
+                rows_per_point, origin, b, out, out_ld);
     DV3D_LAUNCHED();
     return DV3D_OK;
 }

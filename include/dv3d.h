@@ -266,6 +266,11 @@ int dv3d_level_points(const int* coords, long long n, const float* origin, float
 int dv3d_sparse_interp(const float* pts, const long long* pts_batch, long long n_pts, int n_hyp, int rows_per_point,
                        const float* origin, float res, int stride, const void* table, size_t table_bytes,
                        const float* feat, int C, float* out, int out_ld, int out_off, void* stream);
+/* the same interpolation for up to 4 levels with one launch (HOST arrays of per-level values) */
+int dv3d_sparse_interp_batch(const float* pts, const long long* pts_batch, long long n_pts, int n_hyp,
+                             int rows_per_point, const float* origin, int n_levels, const float* res, const int* stride,
+                             const void* const* table, const size_t* table_bytes, const float* const* feat, const int* C,
+                             const int* out_off, float* out, int out_ld, void* stream);
 /* Conv1d(k=3,pad=1,no bias)+BN(folded scale/shift)+ReLU over the hypothesis axis on the padded
  * layout: x [n_pts*8, ldx] -> y [n_pts*8, ldy] (row 7 of every point written as 0);
  * weight_tkn [3, Cin, Cout] = torch weight [Cout,Cin,3] permuted (2,1,0). */
