@@ -249,13 +249,12 @@ class PL3DVNet(nn.Module):
             return self.refine_depth(depth, depth_batch, feats_quarter, rotmats, tvecs, K, plan, offsets_list)
 
     def upsample(self, depth, ref_idx, feats_quarter, feats_half, images):
-        """nearest upsampling + the three PropagationNets (lightningmodel.py:84-112)"""
-        d = F.interpolate(depth.unsqueeze(1), feats_quarter.shape[-2:], mode='nearest')
-        d = self.refine_quarter(feats_quarter[ref_idx], d)
-        d = F.interpolate(d.unsqueeze(1), feats_half.shape[-2:], mode='nearest')
-        d = self.refine_half(feats_half[ref_idx], d)
-        d = F.interpolate(d.unsqueeze(1), images.shape[-2:], mode='nearest')
-        return self.refine_full(images[ref_idx], d)
+        """nearest upsampling + the three PropagationNets (lightningmodel.py:84-112,
+        eval-3dvnet.py:101-125): [n_ref,h,w] -> [n_ref,H,W]; the nearest upsampling is fused into
+        each PropagationNet's input kernel"""
+        d = self.refine_quarter.forward_from(feats_quarter[ref_idx], depth)
+        d = self.refine_half.forward_from(feats_half[ref_idx], d)
+        return self.refine_full.forward_from(images[ref_idx], d)
 
     def forward(self, batch, offsets, n_iters):
         """Inference-only counterpart of lightningmodel.py:48-122: returns the depth maps of every

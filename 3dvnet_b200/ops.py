@@ -444,6 +444,50 @@ def decoder_head(x, n_hyp, weight, bias, offset, want_prob=False):
     return off, prob
 
 
+# ----------------------------------------------------------------------------- upsampling
+_grid_maps = {}
+
+
+def grid_map_2d(n, H, W, device):
+    """[n*H*W, 9] int32 neighbour rows of a dense image grid (-1 = zero padding), cached per shape"""
+    key = (n, H, W, str(device))
+    m = _grid_maps.get(key)
+    if m is None:
+        if len(_grid_maps) > 16:
+            _grid_maps.clear()
+        m = torch.empty((n * H * W, 9), dtype=torch.int32, device=device)
+        lib().call('dv3d_grid_map_2d', n, H, W, _p(m), _stream())
+        _grid_maps[key] = m
+    return m
+
+
+def propagation_net(features, depth_lo, layers):
+    """PropagationNet (upsampling.py:14-36) on depth_lo [n,h,w] nearest-upsampled to the feature
+    resolution (eval-3dvnet.py:101-125). features [n,C,H,W]; layers: four (W_kn [9*Cin,64], packed,
+    scale [64], shift [64]) -> [n,H,W]."""
+    _chk(features, torch.float32, 'features', 4), _chk(depth_lo, torch.float32, 'depth', 3)
+    n, C, H, W = features.shape
+    h, w = depth_lo.shape[1:]
+    dev = features.device
+    M = n * H * W
+    ld0 = layers[0][0].shape[0] // 9
+    x = torch.empty((M, ld0), dtype=torch.float32, device=dev)
+    depth_up = torch.empty((n, H, W), dtype=torch.float32, device=dev)
+    lib().call('dv3d_propagation_input', _p(features), C, _p(depth_lo), n, h, w, H, W, ld0, _p(x), _p(depth_up), _stream())
+    nbr = grid_map_2d(n, H, W, dev)
+    a = torch.empty((M, 64), dtype=torch.float32, device=dev)
+    b = torch.empty((M, 64), dtype=torch.float32, device=dev)
+    src, ldx = x, ld0
+    for i, (W_kn, packed, scale, shift) in enumerate(layers):
+        dst = a if i % 2 == 0 else b
+        lib().call('dv3d_conv2d3x3_bn_relu_rows', _p(src), M, W_kn.shape[0] // 9, ldx, _p(nbr), _p(W_kn), _p(packed),
+                   _p(scale), _p(shift), 64, _p(dst), 64, _stream())
+        src, ldx = dst, 64
+    out = torch.empty((n, H, W), dtype=torch.float32, device=dev)
+    lib().call('dv3d_propagation_output', _p(src), 64, _p(depth_up), n, H, W, _p(out), _stream())
+    return out
+
+
 # ----------------------------------------------------------------------------- engine
 class Conv3dParams(ctypes.Structure):
     """dv3d_conv3d_params_t"""

@@ -284,6 +284,29 @@ int dv3d_decoder_head(const float* x, long long n_pts, int n_hyp, int rows_per_p
                       void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Coarse-to-fine depth upsampling: the step right after the hot path.
+ * PropagationNet (upsampling.py:14-36): four Conv2d(3x3, pad 1, no bias)+BN+ReLU, softmax over
+ * the 9 output channels, weighted sum of the replicate-padded 3x3 depth neighbourhood; in front of
+ * it F.interpolate(mode='nearest') of the depth map (eval-3dvnet.py:101-125).
+ * Activations are channels-last rows [n*H*W, ld]; the convolutions run on the tcgen05 gather-GEMM.
+ */
+/* nbr [n*H*W, 9] int32: row of pixel (y+dy, x+dx), t = (dy+1)*3 + (dx+1); -1 = zero padding */
+int dv3d_grid_map_2d(int n, int H, int W, int* nbr, void* stream);
+/* x [n*H*W, ld] = [features (C channels of feats_nchw [n,C,H,W]) | depth_up | 0 ...], ld % 32 == 0, ld > C;
+ * depth_up [n,H,W] = nearest upsampling of depth_lo [n,h,w] (src = min(floor(dst * (h/H)), h-1) in fp32, as ATen) */
+int dv3d_propagation_input(const float* feats_nchw, int C, const float* depth_lo, int n, int h, int w, int H, int W,
+                           int ld, float* x, float* depth_up, void* stream);
+/* y [M, ldy] (first Cout columns) = relu(conv3x3(x)[.,0:Cout] * scale + shift); x [M, ldx] (first Cin channels,
+ * Cin % 32 == 0); W_kn [9*Cin, Cout] with row t*Cin + ci = weight[co][ci][t/3][t%3], Cout in {64,128} (zero-pad
+ * the layer's output channels; padded scale/shift = 0); W_packed from dv3d_gemm_pack_weights or NULL */
+int dv3d_conv2d3x3_bn_relu_rows(const float* x, long long M, int Cin, int ldx, const int* nbr, const float* W_kn,
+                                const void* W_packed, const float* scale, const float* shift, int Cout, float* y,
+                                int ldy, void* stream);
+/* out [n,H,W] = sum_t softmax(logits[m, 0:9])_t * depth[clamp(y+dy), clamp(x+dx)]; logits rows 16-byte aligned */
+int dv3d_propagation_output(const float* logits, int ld, const float* depth, int n, int H, int W, float* out,
+                            void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Engine: the whole hot path enqueued by ONE call from native code.
  *
  * The reference drives its hot path from Python, one library call per tensor op

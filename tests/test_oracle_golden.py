@@ -89,3 +89,21 @@ def test_refinement_schedule_matches_reference(name, synth):
                           t['rotmats'], t['tvecs'], t['K'], t['ref_src_edges'], float(g['edge_len']), img_size, p,
                           offsets_list=g['offsets'].tolist())
     np.testing.assert_allclose(out.numpy(), g['ref_depth_final'], rtol=0, atol=5e-5)
+
+
+def test_propagation_oracle_matches_reference_golden():
+    """oracle/upsample.py against outputs of the unmodified reference PropagationNet cascade"""
+    import os
+    import numpy as np
+    import torch
+    from oracle import upsample
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'propagation.npz'))
+    t = {k: torch.from_numpy(g[k]) for k in g.files}
+    p = {name: {k[len(name) + 1:]: v for k, v in t.items() if k.startswith(name + '.')} for name in ('quarter', 'half', 'full')}
+    with torch.no_grad():
+        dq = upsample.propagation_net(t['feats_quarter'], torch.nn.functional.interpolate(
+            t['depth'].unsqueeze(1), t['feats_quarter'].shape[-2:], mode='nearest'), p['quarter'])
+        full = upsample.upsample_cascade(t['depth'], t['feats_quarter'], t['feats_half'], t['images'], p['quarter'],
+                                         p['half'], p['full'])
+    np.testing.assert_array_equal(dq.numpy(), g['ref_quarter'])
+    np.testing.assert_array_equal(full.numpy(), g['ref_full'])

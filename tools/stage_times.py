@@ -57,6 +57,10 @@ def main():
     with torch.no_grad():
         depth = mvs()
         xs = net.model_scene(depth, depth_batch, d['feats_quarter'], d['rotmats'], d['tvecs'], d['K'], plan)
+        g = torch.Generator().manual_seed(1)
+        n_imgs = d['feats_quarter'].shape[0]
+        feats_half = torch.randn(n_imgs, 32, bench.IMG_SIZE[0] // 2, bench.IMG_SIZE[1] // 2, generator=g).to(dev)
+        images = torch.randn(n_imgs, 3, *bench.IMG_SIZE, generator=g).to(dev)
         stages = [
             ('mvs (plane sweep + CostRegNet + soft-argmin)', mvs),
             ('cost volume only', lambda: net.mvsnet.cost_volume(d['feats_quarter'], batch, cfg['depth_start'],
@@ -66,6 +70,8 @@ def main():
                                                     d['K'], plan)),
             ('run_pointflow', lambda: net.run_pointflow(xs, depth, depth_batch, d['feats_quarter'], d['rotmats'],
                                                         d['tvecs'], d['K'], plan, 0.05, 3)),
+            ('upsample: 3 PropagationNets, 56x56 -> 256x320 (after the path, SURVEY 8f.1)',
+             lambda: net.upsample(depth, plan.ref_idx, d['feats_quarter'], feats_half, images)),
             ('hot_path (whole step)', lambda: net.hot_path(d['feats_quarter'], d['rotmats'], d['tvecs'], d['K'],
                                                            b.ref_src_edges, d['images_batch'], cfg, bench.OFFSETS_LIST)),
         ]
