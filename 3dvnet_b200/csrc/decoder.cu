@@ -70,7 +70,8 @@ using namespace dv3d;
 
 extern "C" int dv3d_conv1d_bn_relu(const float* x, long long n_pts, int rows_per_point, int Cin, int ldx,
                                    const float* weight_tkn, const void* W_packed, const float* scale,
-                                   const float* shift, int Cout, float* y, int ldy, void* stream) {
+                                   const float* shift, int Cout, float* y, int ldy, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
     DV3D_REQUIRE(x && (weight_tkn || W_packed) && scale && shift && y && n_pts >= 0, "conv1d: bad arguments");
     DV3D_REQUIRE(rows_per_point == 8, "conv1d: the operand layout is [n_pts, 8, C] (7 hypotheses + 1 zero row)");
     GemmDesc d = {};
@@ -88,7 +89,40 @@ extern "C" int dv3d_conv1d_bn_relu(const float* x, long long n_pts, int rows_per
     d.zero_row_val = rows_per_point - 1;
     d.out = y;
     d.out_ld = ldy;
-    return launch_gather_gemm(d, (cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    // Wave quantisation: the tensor-core kernel runs one 128-row tile per SM, so 148 q + r tiles take
+    // q + 1 rounds.  When the last round is less than half full its tiles are launched separately
+    // with the three taps split over three CTAs each (partials added in tap order by the last CTA
+    // to arrive: deterministic) - C2: 196 tiles = one full round + 48 tiles x 3 splits.
+    // A tile boundary is a point boundary (128 = 16 points x 8 rows), so the row shifts of the
+    // second launch see the same zero rows as in the single launch.  Measured at C2: 81 -> 71 us for
+    // K = 3 x 352, but a loss for K = 3 x 128 (the extra launch and the reduction cost more than the
+    // saved half round), hence the K threshold.
+    const long long tiles = (d.M + 127) / 128, q = tiles / kNumSMs, r = tiles % kNumSMs;
+    const int split = r > 0 ? (int)(kNumSMs / r) : 1;
+    constexpr size_t kCounterBytes = 4096;
+    if (W_packed && workspace && split >= 2 && 3 * Cin >= 768 && workspace_bytes >= kCounterBytes + (size_t)r * 3 * 128 * Cout * sizeof(float) &&
+        r * sizeof(int) <= kCounterBytes) {
+        DV3D_REQUIRE(((uintptr_t)workspace & 255) == 0, "conv1d: workspace must be 256-byte aligned");
+        const long long M_main = q * kNumSMs * 128;
+        if (q > 0) {
+            GemmDesc m = d;
+            m.M = M_main;
+            int rc = launch_gather_gemm(m, st);
+            if (rc) return rc;
+        }
+        GemmDesc t = d;
+        for (int i = 0; i < 3; ++i) t.slice[i].src = x + (size_t)M_main * ldx;
+        t.out = y + (size_t)M_main * ldy;
+        t.M = d.M - M_main;
+        t.n_src_rows = t.M;
+        t.split_counters = (int*)workspace;
+        t.split_ws = (float*)((char*)workspace + kCounterBytes);
+        t.split_ws_bytes = workspace_bytes - kCounterBytes;
+        t.split_hint = split < 3 ? split : 3;
+        return launch_gather_gemm(t, st);
+    }
+    return launch_gather_gemm(d, st);
 }
 
 extern "C" int dv3d_decoder_head(const float* x, long long n_pts, int n_hyp, int rows_per_point, int Cin, int ldx,

@@ -536,7 +536,8 @@ extern "C" int dv3d_hot_path(const dv3d_net_params_t* netp, const float* feats_n
         float* dec_b = ar.get<float>((size_t)Np * 8 * net.dec[1].N);
         float* pts_hyp = ar.get<float>((size_t)Np * 7 * 3);
         long long* pts_batch = ar.get<long long>((size_t)Np);
-        void* split_ws = ar.get<char>(dv3d_sparse_conv_workspace_bytes(128));
+        const size_t split_ws_bytes = dv3d_sparse_conv_workspace_bytes(128);
+        void* split_ws = ar.get<char>(split_ws_bytes);
         ARENA_CHECK(ar);
         DV3D_CUDA(cudaMemsetAsync(operand, 0, sizeof(float) * Np * 8 * in_dim, cs));
         DV3D_CUDA(cudaMemsetAsync(split_ws, 0, dv3d_sparse_conv_workspace_bytes(128), cs));
@@ -593,14 +594,14 @@ extern "C" int dv3d_hot_path(const dv3d_net_params_t* netp, const float* feats_n
                 {
                     Prof pr(DV3D_STAGE_DEC_GEMM0, cs);
                     TRY(dv3d_conv1d_bn_relu(operand, Np, 8, in_dim, in_dim, net.dec[0].W, net.dec[0].Wp, net.dec[0].a,
-                                            net.dec[0].b, net.dec[0].N, dec_a, net.dec[0].N, stream));
+                                            net.dec[0].b, net.dec[0].N, dec_a, net.dec[0].N, split_ws, split_ws_bytes, stream));
                 }
                 {
                     Prof pr(DV3D_STAGE_DEC_REST, cs);
                     TRY(dv3d_conv1d_bn_relu(dec_a, Np, 8, net.dec[1].K / 3, net.dec[0].N, net.dec[1].W, net.dec[1].Wp,
-                                            net.dec[1].a, net.dec[1].b, net.dec[1].N, dec_b, net.dec[1].N, stream));
+                                            net.dec[1].a, net.dec[1].b, net.dec[1].N, dec_b, net.dec[1].N, split_ws, split_ws_bytes, stream));
                     TRY(dv3d_conv1d_bn_relu(dec_b, Np, 8, net.dec[2].K / 3, net.dec[1].N, net.dec[2].W, net.dec[2].Wp,
-                                            net.dec[2].a, net.dec[2].b, net.dec[2].N, dec_a, net.dec[2].N, stream));
+                                            net.dec[2].a, net.dec[2].b, net.dec[2].N, dec_a, net.dec[2].N, split_ws, split_ws_bytes, stream));
                     TRY(dv3d_decoder_head(dec_a, Np, 7, 8, net.dec[2].N, net.dec[2].N, net.dec_head_weight, net.dec_head_bias,
                                           offset, nullptr, offs, stream));
                     DV3D_LAUNCH((add_inplace_kernel), cdiv(Np, 256), 256, 0, cs, depth, offs, Np);

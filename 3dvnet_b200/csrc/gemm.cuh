@@ -52,6 +52,7 @@ struct GemmDesc {
     float* split_ws;        // optional K-split workspace of the tcgen05 kernel (see gemm_tc.cu)
     size_t split_ws_bytes;
     int* split_counters;    // one int per 128-row tile, zero on entry, left zero on exit
+    int split_hint;         // > 1: use exactly this many K splits (caller sized the workspace); 0: automatic
     float* out;             // [M, out_ld]
     int out_ld;
 };

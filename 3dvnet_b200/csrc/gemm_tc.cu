@@ -502,7 +502,8 @@ int launch_gather_gemm_tc(const GemmDesc& d, cudaStream_t st) {
     const int tiles = cdiv(d.M, TC_BM);
     int split = 1;
     if (d.split_ws && d.split_counters && !d.tile_wslice) {
-        split = gather_gemm_tc_splits(d.M, d.n_slices);
+        split = d.split_hint > 1 ? (d.split_hint < d.n_slices ? d.split_hint : d.n_slices) : gather_gemm_tc_splits(d.M, d.n_slices);
+        if (split > TC_MAX_SPLIT) split = TC_MAX_SPLIT;
         const size_t need = (size_t)tiles * split * TC_BM * d.N * sizeof(float);
         if (d.split_ws_bytes < need) split = 1;  // tiles * split <= 148 partials fit a dv3d_sparse_conv_workspace_bytes buffer
     }

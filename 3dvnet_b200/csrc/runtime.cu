@@ -31,5 +31,5 @@ bool pdl_enabled() {
 }  // namespace dv3d
 
 extern "C" const char* dv3d_last_error(void) { return dv3d::g_err; }
-extern "C" int dv3d_abi_version(void) { return 2; }
+extern "C" int dv3d_abi_version(void) { return 3; }
 extern "C" long long dv3d_launch_count(void) { return dv3d::g_launches.load(std::memory_order_relaxed); }

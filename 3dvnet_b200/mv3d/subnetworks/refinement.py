@@ -26,6 +26,7 @@ class HypothesisDecoder(nn.Module):
                                  nn.Conv1d(h_dim, 1, kernel_size, 1, padding))
         self._pack = PackCache()
         self._operand = None
+        self._ws = None
 
     def _weights(self):
         def build():
@@ -57,8 +58,10 @@ class HypothesisDecoder(nn.Module):
     def run(self, operand, n_hyp, offset=None, want_prob=True):
         layers, head = self._weights()
         x = operand
+        if self._ws is None or self._ws.device != operand.device:
+            self._ws = ops.sparse_conv_workspace(128, operand.device)   # zeroed once; launches leave it zero
         for w, scale, shift, packed in layers:
-            x = ops.conv1d_bn_relu(x, w, scale, shift, packed=packed)
+            x = ops.conv1d_bn_relu(x, w, scale, shift, packed=packed, workspace=self._ws)
         return ops.decoder_head(x, n_hyp, head[0], head[1], 0.0 if offset is None else offset, want_prob)
 
     def forward(self, xs, pts, pts_feat, pts_batch):

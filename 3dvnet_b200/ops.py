@@ -424,14 +424,16 @@ def sparse_interp(pts, pts_batch, n_hyp, level, origin, res, feat, out, out_off)
                out_off, _stream())
 
 
-def conv1d_bn_relu(x, weight_tkn, scale, shift, out=None, packed=None):
-    """x [n_pts, 8, Cin] -> [n_pts, 8, Cout] (refinement.py:8-13)."""
+def conv1d_bn_relu(x, weight_tkn, scale, shift, out=None, packed=None, workspace=None):
+    """x [n_pts, 8, Cin] -> [n_pts, 8, Cout] (refinement.py:8-13). workspace: sparse_conv_workspace()
+    buffer that lets a thin last round of tiles split its taps over CTAs."""
     n_pts, rows, ldx = x.shape
     Cin, Cout = weight_tkn.shape[1], weight_tkn.shape[2]
     if out is None:
         out = torch.empty((n_pts, rows, Cout), dtype=torch.float32, device=x.device)
+    ws_bytes = 0 if workspace is None else workspace.numel()
     lib().call('dv3d_conv1d_bn_relu', _p(x), n_pts, rows, Cin, ldx, _p(weight_tkn), _p(packed), _p(scale), _p(shift),
-               Cout, _p(out), out.shape[2], _stream())
+               Cout, _p(out), out.shape[2], _p(workspace) if ws_bytes else None, ws_bytes, _stream())
     return out
 
 

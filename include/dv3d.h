@@ -276,7 +276,7 @@ int dv3d_sparse_interp_batch(const float* pts, const long long* pts_batch, long 
  * weight_tkn [3, Cin, Cout] = torch weight [Cout,Cin,3] permuted (2,1,0). */
 int dv3d_conv1d_bn_relu(const float* x, long long n_pts, int rows_per_point, int Cin, int ldx,
                         const float* weight_tkn, const void* W_packed, const float* scale, const float* shift,
-                        int Cout, float* y, int ldy, void* stream);
+                        int Cout, float* y, int ldy, void* workspace, size_t workspace_bytes, void* stream);
 /* last Conv1d (Cin->1, bias; weight [1,Cin,3] torch layout) + softmax over hypotheses + expected
  * offset sum_i p_i * linspace(-n*offset, n*offset)_i; prob_out optional [n_pts,n_hyp]; offset_out [n_pts] */
 int dv3d_decoder_head(const float* x, long long n_pts, int n_hyp, int rows_per_point, int Cin, int ldx,

@@ -114,7 +114,7 @@ def test_sparse_conv(ops, mode, n_in, n_out, Cin, Cout, density):
 
 
 @pytest.mark.parametrize('mode', ['tf32x3', 'f32'])
-@pytest.mark.parametrize('n_pts,Cin', [(3136, 352), (100, 128), (3136 * 4, 128)])
+@pytest.mark.parametrize('n_pts,Cin', [(3136, 352), (100, 128), (3136 * 4, 128), (2400, 128), (16 * 150, 352)])
 def test_conv1d_rows(ops, mode, n_pts, Cin):
     ops.set_gemm_mode(mode)
     x = rnd(n_pts, 8, Cin, seed=21)
@@ -128,6 +128,15 @@ def test_conv1d_rows(ops, mode, n_pts, Cin):
     ref = torch.relu(ref).permute(0, 2, 1)
     check(y[:, :7], ref, mode)
     assert (y[:, 7] == 0).all()
+    # thin last round of tiles launched separately with its taps split over CTAs (C2: 196 = 148 + 48 tiles)
+    ws = ops.sparse_conv_workspace(128, DEV)
+    if ws is not None:
+        y_s = ops.conv1d_bn_relu(x, w, scale, shift, packed=ops.pack_weights(w.reshape(-1, 128).contiguous()), workspace=ws)
+        check(y_s[:, :7], ref, mode)
+        assert (y_s[:, 7] == 0).all()
+        y_s2 = ops.conv1d_bn_relu(x, w, scale, shift, packed=ops.pack_weights(w.reshape(-1, 128).contiguous()), workspace=ws)
+        assert torch.equal(y_s, y_s2)
+        assert int(ws[:4096].max()) == 0  # counters left zero
 
 
 @pytest.mark.parametrize('mode', ['tf32x3', 'f32'])
