@@ -439,53 +439,72 @@ deconv3d_block_kernel(const float* __restrict__ x, int Cin, int Di, int Hi, int 
 }
 
 // ------------------------------------------------------------------ prob conv + soft-argmin
-// CTA = 8 consecutive pixels of one image row x 32 depth lanes.  A thread convolves the planes
-// d = lane, lane + 32, ... of its pixel (Cin -> 1 channels, 3x3x3, bias; a warp reads four
-// 32-byte row segments per tap) and folds them into an online softmax(-x) state with the plane
-// depth as value; the 32 states of a pixel are merged through shared memory.  The regularised
-// volume itself is only written on request.
-constexpr int PS_TX = 8, PS_DL = 32;
+// Thread = (pixel, depth segment of 8 planes); CTA = 8 consecutive pixels of one image row x all
+// the segments of their depth column.  A thread walks the 10 input planes of its segment once:
+// the 3x3xCin neighbourhood of a plane (72 loads at Cin = 8) feeds the three outputs it touches
+// (kd = 0,1,2), so every loaded value is used three times instead of once.  The 8 logits of the
+// segment are folded into an online softmax(-x) state with the plane depth as value and the
+// states of a pixel are merged through shared memory.  The regularised volume itself is only
+// written on request.
+constexpr int PS_TX = 8, PS_SEG = 8, PS_MAXSEG = 32;
 
-__global__ void __launch_bounds__(PS_TX * PS_DL)
-prob_softargmin_kernel(const float* __restrict__ x, int Cin, int D, int H, int W, const float* __restrict__ wgt,
-                       float bias, float d_start, float d_end, float* __restrict__ x_reg, float* __restrict__ depth) {
+template <int CIN>
+__global__ void __launch_bounds__(PS_TX * PS_MAXSEG)
+prob_softargmin_kernel(const float* __restrict__ x, int D, int H, int W, const float* __restrict__ wgt, float bias,
+                       float d_start, float d_end, float* __restrict__ x_reg, float* __restrict__ depth) {
     pdl_wait();
-    extern __shared__ float s_w[];  // [27][Cin]
-    __shared__ float s_m[PS_DL][PS_TX], s_s[PS_DL][PS_TX], s_t[PS_DL][PS_TX];
-    for (int i = threadIdx.x; i < Cin * 27; i += blockDim.x) s_w[(i % 27) * Cin + i / 27] = __ldg(wgt + i);
+    __shared__ __align__(16) float s_w[27 * CIN];  // [kd][kh][kw][ci]
+    __shared__ float s_m[PS_MAXSEG][PS_TX], s_s[PS_MAXSEG][PS_TX], s_t[PS_MAXSEG][PS_TX];
+    const int tid = threadIdx.y * PS_TX + threadIdx.x;
+    for (int i = tid; i < CIN * 27; i += PS_TX * blockDim.y) s_w[(i % 27) * CIN + i / 27] = __ldg(wgt + i);
     __syncthreads();
-    const int px = threadIdx.x % PS_TX, dl = threadIdx.x / PS_TX;
+    const int px = threadIdx.x, sg = threadIdx.y;
     const int ox = blockIdx.x * PS_TX + px, oy = blockIdx.y, n = blockIdx.z;
     const size_t plane = (size_t)H * W, vol = plane * D;
-    const float* xn = x + (size_t)n * Cin * vol;
+    const float* xn = x + (size_t)n * CIN * vol;
     const bool inside = ox < W;
+    const int n_seg = (D + PS_SEG - 1) / PS_SEG;
 
     float m = -INFINITY, s = 0.f, t = 0.f;
-    if (inside) {
-        for (int d = dl; d < D; d += PS_DL) {
-            float part[3] = {0.f, 0.f, 0.f};  // one chain per kd: three independent FMA chains
+    for (int seg = sg; seg < n_seg && inside; seg += blockDim.y) {
+        const int d0 = seg * PS_SEG;
+        float acc[PS_SEG];
 #pragma unroll
-            for (int kd = 0; kd < 3; ++kd) {
-                const int z = d + kd - 1;
-                if (z < 0 || z >= D) continue;
+        for (int j = 0; j < PS_SEG; ++j) acc[j] = 0.f;
 #pragma unroll
-                for (int kh = 0; kh < 3; ++kh) {
-                    const int yy = oy + kh - 1;
-                    if (yy < 0 || yy >= H) continue;
+        for (int zi = 0; zi < PS_SEG + 2; ++zi) {  // input plane z = d0 - 1 + zi
+            const int z = d0 - 1 + zi;
+            if (z < 0 || z >= D) continue;
 #pragma unroll
-                    for (int kw = 0; kw < 3; ++kw) {
-                        const int xx = ox + kw - 1;
-                        if (xx < 0 || xx >= W) continue;
-                        const float* xp = xn + (size_t)z * plane + (size_t)yy * W + xx;
-                        const float* wp = s_w + ((kd * 3 + kh) * 3 + kw) * Cin;
-#pragma unroll 8
-                        for (int ci = 0; ci < Cin; ++ci) part[kd] = fmaf(__ldg(xp + (size_t)ci * vol), wp[ci], part[kd]);
+            for (int kh = 0; kh < 3; ++kh) {
+                const int yy = oy + kh - 1;
+                if (yy < 0 || yy >= H) continue;
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) {
+                    const int xx = ox + kw - 1;
+                    if (xx < 0 || xx >= W) continue;
+                    const float* xp = xn + (size_t)z * plane + (size_t)yy * W + xx;
+                    float v[CIN];
+#pragma unroll
+                    for (int ci = 0; ci < CIN; ++ci) v[ci] = __ldg(xp + (size_t)ci * vol);
+#pragma unroll
+                    for (int kd = 0; kd < 3; ++kd) {  // output plane d = z - kd + 1, j = d - d0 = zi - kd
+                        const int j = zi - kd;
+                        if (j < 0 || j >= PS_SEG) continue;  // compile-time
+                        const float* wp = s_w + ((kd * 3 + kh) * 3 + kw) * CIN;
+#pragma unroll
+                        for (int ci = 0; ci < CIN; ++ci) acc[j] = fmaf(v[ci], wp[ci], acc[j]);
                     }
                 }
             }
-            const float acc = bias + ((part[0] + part[1]) + part[2]);
-            if (x_reg) x_reg[((size_t)n * D + d) * plane + (size_t)oy * W + ox] = acc;
-            const float v = -acc;
+        }
+#pragma unroll
+        for (int j = 0; j < PS_SEG; ++j) {
+            const int d = d0 + j;
+            if (d >= D) break;
+            const float a = bias + acc[j];
+            if (x_reg) x_reg[((size_t)n * D + d) * plane + (size_t)oy * W + ox] = a;
+            const float v = -a;
             const float mn = fmaxf(m, v);
             const float corr = expf(m - mn), e = expf(v - mn);
             s = s * corr + e;
@@ -493,18 +512,16 @@ prob_softargmin_kernel(const float* __restrict__ x, int Cin, int D, int H, int W
             m = mn;
         }
     }
-    s_m[dl][px] = m;
-    s_s[dl][px] = s;
-    s_t[dl][px] = t;
+    s_m[sg][px] = m;
+    s_s[sg][px] = s;
+    s_t[sg][px] = t;
     __syncthreads();
-    if (dl == 0 && inside) {
+    if (sg == 0 && inside) {
         float M = -INFINITY;
-#pragma unroll
-        for (int i = 0; i < PS_DL; ++i) M = fmaxf(M, s_m[i][px]);
+        for (int i = 0; i < (int)blockDim.y; ++i) M = fmaxf(M, s_m[i][px]);
         float S = 0.f, T = 0.f;
-#pragma unroll
-        for (int i = 0; i < PS_DL; ++i) {
-            const float c = expf(s_m[i][px] - M);  // lanes that saw no plane carry m = -inf -> 0
+        for (int i = 0; i < (int)blockDim.y; ++i) {
+            const float c = expf(s_m[i][px] - M);  // segments that saw no plane carry m = -inf -> 0
             S = fmaf(s_s[i][px], c, S);
             T = fmaf(s_t[i][px], c, T);
         }
@@ -639,11 +656,18 @@ extern "C" int dv3d_prob_softargmin(const float* x, int n, int Cin, int D, int H
                                     float bias, float depth_start, float depth_end, float* x_reg_out,
                                     float* depth_out, void* stream) {
     DV3D_REQUIRE(x && weight && depth_out, "prob_softargmin: null pointer");
-    DV3D_REQUIRE(n >= 0 && Cin > 0 && Cin <= 64 && D > 0 && H > 0 && W > 0, "prob_softargmin: bad shape");
+    DV3D_REQUIRE(n >= 0 && (Cin == 8 || Cin == 16) && D > 0 && H > 0 && W > 0,
+                 "prob_softargmin: bad shape (Cin must be 8 or 16, got %d)", Cin);
     if (n == 0) return DV3D_OK;
     DV3D_REQUIRE(H <= 65535 && n <= 65535, "prob_softargmin: H or n > 65535");
-    dim3 grid(cdiv(W, PS_TX), H, n);
-    DV3D_LAUNCH((prob_softargmin_kernel), grid, PS_TX * PS_DL, sizeof(float) * Cin * 27, (cudaStream_t)stream, x, Cin, D, H, W, weight, bias, depth_start, depth_end, x_reg_out, depth_out);
+    const int n_seg = cdiv(D, PS_SEG);
+    dim3 grid(cdiv(W, PS_TX), H, n), block(PS_TX, n_seg < PS_MAXSEG ? n_seg : PS_MAXSEG);
+    if (Cin == 8)
+        DV3D_LAUNCH((prob_softargmin_kernel<8>), grid, block, 0, (cudaStream_t)stream, x, D, H, W, weight, bias, depth_start,
+                    depth_end, x_reg_out, depth_out);
+    else
+        DV3D_LAUNCH((prob_softargmin_kernel<16>), grid, block, 0, (cudaStream_t)stream, x, D, H, W, weight, bias, depth_start,
+                    depth_end, x_reg_out, depth_out);
     DV3D_LAUNCHED();
     return DV3D_OK;
 }

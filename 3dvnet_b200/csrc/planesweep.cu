@@ -71,9 +71,10 @@ __device__ __forceinline__ void backproject(const float* __restrict__ cam, float
 // weights.  Taps outside the map get weight 0 and a clamped address (zero padding per tap).
 __device__ __forceinline__ void make_record(const float* __restrict__ P, float X0, float X1, float X2,
                                             const SampleGeom& g, int& rec, float4& wt) {
-    float qx = __fmaf_rn(__ldg(P + 3), 1.f, chain3(__ldg(P + 0), __ldg(P + 1), __ldg(P + 2), X0, X1, X2));
-    float qy = __fmaf_rn(__ldg(P + 7), 1.f, chain3(__ldg(P + 4), __ldg(P + 5), __ldg(P + 6), X0, X1, X2));
-    float qz = __fmaf_rn(__ldg(P + 11), 1.f, chain3(__ldg(P + 8), __ldg(P + 9), __ldg(P + 10), X0, X1, X2));
+    // P is the CTA's shared-memory copy of the source camera's projection matrix (broadcast reads)
+    float qx = __fmaf_rn(P[3], 1.f, chain3(P[0], P[1], P[2], X0, X1, X2));
+    float qy = __fmaf_rn(P[7], 1.f, chain3(P[4], P[5], P[6], X0, X1, X2));
+    float qz = __fmaf_rn(P[11], 1.f, chain3(P[8], P[9], P[10], X0, X1, X2));
     float zz = __fadd_rn(fabsf(qz), 1e-8f);
     float x = __fdiv_rn(qx, zz), y = __fdiv_rn(qy, zz);
     float gx = __fsub_rn(__fmul_rn(__fdiv_rn(x, g.wm1), 2.f), 1.f);
@@ -172,6 +173,7 @@ planesweep_var_kernel(const float4* __restrict__ feats, SampleGeom geom, const f
     float4 (*s_wt)[KD][TP] = reinterpret_cast<float4 (*)[KD][TP]>(smem_raw);
     int (*s_rec)[KD][TP] = reinterpret_cast<int (*)[KD][TP]>(smem_raw + sizeof(float4) * EMAX * KD * TP);
     float* s_out = reinterpret_cast<float*>(smem_raw + (sizeof(float4) + sizeof(int)) * EMAX * KD * TP);
+    __shared__ float s_P[EMAX][12];  // projection matrices of the staged edges
 
     const int tid = threadIdx.x;
     const int r = blockIdx.y;
@@ -204,11 +206,13 @@ planesweep_var_kernel(const float4* __restrict__ feats, SampleGeom geom, const f
 
         for (int eb = e0; eb < e1; eb += EMAX) {
             const int n_e = min(EMAX, e1 - eb);
-            if (eb != e0) __syncthreads();  // previous pass fully consumed
+            __syncthreads();  // previous pass / chunk fully consumed (records, camera rows, output tile)
+            if (tid < n_e * 12) s_P[tid / 12][tid % 12] = __ldg(cams + (size_t)__ldg(esrc + eb + tid / 12) * CAM_STRIDE + CAM_P + tid % 12);
+            __syncthreads();
             for (int e = 0; e < n_e; ++e) {
                 int rec;
                 float4 wt;
-                make_record(cams + (size_t)__ldg(esrc + eb + e) * CAM_STRIDE + CAM_P, X0, X1, X2, geom, rec, wt);
+                make_record(s_P[e], X0, X1, X2, geom, rec, wt);
                 s_rec[e][pk][pv] = rec;
                 s_wt[e][pk][pv] = wt;
             }
@@ -237,9 +241,8 @@ planesweep_var_kernel(const float4* __restrict__ feats, SampleGeom geom, const f
                     out[(((size_t)r * 32 + c) * D + d) * P + p0 + lane] = s_out[c * CS + k * TP + lane];
             }
         }
-        // the next chunk's first __syncthreads (after its records are written) orders these
-        // reads of s_out before the next writes; records are rewritten only after every
-        // thread has passed the barrier above, i.e. finished consuming them.
+        // the __syncthreads at the top of the next chunk's first pass orders these reads of s_out
+        // (and the consumption of the records) before anything is rewritten.
     }
 }
 
@@ -254,6 +257,7 @@ points_var_kernel(const float4* __restrict__ feats, SampleGeom geom, const float
     pdl_wait();
     __shared__ int s_rec[EMAX][KD][TP];
     __shared__ float4 s_wt[EMAX][KD][TP];
+    __shared__ float s_P[EMAX][12];
 
     const int tid = threadIdx.x;
     const int r = blockIdx.y;
@@ -291,12 +295,14 @@ points_var_kernel(const float4* __restrict__ feats, SampleGeom geom, const float
 
     for (int eb = e0; eb < e1; eb += EMAX) {
         const int n_e = min(EMAX, e1 - eb);
-        if (eb != e0) __syncthreads();
+        __syncthreads();
+        if (tid < n_e * 12) s_P[tid / 12][tid % 12] = __ldg(cams + (size_t)__ldg(esrc + eb + tid / 12) * CAM_STRIDE + CAM_P + tid % 12);
+        __syncthreads();
         if (pk < n_hyp) {
             for (int e = 0; e < n_e; ++e) {
                 int rec;
                 float4 wt;
-                make_record(cams + (size_t)__ldg(esrc + eb + e) * CAM_STRIDE + CAM_P, X0, X1, X2, geom, rec, wt);
+                make_record(s_P[e], X0, X1, X2, geom, rec, wt);
                 s_rec[e][pk][pv] = rec;
                 s_wt[e][pk][pv] = wt;
             }

@@ -12,7 +12,7 @@ cap() {  # region, kernel regex, launch-skip, launch-count
   echo "$1 rc=$?"
   ncu -i gpurun_out/${TAG}_$1.ncu-rep --page raw --csv > gpurun_out/${TAG}_$1_raw.csv 2>/dev/null
 }
-cap mvs 'planesweep_var|s1_tiled|prob_softargmin|conv3d_direct' 0 5
-cap flow 'points_var|sparse_interp|gather_gemm|decoder_head' 0 9
-cap scene 'gather_gemm' 6 6
+cap mvs 'planesweep_var|s1_tiled|prob_softargmin|conv3d_direct|deconv3d' 0 6
+cap flow 'points_var|sparse_interp|gather_gemm|decoder_head' 0 8
+cap scene 'gather_gemm|pair_reduce|pair_fill|kernel_map' 6 8
 du -sh gpurun_out; ls -la gpurun_out/ | head -30
