@@ -9,6 +9,7 @@
 // as the parity cross-check: tests assert bit-identical depth).
 #include <string.h>
 
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -56,19 +57,30 @@ struct Prof {
 // depend only on the voxelisation: they run concurrently, the latter on a per-device side stream
 // (it contains the host read-backs of the level sizes, which then overlap PointNet's kernels).
 struct SideStream {
+    cudaStream_t main;  // the caller's stream this side stream belongs to
+    int device;
     cudaStream_t stream;
     cudaEvent_t fork, join;
 };
-static SideStream* side_stream() {
-    static SideStream per_dev[64] = {};
+// one side stream per (device, caller stream): concurrent dv3d_hot_path calls on different
+// streams (one host thread each) must not share fork / join events
+static SideStream* side_stream(cudaStream_t main) {
+    static SideStream table[32] = {};
+    static int n_used = 0;
+    static std::mutex mu;
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-    SideStream& s = per_dev[dev];
-    if (!s.stream) {
-        if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-        cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming);
-    }
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    for (int i = 0; i < n_used; ++i)
+        if (table[i].main == main && table[i].device == dev) return &table[i];
+    if (n_used == 32) return nullptr;
+    SideStream& s = table[n_used];
+    if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming);
+    s.main = main;
+    s.device = dev;
+    ++n_used;
     return &s;
 }
 
@@ -206,8 +218,8 @@ static int kernel_map(const Level& out_lv, const Level& in_lv, int step, bool wa
 static int model_scene(const dv3d_net_params_t& net, const float* pts, const float* pts_feat, const long long* pts_batch,
                        long long N, double edge_len, Scene& sc, Arena& ar, void* st) {
     cudaStream_t cs = (cudaStream_t)st;
-    SideStream* side = side_stream();
-    DV3D_REQUIRE(side, "hot_path: cannot create the side stream");
+    SideStream* side = side_stream(cs);
+    DV3D_REQUIRE(side, "hot_path: cannot create the side stream (more than 32 caller streams?)");
     // ---- voxelise (utils.py:38-64)
     Prof* pr = new Prof(DV3D_STAGE_VOXELIZE, cs);
     struct ProfGuard {  // closes the open stage on every return path

@@ -542,9 +542,10 @@ def hot_path_engine(net_params, feats_nhwc, rotmats, tvecs, K, plan, depth_batch
     dev = feats_nhwc.device
     L = lib()
     need = L.raw('dv3d_hot_path_workspace_bytes')(ctypes.byref(net_params), n_imgs, plan.n_ref, D, h, w)
-    arena = _arena.get(dev)
+    akey = (dev, torch.cuda.current_stream().cuda_stream)   # concurrent calls on different streams: one arena each
+    arena = _arena.get(akey)
     if arena is None or arena.numel() < need:
-        arena = _arena[dev] = torch.empty(need, dtype=torch.uint8, device=dev)
+        arena = _arena[akey] = torch.empty(need, dtype=torch.uint8, device=dev)
     n_outer = len(offsets_list)
     n_inner = len(offsets_list[0]) if n_outer else 0
     if any(len(o) != n_inner for o in offsets_list):
