@@ -77,3 +77,39 @@ def test_engine_rejects_bad_arguments(mods):
                      b.images_batch.to(DEV), cfg, [[0.05]])
     with pytest.raises(RuntimeError, match='CUDA tensor'):
         net.hot_path(b.feats_quarter, b.rotmats, b.tvecs, b.K, b.ref_src_edges, b.images_batch, cfg, [[0.05]])
+
+
+def test_engine_concurrent_streams_bit_identical(mods):
+    """dv3d_hot_path is re-entrant: four host threads, each on its own CUDA stream (own arena and side
+    stream), produce the bits of the sequential run"""
+    import threading
+    img_size, plane, D = (64, 80), (16, 24), 16
+    cfg = dict(depth_start=0.5, depth_interval=0.3, n_intervals=D, size=plane)
+    net = _net(mods, cfg, 0.3, img_size)
+    batches = [mods['synth'].make_batch(1, 4, img_size, plane, 32, 1, 1, False, 10 + i) for i in range(4)]
+    args = [(b.feats_quarter.to(DEV), b.rotmats.to(DEV), b.tvecs.to(DEV), b.K.to(DEV), b.ref_src_edges,
+             b.images_batch.to(DEV), cfg, [[0.05, 0.025]]) for b in batches]
+    ref = [net.hot_path(*a).cpu() for a in args]
+    torch.cuda.synchronize()
+    out, err = [None] * 4, []
+
+    def worker(i):
+        try:
+            torch.cuda.set_device(0)
+            st = torch.cuda.Stream()
+            with torch.cuda.stream(st):
+                for _ in range(5):
+                    got = net.hot_path(*args[i])
+                st.synchronize()
+                out[i] = got.cpu()
+        except Exception as e:   # surfaced below
+            err.append(e)
+
+    th = [threading.Thread(target=worker, args=(i,)) for i in range(4)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not err, err
+    for i in range(4):
+        np.testing.assert_array_equal(out[i].numpy().view(np.int32), ref[i].numpy().view(np.int32))
