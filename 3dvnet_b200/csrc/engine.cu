@@ -289,19 +289,25 @@ static int model_scene(const dv3d_net_params_t& net, const float* pts, const flo
     ARENA_CHECK(ar);
     TRY(dv3d_make_coords(a_idx, a_batch, nv, sc.lv[0].coords, sst));
     TRY(build_level(sc.lv[0], err_flag, ar, sst));
-    for (int l = 1; l < nl; ++l) {
-        const int ns = sc.lv[l - 1].stride * 2;
-        const size_t cws_bytes = dv3d_coarsen_workspace_bytes((int)grid.n_cells[0], (int)grid.n_cells[1], (int)grid.n_cells[2],
-                                                               (int)grid.n_batch, ns);
-        void* cws = ar.get<char>(cws_bytes);
-        sc.lv[l].coords = ar.get<int>((size_t)sc.lv[l - 1].n * 4);
-        ARENA_CHECK(ar);
-        long long n_out = 0;
-        TRY(dv3d_coarsen(sc.lv[l - 1].coords, sc.lv[l - 1].n, ns, (int)grid.n_cells[0], (int)grid.n_cells[1],
-                         (int)grid.n_cells[2], (int)grid.n_batch, cws, cws_bytes, sc.lv[l - 1].n, sc.lv[l].coords, &n_out, sst));
-        sc.lv[l].n = n_out;
-        sc.lv[l].stride = ns;
-        TRY(build_level(sc.lv[l], err_flag, ar, sst));
+    // every coarser level straight from the finest coordinates (floor(c / 2^l) * 2^l), one sync for all counts
+    {
+        void* cws[DV3D_MAX_LEVELS] = {};
+        const int gx = (int)grid.n_cells[0], gy = (int)grid.n_cells[1], gz = (int)grid.n_cells[2], gb = (int)grid.n_batch;
+        for (int l = 1; l < nl; ++l) {
+            const int ns = 1 << l;
+            const size_t cws_bytes = dv3d_coarsen_workspace_bytes(gx, gy, gz, gb, ns);
+            cws[l] = ar.get<char>(cws_bytes);
+            sc.lv[l].coords = ar.get<int>((size_t)nv * 4);
+            ARENA_CHECK(ar);
+            TRY(dv3d_coarsen_enqueue(sc.lv[0].coords, nv, ns, gx, gy, gz, gb, cws[l], cws_bytes, nv, sc.lv[l].coords, sst));
+        }
+        for (int l = 1; l < nl; ++l) {
+            long long n_out = 0;
+            TRY(dv3d_coarsen_finish(cws[l], 1 << l, gx, gy, gz, gb, nv, &n_out, sst));
+            sc.lv[l].n = n_out;
+            sc.lv[l].stride = 1 << l;
+        }
+        for (int l = 1; l < nl; ++l) TRY(build_level(sc.lv[l], err_flag, ar, sst));
     }
 
     // every kernel map of the U-Net and its pair-major plan, then ONE sync for the counts

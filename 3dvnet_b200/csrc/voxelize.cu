@@ -499,11 +499,11 @@ extern "C" size_t dv3d_coarsen_workspace_bytes(int dim_x, int dim_y, int dim_z, 
     return scan_space_bytes(n_words);
 }
 
-extern "C" int dv3d_coarsen(const int* coords, long long n, int new_stride, int dim_x, int dim_y, int dim_z,
-                            int n_batch, void* workspace, size_t workspace_bytes, long long cap, int* coarse_coords,
-                            long long* n_coarse_host, void* stream) {
-    DV3D_REQUIRE(coords && workspace && coarse_coords && n_coarse_host && n > 0 && cap > 0 && new_stride > 0,
-                 "coarsen: bad arguments");
+// the kernels of a coarsening step, without the read-back of the count
+extern "C" int dv3d_coarsen_enqueue(const int* coords, long long n, int new_stride, int dim_x, int dim_y, int dim_z,
+                                    int n_batch, void* workspace, size_t workspace_bytes, long long cap,
+                                    int* coarse_coords, void* stream) {
+    DV3D_REQUIRE(coords && workspace && coarse_coords && n > 0 && cap > 0 && new_stride > 0, "coarsen: bad arguments");
     size_t need = dv3d_coarsen_workspace_bytes(dim_x, dim_y, dim_z, n_batch, new_stride);
     DV3D_REQUIRE(need > 0, "coarsen: bad lattice dimensions");
     if (workspace_bytes < need) {
@@ -521,6 +521,17 @@ extern "C" int dv3d_coarsen(const int* coords, long long n, int new_stride, int 
     if (rc) return rc;
     DV3D_LAUNCH((emit_coarse_kernel), cdiv(n_words, 256), 256, 0, st, s.bitmap, s.prefix, s.block_sums, n_words, L, cap, coarse_coords);
     DV3D_LAUNCHED();
+    return DV3D_OK;
+}
+
+// reads the count of an enqueued coarsening step back (SYNCS)
+extern "C" int dv3d_coarsen_finish(const void* workspace, int new_stride, int dim_x, int dim_y, int dim_z, int n_batch,
+                                   long long cap, long long* n_coarse_host, void* stream) {
+    DV3D_REQUIRE(workspace && n_coarse_host && new_stride > 0, "coarsen_finish: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    LevelDims L = {cdiv(dim_x, new_stride), cdiv(dim_y, new_stride), cdiv(dim_z, new_stride), new_stride};
+    const long long n_words = ((long long)L.X * L.Y * L.Z * n_batch + 31) / 32;
+    ScanSpace s = carve(const_cast<void*>(workspace), n_words);
     long long host[2] = {0, 0};
     DV3D_CUDA(cudaMemcpyAsync(host, s.total, 16, cudaMemcpyDeviceToHost, st));
     DV3D_CUDA(cudaStreamSynchronize(st));
@@ -531,6 +542,16 @@ extern "C" int dv3d_coarsen(const int* coords, long long n, int new_stride, int 
         return DV3D_ENOSPC;
     }
     return DV3D_OK;
+}
+
+extern "C" int dv3d_coarsen(const int* coords, long long n, int new_stride, int dim_x, int dim_y, int dim_z,
+                            int n_batch, void* workspace, size_t workspace_bytes, long long cap, int* coarse_coords,
+                            long long* n_coarse_host, void* stream) {
+    DV3D_REQUIRE(n_coarse_host, "coarsen: bad arguments");
+    int rc = dv3d_coarsen_enqueue(coords, n, new_stride, dim_x, dim_y, dim_z, n_batch, workspace, workspace_bytes, cap,
+                                  coarse_coords, stream);
+    if (rc) return rc;
+    return dv3d_coarsen_finish(workspace, new_stride, dim_x, dim_y, dim_z, n_batch, cap, n_coarse_host, stream);
 }
 
 extern "C" int dv3d_batch_origin(const float* anchor_pts, const int* idx3d, const long long* batch, long long n,

@@ -194,6 +194,12 @@ size_t dv3d_coarsen_workspace_bytes(int dim_x, int dim_y, int dim_z, int n_batch
 int dv3d_coarsen(const int* coords, long long n, int new_stride, int dim_x, int dim_y, int dim_z, int n_batch,
                  void* workspace, size_t workspace_bytes, long long cap, int* coarse_coords,
                  long long* n_coarse_host, void* stream);
+/* the same in two halves, so that several levels can be coarsened from the finest coordinates
+ * (floor(floor(c/2)*2/4)*4 = floor(c/4)*4) with ONE sync: enqueue every level, then finish each */
+int dv3d_coarsen_enqueue(const int* coords, long long n, int new_stride, int dim_x, int dim_y, int dim_z, int n_batch,
+                         void* workspace, size_t workspace_bytes, long long cap, int* coarse_coords, void* stream);
+int dv3d_coarsen_finish(const void* workspace, int new_stride, int dim_x, int dim_y, int dim_z, int n_batch,
+                        long long cap, long long* n_coarse_host, void* stream);
 /* kernel map: nbr[o*27+k] = row of coords_out[o] + offset_k*step in the input level, or -1
  * (offset_k x fastest).  k3s1: same level, step = ts.  k3s2: out = coarse, in = fine table,
  * step = ts_fine.  transposed k3s2: out = fine, in = coarse table, step = -ts_fine
