@@ -35,6 +35,7 @@ constexpr int CS = KD * TP + 1;  // padded channel stride of the output tile (ba
 struct SampleGeom {
     int Hf, Wf;
     float wm1, hm1;    // W-1, H-1 of the FULL image (mvsnet.py:205-206)
+    double rwm1, rhm1; // 1 / (W-1), 1 / (H-1) in fp64 (div_small_int)
     float wfm1, hfm1;  // Wf-1, Hf-1 (grid_sample align_corners=True un-normalisation)
 };
 
@@ -46,6 +47,14 @@ struct SampleGeom {
 // Per image the host-visible table holds Kinv (9) | P = K [R|t] (12) | R (9) | t (3).
 constexpr int CAM_STRIDE = 36;
 constexpr int CAM_KINV = 0, CAM_P = 9, CAM_R = 21, CAM_T = 30;
+
+// a / n correctly rounded to fp32 for a SMALL INTEGER n (< 2^20), without the ~10-instruction IEEE
+// division sequence: d = (double)a * RN64(1/n) is within 2^-52 of a/n, and a/n with a 24-bit
+// numerator can be neither an fp32 rounding tie (that needs n | 2^k (2j+1) with an impossible
+// magnitude) nor closer than ~2^-24/n to one, so rounding d to fp32 equals rounding a/n
+// (double rounding is innocuous here).  Used for the divisions by the image size (W-1, H-1) and by the
+// edge count; bit-exactness against the reference is asserted by the golden tests.
+__device__ __forceinline__ float div_small_int(float a, double rcp_n) { return (float)__dmul_rn((double)a, rcp_n); }
 
 __device__ __forceinline__ float chain3(float a0, float a1, float a2, float b0, float b1, float b2) {
     return __fmaf_rn(a2, b2, __fmaf_rn(a1, b1, __fmul_rn(a0, b0)));
@@ -77,8 +86,8 @@ __device__ __forceinline__ void make_record(const float* __restrict__ P, float X
     float qz = __fmaf_rn(P[11], 1.f, chain3(P[8], P[9], P[10], X0, X1, X2));
     float zz = __fadd_rn(fabsf(qz), 1e-8f);
     float x = __fdiv_rn(qx, zz), y = __fdiv_rn(qy, zz);
-    float gx = __fsub_rn(__fmul_rn(__fdiv_rn(x, g.wm1), 2.f), 1.f);
-    float gy = __fsub_rn(__fmul_rn(__fdiv_rn(y, g.hm1), 2.f), 1.f);
+    float gx = __fsub_rn(__fmul_rn(div_small_int(x, g.rwm1), 2.f), 1.f);
+    float gy = __fsub_rn(__fmul_rn(div_small_int(y, g.rhm1), 2.f), 1.f);
     float ix = __fmul_rn(__fmul_rn(__fadd_rn(gx, 1.f), 0.5f), g.wfm1);
     float iy = __fmul_rn(__fmul_rn(__fadd_rn(gy, 1.f), 0.5f), g.hfm1);
     rec = 0;
@@ -149,9 +158,9 @@ __device__ __forceinline__ void consume_edges(const float4* __restrict__ feats, 
     }
 }
 
-__device__ __forceinline__ float var_of(float s, float q, float n) {
-    float m = __fdiv_rn(s, n);
-    return __fsub_rn(__fdiv_rn(q, n), __fmul_rn(m, m));  // E[x^2] - E[x]^2 (mvsnet.py:216)
+__device__ __forceinline__ float var_of(float s, float q, double rcp_n) {
+    float m = div_small_int(s, rcp_n);
+    return __fsub_rn(div_small_int(q, rcp_n), __fmul_rn(m, m));  // E[x^2] - E[x]^2 (mvsnet.py:216)
 }
 
 // numpy.linspace(start, stop, n, dtype=float32): float64 arithmetic, last point == stop
@@ -180,7 +189,7 @@ planesweep_var_kernel(const float4* __restrict__ feats, SampleGeom geom, const f
     const int P = h * w;
     const int p0 = blockIdx.x * TP;
     const int e0 = rowptr[r], e1 = rowptr[r + 1];
-    const float n_edges = (float)(e1 - e0);
+    const double n_edges = 1.0 / (double)(e1 - e0);  // reciprocal of the edge count (var_of)
     const int img_stride4 = geom.Hf * geom.Wf * 8;
 
     // phase-1 role: warp = plane pk, lane = pixel pv (conflict-free record stores);
@@ -264,7 +273,7 @@ points_var_kernel(const float4* __restrict__ feats, SampleGeom geom, const float
     const int P = h * w;
     const int p0 = blockIdx.x * TP;
     const int e0 = rowptr[r], e1 = rowptr[r + 1];
-    const float n_edges = (float)(e1 - e0);
+    const double n_edges = 1.0 / (double)(e1 - e0);  // reciprocal of the edge count (var_of)
     const int img_stride4 = geom.Hf * geom.Wf * 8;
     const int n_hyp = 2 * n_side + 1;
 
@@ -401,6 +410,7 @@ static SampleGeom make_geom(int Hf, int Wf, int H, int W) {
     SampleGeom g;
     g.Hf = Hf; g.Wf = Wf;
     g.wm1 = (float)(W - 1); g.hm1 = (float)(H - 1);
+    g.rwm1 = 1.0 / (double)(W - 1); g.rhm1 = 1.0 / (double)(H - 1);
     g.wfm1 = (float)(Wf - 1); g.hfm1 = (float)(Hf - 1);
     return g;
 }
