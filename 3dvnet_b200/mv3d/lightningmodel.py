@@ -9,10 +9,8 @@ from argparse import Namespace
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from .. import ops
-from . import utils
 from ._pack import PackCache, fold_bn, require_eval
 from .subnetworks.mvsnet import MVSNet
 from .subnetworks.scenemodeling import PointNet, SparseUNet, SparseScene

@@ -3,7 +3,6 @@
 (SURVEY.md §8f.1): the four Conv2d+BN+ReLU layers run as 9-slice gather-GEMMs on the tcgen05
 kernel, the nearest upsampling in front (eval-3dvnet.py:101-125) and the softmax-weighted 3x3
 gather behind them as two small kernels (csrc/upsample.cu)."""
-import torch
 import torch.nn as nn
 
 from ... import ops

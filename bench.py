@@ -149,7 +149,11 @@ def main():
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=dev)
 
-    importlib.import_module('3dvnet_b200.build').build()
+    # the in-tree library: rank 0 (re)builds it if needed, the others wait and only load it
+    if local == 0:
+        importlib.import_module('3dvnet_b200.build').build()
+    if dist is not None:
+        dist.barrier()
     ops = importlib.import_module('3dvnet_b200.ops')
     lm = importlib.import_module('3dvnet_b200.mv3d.lightningmodel')
     warm = max(args.warmup, 3)

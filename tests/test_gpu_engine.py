@@ -6,8 +6,6 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import load_golden, golden_inputs
-
 pytestmark = pytest.mark.gpu
 DEV = 'cuda'
 
@@ -46,7 +44,6 @@ def test_engine_equals_composed_path(mods, n_scenes, n_imgs, offsets):
 
 def test_engine_c2_size_and_stage_profile(mods):
     """BASELINE configs[1] shape through the engine, with the stage timing hooks bench.py uses"""
-    import ctypes
     bench = importlib.import_module('bench')
     ops = mods['ops']
     b, params = bench.synth_inputs(1, 1)

@@ -5,7 +5,6 @@ contraction, and against the fp32 CUDA-core kernel. 3xTF32 must be fp32-grade (t
 is that of an fp32 GEMM); plain TF32 is checked at its own (10-bit mantissa) tolerance."""
 import importlib
 
-import numpy as np
 import pytest
 import torch
 
