@@ -313,6 +313,21 @@ int dv3d_propagation_output(const float* logits, int ld, const float* depth, int
                             void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Depth-map fusion (pointcloudfusion_custom.py:10-116), the consumer of the path's output
+ * (SURVEY.md §8f.4): for the reference images 0..n_ref-1 of a scene, every pixel is back-projected,
+ * re-projected into every OTHER image, compared with the nearest-sampled depth there
+ * (|z - z_sample| < z_thresh, inside the image, z > 1e-4) and averaged with the consistent samples.
+ *   depths [n_imgs,h,w]; poses [n_imgs,4,4] world->camera; K [n_imgs,3,3] at depth-map resolution
+ *   pts_avg [n_ref,h*w,3] = (pts + sum of consistent back-projected samples) / (n_valid + 1)
+ *   n_valid [n_ref,h*w] int32; valid [n_ref,h*w] uint8 = n_valid >= n_consistent_thresh
+ *   workspace: dv3d_depth_fusion_workspace_bytes(n_imgs) (per-image K, K^-1, P, P^-1, inverted in fp64)
+ */
+size_t dv3d_depth_fusion_workspace_bytes(int n_imgs);
+int dv3d_depth_fusion(const float* depths, const float* poses, const float* K, int n_imgs, int n_ref, int h, int w,
+                      float z_thresh, int n_consistent_thresh, void* workspace, size_t workspace_bytes, float* pts_avg,
+                      int* n_valid, unsigned char* valid, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Engine: the whole hot path enqueued by ONE call from native code.
  *
  * The reference drives its hot path from Python, one library call per tensor op

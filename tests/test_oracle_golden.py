@@ -107,3 +107,18 @@ def test_propagation_oracle_matches_reference_golden():
                                          p['half'], p['full'])
     np.testing.assert_array_equal(dq.numpy(), g['ref_quarter'])
     np.testing.assert_array_equal(full.numpy(), g['ref_full'])
+
+
+def test_fusion_oracle_matches_reference_golden():
+    """oracle/fusion.py against the unmodified reference pointcloudfusion_custom.process_scene (CPU-patched .cuda())"""
+    import os
+    import numpy as np
+    import torch
+    from oracle import fusion
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'fusion.npz'))
+    d, p, k = (torch.from_numpy(g[n]) for n in ('depth', 'poses', 'K'))
+    pts, n_valid, valid = fusion.process_scene(d, p, k, 0.1, 3)
+    np.testing.assert_array_equal(valid.numpy(), g['ref_valid'])
+    fused = pts[valid.view(valid.shape[0], -1)].numpy()
+    np.testing.assert_allclose(fused, g['ref_pts'], rtol=0, atol=1e-6)
+    np.testing.assert_array_equal(valid[0].numpy(), g['ref_valid0'])
