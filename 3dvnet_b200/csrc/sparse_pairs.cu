@@ -183,8 +183,25 @@ pair_fill_kernel(const __grid_constant__ PlanBatch pb) {
     }
 }
 
-// out[m] = epilogue(sum_k P[pair_slot[m][k]]): thread = (row, 4 channels); a row's lanes are
-// consecutive, so the GroupNorm shuffles of epilogue4 stay inside the row
+// 16-byte read-only load that the compiler may not sink next to its use: the loads of a batch are
+// issued back to back (memory-level parallelism), the ordered adds follow
+__device__ __forceinline__ float4 ldg4_issue(const float4* p, bool pred) {
+    // predicated inside the asm block (no branch): the nine loads of a batch stay in one basic block
+    float4 v;
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "setp.ne.s32 q, %5, 0;\n\t"
+        "mov.f32 %0, 0f00000000;\n\tmov.f32 %1, 0f00000000;\n\tmov.f32 %2, 0f00000000;\n\tmov.f32 %3, 0f00000000;\n\t"
+        "@q ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"
+        : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+        : "l"(p), "r"((int)pred));
+    return v;
+}
+
+// out[m] = epilogue(sum_k P[pair_slot[m][k]]): thread = (row, 4 channels); a row's UNITS = N/4 lanes are
+// consecutive, so the GroupNorm shuffles of epilogue4 stay inside the row.  The row's 27 slots are
+// loaded once (one or two per lane) and broadcast by shuffles; the partial rows are fetched in
+// three batches of nine independent loads and added in ascending offset order.
 template <int N>
 __global__ void __launch_bounds__(256)
 pair_reduce_kernel(const __grid_constant__ GemmDesc d, const float* __restrict__ P, const int* __restrict__ pair_slot) {
@@ -193,17 +210,22 @@ pair_reduce_kernel(const __grid_constant__ GemmDesc d, const float* __restrict__
     const int u = threadIdx.x % UNITS;
     const long long m = (long long)blockIdx.x * ROWS + threadIdx.x / UNITS;
     const bool live = m < d.M;
-    int slot[27];
-#pragma unroll
-    for (int k = 0; k < 27; ++k) slot[k] = live ? __ldg(pair_slot + m * 27 + k) : -1;
-    float4 v[27];
-#pragma unroll
-    for (int k = 0; k < 27; ++k)
-        v[k] = slot[k] >= 0 ? __ldg(reinterpret_cast<const float4*>(P + (size_t)slot[k] * N) + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const int s_a = (live && u < 27) ? __ldg(pair_slot + m * 27 + u) : -1;
+    const int s_b = (live && UNITS < 27 && u + UNITS < 27) ? __ldg(pair_slot + m * 27 + u + UNITS) : -1;
     float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int k = 0; k < 27; ++k) {  // offsets in ascending order; absent pairs add +0
-        y.x += v[k].x; y.y += v[k].y; y.z += v[k].z; y.w += v[k].w;
+    for (int k0 = 0; k0 < 27; k0 += 9) {
+        float4 v[9];
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+            const int k = k0 + j;
+            const int slot = __shfl_sync(0xffffffffu, k < UNITS ? s_a : s_b, k % UNITS, UNITS);
+            v[j] = ldg4_issue(reinterpret_cast<const float4*>(P + (size_t)(slot < 0 ? 0 : slot) * N) + u, slot >= 0);
+        }
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {  // offsets in ascending order; absent pairs add +0
+            y.x += v[j].x; y.y += v[j].y; y.z += v[j].z; y.w += v[j].w;
+        }
     }
     epilogue4(d, y, m, 4 * u, live, false);
 }

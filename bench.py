@@ -329,7 +329,8 @@ def main():
                                           + edges.numel() * 4 + 64),
                 'd2h_bytes_per_step': int(out_host.numel() * 4), 'ms_per_step': ms_e2e / args.steps},
         'gpu_launches': launches,
-        'roofline': {'kernel': 'gather_gemm_tc_kernel<128> (first decoder Conv1d, M=%d K=1056 N=128)' % (n_ref * 25088),
+        'roofline': {'kernel': 'gather_gemm_tc_kernel<128> (first decoder Conv1d, M=%d K=1056 N=128; full rounds + '
+                               'tap-split tail launch, timed together)' % (n_ref * 25088),
                      'bound': 'tensor', 'achieved': g_achieved, 'peak': tpeak, 'unit': 'TFLOP/s',
                      'frac': g_achieved / tpeak, 'traffic': traffic.get('gather_gemm_tc_decoder0'),
                      'peak_source': tpeak_src, 'algorithmic_flops_per_launch': gemm_flops, 'kernel_ms': g_ms,
