@@ -120,11 +120,16 @@ __device__ __forceinline__ float2 hi2(const float4& t) { return make_float2(t.z,
 
 // Phase 2 for one staged pass of edges. NK = number of live planes/hypotheses in the chunk.
 // Accumulators are channel pairs: acc_s[k][0] = channels (0,1), [1] = (2,3) of the thread's group.
-template <int NK>
+// REUSE: keep the four taps while consecutive planes fall into the same 2x2 footprint (plane sweep: most
+// far planes do).  Without it (PointFlow hypotheses, few and far apart) every sample issues its four
+// independent loads unconditionally, so the unrolled loop keeps dozens of loads in flight instead of
+// serialising 49 load -> use round trips per thread.
+template <int NK, bool REUSE>
 __device__ __forceinline__ void consume_edges(const float4* __restrict__ feats, const int* __restrict__ esrc,
                                               int e_begin, int n_e, int img_stride4, int Wf, int v, int g,
                                               const int (*s_rec)[KD][TP], const float4 (*s_wt)[KD][TP],
                                               float2 (&acc_s)[KD][2], float2 (&acc_q)[KD][2]) {
+#pragma unroll(REUSE ? 1 : 2)
     for (int e = 0; e < n_e; ++e) {
         const float4* base = feats + (size_t)__ldg(esrc + e_begin + e) * img_stride4 + g;
         int prev = -1;
@@ -133,7 +138,7 @@ __device__ __forceinline__ void consume_edges(const float4* __restrict__ feats, 
         for (int k = 0; k < NK; ++k) {
             int rec = s_rec[e][k][v];
             float4 wt = s_wt[e][k][v];
-            if (rec != prev) {
+            if (!REUSE || rec != prev) {
                 const float4* p = base + (size_t)(rec >> 2) * 8;
                 int dx = (rec & 1) * 8, dy = ((rec >> 1) & 1) * Wf * 8;
                 t00 = ldg4(p);
@@ -226,7 +231,7 @@ planesweep_var_kernel(const float4* __restrict__ feats, SampleGeom geom, const f
                 s_wt[e][pk][pv] = wt;
             }
             __syncthreads();
-            consume_edges<KD>(feats, esrc, eb, n_e, img_stride4, geom.Wf, v, g, s_rec, s_wt, acc_s, acc_q);
+            consume_edges<KD, true>(feats, esrc, eb, n_e, img_stride4, geom.Wf, v, g, s_rec, s_wt, acc_s, acc_q);
         }
 
         // phase 3: variance -> shared tile -> coalesced rows
@@ -257,7 +262,7 @@ planesweep_var_kernel(const float4* __restrict__ feats, SampleGeom geom, const f
 
 // Point-level variant: the "planes" of a pixel are its 2n+1 depth hypotheses around the
 // current depth estimate (lightningmodel.py:201-205); outputs are point-major.
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, 1)  // 98 CTAs at C2: registers are better spent on loads in flight
 points_var_kernel(const float4* __restrict__ feats, SampleGeom geom, const float* __restrict__ cams,
                   const int* __restrict__ ref_img, const int* __restrict__ rowptr, const int* __restrict__ esrc,
                   const float* __restrict__ depth, int h, int w, int H, int W, int n_side, double offset,
@@ -318,9 +323,9 @@ points_var_kernel(const float4* __restrict__ feats, SampleGeom geom, const float
         }
         __syncthreads();
         if (n_hyp == 1)
-            consume_edges<1>(feats, esrc, eb, n_e, img_stride4, geom.Wf, v, g, s_rec, s_wt, acc_s, acc_q);
+            consume_edges<1, false>(feats, esrc, eb, n_e, img_stride4, geom.Wf, v, g, s_rec, s_wt, acc_s, acc_q);
         else
-            consume_edges<7>(feats, esrc, eb, n_e, img_stride4, geom.Wf, v, g, s_rec, s_wt, acc_s, acc_q);
+            consume_edges<7, false>(feats, esrc, eb, n_e, img_stride4, geom.Wf, v, g, s_rec, s_wt, acc_s, acc_q);
     }
     if (p0 + v < P) {
         const int p = p0 + v;
