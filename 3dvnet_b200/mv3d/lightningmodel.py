@@ -227,7 +227,11 @@ class PL3DVNet(nn.Module):
         depth_batch = images_batch[plan.ref_idx].long().contiguous()
         # the channels-last copy is made on every call (one small kernel): the storage-keyed cache
         # of the composed path must not be trusted for freshly uploaded tensors
-        nhwc = ops.nchw_to_nhwc(feats_quarter.detach().float().contiguous())
+        fq = feats_quarter.detach().float()
+        if fq.dim() == 4 and fq.is_contiguous(memory_format=torch.channels_last) and not fq.is_contiguous():
+            nhwc = fq.permute(0, 2, 3, 1)   # a channels-last backbone already emits the layout the warp kernel wants
+        else:
+            nhwc = ops.nchw_to_nhwc(fq.contiguous())
         return ops.hot_path_engine(self.engine_params(), nhwc, rotmats.float().contiguous(),
                                    tvecs.float().contiguous(), K.float().contiguous(), plan, depth_batch, depth_config,
                                    self.hparams.img_size, self.edge_len, offsets_list, want_init=return_init)

@@ -148,7 +148,11 @@ class MVSNet(nn.Module):
         """x_var [n_ref,C,D,h,w] (mvsnet.py:187-216) without materialising x_vox."""
         plan = ops.edge_plan(batch.ref_src_edges, features_quarter.device) if plan is None else plan
         if feats_nhwc is None:
-            feats_nhwc = ops.nchw_to_nhwc(features_quarter.detach().float().contiguous())
+            fq = features_quarter.detach().float()
+            if fq.is_contiguous(memory_format=torch.channels_last) and not fq.is_contiguous():
+                feats_nhwc = fq.permute(0, 2, 3, 1)
+            else:
+                feats_nhwc = ops.nchw_to_nhwc(fq.contiguous())
         cams = ops.camera_tables(batch.rotmats.float().contiguous(), batch.tvecs.float().contiguous(),
                                  batch.K.float().contiguous())
         return ops.planesweep_var(feats_nhwc, cams, plan, depth_start, depth_interval, n_planes,
@@ -165,6 +169,9 @@ class MVSNet(nn.Module):
     def forward(self, batch, depth_start, depth_interval, n_planes, depth_img_size):
         """-> depth_img [n_ref,h,w], features_half, features_quarter, features_eighth (mvsnet.py:176-229)"""
         require_eval(self)
-        fh, fq, fe, _, _ = self.feat_shrinker(*self.feat_extractor(batch.images))
+        # channels-last through the cuDNN backbone: the FPN then emits NHWC feature maps, which the warp
+        # kernels consume without a transposition pass (SURVEY.md §8f.2)
+        images = batch.images.contiguous(memory_format=torch.channels_last)
+        fh, fq, fe, _, _ = self.feat_shrinker(*self.feat_extractor(images))
         depth = self.depth_from_features(fq, batch, depth_start, depth_interval, n_planes, depth_img_size)
         return depth, fh, fq, fe

@@ -110,3 +110,56 @@ def test_engine_concurrent_streams_bit_identical(mods):
     assert not err, err
     for i in range(4):
         np.testing.assert_array_equal(out[i].numpy().view(np.int32), ref[i].numpy().view(np.int32))
+
+
+def test_hot_path_accepts_channels_last_features(mods):
+    """a channels-last backbone output is consumed without the transposition kernel, same bits"""
+    img_size, plane, D = (64, 80), (16, 16), 16
+    cfg = dict(depth_start=0.5, depth_interval=0.3, n_intervals=D, size=plane)
+    b = mods['synth'].make_batch(1, 3, img_size, plane, 32, 1, 1, False, 4)
+    net = _net(mods, cfg, 0.3, img_size)
+    fq = b.feats_quarter.to(DEV)
+    rest = (b.rotmats.to(DEV), b.tvecs.to(DEV), b.K.to(DEV), b.ref_src_edges, b.images_batch.to(DEV), cfg, [[0.05]])
+    net.hot_path(fq, *rest)   # first call packs the weights
+    before = mods['ops'].launch_count()
+    a = net.hot_path(fq, *rest)
+    n_a = mods['ops'].launch_count() - before
+    before = mods['ops'].launch_count()
+    c = net.hot_path(fq.contiguous(memory_format=torch.channels_last), *rest)
+    n_c = mods['ops'].launch_count() - before
+    np.testing.assert_array_equal(a.cpu().numpy().view(np.int32), c.cpu().numpy().view(np.int32))
+    assert n_c == n_a - 1
+
+
+def test_reference_driver_flow_with_backbone(mods):
+    """the reference's eval flow on the drop-in model (eval-3dvnet.py:58-125): backbone -> initial depth ->
+    scene model + PointFlow -> upsampling, from images; consistency with hot_path on the same features"""
+    from argparse import Namespace
+    img_size, plane, D = (64, 80), (16, 16), 16
+    cfg = dict(depth_start=0.5, depth_interval=0.3, n_intervals=D, size=plane)
+    b = mods['synth'].make_batch(1, 3, img_size, plane, 32, 1, 1, False, 8)
+    torch.manual_seed(0)
+    net = mods['lm'].PL3DVNet(cfg, cfg, 0.3, feat_dim=32, img_size=img_size)
+    net.load_state_dict(mods['synth'].make_params(0), strict=False)
+    net = net.to(DEV).eval()
+    images = torch.randn(3, 3, *img_size, generator=torch.Generator().manual_seed(1)).to(DEV)
+    batch = Namespace(images=images, rotmats=b.rotmats.to(DEV), tvecs=b.tvecs.to(DEV), K=b.K.to(DEV),
+                      ref_src_edges=b.ref_src_edges, images_batch=b.images_batch.to(DEV))
+    with torch.no_grad():
+        depth, depth_batch, fh, fq, fe, ref_idx = net.make_initial_depth_predictions(batch, cfg)
+        assert depth.shape == (1, 16, 16) and fq.shape == (3, 32, 16, 20) and fh.shape == (3, 32, 32, 40)
+        assert torch.isfinite(depth).all() and ref_idx.tolist() == [1]
+        # the engine on the backbone's (channels-last) features starts from the same initial depth, bit for bit
+        final, init = net.hot_path(fq, batch.rotmats, batch.tvecs, batch.K, batch.ref_src_edges, batch.images_batch, cfg,
+                                   [[0.05, 0.025]], return_init=True)
+        np.testing.assert_array_equal(init.cpu().numpy().view(np.int32), depth.cpu().numpy().view(np.int32))
+        xs = net.model_scene(depth, depth_batch, fq, batch.rotmats, batch.tvecs, batch.K, batch.ref_src_edges)
+        d = depth.clone()
+        for off in (0.05, 0.025):
+            d += net.run_pointflow(xs, d, depth_batch, fq, batch.rotmats, batch.tvecs, batch.K, batch.ref_src_edges, off, 3)
+        np.testing.assert_array_equal(d.cpu().numpy().view(np.int32), final.cpu().numpy().view(np.int32))
+        full = net.upsample(final, ref_idx, fq, fh, images)
+        assert full.shape == (1, 64, 80) and torch.isfinite(full).all()
+        out = net(batch, [0.05, 0.025], 1)
+        np.testing.assert_array_equal(out['ref'].cpu().numpy().view(np.int32), final.cpu().numpy().view(np.int32))
+        np.testing.assert_array_equal(out['final'].cpu().numpy().view(np.int32), full.cpu().numpy().view(np.int32))
