@@ -293,13 +293,26 @@ static int model_scene(const dv3d_net_params_t& net, const float* pts, const flo
     {
         void* cws[DV3D_MAX_LEVELS] = {};
         const int gx = (int)grid.n_cells[0], gy = (int)grid.n_cells[1], gz = (int)grid.n_cells[2], gb = (int)grid.n_batch;
+        size_t cws_bytes[DV3D_MAX_LEVELS] = {};
+        int strides[DV3D_MAX_LEVELS] = {};
+        int* ccoords[DV3D_MAX_LEVELS] = {};
+        size_t cws_total = 0;
         for (int l = 1; l < nl; ++l) {
-            const int ns = 1 << l;
-            const size_t cws_bytes = dv3d_coarsen_workspace_bytes(gx, gy, gz, gb, ns);
-            cws[l] = ar.get<char>(cws_bytes);
-            sc.lv[l].coords = ar.get<int>((size_t)nv * 4);
+            strides[l] = 1 << l;
+            cws_bytes[l] = (dv3d_coarsen_workspace_bytes(gx, gy, gz, gb, strides[l]) + 255) & ~(size_t)255;
+            cws_total += cws_bytes[l];
+        }
+        if (nl > 1) {
+            // one contiguous span, so that a single memset clears every level's bitmap and counters
+            char* span = ar.get<char>(cws_total);
+            for (int l = 1; l < nl; ++l) {
+                cws[l] = span;
+                span += cws_bytes[l];
+                ccoords[l] = sc.lv[l].coords = ar.get<int>((size_t)nv * 4);
+            }
             ARENA_CHECK(ar);
-            TRY(dv3d_coarsen_enqueue(sc.lv[0].coords, nv, ns, gx, gy, gz, gb, cws[l], cws_bytes, nv, sc.lv[l].coords, sst));
+            TRY(dv3d_coarsen_enqueue_batch(sc.lv[0].coords, nv, strides + 1, nl - 1, gx, gy, gz, gb, cws + 1, cws_bytes + 1, nv,
+                                           ccoords + 1, sst));
         }
         for (int l = 1; l < nl; ++l) {
             long long n_out = 0;
@@ -307,7 +320,23 @@ static int model_scene(const dv3d_net_params_t& net, const float* pts, const flo
             sc.lv[l].n = n_out;
             sc.lv[l].stride = 1 << l;
         }
-        for (int l = 1; l < nl; ++l) TRY(build_level(sc.lv[l], err_flag, ar, sst));
+        if (nl > 1) {
+            const int* hc[DV3D_MAX_LEVELS];
+            long long hn[DV3D_MAX_LEVELS];
+            void* ht[DV3D_MAX_LEVELS];
+            size_t hb[DV3D_MAX_LEVELS];
+            for (int l = 1; l < nl; ++l) {
+                Level& L = sc.lv[l];
+                L.table_bytes = dv3d_hash_bytes(L.n);
+                L.table = ar.get<char>(L.table_bytes);
+                hc[l] = L.coords;
+                hn[l] = L.n;
+                ht[l] = L.table;
+                hb[l] = L.table_bytes;
+            }
+            ARENA_CHECK(ar);
+            TRY(dv3d_hash_build_batch(hc + 1, hn + 1, ht + 1, hb + 1, nl - 1, err_flag, sst));
+        }
     }
 
     // every kernel map of the U-Net and its pair-major plan, then ONE sync for the counts

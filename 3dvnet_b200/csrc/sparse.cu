@@ -6,6 +6,8 @@
 // map swapped, interpolation takes the 8 corners lower + {0,ts}^3 and missing voxels add 0.
 #include <math.h>
 
+#include <algorithm>
+
 #include "gemm.cuh"
 
 namespace dv3d {
@@ -35,6 +37,48 @@ hash_insert_kernel(const int* __restrict__ coords, long long n, HashView t, int*
     while (true) {
         unsigned long long prev = atomicCAS(t.keys + slot, kEmptyKey, key);
         if (prev == kEmptyKey || prev == key) {  // duplicate coordinates: lowest row wins deterministically
+            atomicMin(t.rows + slot, (int)i);
+            return;
+        }
+        slot = (slot + 1) & t.mask;
+    }
+}
+
+// several tables in two launches: blockIdx.y selects the table
+constexpr int HB_MAX = 4;
+struct HashBatch {
+    const int* coords[HB_MAX];
+    long long n[HB_MAX];
+    HashView t[HB_MAX];
+};
+__global__ void __launch_bounds__(256)
+hash_clear_batch_kernel(const __grid_constant__ HashBatch b) {
+    pdl_wait();
+    const HashView& t = b.t[blockIdx.y];
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= (size_t)t.mask) {
+        t.keys[i] = kEmptyKey;
+        t.rows[i] = INT_MAX;
+    }
+}
+__global__ void __launch_bounds__(256)
+hash_insert_batch_kernel(const __grid_constant__ HashBatch b, int* __restrict__ err) {
+    pdl_wait();
+    const int j = blockIdx.y;
+    const HashView t = b.t[j];
+    const int* __restrict__ coords = b.coords[j];
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= b.n[j]) return;
+    int bb = coords[4 * i], x = coords[4 * i + 1], y = coords[4 * i + 2], z = coords[4 * i + 3];
+    if (!coord_in_range(bb, x, y, z)) {
+        *err = 1;
+        return;
+    }
+    unsigned long long key = coord_key(bb, x, y, z);
+    unsigned slot = hash_mix(key) & t.mask;
+    while (true) {
+        unsigned long long prev = atomicCAS(t.keys + slot, kEmptyKey, key);
+        if (prev == kEmptyKey || prev == key) {
             atomicMin(t.rows + slot, (int)i);
             return;
         }
@@ -193,6 +237,31 @@ extern "C" int dv3d_hash_build(const int* coords, long long n, void* table, size
     DV3D_LAUNCHED();
     if (n == 0) return DV3D_OK;
     DV3D_LAUNCH((hash_insert_kernel), cdiv(n, 256), 256, 0, st, coords, n, t, err_flag);
+    DV3D_LAUNCHED();
+    return DV3D_OK;
+}
+
+extern "C" int dv3d_hash_build_batch(const int* const* coords, const long long* n, void* const* tables,
+                                     const size_t* table_bytes, int n_tables, int* err_flag, void* stream) {
+    DV3D_REQUIRE(coords && n && tables && table_bytes && err_flag && n_tables >= 1 && n_tables <= HB_MAX,
+                 "hash_build_batch: bad arguments (1..%d tables)", HB_MAX);
+    HashBatch b = {};
+    size_t max_cap = 0;
+    long long max_n = 0;
+    for (int j = 0; j < n_tables; ++j) {
+        DV3D_REQUIRE(coords[j] && tables[j] && n[j] >= 0, "hash_build_batch: bad table %d", j);
+        DV3D_REQUIRE(hash_view(tables[j], table_bytes[j], &b.t[j]) && (size_t)b.t[j].mask + 1 >= (size_t)(2 * n[j]),
+                     "hash_build: table_bytes must be dv3d_hash_bytes(n)");
+        b.coords[j] = coords[j];
+        b.n[j] = n[j];
+        max_cap = std::max(max_cap, (size_t)b.t[j].mask + 1);
+        max_n = std::max(max_n, n[j]);
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    DV3D_LAUNCH((hash_clear_batch_kernel), dim3(cdiv(max_cap, 256), n_tables), 256, 0, st, b);
+    DV3D_LAUNCHED();
+    if (max_n == 0) return DV3D_OK;
+    DV3D_LAUNCH((hash_insert_batch_kernel), dim3(cdiv(max_n, 256), n_tables), 256, 0, st, b, err_flag);
     DV3D_LAUNCHED();
     return DV3D_OK;
 }

@@ -114,10 +114,8 @@ mark_points_kernel(const float* __restrict__ pts, const long long* __restrict__ 
 }
 
 // exclusive scan of popcounts, stage 1: per block of SCAN_BLK words
-__global__ void __launch_bounds__(SCAN_T)
-scan_words_kernel(const unsigned* __restrict__ bitmap, long long n_words, unsigned* __restrict__ prefix,
-                  unsigned* __restrict__ block_sums) {
-    pdl_wait();
+__device__ __forceinline__ void scan_words_body(const unsigned* __restrict__ bitmap, long long n_words,
+                                                unsigned* __restrict__ prefix, unsigned* __restrict__ block_sums) {
     __shared__ unsigned s_warp[SCAN_T / 32];
     const long long base = (long long)blockIdx.x * SCAN_BLK + (long long)threadIdx.x * SCAN_W;
     unsigned c[SCAN_W], tot = 0;
@@ -144,11 +142,15 @@ scan_words_kernel(const unsigned* __restrict__ bitmap, long long n_words, unsign
     }
     if (threadIdx.x == SCAN_T - 1) block_sums[blockIdx.x] = woff + incl;
 }
+__global__ void __launch_bounds__(SCAN_T)
+scan_words_kernel(const unsigned* __restrict__ bitmap, long long n_words, unsigned* __restrict__ prefix,
+                  unsigned* __restrict__ block_sums) {
+    pdl_wait();
+    scan_words_body(bitmap, n_words, prefix, block_sums);
+}
 
 // stage 2: one block turns block_sums into exclusive offsets and writes the grand total
-__global__ void __launch_bounds__(1024)
-scan_blocks_kernel(unsigned* __restrict__ block_sums, int n_blocks, long long* __restrict__ total) {
-    pdl_wait();
+__device__ __forceinline__ void scan_blocks_body(unsigned* __restrict__ block_sums, int n_blocks, long long* __restrict__ total) {
     __shared__ unsigned s_warp[32];
     __shared__ unsigned s_carry;
     if (threadIdx.x == 0) s_carry = 0;
@@ -173,6 +175,11 @@ scan_blocks_kernel(unsigned* __restrict__ block_sums, int n_blocks, long long* _
         __syncthreads();
     }
     if (threadIdx.x == 0) *total = (long long)s_carry;
+}
+__global__ void __launch_bounds__(1024)
+scan_blocks_kernel(unsigned* __restrict__ block_sums, int n_blocks, long long* __restrict__ total) {
+    pdl_wait();
+    scan_blocks_body(block_sums, n_blocks, total);
 }
 
 __device__ __forceinline__ unsigned rank_of(long long id, const unsigned* bitmap, const unsigned* prefix,
@@ -250,10 +257,8 @@ struct LevelDims {
     int stride;    // new tensor stride
 };
 
-__global__ void __launch_bounds__(256)
-mark_coarse_kernel(const int* __restrict__ coords, long long n, LevelDims L, int n_batch,
-                   unsigned* __restrict__ bitmap, int* __restrict__ err) {
-    pdl_wait();
+__device__ __forceinline__ void mark_coarse_body(const int* __restrict__ coords, long long n, LevelDims L, int n_batch,
+                                                 unsigned* __restrict__ bitmap, int* __restrict__ err) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int b = coords[4 * i], x = coords[4 * i + 1], y = coords[4 * i + 2], z = coords[4 * i + 3];
@@ -266,12 +271,16 @@ mark_coarse_kernel(const int* __restrict__ coords, long long n, LevelDims L, int
     long long cell = (((long long)b * L.Z + cz) * L.Y + cy) * L.X + cx;  // (b, z, y, x) order
     atomicOr(bitmap + (cell >> 5), 1u << (cell & 31));
 }
-
 __global__ void __launch_bounds__(256)
-emit_coarse_kernel(const unsigned* __restrict__ bitmap, const unsigned* __restrict__ prefix,
-                   const unsigned* __restrict__ block_offs, long long n_words, LevelDims L, long long cap,
-                   int* __restrict__ coarse) {
+mark_coarse_kernel(const int* __restrict__ coords, long long n, LevelDims L, int n_batch,
+                   unsigned* __restrict__ bitmap, int* __restrict__ err) {
     pdl_wait();
+    mark_coarse_body(coords, n, L, n_batch, bitmap, err);
+}
+
+__device__ __forceinline__ void emit_coarse_body(const unsigned* __restrict__ bitmap, const unsigned* __restrict__ prefix,
+                                                 const unsigned* __restrict__ block_offs, long long n_words, LevelDims L,
+                                                 long long cap, int* __restrict__ coarse) {
     long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= n_words) return;
     unsigned bits = bitmap[w];
@@ -295,6 +304,51 @@ emit_coarse_kernel(const unsigned* __restrict__ bitmap, const unsigned* __restri
         }
         ++rank;
     }
+}
+__global__ void __launch_bounds__(256)
+emit_coarse_kernel(const unsigned* __restrict__ bitmap, const unsigned* __restrict__ prefix,
+                   const unsigned* __restrict__ block_offs, long long n_words, LevelDims L, long long cap,
+                   int* __restrict__ coarse) {
+    pdl_wait();
+    emit_coarse_body(bitmap, prefix, block_offs, n_words, L, cap, coarse);
+}
+
+// every coarser level of a scene in one pass over the finest coordinates: blockIdx.y selects the level
+constexpr int CB_MAX = 4;
+struct CoarsenBatch {
+    LevelDims L[CB_MAX];
+    long long n_words[CB_MAX];
+    unsigned* bitmap[CB_MAX];
+    unsigned* prefix[CB_MAX];
+    unsigned* block_sums[CB_MAX];
+    long long* total[CB_MAX];
+    int* err[CB_MAX];
+    int* coarse[CB_MAX];
+};
+__global__ void __launch_bounds__(256)
+mark_coarse_batch_kernel(const int* __restrict__ coords, long long n, int n_batch, const __grid_constant__ CoarsenBatch b) {
+    pdl_wait();
+    const int l = blockIdx.y;
+    mark_coarse_body(coords, n, b.L[l], n_batch, b.bitmap[l], b.err[l]);
+}
+__global__ void __launch_bounds__(SCAN_T)
+scan_words_batch_kernel(const __grid_constant__ CoarsenBatch b) {
+    pdl_wait();
+    const int l = blockIdx.y;
+    if ((long long)blockIdx.x * SCAN_BLK >= b.n_words[l]) return;
+    scan_words_body(b.bitmap[l], b.n_words[l], b.prefix[l], b.block_sums[l]);
+}
+__global__ void __launch_bounds__(1024)
+scan_blocks_batch_kernel(const __grid_constant__ CoarsenBatch b) {
+    pdl_wait();
+    const int l = blockIdx.x;
+    scan_blocks_body(b.block_sums[l], (int)((b.n_words[l] + SCAN_BLK - 1) / SCAN_BLK), b.total[l]);
+}
+__global__ void __launch_bounds__(256)
+emit_coarse_batch_kernel(const __grid_constant__ CoarsenBatch b, long long cap) {
+    pdl_wait();
+    const int l = blockIdx.y;
+    emit_coarse_body(b.bitmap[l], b.prefix[l], b.block_sums[l], b.n_words[l], b.L[l], cap, b.coarse[l]);
 }
 
 // positions and reference-style views of a level (scenemodeling.py:211-226):
@@ -520,6 +574,55 @@ extern "C" int dv3d_coarsen_enqueue(const int* coords, long long n, int new_stri
     int rc = run_scan(s, n_words, st);
     if (rc) return rc;
     DV3D_LAUNCH((emit_coarse_kernel), cdiv(n_words, 256), 256, 0, st, s.bitmap, s.prefix, s.block_sums, n_words, L, cap, coarse_coords);
+    DV3D_LAUNCHED();
+    return DV3D_OK;
+}
+
+// several coarser levels from the same (finest) coordinates with four launches in total
+extern "C" int dv3d_coarsen_enqueue_batch(const int* coords, long long n, const int* new_strides, int n_levels, int dim_x,
+                                          int dim_y, int dim_z, int n_batch, void* const* workspaces,
+                                          const size_t* workspace_bytes, long long cap, int* const* coarse_coords,
+                                          void* stream) {
+    DV3D_REQUIRE(coords && new_strides && workspaces && workspace_bytes && coarse_coords && n > 0 && cap > 0 && n_levels >= 1 &&
+                     n_levels <= CB_MAX,
+                 "coarsen_batch: bad arguments (1..%d levels)", CB_MAX);
+    cudaStream_t st = (cudaStream_t)stream;
+    CoarsenBatch b = {};
+    long long max_words = 0;
+    for (int l = 0; l < n_levels; ++l) {
+        DV3D_REQUIRE(workspaces[l] && coarse_coords[l] && new_strides[l] > 0, "coarsen_batch: bad level %d", l);
+        const size_t need = dv3d_coarsen_workspace_bytes(dim_x, dim_y, dim_z, n_batch, new_strides[l]);
+        DV3D_REQUIRE(need > 0, "coarsen: bad lattice dimensions");
+        if (workspace_bytes[l] < need) {
+            set_error("coarsen: workspace of %zu bytes is too small, need %zu", workspace_bytes[l], need);
+            return DV3D_ENOSPC;
+        }
+        b.L[l] = LevelDims{cdiv(dim_x, new_strides[l]), cdiv(dim_y, new_strides[l]), cdiv(dim_z, new_strides[l]), new_strides[l]};
+        b.n_words[l] = ((long long)b.L[l].X * b.L[l].Y * b.L[l].Z * n_batch + 31) / 32;
+        ScanSpace s = carve(workspaces[l], b.n_words[l]);
+        b.bitmap[l] = s.bitmap;
+        b.prefix[l] = s.prefix;
+        b.block_sums[l] = s.block_sums;
+        b.total[l] = s.total;
+        b.err[l] = s.err;
+        b.coarse[l] = coarse_coords[l];
+        if (b.n_words[l] > max_words) max_words = b.n_words[l];
+        // contiguous workspaces are cleared by the memset of the first one
+        const bool merged = l > 0 && (char*)workspaces[l] == (char*)workspaces[l - 1] + workspace_bytes[l - 1];
+        if (!merged) {
+            size_t span = workspace_bytes[l];
+            for (int k = l + 1; k < n_levels && (char*)workspaces[k] == (char*)workspaces[k - 1] + workspace_bytes[k - 1]; ++k)
+                span += workspace_bytes[k];
+            DV3D_CUDA(cudaMemsetAsync(workspaces[l], 0, span, st));
+        }
+    }
+    DV3D_LAUNCH((mark_coarse_batch_kernel), dim3(cdiv(n, 256), n_levels), 256, 0, st, coords, n, n_batch, b);
+    DV3D_LAUNCHED();
+    DV3D_LAUNCH((scan_words_batch_kernel), dim3(cdiv(max_words, SCAN_BLK), n_levels), SCAN_T, 0, st, b);
+    DV3D_LAUNCHED();
+    DV3D_LAUNCH((scan_blocks_batch_kernel), n_levels, 1024, 0, st, b);
+    DV3D_LAUNCHED();
+    DV3D_LAUNCH((emit_coarse_batch_kernel), dim3(cdiv(max_words, 256), n_levels), 256, 0, st, b, cap);
     DV3D_LAUNCHED();
     return DV3D_OK;
 }

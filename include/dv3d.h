@@ -188,6 +188,9 @@ int dv3d_make_coords(const int* idx3d, const long long* batch, long long n, int*
 size_t dv3d_hash_bytes(long long n_rows);
 /* build the table of a level; *err_flag (device int, caller-zeroed) is set on out-of-range coordinates */
 int dv3d_hash_build(const int* coords, long long n, void* table, size_t table_bytes, int* err_flag, void* stream);
+/* n_tables (<= 4) tables in two launches; coords/n/tables/table_bytes are HOST arrays */
+int dv3d_hash_build_batch(const int* const* coords, const long long* n, void* const* tables, const size_t* table_bytes,
+                          int n_tables, int* err_flag, void* stream);
 /* coarser level of a stride-2 convolution: unique(floor(c / new_stride) * new_stride) in
  * (batch,z,y,x) order.  dim_* bound the finest-level index range (cells per axis).  SYNCS once. */
 size_t dv3d_coarsen_workspace_bytes(int dim_x, int dim_y, int dim_z, int n_batch, int new_stride);
@@ -198,6 +201,10 @@ int dv3d_coarsen(const int* coords, long long n, int new_stride, int dim_x, int 
  * (floor(floor(c/2)*2/4)*4 = floor(c/4)*4) with ONE sync: enqueue every level, then finish each */
 int dv3d_coarsen_enqueue(const int* coords, long long n, int new_stride, int dim_x, int dim_y, int dim_z, int n_batch,
                          void* workspace, size_t workspace_bytes, long long cap, int* coarse_coords, void* stream);
+/* n_levels (<= 4) coarser levels from the same coordinates with four launches; HOST arrays */
+int dv3d_coarsen_enqueue_batch(const int* coords, long long n, const int* new_strides, int n_levels, int dim_x, int dim_y,
+                               int dim_z, int n_batch, void* const* workspaces, const size_t* workspace_bytes,
+                               long long cap, int* const* coarse_coords, void* stream);
 int dv3d_coarsen_finish(const void* workspace, int new_stride, int dim_x, int dim_y, int dim_z, int n_batch,
                         long long cap, long long* n_coarse_host, void* stream);
 /* kernel map: nbr[o*27+k] = row of coords_out[o] + offset_k*step in the input level, or -1

@@ -113,3 +113,58 @@ def test_hot_path_c2_is_deterministic(mods):
     outs = [net.hot_path(*args).cpu() for _ in range(3)]
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
     assert torch.isfinite(outs[0]).all() and float(outs[0].min()) > 0.2 and float(outs[0].max()) < 6.0
+
+
+def test_batched_levels_equal_single_level_calls(mods):
+    """dv3d_coarsen_enqueue_batch / dv3d_hash_build_batch (what the engine uses) give exactly the levels,
+    and tables answering exactly the lookups, of the one-level entry points (what the composed path uses)."""
+    import ctypes
+    ops = mods['ops']
+    L = ops.lib()
+    g = torch.Generator().manual_seed(21)
+    dims, n_batch = (97, 83, 41), 3
+    cells = torch.unique(torch.randint(0, dims[0] * dims[1] * dims[2] * n_batch, (60_000,), generator=g))
+    b = cells // (dims[0] * dims[1] * dims[2])
+    r = cells % (dims[0] * dims[1] * dims[2])
+    coords = torch.stack([b, r % dims[0], (r // dims[0]) % dims[1], r // (dims[0] * dims[1])], 1).int().to(DEV)
+    n = coords.shape[0]
+    err = torch.zeros(1, dtype=torch.int32, device=DEV)
+    fine = ops.SparseLevel(coords, 1, err)
+    single = [ops.coarsen(fine, dims, n_batch, err)]
+    single.append(ops.coarsen(single[0], dims, n_batch, err))
+
+    strides = (ctypes.c_int * 2)(2, 4)
+    wsb = [(L.raw('dv3d_coarsen_workspace_bytes')(dims[0], dims[1], dims[2], n_batch, s) + 255) // 256 * 256 for s in (2, 4)]
+    span = torch.empty(sum(wsb), dtype=torch.uint8, device=DEV)
+    ws = (ctypes.c_void_p * 2)(span.data_ptr(), span.data_ptr() + wsb[0])
+    wsbytes = (ctypes.c_size_t * 2)(*wsb)
+    outs = [torch.full((n, 4), -7, dtype=torch.int32, device=DEV) for _ in range(2)]
+    outp = (ctypes.c_void_p * 2)(*[o.data_ptr() for o in outs])
+    stream = torch.cuda.current_stream().cuda_stream
+    L.call('dv3d_coarsen_enqueue_batch', coords.data_ptr(), n, strides, 2, dims[0], dims[1], dims[2], n_batch, ws, wsbytes,
+           n, outp, stream)
+    counts = []
+    for l in range(2):
+        n_out = ctypes.c_longlong(0)
+        L.call('dv3d_coarsen_finish', ws[l], 2 << l, dims[0], dims[1], dims[2], n_batch, n, ctypes.byref(n_out), stream)
+        counts.append(n_out.value)
+    for l in range(2):
+        assert counts[l] == single[l].n
+        assert torch.equal(outs[l][:counts[l]], single[l].coords)
+
+    # batched tables: the kernel maps built from them equal those of the single-table build
+    tb = [L.raw('dv3d_hash_bytes')(c) for c in counts]
+    tables = [torch.empty(t, dtype=torch.uint8, device=DEV) for t in tb]
+    L.call('dv3d_hash_build_batch', (ctypes.c_void_p * 2)(*[outs[l].data_ptr() for l in range(2)]),
+           (ctypes.c_longlong * 2)(*counts), (ctypes.c_void_p * 2)(*[t.data_ptr() for t in tables]),
+           (ctypes.c_size_t * 2)(*tb), 2, err.data_ptr(), stream)
+    for l in range(2):
+        want = single[l].kernel_map(single[l], single[l].stride).nbr
+        got = torch.empty_like(want)
+        L.call('dv3d_kernel_map', single[l].coords.data_ptr(), counts[l], tables[l].data_ptr(), tb[l], single[l].stride,
+               got.data_ptr(), stream)
+        assert torch.equal(got, want)
+    assert int(err.item()) == 0
+    with pytest.raises(ops.Dv3dError):
+        L.call('dv3d_coarsen_enqueue_batch', coords.data_ptr(), n, strides, 5, dims[0], dims[1], dims[2], n_batch, ws,
+               wsbytes, n, outp, stream)
