@@ -28,6 +28,7 @@ struct GemmSlice {
     int K;              // multiple of 16
 };
 
+constexpr int kMaxPeers = 7;
 struct GemmDesc {
     GemmSlice slice[kMaxSlices];
     int n_slices;
@@ -55,6 +56,11 @@ struct GemmDesc {
     int split_hint;         // > 1: use exactly this many K splits (caller sized the workspace); 0: automatic
     float* out;             // [M, out_ld]
     int out_ld;
+    // Row-sharded layers of a scene spanning GPUs (symm.cu): the finished rows are also stored into the same rows
+    // of every peer's copy of the buffer over NVLink, straight from the epilogue.  Filled in by the launchers from
+    // the registered symmetric regions (symm_attach); callers leave it zero.
+    float* peer_out[kMaxPeers];
+    int n_peers;
 };
 
 // Epilogue of one 16-byte unit (4 channels c0..c0+3 of output row m).  The 4 lanes that hold
@@ -95,11 +101,15 @@ __device__ __forceinline__ void epilogue4(const GemmDesc& d, float4 y, long long
         y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f);
     }
     if (zero_row) y = make_float4(0.f, 0.f, 0.f, 0.f);
-    *reinterpret_cast<float4*>(d.out + (size_t)m * d.out_ld + c0) = y;
+    const size_t at = (size_t)m * d.out_ld + c0;
+    *reinterpret_cast<float4*>(d.out + at) = y;
+    for (int p = 0; p < d.n_peers; ++p) *reinterpret_cast<float4*>(d.peer_out[p] + at) = y;
 }
 
 // d.Wp == nullptr: fp32 CUDA-core kernel (gemm.cu); otherwise the tcgen05 kernel (gemm_tc.cu),
 // 3xTF32 or TF32 according to dv3d_set_gemm_precision.
+// fills d.peer_out / d.n_peers when d.out lies inside a region registered with dv3d_symm_register
+void symm_attach(GemmDesc& d);
 int launch_gather_gemm(const GemmDesc& d, cudaStream_t st);
 int launch_gather_gemm_tc(const GemmDesc& d, cudaStream_t st);
 int gather_gemm_tc_splits(long long M, int n_slices);

@@ -491,7 +491,9 @@ int gather_gemm_tc_splits(long long M, int n_slices) {
     return split < 1 ? 1 : split;
 }
 
-int launch_gather_gemm_tc(const GemmDesc& d, cudaStream_t st) {
+int launch_gather_gemm_tc(const GemmDesc& d_in, cudaStream_t st) {
+    GemmDesc d = d_in;
+    symm_attach(d);
     const float* Wp = d.Wp;
     int rc = validate_gather_gemm(d, TC_KC);
     if (rc) return rc;

@@ -328,6 +328,7 @@ extern "C" int dv3d_sparse_conv_pairs(const float* feat, long long n_in, int Cin
     e.relu_out = relu;
     e.out = out;
     e.out_ld = Cout;
+    symm_attach(e);
     DV3D_REQUIRE(!gn_weight || gn_bias, "sparse_conv_pairs: GroupNorm needs weight and bias");
     if (Cout == 128)
         DV3D_LAUNCH((pair_reduce_kernel<128>), cdiv(n_out, 8), 256, 0, st, e, P, pv.pair_slot);

@@ -113,12 +113,13 @@ def edge_plan(ref_src_edges, device):
     if isinstance(ref_src_edges, EdgePlan):
         return ref_src_edges
     key = (ref_src_edges.data_ptr(), ref_src_edges._version, tuple(ref_src_edges.shape), str(device))
-    plan = _plan_cache.get(key)
-    if plan is None:
+    hit = _plan_cache.get(key)
+    if hit is None:
         if len(_plan_cache) > 64:
             _plan_cache.clear()
-        plan = _plan_cache[key] = EdgePlan(ref_src_edges, device)
-    return plan
+        # the entry keeps the edge tensor alive: its address cannot be handed to another tensor while cached
+        hit = _plan_cache[key] = (EdgePlan(ref_src_edges, device), ref_src_edges)
+    return hit[0]
 
 
 # ----------------------------------------------------------------------------- path A
@@ -367,32 +368,42 @@ def sparse_conv_workspace(Cout, device):
     return torch.zeros(lib().raw('dv3d_sparse_conv_workspace_bytes')(Cout), dtype=torch.uint8, device=device)
 
 
-def sparse_conv(feat, nbr, W, gn_weight=None, gn_bias=None, residual=None, relu=False, packed=None, workspace=None):
-    """nbr: [n_out,27] int32 tensor, or a KernelMap (which may route to the pair-major variant)"""
+def sparse_conv(feat, nbr, W, gn_weight=None, gn_bias=None, residual=None, relu=False, packed=None, workspace=None,
+                out=None):
+    """nbr: [n_out,27] int32 tensor, or a KernelMap (which may route to the pair-major variant).
+    out: optional contiguous [n_out, Cout] destination (e.g. this rank's rows of a symmetric buffer)"""
     n_in, Cin = feat.shape
     Cout = W.shape[2]
     assert W.shape[0] == 27 and W.shape[1] == Cin
     if isinstance(nbr, KernelMap):
         km, nbr = nbr, nbr.nbr
         if km.use_pairs and packed is not None:
-            out = torch.empty((km.n_out, Cout), dtype=torch.float32, device=feat.device)
+            out = _out_rows(out, km.n_out, Cout, feat.device)
             P = km.workspace(Cout)
             lib().call('dv3d_sparse_conv_pairs', _p(feat), n_in, Cin, _p(km.plan), km.n_tiles, km.n_out, _p(packed), Cout,
                        _p(gn_weight), _p(gn_bias), _p(residual), int(relu), _p(P), P.numel(), _p(out), _stream())
             return out
     n_out = nbr.shape[0]
-    out = torch.empty((n_out, Cout), dtype=torch.float32, device=feat.device)
+    out = _out_rows(out, n_out, Cout, feat.device)
     ws_bytes = 0 if workspace is None else workspace.numel()
     lib().call('dv3d_sparse_conv', _p(feat), n_in, Cin, _p(nbr), n_out, _p(W), _p(packed), Cout, _p(gn_weight),
                _p(gn_bias), _p(residual), int(relu), _p(workspace) if ws_bytes else None, ws_bytes, _p(out), _stream())
     return out
 
 
-def concat_linear_gn_relu(a, b, W, gn_weight, gn_bias, packed=None):
+def _out_rows(out, n, C, device):
+    if out is None:
+        return torch.empty((n, C), dtype=torch.float32, device=device)
+    if tuple(out.shape) != (n, C) or out.dtype != torch.float32 or not out.is_contiguous():
+        raise RuntimeError('out must be a contiguous float32 [%d, %d] tensor, got %s' % (n, C, tuple(out.shape)))
+    return out
+
+
+def concat_linear_gn_relu(a, b, W, gn_weight, gn_bias, packed=None, out=None):
     n, Ca = a.shape
     Cb = b.shape[1]
     Cout = W.shape[1]
-    out = torch.empty((n, Cout), dtype=torch.float32, device=a.device)
+    out = _out_rows(out, n, Cout, a.device)
     lib().call('dv3d_concat_linear_gn_relu', _p(a), Ca, _p(b), Cb, n, _p(W), _p(packed), Cout, _p(gn_weight),
                _p(gn_bias), _p(out), _stream())
     return out

@@ -428,6 +428,24 @@ int dv3d_hot_path(const dv3d_net_params_t* net, const float* feats_nhwc, int n_i
                   const double* offsets_host, int n_outer, int n_inner, void* workspace, size_t workspace_bytes,
                   float* depth_init_out, float* depth_out, void* stream);
 
+/* ---- one scene spanning GPUs: symmetric regions (csrc/symm.cu; host side 3dvnet_b200/parallel.py) --------------
+ * The reference is single-GPU (mv3d/config.py:3-5); this is the SURVEY.md section 8e "shard UNet by voxel-id range"
+ * path.  Every rank owns one buffer of the same size (dv3d_symm_alloc) and maps its peers' copies (dv3d_symm_open on
+ * the handles the host side exchanged; legacy CUDA IPC, one process per GPU).
+ * Once registered, every sparse-convolution / concat-linear launch whose `out` lies inside the local region also
+ * stores its rows at the same offset of every peer copy (NVLink stores from the epilogue), so a row-sharded layer
+ * needs no separate all-gather.  dv3d_symm_barrier enqueues the cross-GPU barrier between layers: flags are
+ * n_ranks 32-bit words inside the region (zero at start), peers in ascending rank order with this rank left out,
+ * epoch strictly increasing.  A peer that does not arrive within ~4 s sets *err_flag instead of hanging. */
+int dv3d_symm_alloc(size_t bytes, void** ptr, void* handle64);   /* zeroed cudaMalloc block + its 64-byte IPC handle */
+int dv3d_symm_open(const void* handle64, void** ptr);            /* a PEER process's block, mapped for the current device */
+int dv3d_symm_close(void* ptr);
+int dv3d_symm_free(void* ptr);
+int dv3d_symm_register(const void* base, size_t bytes, void* const* peer_bases, int n_peers);
+int dv3d_symm_unregister(const void* base);
+int dv3d_symm_barrier(void* local_flags, void* const* peer_flags, int n_peers, int rank, int epoch, int* err_flag,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif
