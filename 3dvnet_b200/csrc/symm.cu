@@ -51,9 +51,10 @@ __global__ void symm_barrier_kernel(unsigned* local_flags, SymmRegion peers, int
     unsigned seen;
     do {
         asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(local_flags + src_rank) : "memory");
-        if (clock64() - t0 > 8000000000ll) {  // ~4 s: a peer died; report instead of hanging the GPU
-            *err = 1;
-            return;
+        if (clock64() - t0 > 40000000000ll) {  // ~20 s: a peer died. Fail loudly instead of hanging the GPU or
+            *err = 1;                           // letting later layers read rows that never arrived
+            __threadfence_system();
+            __trap();
         }
     } while ((int)(seen - epoch) < 0);
     __threadfence_system();

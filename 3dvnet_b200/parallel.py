@@ -223,6 +223,12 @@ class SymmHeap(object):
         self.ptr = None
 
 
+def row_range(n, world, rank):
+    """rows [rank*m, min((rank+1)*m, n)) with m = ceil(n / world): equal blocks, the tail ranks may be short or empty"""
+    m = (n + world - 1) // world
+    return min(rank * m, n), min((rank + 1) * m, n)
+
+
 class ShardedScene(object):
     """Coordinate levels and hash tables of the whole scene (identical on every rank) with kernel maps and
     pair-major plans for THIS rank's rows of every level: rows [rank*m, min((rank+1)*m, n)), m = ceil(n / world)."""
@@ -236,10 +242,7 @@ class ShardedScene(object):
         self.levels = [ops.SparseLevel(ops.make_coords(idx.int().contiguous(), batch.long().contiguous()), 1, self.err)]
         for _ in range(1, n_levels):
             self.levels.append(ops.coarsen(self.levels[-1], dims[:3], dims[3], self.err))
-        self.range = []
-        for lv in self.levels:
-            m = (lv.n + world - 1) // world
-            self.range.append((min(rank * m, lv.n), min((rank + 1) * m, lv.n)))
+        self.range = [row_range(lv.n, world, rank) for lv in self.levels]
         self.ws = ops.sparse_conv_workspace(128, dev)
         L = ops.lib()
 

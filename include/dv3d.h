@@ -436,7 +436,8 @@ int dv3d_hot_path(const dv3d_net_params_t* net, const float* feats_nhwc, int n_i
  * stores its rows at the same offset of every peer copy (NVLink stores from the epilogue), so a row-sharded layer
  * needs no separate all-gather.  dv3d_symm_barrier enqueues the cross-GPU barrier between layers: flags are
  * n_ranks 32-bit words inside the region (zero at start), peers in ascending rank order with this rank left out,
- * epoch strictly increasing.  A peer that does not arrive within ~4 s sets *err_flag instead of hanging. */
+ * epoch strictly increasing.  A peer that does not arrive within ~20 s sets *err_flag and traps the kernel (every later
+ * CUDA call of the process then fails) instead of hanging. */
 int dv3d_symm_alloc(size_t bytes, void** ptr, void* handle64);   /* zeroed cudaMalloc block + its 64-byte IPC handle */
 int dv3d_symm_open(const void* handle64, void** ptr);            /* a PEER process's block, mapped for the current device */
 int dv3d_symm_close(void* ptr);

@@ -75,3 +75,40 @@ def test_shard_plan_and_local_edges():
         assert torch.equal(le, e[:, keep])
         seen += le.shape[1]
     assert seen == e.shape[1]
+
+
+def test_row_ranges_partition_every_level():
+    par = importlib.import_module('3dvnet_b200.parallel')
+    for n in (0, 1, 7, 8, 9, 1000, 200_704):
+        for world in (2, 3, 8):
+            got = [par.row_range(n, world, r) for r in range(world)]
+            assert got[0][0] == 0 and got[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(got, got[1:]))           # contiguous, in rank order
+            assert max(b - a for a, b in got) == (n + world - 1) // world
+
+
+def test_symm_heap_blocks_are_recycled_at_identical_offsets():
+    """the bump allocator of the symmetric heap must hand out the same offsets on every rank for the same
+    sequence of rows()/release() calls (pure host logic; the device side is covered on 2 GPUs)"""
+    par = importlib.import_module('3dvnet_b200.parallel')
+
+    def run():
+        h = par.SymmHeap.__new__(par.SymmHeap)
+        h.nbytes = 1 << 20
+        h.buf = torch.zeros(h.nbytes, dtype=torch.uint8)
+        h.reset()
+        base = h.buf.data_ptr()
+        a, b = h.rows(100, 64), h.rows(100, 64)
+        c = h.rows(50, 128)
+        h.release(a)
+        d = h.rows(100, 64)                       # reuses a
+        e = h.rows(100, 64)                       # fresh
+        offs = [t.data_ptr() - base for t in (a, b, c, d, e)]
+        with pytest.raises(RuntimeError):
+            h.rows(1 << 20, 64)
+        return offs
+
+    o1, o2 = run(), run()
+    assert o1 == o2
+    assert o1[0] == 256 and o1[3] == o1[0] and len(set(o1[:3] + o1[4:])) == 4
+    assert all(o % 256 == 0 for o in o1)
