@@ -1,6 +1,7 @@
 // Shared helpers for lib3dvnet_b200 (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -45,6 +46,9 @@ void count_launch(int n = 1);
 // dependents' CTAs then spin next to the running kernel and the step got 1.5 % slower.)
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 bool pdl_enabled();
+// Function attributes (cudaFuncSetAttribute) are per device: true the first time a call site runs on the
+// current device.  `mask` is a static std::atomic<unsigned long long> of the call site (bit = device).
+bool first_use_on_device(std::atomic<unsigned long long>& mask);
 
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,

@@ -551,12 +551,10 @@ static int launch_direct(const float* x, int n, int Cin, int Di, int Hi, int Wi,
     const int ns = pick_slices(total, Cin, cogs, 2 * kNumSMs);
     const size_t smem = sizeof(float) * ((size_t)Cin * 27 * CO_T + (ns > 1 ? DC_THREADS * CO_T : 0));
     DV3D_REQUIRE(smem <= 200 * 1024, "conv3d: weights of one channel group (%zu bytes) do not fit shared memory", smem);
-    static size_t attr = 0;  // per instantiation
-    if (smem > attr) {
+    static std::atomic<unsigned long long> attr{0};  // per instantiation; the opt-in covers the 200 KB bound above
+    if (first_use_on_device(attr))
         DV3D_CUDA(cudaFuncSetAttribute(conv3d_direct_kernel<STRIDE, CO_T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem));
-        attr = smem;
-    }
+                                       200 * 1024));
     dim3 grid(cdiv(total, DC_THREADS / ns), cogs);
     DV3D_REQUIRE(grid.y <= 65535, "conv3d: too many channel groups");
     DV3D_LAUNCH((conv3d_direct_kernel<STRIDE, CO_T>), grid, DC_THREADS, smem, st, x, Cin, Di, Hi, Wi, w, scale, shift, Cout, Do, Ho, Wo, skip, y, total, ns);
@@ -584,11 +582,9 @@ static int launch_deconv(const float* x, int n, int Cin, int Di, int Hi, int Wi,
     const int ns = pick_slices(total, Cin, cogs, kNumSMs - 8);
     const size_t smem = sizeof(float) * ((size_t)Cin * 27 * CO_T + (ns > 1 ? DC_THREADS * CO_T : 0));
     DV3D_REQUIRE(smem <= 200 * 1024, "deconv3d: weights of one channel group (%zu bytes) do not fit shared memory", smem);
-    static size_t attr = 0;
-    if (smem > attr) {
-        DV3D_CUDA(cudaFuncSetAttribute(deconv3d_block_kernel<CO_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = smem;
-    }
+    static std::atomic<unsigned long long> attr{0};
+    if (first_use_on_device(attr))
+        DV3D_CUDA(cudaFuncSetAttribute(deconv3d_block_kernel<CO_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     dim3 grid(cdiv(total, DC_THREADS / ns), cogs);
     DV3D_REQUIRE(grid.y <= 65535, "deconv3d: too many channel groups");
     DV3D_LAUNCH((deconv3d_block_kernel<CO_T>), grid, DC_THREADS, smem, st, x, Cin, Di, Hi, Wi, w, scale, shift, Cout, skip, y, total, ns);
@@ -599,12 +595,10 @@ static int launch_deconv(const float* x, int n, int Cin, int Di, int Hi, int Wi,
 template <int TZ>
 static int launch_s1_tiled(const float* x, int n, int Cin, int D, int H, int W, const float* weight, const float* scale,
                            const float* shift, int Cout, const float* skip, float* y, cudaStream_t st) {
-    static bool attr = false;
-    if (!attr) {
+    static std::atomic<unsigned long long> attr{0};
+    if (first_use_on_device(attr))
         DV3D_CUDA(cudaFuncSetAttribute(conv3d_s1_tiled_kernel<TZ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)s1_smem(TZ)));
-        attr = true;
-    }
     const int tiles_x = cdiv(W, TX), tiles_y = cdiv(H, TY);
     dim3 grid(tiles_x * tiles_y, cdiv(D, TZ), n * (Cout / COT));
     DV3D_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "conv3d: grid too large");

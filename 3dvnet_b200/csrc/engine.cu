@@ -24,11 +24,12 @@ struct ProfRec {
     cudaEvent_t a, b;
 };
 static bool g_prof = false;
+static std::mutex g_prof_mu;  // hot-path calls may come from several host threads (one stream each)
 static std::vector<ProfRec> g_recs;
 static std::vector<cudaEvent_t> g_pool;
 static size_t g_pool_used = 0;
 
-static cudaEvent_t prof_event() {
+static cudaEvent_t prof_event() {  // g_prof_mu held
     if (g_pool_used == g_pool.size()) {
         cudaEvent_t e;
         cudaEventCreate(&e);
@@ -42,10 +43,14 @@ struct Prof {
     bool on;
     Prof(int id, cudaStream_t s) : st(s), b(nullptr), on(g_prof) {
         if (!on) return;
-        cudaEvent_t a = prof_event();
-        b = prof_event();
+        cudaEvent_t a;
+        {
+            std::lock_guard<std::mutex> lock(g_prof_mu);
+            a = prof_event();
+            b = prof_event();
+            g_recs.push_back(ProfRec{id, a, b});
+        }
         cudaEventRecord(a, st);
-        g_recs.push_back(ProfRec{id, a, b});
     }
     ~Prof() {
         if (on) cudaEventRecord(b, st);
@@ -449,6 +454,7 @@ static int model_scene(const dv3d_net_params_t& net, const float* pts, const flo
 using namespace dv3d;
 
 extern "C" int dv3d_engine_profile(int enable) {
+    std::lock_guard<std::mutex> lock(g_prof_mu);
     g_prof = enable != 0;
     g_recs.clear();
     g_pool_used = 0;
@@ -456,6 +462,7 @@ extern "C" int dv3d_engine_profile(int enable) {
 }
 
 extern "C" int dv3d_engine_profile_read(int* ids, float* ms, int cap) {
+    std::lock_guard<std::mutex> lock(g_prof_mu);
     int n = 0;
     for (const ProfRec& r : g_recs) {
         if (n >= cap) break;

@@ -28,6 +28,15 @@ bool pdl_enabled() {
     return on;
 }
 
+bool first_use_on_device(std::atomic<unsigned long long>& mask) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (mask.load(std::memory_order_acquire) & bit) return false;
+    mask.fetch_or(bit, std::memory_order_acq_rel);  // two racing first users both set the attribute: harmless
+    return true;
+}
+
 }  // namespace dv3d
 
 extern "C" const char* dv3d_last_error(void) { return dv3d::g_err; }

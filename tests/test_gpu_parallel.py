@@ -80,3 +80,27 @@ def test_model_scene_sharded_equals_single_gpu(tmp_path):
         # and the K-split depend on the number of local rows, so the summation order differs from one GPU)
         assert idx_same == 1 and feat_err < 1e-4, feat_err
         assert rel_sh < 1e-3, rel_sh
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
+def test_two_devices_in_one_process_agree():
+    """kernel attributes (opt-in shared memory) are per device: the same pass on cuda:0 and then cuda:1 of ONE
+    process must run and give bit-identical depth maps"""
+    importlib.import_module('3dvnet_b200.build').build()
+    synth = importlib.import_module('3dvnet_b200.synth')
+    lm = importlib.import_module('3dvnet_b200.mv3d.lightningmodel')
+    img, plane = (64, 80), (16, 16)
+    cfg = dict(depth_start=0.5, depth_interval=0.3, n_intervals=16, size=plane)
+    b = synth.make_batch(1, 5, img, plane, 32, 2, 2, True, 1)
+    outs = []
+    for d in (0, 1):
+        dev = torch.device('cuda', d)
+        with torch.cuda.device(dev), torch.no_grad():
+            net = lm.PL3DVNet(cfg, cfg, 0.3, feat_dim=32, img_size=img)
+            net.load_state_dict(synth.make_params(0), strict=False)
+            net = net.to(dev).eval()
+            depth = net.hot_path(b.feats_quarter.to(dev), b.rotmats.to(dev), b.tvecs.to(dev), b.K.to(dev),
+                                 b.ref_src_edges, b.images_batch.to(dev), cfg, [[0.3, 0.15]])
+            torch.cuda.synchronize(dev)
+            outs.append(depth.cpu())
+    assert torch.isfinite(outs[0]).all() and torch.equal(outs[0], outs[1])
