@@ -112,7 +112,10 @@ def run_reference(args, rank):
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'ref-views/s', 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': WORKLOAD, 'refs_per_step': args.refs_per_step},
+        'config': {'workload': WORKLOAD, 'refs_per_step': args.refs_per_step,
+                   'imgs_per_step': args.refs_per_step + N_SRC,
+                   'parallelism': 'rank 0 only: the reference is single-process (mv3d/config.py:3-5)',
+                   'l2': 'n/a (CPU)', 'timing': 'host wall clock around the timed steps'},
         'cpu_baseline': {'value': value, 'unit': 'ref-views/s', 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': value, 'unit': 'ref-views/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0}))
