@@ -278,3 +278,50 @@ def test_refinement_schedule_teacher_forced(name, mods):
                 np.testing.assert_allclose(off.cpu().numpy(), off_o.numpy(), rtol=0, atol=2e-5)
                 depth += off_o
     np.testing.assert_allclose(depth.numpy(), g['ref_depth_final'], rtol=0, atol=1e-5)
+
+
+def _edge_cases(n_imgs):
+    """edge lists the reference's collation can produce beyond the golden cases: ragged (1 / 3 / 7 sources per
+    reference), shuffled (PyG keeps no order), references that are not consecutive images, a reference whose only
+    edge is a self-edge, a duplicated edge (counted twice by the scatter mean)"""
+    g = torch.Generator().manual_seed(5)
+    ragged = [(0, 1)] + [(3, s) for s in (1, 2, 4)] + [(6, s) for s in (1, 2, 3, 4, 5, 7, 8)]
+    e_ragged = torch.tensor(ragged, dtype=torch.int64).t().contiguous()
+    e_shuffled = e_ragged[:, torch.randperm(e_ragged.shape[1], generator=g)].contiguous()
+    e_self = torch.tensor([(2, 2), (5, 4), (5, 5), (5, 6)], dtype=torch.int64).t().contiguous()
+    e_dup = torch.tensor([(4, 3), (4, 3), (4, 5)], dtype=torch.int64).t().contiguous()
+    assert int(max(e.max() for e in (e_ragged, e_self, e_dup))) < n_imgs
+    return {'ragged': e_ragged, 'shuffled': e_shuffled, 'self_only': e_self, 'duplicate': e_dup}
+
+
+@pytest.mark.parametrize('case', ['ragged', 'shuffled', 'self_only', 'duplicate'])
+def test_ragged_edge_lists_match_oracle_bitwise(case, mods):
+    """warp + variance (volume and point level) on irregular edge lists: bit-identical to the CPU oracle"""
+    import oracle.planesweep as ops_a
+    import oracle.pointcloud as ops_b
+    img, plane, D = (64, 80), (16, 16), 16
+    b = mods['synth'].make_batch(1, 9, img, plane, 32, 2, 2, False, 11)
+    e = _edge_cases(9)[case]
+    cfg = dict(depth_start=0.5, depth_interval=0.3, n_intervals=D, size=plane)
+    net = mods['lm'].PL3DVNet(cfg, cfg, 0.3, feat_dim=32, img_size=img).to(DEV).eval()
+    ref_idx = torch.unique(e[0])
+    n_ref = len(ref_idx)
+    g = torch.Generator().manual_seed(3)
+    depth = 0.6 + 4.0 * torch.rand(n_ref, *plane, generator=g)
+    depth_batch = b.images_batch[ref_idx]
+    want_var = ops_a.planesweep_var(b.feats_quarter, b.rotmats, b.tvecs, b.K, e, 0.5, 0.3, D, img, plane)
+    want_pts, want_feat, want_batch = ops_b.feature_rich_pointcloud(depth, depth_batch, b.feats_quarter, b.rotmats,
+                                                                    b.tvecs, b.K, e, img)
+    bb = B()
+    bb.rotmats, bb.tvecs, bb.K, bb.ref_src_edges = b.rotmats.to(DEV), b.tvecs.to(DEV), b.K.to(DEV), e
+    with torch.no_grad():
+        got_var = net.mvsnet.cost_volume(b.feats_quarter.to(DEV), bb, 0.5, 0.3, D, plane)
+        pts, feat, batch = net.construct_feature_rich_pointcloud(depth.to(DEV), depth_batch.to(DEV),
+                                                                 b.feats_quarter.to(DEV), bb.rotmats, bb.tvecs, bb.K, e)
+    assert got_var.shape == want_var.shape == (n_ref, 32, D) + plane
+    np.testing.assert_array_equal(got_var.cpu().numpy().view(np.int32), want_var.numpy().view(np.int32))
+    np.testing.assert_array_equal(pts.cpu().numpy().view(np.int32), want_pts.numpy().view(np.int32))
+    np.testing.assert_array_equal(feat.cpu().numpy().view(np.int32), want_feat.numpy().view(np.int32))
+    np.testing.assert_array_equal(batch.cpu().numpy(), want_batch.numpy())
+    if case == 'self_only':   # a lone self-edge has zero variance wherever the warp lands inside the image
+        assert float(got_var[0].abs().max()) < 1e-5
