@@ -290,18 +290,20 @@ def _edge_cases(n_imgs):
     e_shuffled = e_ragged[:, torch.randperm(e_ragged.shape[1], generator=g)].contiguous()
     e_self = torch.tensor([(2, 2), (5, 4), (5, 5), (5, 6)], dtype=torch.int64).t().contiguous()
     e_dup = torch.tensor([(4, 3), (4, 3), (4, 5)], dtype=torch.int64).t().contiguous()
+    # more edges than one staging pass of the warp kernels holds (EMAX = 8): every other image is a source
+    e_many = torch.tensor([(6, s) for s in range(n_imgs) if s != 6] + [(1, 0)], dtype=torch.int64).t().contiguous()
     assert int(max(e.max() for e in (e_ragged, e_self, e_dup))) < n_imgs
-    return {'ragged': e_ragged, 'shuffled': e_shuffled, 'self_only': e_self, 'duplicate': e_dup}
+    return {'ragged': e_ragged, 'shuffled': e_shuffled, 'self_only': e_self, 'duplicate': e_dup, 'many': e_many}
 
 
-@pytest.mark.parametrize('case', ['ragged', 'shuffled', 'self_only', 'duplicate'])
+@pytest.mark.parametrize('case', ['ragged', 'shuffled', 'self_only', 'duplicate', 'many'])
 def test_ragged_edge_lists_match_oracle_bitwise(case, mods):
     """warp + variance (volume and point level) on irregular edge lists: bit-identical to the CPU oracle"""
     import oracle.planesweep as ops_a
     import oracle.pointcloud as ops_b
     img, plane, D = (64, 80), (16, 16), 16
-    b = mods['synth'].make_batch(1, 9, img, plane, 32, 2, 2, False, 11)
-    e = _edge_cases(9)[case]
+    b = mods['synth'].make_batch(1, 13, img, plane, 32, 2, 2, False, 11)
+    e = _edge_cases(13)[case]
     cfg = dict(depth_start=0.5, depth_interval=0.3, n_intervals=D, size=plane)
     net = mods['lm'].PL3DVNet(cfg, cfg, 0.3, feat_dim=32, img_size=img).to(DEV).eval()
     ref_idx = torch.unique(e[0])
