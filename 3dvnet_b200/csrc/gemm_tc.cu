@@ -248,7 +248,8 @@ gather_gemm_tc_kernel(const __grid_constant__ GemmDesc d, int precision_and_flag
         s_misc[1] = 0;
         fence_mbar_init();
     }
-    if (warp == 8) tmem_alloc(smem_u32(s_misc), BN);
+    // 3xTF32: columns [0, BN) collect A_big*B_big + A_small*B_big, columns [BN, 2BN) collect A_big*B_small
+    if (warp == 8) tmem_alloc(smem_u32(s_misc), 2 * BN);
     // everything above is independent of the previous kernel in the stream (PDL prologue)
     pdl_wait();
     __syncthreads();
@@ -351,6 +352,9 @@ gather_gemm_tc_kernel(const __grid_constant__ GemmDesc d, int precision_and_flag
         if (lane == 0 && n_it > 0) {
             // ===================== MMA issuer
             constexpr uint32_t idesc = umma_idesc_tf32(TC_BM, BN);
+            // B_big and B_small are adjacent in the stage: together they are ONE K-major operand of 2 BN rows, so
+            // A_big is read from shared memory once for both of its products (20 KB instead of 24 KB per K step)
+            constexpr uint32_t idesc_pair = umma_idesc_tf32(TC_BM, 2 * BN);
             uint32_t acc = 0;
             for (int it = 0; it < n_it; ++it) {
                 const int st = it % TC_STAGES;
@@ -364,11 +368,11 @@ gather_gemm_tc_kernel(const __grid_constant__ GemmDesc d, int precision_and_flag
                     const uint32_t ko = kk * 32;  // 8 tf32 = 32 bytes inside the swizzle row
                     if (dbg_no_mma) continue;
                     if (precision == 1) {
-                        umma_tf32(tmem_base, umma_desc_sw128(a_small + ko), umma_desc_sw128(b_big + ko), idesc, acc);
-                        acc = 1;
-                        umma_tf32(tmem_base, umma_desc_sw128(a_big + ko), umma_desc_sw128(b_small + ko), idesc, 1);
+                        umma_tf32(tmem_base, umma_desc_sw128(a_big + ko), umma_desc_sw128(b_big + ko), idesc_pair, acc);
+                        umma_tf32(tmem_base, umma_desc_sw128(a_small + ko), umma_desc_sw128(b_big + ko), idesc, 1);
+                    } else {
+                        umma_tf32(tmem_base, umma_desc_sw128(a_big + ko), umma_desc_sw128(b_big + ko), idesc, acc);
                     }
-                    umma_tf32(tmem_base, umma_desc_sw128(a_big + ko), umma_desc_sw128(b_big + ko), idesc, acc);
                     acc = 1;
                 }
                 umma_commit(bar_empty + 8 * st);  // frees the stage once these MMAs have read it
@@ -421,6 +425,12 @@ gather_gemm_tc_kernel(const __grid_constant__ GemmDesc d, int precision_and_flag
             float y[16];
             if (n_it > 0) {
                 tmem_ld16(trow + (uint32_t)c0, y);
+                if (precision == 1) {
+                    float z[16];
+                    tmem_ld16(trow + (uint32_t)(BN + c0), z);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) y[i] += z[i];
+                }
             } else {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) y[i] = 0.f;
@@ -432,7 +442,7 @@ gather_gemm_tc_kernel(const __grid_constant__ GemmDesc d, int precision_and_flag
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) tmem_dealloc(tmem_base, BN);
+    if (warp == 8) tmem_dealloc(tmem_base, 2 * BN);
 
     // ===================== epilogue on 16-byte units, all warps
     constexpr int UNITS = BN / 4;          // per row
