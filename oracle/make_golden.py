@@ -130,6 +130,39 @@ def case_pipeline(name, n_scenes, n_imgs, img_size, plane, D, interval, edge_len
     np.savez_compressed(os.path.join(GOLD, name + '.npz'), **save)
 
 
+def case_irregular_edges(name, seed):
+    """Path A + the feature-rich point cloud of the reference on edge lists its collation can produce but the
+    pipeline cases do not: ragged (1 / 3 / 12 sources per reference), shuffled, non-consecutive references, a
+    reference whose only edge is a self-edge, a duplicated edge."""
+    img_size, plane, D = (64, 80), (16, 16), 16
+    depth_cfg = dict(depth_start=0.5, depth_interval=0.3, n_intervals=D, size=plane)
+    b = synth.make_batch(1, 13, img_size, plane, 32, 2, 2, False, seed)
+    g = torch.Generator().manual_seed(seed)
+    edges = [(0, 1)] + [(3, s) for s in (1, 2, 4)] + [(6, s) for s in range(13) if s != 6] + [(9, 9)] + \
+            [(11, 10), (11, 10), (11, 12)]
+    e = torch.tensor(edges, dtype=torch.int64).t().contiguous()
+    b.ref_src_edges = e[:, torch.randperm(e.shape[1], generator=g)].contiguous()
+    net, params = build_reference_net(img_size, depth_cfg, 0.3, seed)
+    net.mvsnet.feat_shrinker.feats = b.feats_quarter
+    b.images = torch.zeros(b.feats_quarter.shape[0], 3, *img_size)
+    cap = {}
+    h = net.mvsnet.cnn_3d.register_forward_hook(lambda m, i, o: cap.update(x_var=i[0].detach()))
+    with torch.no_grad():
+        depth, depth_batch, _, _, _, ref_idx = net.make_initial_depth_predictions(b, depth_cfg)
+        h.remove()
+        pts, pts_feat, pts_batch = net.construct_feature_rich_pointcloud(depth, depth_batch, b.feats_quarter, b.rotmats,
+                                                                         b.tvecs, b.K, b.ref_src_edges)
+    print(name, 'edges', tuple(b.ref_src_edges.shape), 'refs', ref_idx.tolist(), 'x_var', tuple(cap['x_var'].shape))
+    np.savez_compressed(
+        os.path.join(GOLD, name + '.npz'), feats_quarter=b.feats_quarter.numpy(), rotmats=b.rotmats.numpy(),
+        tvecs=b.tvecs.numpy(), K=b.K.numpy(), ref_src_edges=b.ref_src_edges.numpy(), images_batch=b.images_batch.numpy(),
+        img_size=np.array(img_size), plane=np.array(plane), D=np.array(D), depth_start=np.array(0.5),
+        depth_interval=np.array(0.3), edge_len=np.array(0.3), seed=np.array(seed),
+        params_checksum=np.array(synth.params_checksum(params)), ref_x_var=cap['x_var'].numpy(),
+        ref_depth_init=depth.numpy(), ref_ref_idx=ref_idx.numpy(), ref_pts=pts.numpy(), ref_pts_feat=pts_feat.numpy(),
+        ref_pts_batch=pts_batch.numpy())
+
+
 def case_voxelize(name, seed):
     """utils.voxelize on adversarial point sets: points exactly on cell boundaries, an
     extent that is an exact multiple of the edge (ceil vs trunc+1), several batches."""
@@ -158,3 +191,4 @@ if __name__ == '__main__':
     case_pipeline('c1_selfedge_2scenes', 2, 6, (64, 80), (16, 24), 16, 0.3, 0.2, 2, 2, True, 1,
                   [[0.05, 0.05, 0.025], [0.05, 0.05, 0.025]])
     case_voxelize('voxelize_adversarial', 3)
+    case_irregular_edges('c1_irregular_edges', 4)

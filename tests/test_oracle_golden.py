@@ -122,3 +122,26 @@ def test_fusion_oracle_matches_reference_golden():
     fused = pts[valid.view(valid.shape[0], -1)].numpy()
     np.testing.assert_allclose(fused, g['ref_pts'], rtol=0, atol=1e-6)
     np.testing.assert_array_equal(valid[0].numpy(), g['ref_valid0'])
+
+
+def test_irregular_edge_lists_match_reference(synth):
+    """ragged / shuffled / self-only / duplicated / 12-source edge lists: the oracle against the unmodified
+    reference (oracle/make_golden.py::case_irregular_edges). tests/test_gpu_parity.py compares the CUDA kernels
+    with the oracle bit for bit on edge lists of the same kinds."""
+    g = load_golden('c1_irregular_edges')
+    t, cfg, img_size = golden_inputs(g)
+    p = _params(synth, g)
+    e = t['ref_src_edges']
+    assert e.shape == (2, 20) and torch.unique(e[0]).tolist() == g['ref_ref_idx'].tolist() == [0, 3, 6, 9, 11]
+    depth, x_var, _ = pipeline.initial_depth(t['feats_quarter'], t['rotmats'], t['tvecs'], t['K'], e, cfg, img_size, p,
+                                             return_all=True)
+    np.testing.assert_allclose(x_var.numpy(), g['ref_x_var'], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(depth.numpy(), g['ref_depth_init'], rtol=0, atol=2e-5)
+    assert float(np.abs(g['ref_x_var'][3]).max()) == 0.0          # reference 9 has only its self-edge
+    ref_depth = torch.from_numpy(g['ref_depth_init'])
+    depth_batch = t['images_batch'][torch.unique(e[0])]
+    pts, feat, batch = pointcloud.feature_rich_pointcloud(ref_depth, depth_batch, t['feats_quarter'], t['rotmats'],
+                                                          t['tvecs'], t['K'], e, img_size)
+    np.testing.assert_array_equal(pts.numpy().view(np.int32), g['ref_pts'].view(np.int32))
+    np.testing.assert_allclose(feat.numpy(), g['ref_pts_feat'], rtol=0, atol=1e-6)
+    np.testing.assert_array_equal(batch.numpy(), g['ref_pts_batch'])
