@@ -139,8 +139,8 @@ class _RawCuda(object):
 
 class SymmHeap(object):
     """One buffer of `nbytes` per rank plus mappings of every peer's copy (CUDA IPC: dv3d_symm_alloc /
-    dv3d_symm_open, handles exchanged with one all_gather_object), registered with the library so that sparse-convolution epilogues writing into the local copy also
-    store into the peers' (csrc/symm.cu). A bump allocator hands out the same offsets on every rank as long as the
+    dv3d_symm_open, handles exchanged with one all_gather_object), registered with the library so that
+    sparse-convolution epilogues writing into the local copy also store into the peers' (csrc/symm.cu). A bump allocator hands out the same offsets on every rank as long as the
     ranks allocate the same sizes in the same order (they do: the coordinate levels are identical on all ranks).
     The first 256 bytes hold the barrier flags."""
 
