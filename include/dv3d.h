@@ -188,7 +188,8 @@ int dv3d_make_coords(const int* idx3d, const long long* batch, long long n, int*
 size_t dv3d_hash_bytes(long long n_rows);
 /* build the table of a level; *err_flag (device int, caller-zeroed) is set on out-of-range coordinates */
 int dv3d_hash_build(const int* coords, long long n, void* table, size_t table_bytes, int* err_flag, void* stream);
-/* n_tables (<= 4) tables in two launches; coords/n/tables/table_bytes are HOST arrays */
+/* n_tables (<= 4) tables in two launches (the coordinate maps MinkowskiEngine's manager creates for the strided
+ * convolutions of scenemodeling.py:160-162); coords / n / tables / table_bytes are HOST arrays of device pointers */
 int dv3d_hash_build_batch(const int* const* coords, const long long* n, void* const* tables, const size_t* table_bytes,
                           int n_tables, int* err_flag, void* stream);
 /* coarser level of a stride-2 convolution: unique(floor(c / new_stride) * new_stride) in
@@ -201,7 +202,9 @@ int dv3d_coarsen(const int* coords, long long n, int new_stride, int dim_x, int 
  * (floor(floor(c/2)*2/4)*4 = floor(c/4)*4) with ONE sync: enqueue every level, then finish each */
 int dv3d_coarsen_enqueue(const int* coords, long long n, int new_stride, int dim_x, int dim_y, int dim_z, int n_batch,
                          void* workspace, size_t workspace_bytes, long long cap, int* coarse_coords, void* stream);
-/* n_levels (<= 4) coarser levels from the same coordinates with four launches; HOST arrays */
+/* n_levels (<= 4) coarser levels (output coordinates of the stride-2 convolutions, scenemodeling.py:160-162,194-204)
+ * from the same finest coordinates with four launches and one memset when the workspaces are contiguous;
+ * new_strides / workspaces / workspace_bytes / coarse_coords are HOST arrays; finish each with dv3d_coarsen_finish */
 int dv3d_coarsen_enqueue_batch(const int* coords, long long n, const int* new_strides, int n_levels, int dim_x, int dim_y,
                                int dim_z, int n_batch, void* const* workspaces, const size_t* workspace_bytes,
                                long long cap, int* const* coarse_coords, void* stream);
