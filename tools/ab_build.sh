@@ -7,6 +7,10 @@
 # Only csrc/ changes are A/B-able this way (both libraries must export the header's symbols).
 set -eu
 cd "$(dirname "$0")/.."
+if git diff --quiet -- 3dvnet_b200/csrc; then
+  echo "no uncommitted change under 3dvnet_b200/csrc: nothing to compare" >&2
+  exit 1
+fi
 python 3dvnet_b200/build.py > /dev/null
 cp 3dvnet_b200/lib3dvnet_b200.so ab_new.so
 git stash -q
