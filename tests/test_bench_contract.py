@@ -49,3 +49,17 @@ def test_product_arm_refuses_to_run_without_cuda():
     r = _run(['--steps', '1', '--warmup', '0'])
     assert r.returncode != 0                                  # no CPU fallback, no oracle behind the product path
     assert not [l for l in r.stdout.splitlines() if l.startswith('{')]
+
+
+def test_graft_entry_builds_and_smoke_needs_a_gpu():
+    """build() is the driver's CPU-side "does it build" check; smoke() must refuse to run without cuda:0 rather
+    than check the oracle against itself"""
+    import importlib
+    import torch
+    sys.path.insert(0, ROOT)
+    g = importlib.import_module('__graft_entry__')
+    g.build()
+    assert os.path.exists(os.path.join(ROOT, '3dvnet_b200', 'lib3dvnet_b200.so'))
+    if not torch.cuda.is_available():
+        with pytest.raises(AssertionError, match='cuda:0'):
+            g.smoke()
