@@ -112,3 +112,107 @@ def test_symm_heap_blocks_are_recycled_at_identical_offsets():
     assert o1 == o2
     assert o1[0] == 256 and o1[3] == o1[0] and len(set(o1[:3] + o1[4:])) == 4
     assert all(o % 256 == 0 for o in o1)
+
+
+def test_sharded_unet_schedule_is_symmetric_and_never_reuses_a_block_too_early(monkeypatch):
+    """Host-side model of `sparse_unet_sharded`: with the CUDA ops replaced by recorders, every rank (also one
+    whose row range is empty) must issue the SAME sequence of heap allocations / releases / barriers - that is what
+    keeps the offsets symmetric - and a recycled block may only be written after a barrier that follows the last
+    read of its previous contents (the peers write into it from their side)."""
+    par = importlib.import_module('3dvnet_b200.parallel')
+    ops = importlib.import_module('3dvnet_b200.ops')
+    sm = importlib.import_module('3dvnet_b200.mv3d.subnetworks.scenemodeling')
+    monkeypatch.setattr(sm.SparseConvolution, 'weights', lambda self: (self.kernel.detach(), None))
+    unet = sm.SparseUNet().eval()
+    n_rows = [9, 5, 1]                                          # level sizes; the coarsest has ONE row
+
+    class Level(object):
+        def __init__(self, n, stride):
+            self.n, self.stride = n, stride
+
+    class Heap(object):
+        def __init__(self, log):
+            self.log, self.free, self.next_id, self.ids = log, {}, 0, {}
+
+        def rows(self, n, C):
+            pool = self.free.get((n, C))
+            if pool:
+                t = pool.pop()
+                self.log.append(('reuse', self.ids[id(t)]))
+                return t
+            t = torch.zeros(n, C)
+            self.ids[id(t)] = self.next_id
+            self.keep = getattr(self, 'keep', []) + [t]
+            self.log.append(('alloc', self.next_id, n, C))
+            self.next_id += 1
+            return t
+
+        def release(self, t):
+            self.log.append(('release', self.ids[id(t)]))
+            self.free.setdefault(tuple(t.shape), []).append(t)
+
+        def barrier(self):
+            self.log.append(('barrier',))
+
+    def run(world, rank):
+        log = []
+        heap = Heap(log)
+
+        def base_id(t):                      # a row slice shares storage with its heap block
+            for blk in heap.keep:
+                if t.untyped_storage().data_ptr() == blk.untyped_storage().data_ptr():
+                    return heap.ids[id(blk)]
+            return None                      # not a heap block (PointNet features, local `up`)
+
+        def sparse_conv(feat, km, W, gw, gb, residual, relu, packed=None, workspace=None, out=None):
+            reads = [base_id(feat)] + ([base_id(residual)] if residual is not None else [])
+            if out is None:
+                out = torch.zeros(km, W.shape[-1])
+            log.append(('conv', tuple(r for r in reads if r is not None), base_id(out)))
+            return out
+
+        def concat_linear(a, b, W, gw, gb, packed=None, out=None):
+            log.append(('conv', tuple(r for r in (base_id(a), base_id(b)) if r is not None), base_id(out)))
+            return out
+
+        monkeypatch.setattr(ops, 'sparse_conv', sparse_conv)
+        monkeypatch.setattr(ops, 'concat_linear_gn_relu', concat_linear)
+        monkeypatch.setattr(ops, 'batch_origin', lambda *a: torch.zeros(1, 3))
+        monkeypatch.setattr(ops, 'level_points', lambda lv, o, r: (torch.zeros(lv.n, 3),) * 3)
+        scene = type('S', (), {})()
+        scene.levels = [Level(n, 1 << l) for l, n in enumerate(n_rows)]
+        scene.range = [par.row_range(n, world, rank) for n in n_rows]
+        scene.n_batch, scene.ws = 1, None
+        rows = lambda l: scene.range[l][1] - scene.range[l][0]
+        scene.same = [rows(l) or None for l in range(3)]        # the recorder only needs the local row count
+        scene.down = [rows(l + 1) or None for l in range(2)]
+        scene.up = [rows(l) or None for l in range(2)]
+        out = par.sparse_unet_sharded(unet, torch.zeros(n_rows[0], 64), torch.zeros(n_rows[0], 3),
+                                      torch.zeros(n_rows[0], 3, dtype=torch.int32),
+                                      torch.zeros(n_rows[0], dtype=torch.int64), 0.04, scene, heap)
+        assert [o['feats'].shape[0] for o in out] == n_rows[::-1]
+        return log
+
+    logs = {(w, r): run(w, r) for w, r in ((2, 0), (2, 1), (4, 0), (4, 3))}
+    assert par.row_range(1, 4, 3) == (1, 1)                      # rank 3 of 4 owns no row of the coarsest level
+    heap_events = lambda log: [e for e in log if e[0] != 'conv']
+    for key in ((2, 1), (4, 0), (4, 3)):
+        assert heap_events(logs[key]) == heap_events(logs[(2, 0)]), key
+    assert sum(e[0] == 'barrier' for e in logs[(2, 0)]) == 22     # 18 residual convs + 2 strided + 2 feature-adjust
+    assert any(e[0] == 'reuse' for e in logs[(2, 0)])
+    # recycling discipline on the rank that computes every layer
+    log = logs[(2, 0)]
+    last_read, barrier_since_read, awaiting_write = {}, {}, set()
+    for ev in log:
+        if ev[0] == 'barrier':
+            for b in barrier_since_read:
+                barrier_since_read[b] = True
+        elif ev[0] == 'conv':
+            for b in ev[1]:
+                assert b not in awaiting_write, 'block %d read between its reuse and its first write' % b
+                barrier_since_read[b] = False
+            if ev[2] is not None and ev[2] in awaiting_write:
+                assert barrier_since_read.get(ev[2], True), 'block %d overwritten before a barrier' % ev[2]
+                awaiting_write.discard(ev[2])
+        elif ev[0] == 'reuse':
+            awaiting_write.add(ev[1])
