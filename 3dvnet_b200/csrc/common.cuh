@@ -46,9 +46,11 @@ void count_launch(int n = 1);
 // dependents' CTAs then spin next to the running kernel and the step got 1.5 % slower.)
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 bool pdl_enabled();
-// Function attributes (cudaFuncSetAttribute) are per device: true the first time a call site runs on the
-// current device.  `mask` is a static std::atomic<unsigned long long> of the call site (bit = device).
-bool first_use_on_device(std::atomic<unsigned long long>& mask);
+// Function attributes (cudaFuncSetAttribute) are per device: sets the dynamic shared-memory opt-in of `func` the
+// first time a call site runs on the current device.  `mask` is a static std::atomic<unsigned long long> of the
+// call site (bit = device), published only after the attribute is in place (safe for concurrent host threads).
+cudaError_t func_smem_once(std::atomic<unsigned long long>& mask, const void* func, int bytes);
+#define DV3D_FUNC_SMEM_ONCE(mask, func, bytes) DV3D_CUDA(dv3d::func_smem_once(mask, (const void*)(func), (int)(bytes)))
 
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,

@@ -552,9 +552,7 @@ static int launch_direct(const float* x, int n, int Cin, int Di, int Hi, int Wi,
     const size_t smem = sizeof(float) * ((size_t)Cin * 27 * CO_T + (ns > 1 ? DC_THREADS * CO_T : 0));
     DV3D_REQUIRE(smem <= 200 * 1024, "conv3d: weights of one channel group (%zu bytes) do not fit shared memory", smem);
     static std::atomic<unsigned long long> attr{0};  // per instantiation; the opt-in covers the 200 KB bound above
-    if (first_use_on_device(attr))
-        DV3D_CUDA(cudaFuncSetAttribute(conv3d_direct_kernel<STRIDE, CO_T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       200 * 1024));
+    DV3D_FUNC_SMEM_ONCE(attr, (conv3d_direct_kernel<STRIDE, CO_T>), 200 * 1024);
     dim3 grid(cdiv(total, DC_THREADS / ns), cogs);
     DV3D_REQUIRE(grid.y <= 65535, "conv3d: too many channel groups");
     DV3D_LAUNCH((conv3d_direct_kernel<STRIDE, CO_T>), grid, DC_THREADS, smem, st, x, Cin, Di, Hi, Wi, w, scale, shift, Cout, Do, Ho, Wo, skip, y, total, ns);
@@ -583,8 +581,7 @@ static int launch_deconv(const float* x, int n, int Cin, int Di, int Hi, int Wi,
     const size_t smem = sizeof(float) * ((size_t)Cin * 27 * CO_T + (ns > 1 ? DC_THREADS * CO_T : 0));
     DV3D_REQUIRE(smem <= 200 * 1024, "deconv3d: weights of one channel group (%zu bytes) do not fit shared memory", smem);
     static std::atomic<unsigned long long> attr{0};
-    if (first_use_on_device(attr))
-        DV3D_CUDA(cudaFuncSetAttribute(deconv3d_block_kernel<CO_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    DV3D_FUNC_SMEM_ONCE(attr, (deconv3d_block_kernel<CO_T>), 200 * 1024);
     dim3 grid(cdiv(total, DC_THREADS / ns), cogs);
     DV3D_REQUIRE(grid.y <= 65535, "deconv3d: too many channel groups");
     DV3D_LAUNCH((deconv3d_block_kernel<CO_T>), grid, DC_THREADS, smem, st, x, Cin, Di, Hi, Wi, w, scale, shift, Cout, skip, y, total, ns);
@@ -596,9 +593,7 @@ template <int TZ>
 static int launch_s1_tiled(const float* x, int n, int Cin, int D, int H, int W, const float* weight, const float* scale,
                            const float* shift, int Cout, const float* skip, float* y, cudaStream_t st) {
     static std::atomic<unsigned long long> attr{0};
-    if (first_use_on_device(attr))
-        DV3D_CUDA(cudaFuncSetAttribute(conv3d_s1_tiled_kernel<TZ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)s1_smem(TZ)));
+    DV3D_FUNC_SMEM_ONCE(attr, (conv3d_s1_tiled_kernel<TZ>), (int)s1_smem(TZ));
     const int tiles_x = cdiv(W, TX), tiles_y = cdiv(H, TY);
     dim3 grid(tiles_x * tiles_y, cdiv(D, TZ), n * (Cout / COT));
     DV3D_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "conv3d: grid too large");

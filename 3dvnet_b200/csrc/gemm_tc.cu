@@ -522,15 +522,11 @@ int launch_gather_gemm_tc(const GemmDesc& d_in, cudaStream_t st) {
     dim3 grid(tiles, split);
     if (d.N == 128) {
         static std::atomic<unsigned long long> attr{0};
-        if (first_use_on_device(attr))
-            DV3D_CUDA(cudaFuncSetAttribute(gather_gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)tc_smem_bytes(128)));
+        DV3D_FUNC_SMEM_ONCE(attr, (gather_gemm_tc_kernel<128>), (int)tc_smem_bytes(128));
         DV3D_LAUNCH((gather_gemm_tc_kernel<128>), grid, TC_THREADS, tc_smem_bytes(128), st, d, g_gemm_precision);
     } else {
         static std::atomic<unsigned long long> attr{0};
-        if (first_use_on_device(attr))
-            DV3D_CUDA(cudaFuncSetAttribute(gather_gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)tc_smem_bytes(64)));
+        DV3D_FUNC_SMEM_ONCE(attr, (gather_gemm_tc_kernel<64>), (int)tc_smem_bytes(64));
         DV3D_LAUNCH((gather_gemm_tc_kernel<64>), grid, TC_THREADS, tc_smem_bytes(64), st, d, g_gemm_precision);
     }
     DV3D_LAUNCHED();

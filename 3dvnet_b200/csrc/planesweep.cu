@@ -463,8 +463,7 @@ extern "C" int dv3d_planesweep_var(const float* feats_nhwc, int n_imgs, int C, i
     double d1 = depth_start + depth_interval * (D - 1);
     const size_t smem = (sizeof(float4) + sizeof(int)) * EMAX * KD * TP + sizeof(float) * 32 * CS;
     static std::atomic<unsigned long long> attr{0};
-    if (first_use_on_device(attr))
-        DV3D_CUDA(cudaFuncSetAttribute(planesweep_var_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DV3D_FUNC_SMEM_ONCE(attr, (planesweep_var_kernel), (int)smem);
     DV3D_LAUNCH((planesweep_var_kernel), grid, 256, smem, (cudaStream_t)stream, reinterpret_cast<const float4*>(feats_nhwc), make_geom(Hf, Wf, H, W), cams, ref_img, edge_rowptr, edge_src, depth_start, d1, D, h, w, H, W, chunks_per_cta, x_var);
     DV3D_LAUNCHED();
     return DV3D_OK;

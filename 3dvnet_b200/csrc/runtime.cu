@@ -1,5 +1,6 @@
 // Error reporting, launch accounting and ABI version of lib3dvnet_b200.
 #include <atomic>
+#include <mutex>
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
@@ -28,13 +29,20 @@ bool pdl_enabled() {
     return on;
 }
 
-bool first_use_on_device(std::atomic<unsigned long long>& mask) {
+cudaError_t func_smem_once(std::atomic<unsigned long long>& mask, const void* func, int bytes) {
     int dev = 0;
-    cudaGetDevice(&dev);
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
     const unsigned long long bit = 1ull << (dev & 63);
-    if (mask.load(std::memory_order_acquire) & bit) return false;
-    mask.fetch_or(bit, std::memory_order_acq_rel);  // two racing first users both set the attribute: harmless
-    return true;
+    if (mask.load(std::memory_order_acquire) & bit) return cudaSuccess;
+    // The bit is published only AFTER the attribute call returned: a second host thread on the same
+    // device either sees it set (attribute in place) or takes the mutex and waits for the first one.
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    if (mask.load(std::memory_order_acquire) & bit) return cudaSuccess;
+    e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) mask.fetch_or(bit, std::memory_order_release);
+    return e;
 }
 
 }  // namespace dv3d

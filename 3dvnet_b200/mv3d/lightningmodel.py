@@ -19,18 +19,20 @@ from .subnetworks.upsampling import PropagationNet
 
 
 class _FeatureCache(object):
-    """channels-last copies of feature tensors, keyed on storage + version"""
+    """channels-last copies of feature tensors, keyed on storage + version. Every entry keeps its
+    SOURCE tensor alive: the caching allocator cannot hand that address to the next scene's
+    same-shape feature map while the entry exists, so a key can never match a different tensor."""
 
-    def __init__(self, size=8):
+    def __init__(self, size=4):
         self.size, self.items = size, []
 
     def get(self, feats):
-        key = (feats.data_ptr(), feats._version, tuple(feats.shape))
-        for k, v in self.items:
-            if k == key:
+        key = (feats.data_ptr(), feats._version, tuple(feats.shape), feats.dtype)
+        for k, src, v in self.items:
+            if k == key and src is feats:
                 return v
         v = ops.nchw_to_nhwc(feats.detach().float().contiguous())
-        self.items = ([(key, v)] + self.items)[:self.size]
+        self.items = ([(key, feats, v)] + self.items)[:self.size]
         return v
 
 
@@ -70,7 +72,13 @@ class PL3DVNet(nn.Module):
         hp = dict(ckpt.get('hyper_parameters', {}))
         hp.update(overrides)
         net = cls(**hp)
-        net.load_state_dict(ckpt['state_dict'], strict=False)
+        # Lightning's loader is strict (lightningmodel.py:33 via LightningModule.load_from_checkpoint):
+        # a checkpoint whose keys drift from the schema must not load with randomly initialised layers
+        missing, unexpected = net.load_state_dict(ckpt['state_dict'], strict=False)
+        missing = [k for k in missing if not k.endswith('num_batches_tracked')]
+        if missing or unexpected:
+            raise RuntimeError('load_from_checkpoint: state_dict does not match the reference schema '
+                               '(missing %s, unexpected %s)' % (missing[:8], list(unexpected)[:8]))
         return net
 
     # ------------------------------------------------------------------ hot path A

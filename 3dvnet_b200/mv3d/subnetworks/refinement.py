@@ -56,6 +56,10 @@ class HypothesisDecoder(nn.Module):
         return off
 
     def run(self, operand, n_hyp, offset=None, want_prob=True):
+        if n_hyp != ops.ROWS_PER_POINT - 1:
+            # the Conv1d gather-GEMM zeroes only row 7 of the 8-row operand: fewer hypotheses would read stale rows
+            raise NotImplementedError('HypothesisDecoder: the kernels implement 7 hypotheses (n=3, '
+                                      'lightningmodel.py:187), got %d' % n_hyp)
         layers, head = self._weights()
         x = operand
         if self._ws is None or self._ws.device != operand.device:

@@ -130,6 +130,15 @@ def hot_path_sharded(net, feats_quarter, rotmats, tvecs, K, ref_src_edges, image
 
 
 # ----------------------------------------------------------------------------- sparse U-Net sharded by voxel rows
+def _require_peer_store_gemm(ops):
+    """Only the tcgen05 gather-GEMM and the pair-reduce kernel store their epilogue into the peers' copies of a
+    symmetric buffer (csrc/gemm_tc.cu, sparse_pairs.cu -> symm_attach). The fp32 CUDA-core verification kernel
+    (csrc/gemm.cu) writes locally only: with it every rank would read stale rows of the ranges other ranks own."""
+    if ops.gemm_mode() == 'f32':
+        raise RuntimeError("the row-sharded sparse U-Net needs a tensor-core GEMM mode ('tf32x3' or 'tf32'): the "
+                           "'f32' verification kernel has no peer-store epilogue (DV3D_GEMM / ops.set_gemm_mode)")
+
+
 class _RawCuda(object):
     """a raw device allocation seen by torch through the CUDA array interface"""
 
@@ -148,6 +157,7 @@ class SymmHeap(object):
         import ctypes
         from . import ops
         self.ops, self.group = ops, group
+        _require_peer_store_gemm(ops)
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         if not 2 <= self.world <= 8:
             raise RuntimeError('SymmHeap: 2..8 ranks, got %d' % self.world)
@@ -271,6 +281,7 @@ def sparse_unet_sharded(unet, F, pts, idx, batch, res, scene, heap):
     consumers (the transposed convolution feeding the 1x1 'feature adjust') stay local. Returns the same list of
     level dicts as the single-GPU module, with full feature tensors on every rank."""
     from . import ops
+    _require_peer_store_gemm(ops)
     nl = unet.n_levels
 
     def conv(x_full, km, mod, gn, level, residual=None):

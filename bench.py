@@ -115,10 +115,91 @@ def run_reference(args, rank):
         'config': {'workload': WORKLOAD, 'refs_per_step': args.refs_per_step,
                    'imgs_per_step': args.refs_per_step + N_SRC,
                    'parallelism': 'rank 0 only: the reference is single-process (mv3d/config.py:3-5)',
+                   'reference_arm': 'port (oracle/pipeline.py, the CPU restatement; the reference itself needs '
+                                    'torch_scatter / torch_geometric / MinkowskiEngine, absent here)',
                    'l2': 'n/a (CPU)', 'timing': 'host wall clock around the timed steps'},
         'cpu_baseline': {'value': value, 'unit': 'ref-views/s', 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': value, 'unit': 'ref-views/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0}))
+
+
+def run_c4(args, rank, world, dev, dist, ops, lm):
+    """BASELINE configs[3] inside the N > 1 line: ONE scene of 64 reference views whose views are sharded over the
+    ranks (3dvnet_b200/parallel.py): one NCCL all-gather of the [N_g, 35] fp32 point rows per scene-model call, the
+    sparse U-Net sharded by voxel rows with epilogue stores into every rank's symmetric buffer over NVLink
+    (csrc/symm.cu). STRONG scaling. Checked here, on the driver's hardware, against the single-GPU pass of the same
+    scene computed on rank 0: depth abs-rel and bit-equality of the voxel indices of every sparse level."""
+    par = importlib.import_module('3dvnet_b200.parallel')
+    synth = importlib.import_module('3dvnet_b200.synth')
+    refs, steps, warm = args.c4_refs, max(2, min(args.steps, 4)), 2
+    b = synth.make_batch(1, refs + N_SRC, IMG_SIZE, PLANE, 32, 4, 3, False, 0)   # identical on every rank (seeded)
+    net = lm.PL3DVNet(DEPTH_CFG, DEPTH_CFG, EDGE_LEN, feat_dim=32, img_size=IMG_SIZE)
+    net.load_state_dict(synth.make_params(0), strict=False)
+    net = net.to(dev).eval()
+    fq, R, t, K = b.feats_quarter.to(dev), b.rotmats.to(dev), b.tvecs.to(dev), b.K.to(dev)
+    e, ib = b.ref_src_edges, b.images_batch.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    heap = par.SymmHeap(2048 << 20)
+
+    def step():
+        return par.hot_path_sharded(net, fq, R, t, K, e, ib, DEPTH_CFG, OFFSETS_LIST, heap=heap)
+
+    with torch.no_grad():
+        for _ in range(warm):
+            depth, rng = step()
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        n0, ep0 = ops.launch_count(), heap.epoch
+        for a, z in ev:
+            flush.zero_()
+            a.record()
+            depth, rng = step()
+            z.record()
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        launches, barriers = ops.launch_count() - n0, (heap.epoch - ep0) // steps
+        heap.check()
+        ms = torch.tensor([sum(a.elapsed_time(z) for a, z in ev)], dtype=torch.float64, device=dev)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        counts = par.shard_counts(refs, world)
+        full = par.all_gather_rows(depth.reshape(depth.shape[0], -1).contiguous(), counts)
+
+        # parity on this hardware: the single-GPU pass of the same scene (rank 0), its initial depth broadcast so
+        # that every rank voxelises the same points in the sharded scene model
+        h, w = PLANE
+        d_init = torch.empty((refs, h, w), dtype=torch.float32, device=dev)
+        abs_rel = None
+        if rank == 0:
+            d_one, d0 = net.hot_path(fq, R, t, K, e, ib, DEPTH_CFG, OFFSETS_LIST, return_init=True)
+            d_init.copy_(d0)
+            abs_rel = float((torch.abs(full.view_as(d_one) - d_one) / (d_one + 1e-7)).mean().item())
+        dist.broadcast(d_init, 0)
+        start, end = par.shard_range(refs, world, rank)
+        xs_sh = par.model_scene_sharded(net, d_init[start:end].contiguous(), ib, fq, R, t, K, e, heap=heap)
+        heap.check()
+        idx_equal, feat_err = None, None
+        if rank == 0:
+            ref_idx = torch.unique(e[0]).to(dev)
+            xs_one = net.model_scene(d_init, ib[ref_idx], fq, R, t, K, e)
+            idx_equal = all(torch.equal(a['idx'], r['idx']) and torch.equal(a['batch'], r['batch'])
+                            for a, r in zip(xs_sh, xs_one))
+            feat_err = max(float((a['feats'] - r['feats']).abs().max() / r['feats'].abs().max())
+                           for a, r in zip(xs_sh, xs_one)) if idx_equal else None
+    heap.close()
+    sec = float(ms.item()) / 1e3
+    return {'workload': 'C4: 1 scene, %d refs + 7 halo keyframes, 256x320, D=96, 7 src, 4cm voxels, 2x(scene model + '
+                        '3 PointFlow), reference views sharded over %d ranks' % (refs, world),
+            'value': steps * refs / sec, 'unit': 'ref-views/s', 'scaling': 'strong', 'steps': steps, 'warmup': warm,
+            'ms_per_step': 1e3 * sec / steps, 'abs_rel_vs_single_gpu': abs_rel, 'voxel_idx_equal': idx_equal,
+            'sparse_feat_max_rel_err_vs_single_gpu': feat_err,
+            'all_gather_bytes': 2 * refs * PLANE[0] * PLANE[1] * 35 * 4, 'all_gathers': 2, 'barriers': barriers,
+            'gpu_launches_per_rank': launches // steps,
+            'collective': 'all_gather_into_tensor of [N_g,35] fp32 point rows, once per scene-model call; sparse U-Net '
+                          'layers exchange rows by epilogue stores into peer memory + one flag barrier per layer',
+            'timing': 'CUDA events on the launching stream, L2 flushed per step, barrier both sides, max over ranks'}
 
 
 def main():
@@ -130,6 +211,9 @@ def main():
     ap.add_argument('--refs-per-step', type=int, default=1,
                     help='reference views per step (BASELINE configs[1] = 1; larger values are a sweep, not the metric)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--c4-refs', type=int, default=64,
+                    help='N > 1 only: reference views of the single sharded scene of the supplementary "c4" block '
+                         '(BASELINE configs[3]; 0 = skip)')
     ap.add_argument('--streams', type=int, default=4,
                     help='supplementary measurement: this many steps in flight on separate CUDA streams, one host '
                          'thread each (0 = skip); the headline value / e2e stay single-stream')
@@ -174,9 +258,12 @@ def main():
     out_host = torch.empty((n_ref,) + PLANE, dtype=torch.float32).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
+    # resident arm: EVERYTHING the step reads is already in HBM, including the CSR form of the edge list
+    plan_resident = ops.edge_plan(edges, dev)
+
     def step_resident():
-        return net.hot_path(resident['feats_quarter'], resident['rotmats'], resident['tvecs'], resident['K'], edges,
-                            resident['images_batch'], DEPTH_CFG, OFFSETS_LIST)
+        return net.hot_path(resident['feats_quarter'], resident['rotmats'], resident['tvecs'], resident['K'],
+                            plan_resident, resident['images_batch'], DEPTH_CFG, OFFSETS_LIST)
 
     # End to end: every step uploads its inputs from pinned host memory and reads its depth map
     # back.  The uploads are double buffered on a copy stream: step i+1's inputs travel while
@@ -200,7 +287,9 @@ def main():
         torch.cuda.current_stream().wait_event(uploaded[i % 2])
         upload((i + 1) % 2)            # the previous step was synchronised: its buffer is free
         d = bufs[i % 2]
-        depth = net.hot_path(d['feats_quarter'], d['rotmats'], d['tvecs'], d['K'], edges, d['images_batch'],
+        # a FRESH host edge tensor every step: the CSR build on the host and its upload (ops.EdgePlan) are paid
+        # inside the timed region, like the other inputs (ops.edge_plan caches on tensor identity)
+        depth = net.hot_path(d['feats_quarter'], d['rotmats'], d['tvecs'], d['K'], edges.clone(), d['images_batch'],
                              DEPTH_CFG, OFFSETS_LIST)
         out_host.copy_(depth, non_blocking=True)
         torch.cuda.current_stream().synchronize()
@@ -229,14 +318,16 @@ def main():
         step_resident()
     torch.cuda.synchronize()
 
-    # kernel / stage timing inside the timed steps: the engine records CUDA events on the launching
-    # stream around its stages (include/dv3d.h: dv3d_engine_profile)
+    # `value`: the timed region proper, nothing but the steps (no stage events inside the engine)
     sampler = ClockSampler(local)
     sampler.start()
-    ops.engine_profile(True)
     launches0 = ops.launch_count()
     ms = timed(step_resident, args.steps)
     launches = ops.launch_count() - launches0
+    # kernel / stage timing: a SECOND pass of the same K steps under the same conditions (L2 flushed per step)
+    # with the engine recording CUDA events on the launching stream around its stages (dv3d_engine_profile)
+    ops.engine_profile(True)
+    ms_profiled = timed(step_resident, args.steps)
     recs = ops.engine_profile_read()
     ops.engine_profile(False)
     sampler.stop_flag = True
@@ -315,8 +406,9 @@ def main():
     if os.path.exists(tpath):
         traffic = json.load(open(tpath))
     # first decoder Conv1d as one launch of the dominant kernel (tcgen05 gather-GEMM): useful FLOPs
-    # 2 M K N with M = n_ref * 3136 points * 8 rows, K = 3 * 352, N = 128
-    gemm_flops = 2.0 * (n_ref * PLANE[0] * PLANE[1] * 8) * (3 * 352) * 128
+    # 2 M K N with M = n_ref * 3136 points * 7 hypothesis rows (the 8th row of a point is all-zero padding and
+    # is NOT counted), K = 3 * 352, N = 128
+    gemm_flops = 2.0 * (n_ref * PLANE[0] * PLANE[1] * 7) * (3 * 352) * 128
     g_achieved = gemm_flops / (g_ms * 1e-3) / 1e12
 
     line = {
@@ -326,7 +418,10 @@ def main():
         'config': {'workload': WORKLOAD, 'refs_per_step': n_ref, 'imgs_per_step': n_ref + N_SRC,
                    'parallelism': 'scenes sharded over %d rank(s), no collective' % world,
                    'l2': 'flushed (256 MiB memset) before every timed step, outside the per-step events',
-                   'timing': 'sum of per-step CUDA events on the launching stream, max over ranks'},
+                   'timing': 'sum of per-step CUDA events on the launching stream, max over ranks; stage / kernel '
+                             'times come from a second pass of the same steps with engine stage events on',
+                   'reference_arm': 'port (oracle/pipeline.py, the CPU restatement; the reference itself needs '
+                                    'torch_scatter / torch_geometric / MinkowskiEngine, absent here)'},
         'e2e': {'value': units / (ms_e2e * 1e-3), 'unit': 'ref-views/s',
                 'h2d_bytes_per_step': int(sum(v.numel() * v.element_size() for v in host.values())
                                           + edges.numel() * 4 + 64),
@@ -343,7 +438,7 @@ def main():
                           'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic.get('planesweep_var_kernel'),
                           'peak_source': peak_src, 'algorithmic_bytes_per_launch': ALGO_BYTES * n_ref,
                           'kernel_ms': k_ms},
-        'stages_ms_per_step': stages_per_step,
+        'stages_ms_per_step': stages_per_step, 'ms_per_step_with_stage_events': ms_profiled / args.steps,
         'multi_stream': None if ms_multi is None else {
             'streams': args.streams, 'steps': per * args.streams, 'value': units_multi * world / (ms_multi * 1e-3),
             'unit': 'ref-views/s', 'note': 'supplementary, rank 0 only: independent steps in flight on separate CUDA '
@@ -367,6 +462,15 @@ def main():
                                 'sample': '%d full steps of the same workload through oracle/pipeline.py '
                                           '(torch CPU, %d threads)' % (n_cpu, cores)}
         line['abs_rel_vs_oracle'] = rel
+    if dist is not None and args.c4_refs > 0:
+        # free the weak-scaling buffers first: the 64-view scene needs ~6 GB per rank
+        del bufs, resident, flush
+        ops._arena.clear()
+        torch.cuda.empty_cache()
+        try:
+            line['c4'] = run_c4(args, rank, world, dev, dist, ops, lm)
+        except Exception as exc:  # the headline line must survive a failure of the supplementary block
+            line['c4'] = {'error': '%s: %s' % (type(exc).__name__, exc)}
     if rank == 0:
         print(json.dumps(line))
     if dist is not None:

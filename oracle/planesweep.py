@@ -13,12 +13,16 @@ def lattice(img_size, plane_size):
     return (np.linspace(0, W - 1, w, dtype=np.float32), np.linspace(0, H - 1, h, dtype=np.float32))
 
 
-def plane_sweep_points(depth_start, depth_interval, n_planes, R, t, K, img_size, plane_size):
+def plane_sweep_points(depth_start, depth_interval, n_planes, R, t, K, img_size, plane_size, planes=None):
     """World coordinates of every frustum voxel of every image, [n,3,D*h*w], flattened
     [d][i][j] (utils.py:86-108). The pixel*depth product is formed in float64 and rounded to
-    float32 once (utils.py:96-100); the two matrix products are float32."""
+    float32 once (utils.py:96-100); the two matrix products are float32.
+    `planes` (a slice; test crops of volumes too large for the CPU) keeps only those depth planes of the
+    full n_planes linspace - every retained voxel is computed exactly as in the full volume."""
     u, v = lattice(img_size, plane_size)
     z = np.linspace(depth_start, depth_start + (n_planes - 1) * depth_interval, n_planes, dtype=np.float32)
+    if planes is not None:
+        z = z[planes]
     uu, vv = np.meshgrid(u, v)  # [h,w]
     pix = np.stack([uu.astype(np.float64), vv.astype(np.float64), np.ones_like(uu, dtype=np.float64)])  # [3,h,w]
     pts = pix[:, None] * z.astype(np.float64)[None, :, None, None]  # [3,D,h,w]
@@ -60,10 +64,12 @@ def group_variance(x, gather_idx, n_ref):
 
 
 def planesweep_var(feats_quarter, rotmats, tvecs, K, ref_src_edges, depth_start, depth_interval, n_planes,
-                   img_size, plane_size):
+                   img_size, plane_size, planes=None):
     """x_var [n_ref,C,D,h,w] exactly as MVSNet.forward builds it (mvsnet.py:179,187-216)."""
     ref_idx, gather_idx = torch.unique(ref_src_edges[0], return_inverse=True)
-    pts = plane_sweep_points(depth_start, depth_interval, n_planes, rotmats, tvecs, K, img_size, plane_size)
+    pts = plane_sweep_points(depth_start, depth_interval, n_planes, rotmats, tvecs, K, img_size, plane_size, planes)
+    if planes is not None:
+        n_planes = len(range(*planes.indices(n_planes)))
     P = projection_matrices(rotmats, tvecs, K)
     grid = project_to_grid(P[ref_src_edges[1]], pts[ref_src_edges[0]], img_size)
     x = F.grid_sample(feats_quarter[ref_src_edges[1]], grid, mode='bilinear', align_corners=True)

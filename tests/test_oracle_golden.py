@@ -145,3 +145,14 @@ def test_irregular_edge_lists_match_reference(synth):
     np.testing.assert_array_equal(pts.numpy().view(np.int32), g['ref_pts'].view(np.int32))
     np.testing.assert_allclose(feat.numpy(), g['ref_pts_feat'], rtol=0, atol=1e-6)
     np.testing.assert_array_equal(batch.numpy(), g['ref_pts_batch'])
+
+
+def test_plane_crop_of_the_oracle_equals_the_full_volume(synth):
+    """oracle.planesweep_var(planes=slice) - used by the C5 GPU crop test - is a bitwise sub-volume of the full one"""
+    import oracle.planesweep as o
+    b = synth.make_batch(1, 5, (64, 80), (16, 16), 32, 2, 2, False, 4)
+    args = (b.feats_quarter, b.rotmats, b.tvecs, b.K, b.ref_src_edges, 0.5, 0.3, 16, (64, 80), (16, 16))
+    full = o.planesweep_var(*args)
+    for lo, hi in ((0, 8), (5, 9), (8, 16)):
+        crop = o.planesweep_var(*args, planes=slice(lo, hi))
+        assert torch.equal(full[:, :, lo:hi].contiguous().view(torch.int32), crop.view(torch.int32))
