@@ -66,7 +66,7 @@ class _Lib(object):
             fn = getattr(self.cdll, name)  # AttributeError if the library lacks a declared symbol
             fn.restype = ret
             fn.argtypes = [t for t, _ in args]
-        assert self.cdll.dv3d_abi_version() == 3
+        assert self.cdll.dv3d_abi_version() == 4
 
     def last_error(self):
         return self.cdll.dv3d_last_error().decode()

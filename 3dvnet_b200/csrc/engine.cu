@@ -645,21 +645,32 @@ extern "C" int dv3d_hot_path(const dv3d_net_params_t* netp, const float* feats_n
                                                  tabb_l, feat_l, C_l, off_l, operand, in_dim, stream));
                 }
                 DV3D_REQUIRE(off_c == var_off, "hot_path: decoder input width %d != level widths %d + 32", in_dim, off_c);
-                {
+                if (net.dec_fused[0] && net.dec_fused[1] && net.dec_fused[2]) {
+                    // the whole decoder + `depth += offset` as one tcgen05 kernel (csrc/decoder_fused.cu)
                     Prof pr(DV3D_STAGE_DEC_GEMM0, cs);
-                    TRY(dv3d_conv1d_bn_relu(operand, Np, 8, in_dim, in_dim, net.dec[0].W, net.dec[0].Wp, net.dec[0].a,
-                                            net.dec[0].b, net.dec[0].N, dec_a, net.dec[0].N, split_ws, split_ws_bytes, stream));
-                }
-                {
-                    Prof pr(DV3D_STAGE_DEC_REST, cs);
-                    TRY(dv3d_conv1d_bn_relu(dec_a, Np, 8, net.dec[1].K / 3, net.dec[0].N, net.dec[1].W, net.dec[1].Wp,
-                                            net.dec[1].a, net.dec[1].b, net.dec[1].N, dec_b, net.dec[1].N, split_ws, split_ws_bytes, stream));
-                    TRY(dv3d_conv1d_bn_relu(dec_b, Np, 8, net.dec[2].K / 3, net.dec[1].N, net.dec[2].W, net.dec[2].Wp,
-                                            net.dec[2].a, net.dec[2].b, net.dec[2].N, dec_a, net.dec[2].N, split_ws, split_ws_bytes, stream));
-                    TRY(dv3d_decoder_head(dec_a, Np, 7, 8, net.dec[2].N, net.dec[2].N, net.dec_head_weight, net.dec_head_bias,
-                                          offset, nullptr, offs, stream));
-                    DV3D_LAUNCH((add_inplace_kernel), cdiv(Np, 256), 256, 0, cs, depth, offs, Np);
-                    DV3D_LAUNCHED();
+                    const void* wp[3] = {net.dec_fused[0], net.dec_fused[1], net.dec_fused[2]};
+                    const float* sc[3] = {net.dec[0].a, net.dec[1].a, net.dec[2].a};
+                    const float* sh[3] = {net.dec[0].b, net.dec[1].b, net.dec[2].b};
+                    TRY(dv3d_decoder_fused(operand, Np, 8, in_dim, in_dim, wp, sc, sh, net.dec[0].N, net.dec_head_weight,
+                                           net.dec_head_bias, offset, dv3d_get_gemm_precision() & 0xff, nullptr, nullptr, depth,
+                                           stream));
+                } else {
+                    {
+                        Prof pr(DV3D_STAGE_DEC_GEMM0, cs);
+                        TRY(dv3d_conv1d_bn_relu(operand, Np, 8, in_dim, in_dim, net.dec[0].W, net.dec[0].Wp, net.dec[0].a,
+                                                net.dec[0].b, net.dec[0].N, dec_a, net.dec[0].N, split_ws, split_ws_bytes, stream));
+                    }
+                    {
+                        Prof pr(DV3D_STAGE_DEC_REST, cs);
+                        TRY(dv3d_conv1d_bn_relu(dec_a, Np, 8, net.dec[1].K / 3, net.dec[0].N, net.dec[1].W, net.dec[1].Wp,
+                                                net.dec[1].a, net.dec[1].b, net.dec[1].N, dec_b, net.dec[1].N, split_ws, split_ws_bytes, stream));
+                        TRY(dv3d_conv1d_bn_relu(dec_b, Np, 8, net.dec[2].K / 3, net.dec[1].N, net.dec[2].W, net.dec[2].Wp,
+                                                net.dec[2].a, net.dec[2].b, net.dec[2].N, dec_a, net.dec[2].N, split_ws, split_ws_bytes, stream));
+                        TRY(dv3d_decoder_head(dec_a, Np, 7, 8, net.dec[2].N, net.dec[2].N, net.dec_head_weight, net.dec_head_bias,
+                                              offset, nullptr, offs, stream));
+                        DV3D_LAUNCH((add_inplace_kernel), cdiv(Np, 256), 256, 0, cs, depth, offs, Np);
+                        DV3D_LAUNCHED();
+                    }
                 }
             }
         }

@@ -26,6 +26,7 @@
 //   sparsity        kernel-map slices with no live row in the tile are skipped by producers and
 //                   issuer alike (flags computed from the staged row table).
 #include "gemm.cuh"
+#include "tc.cuh"
 
 namespace dv3d {
 
@@ -44,98 +45,6 @@ __host__ __device__ constexpr size_t tc_smem_bytes(int N) {
 }
 
 static int g_gemm_precision = 1;  // 1 = 3xTF32, 2 = TF32
-
-// ------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// Bounded wait: a protocol bug must surface as a trapped launch, never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000ll) {
-            printf("dv3d gather_gemm_tc: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-            __trap();
-        }
-    }
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                          uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// K-major operand, SWIZZLE_128B: rows of 128 bytes, 8-row groups 1024 bytes apart
-// (cute::UMMA::SmemDescriptor: start>>4 | LBO>>4 @16 | SBO>>4 @32 | version 1 @46 | layout 2 @61)
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
-    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
-// cute::UMMA::InstrDescriptor: D fp32, A/B tf32, both K-major, N>>3 @17, M>>4 @24
-__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-__device__ __forceinline__ void split_tf32(float x, float& big, float& small) {
-    uint32_t u;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-    big = __uint_as_float(u);
-    small = x - big;  // exact
-}
 
 // ------------------------------------------------------------------ weight packing
 // W [Ktot, N] row-major -> per 32-row chunk the shared-memory image of B as a K-major
@@ -248,8 +157,11 @@ gather_gemm_tc_kernel(const __grid_constant__ GemmDesc d, int precision_and_flag
         s_misc[1] = 0;
         fence_mbar_init();
     }
-    // 3xTF32: columns [0, BN) collect A_big*B_big + A_small*B_big, columns [BN, 2BN) collect A_big*B_small
-    if (warp == 8) tmem_alloc(smem_u32(s_misc), 2 * BN);
+    // 3xTF32: columns [0, BN) collect A_big*B_big, [BN, 2BN) A_big*B_small (one N = 2 BN MMA), [2BN, 3BN) A_small*B_big:
+    // two INDEPENDENT accumulator chains, so consecutive MMAs never wait for each other's write-back
+    // (tools/microbench/umma_rate.cu: a dependent N=256 -> N=128 pair costs ~370 cycles, an independent one 192)
+    constexpr uint32_t TMEM_COLS = BN == 128 ? 512 : 256;
+    if (warp == 8) tmem_alloc(smem_u32(s_misc), TMEM_COLS);
     // everything above is independent of the previous kernel in the stream (PDL prologue)
     pdl_wait();
     __syncthreads();
@@ -349,36 +261,37 @@ gather_gemm_tc_kernel(const __grid_constant__ GemmDesc d, int precision_and_flag
             }
         }
     } else if (warp == 8) {
-        if (lane == 0 && n_it > 0) {
-            // ===================== MMA issuer
-            constexpr uint32_t idesc = umma_idesc_tf32(TC_BM, BN);
-            // B_big and B_small are adjacent in the stage: together they are ONE K-major operand of 2 BN rows, so
-            // A_big is read from shared memory once for both of its products (20 KB instead of 24 KB per K step)
-            constexpr uint32_t idesc_pair = umma_idesc_tf32(TC_BM, 2 * BN);
-            uint32_t acc = 0;
-            for (int it = 0; it < n_it; ++it) {
-                const int st = it % TC_STAGES;
-                const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
-                mbar_wait(bar_full + 8 * st, ph);
-                tc_fence_after();
-                const uint32_t a_big = smem_u32(smem + st * STAGE), a_small = a_big + TC_A_BYTES,
-                               b_big = a_big + 2 * TC_A_BYTES, b_small = b_big + B_IMG;
+        // ===================== MMA issuer: the whole warp walks the pipeline (uniform control flow keeps the
+        // descriptors in uniform registers, no per-MMA R2UR waterfall), one elected lane issues
+        constexpr uint32_t idesc = umma_idesc_tf32(TC_BM, BN);
+        // B_big and B_small are adjacent in the stage: together they are ONE K-major operand of 2 BN rows, so
+        // A_big is read from shared memory once for both of its products (20 KB instead of 24 KB per K step)
+        constexpr uint32_t idesc_pair = umma_idesc_tf32(TC_BM, 2 * BN);
+        for (int it = 0; it < n_it; ++it) {
+            const int st = it % TC_STAGES;
+            const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
+            mbar_wait(bar_full + 8 * st, ph);
+            tc_fence_after();
+            const uint32_t a_big = smem_u32(smem + st * STAGE), a_small = a_big + TC_A_BYTES,
+                           b_big = a_big + 2 * TC_A_BYTES;
+            if (elect_one()) {
 #pragma unroll
                 for (int kk = 0; kk < TC_KC / 8; ++kk) {
                     const uint32_t ko = kk * 32;  // 8 tf32 = 32 bytes inside the swizzle row
+                    const uint32_t acc = (it | kk) ? 1u : 0u;
                     if (dbg_no_mma) continue;
                     if (precision == 1) {
                         umma_tf32(tmem_base, umma_desc_sw128(a_big + ko), umma_desc_sw128(b_big + ko), idesc_pair, acc);
-                        umma_tf32(tmem_base, umma_desc_sw128(a_small + ko), umma_desc_sw128(b_big + ko), idesc, 1);
+                        umma_tf32(tmem_base + 2 * BN, umma_desc_sw128(a_small + ko), umma_desc_sw128(b_big + ko), idesc, acc);
                     } else {
                         umma_tf32(tmem_base, umma_desc_sw128(a_big + ko), umma_desc_sw128(b_big + ko), idesc, acc);
                     }
-                    acc = 1;
                 }
                 umma_commit(bar_empty + 8 * st);  // frees the stage once these MMAs have read it
             }
-            umma_commit(bar_accum);
+            __syncwarp();
         }
+        if (n_it > 0 && elect_one()) umma_commit(bar_accum);
         __syncwarp();
     } else {
         if (lane == 0 && n_it > 0) {
@@ -426,10 +339,11 @@ gather_gemm_tc_kernel(const __grid_constant__ GemmDesc d, int precision_and_flag
             if (n_it > 0) {
                 tmem_ld16(trow + (uint32_t)c0, y);
                 if (precision == 1) {
-                    float z[16];
+                    float z[16], w[16];
                     tmem_ld16(trow + (uint32_t)(BN + c0), z);
+                    tmem_ld16(trow + (uint32_t)(2 * BN + c0), w);
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) y[i] += z[i];
+                    for (int i = 0; i < 16; ++i) y[i] += z[i] + w[i];
                 }
             } else {
 #pragma unroll
@@ -442,7 +356,7 @@ gather_gemm_tc_kernel(const __grid_constant__ GemmDesc d, int precision_and_flag
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) tmem_dealloc(tmem_base, 2 * BN);
+    if (warp == 8) tmem_dealloc(tmem_base, TMEM_COLS);
 
     // ===================== epilogue on 16-byte units, all warps
     constexpr int UNITS = BN / 4;          // per row

@@ -48,5 +48,5 @@ cudaError_t func_smem_once(std::atomic<unsigned long long>& mask, const void* fu
 }  // namespace dv3d
 
 extern "C" const char* dv3d_last_error(void) { return dv3d::g_err; }
-extern "C" int dv3d_abi_version(void) { return 3; }
+extern "C" int dv3d_abi_version(void) { return 4; }
 extern "C" long long dv3d_launch_count(void) { return dv3d::g_launches.load(std::memory_order_relaxed); }

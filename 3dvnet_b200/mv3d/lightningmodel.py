@@ -215,6 +215,10 @@ class PL3DVNet(nn.Module):
                 P.dec[i] = dense(w.reshape(-1, w.shape[2]), packed, scale, shift)
             keep.append(head[0])
             P.dec_head_weight, P.dec_head_bias = head[0].data_ptr(), head[1]
+            if self.decoder._fused is not None:
+                keep.extend(self.decoder._fused)
+                for i, f in enumerate(self.decoder._fused):
+                    P.dec_fused[i] = f.data_ptr()
             return P, keep
         # invalidation key: storage + version of the hot-path parameters only (the module tree is
         # static; walking all ~560 tensors incl. the 2D backbone costs more than a PointFlow pass)

@@ -27,14 +27,18 @@ class HypothesisDecoder(nn.Module):
         self._pack = PackCache()
         self._operand = None
         self._ws = None
+        self._fused = None
 
     def _weights(self):
         def build():
-            layers = []
+            layers, fused = [], []
             for i in range(3):
                 w = self.net[i][0].weight.detach().float().permute(2, 1, 0).contiguous()  # [3, Cin, Cout]
                 layers.append((w,) + fold_bn(self.net[i][1]) + (ops.pack_weights(w.reshape(-1, w.shape[2])),))
+                fused.append(ops.decoder_pack_weights(w))
             head = (self.net[3].weight.detach().float().contiguous(), float(self.net[3].bias.detach().cpu()))
+            # the one-kernel decoder (csrc/decoder_fused.cu) applies when every layer could be packed for it
+            self._fused = fused if all(f is not None for f in fused) else None
             return layers, head
         return self._pack.get([p for p in self.parameters()] + [b for b in self.buffers()], build, ops.gemm_mode())
 
@@ -61,6 +65,10 @@ class HypothesisDecoder(nn.Module):
             raise NotImplementedError('HypothesisDecoder: the kernels implement 7 hypotheses (n=3, '
                                       'lightningmodel.py:187), got %d' % n_hyp)
         layers, head = self._weights()
+        if self._fused is not None:
+            return ops.decoder_fused(operand, layers[0][0].shape[1], self._fused, [l[1] for l in layers],
+                                     [l[2] for l in layers], head[0], head[1], 0.0 if offset is None else offset,
+                                     want_prob)
         x = operand
         if self._ws is None or self._ws.device != operand.device:
             self._ws = ops.sparse_conv_workspace(128, operand.device)   # zeroed once; launches leave it zero

@@ -448,6 +448,35 @@ def conv1d_bn_relu(x, weight_tkn, scale, shift, out=None, packed=None, workspace
     return out
 
 
+def decoder_pack_weights(weight_tkn):
+    """[3, Cin, 128] fp32 -> the tap-stationary image of csrc/decoder_fused.cu, or None when the fused kernel
+    does not apply ('f32' verification mode, hidden width != 128, Cin % 16 != 0)"""
+    if gemm_mode() == 'f32':
+        return None
+    _chk(weight_tkn, torch.float32, 'weight', 3)
+    _, Cin, Cout = weight_tkn.shape
+    nbytes = lib().raw('dv3d_decoder_pack_bytes')(Cin)
+    if nbytes == 0 or Cout != 128:
+        return None
+    out = torch.empty(nbytes, dtype=torch.uint8, device=weight_tkn.device)
+    lib().call('dv3d_decoder_pack_weights', _p(weight_tkn), Cin, Cout, _p(out), _stream())
+    return out
+
+
+def decoder_fused(x, Cin, packed3, scale3, shift3, head_weight, head_bias, offset, want_prob=False, depth_accum=None):
+    """the three Conv1d+BN+ReLU layers, the head, softmax and expected offset in one kernel
+    (refinement.py:42-44 + lightningmodel.py:238-241). x [n_pts, 8, ld] -> (offset [n_pts], prob [n_pts,7] | None)"""
+    n_pts, rows, ldx = x.shape
+    off = torch.empty((n_pts,), dtype=torch.float32, device=x.device)
+    prob = torch.empty((n_pts, 7), dtype=torch.float32, device=x.device) if want_prob else None
+    arr = ctypes.c_void_p * 3
+    lib().call('dv3d_decoder_fused', _p(x), n_pts, rows, Cin, ldx, arr(*[t.data_ptr() for t in packed3]),
+               arr(*[t.data_ptr() for t in scale3]), arr(*[t.data_ptr() for t in shift3]), 128, _p(head_weight),
+               float(head_bias), float(offset), 1 if gemm_mode() == 'tf32x3' else 2, _p(prob), _p(off), _p(depth_accum),
+               _stream())
+    return off, prob
+
+
 def decoder_head(x, n_hyp, weight, bias, offset, want_prob=False):
     n_pts, rows, ldx = x.shape
     off = torch.empty((n_pts,), dtype=torch.float32, device=x.device)
@@ -526,7 +555,8 @@ class NetParams(ctypes.Structure):
                 ('down', DenseParams * (MAX_LEVELS - 1)), ('up', DenseParams * (MAX_LEVELS - 1)),
                 ('feat_adj', DenseParams * (MAX_LEVELS - 1)),
                 ('res_up', ((DenseParams * 2) * MAX_RES) * (MAX_LEVELS - 1)),
-                ('dec', DenseParams * 3), ('dec_head_weight', ctypes.c_void_p), ('dec_head_bias', ctypes.c_float)]
+                ('dec', DenseParams * 3), ('dec_head_weight', ctypes.c_void_p), ('dec_head_bias', ctypes.c_float),
+                ('dec_fused', ctypes.c_void_p * 3)]
 
 
 def dense_params(W, Wp, a, b):

@@ -299,6 +299,23 @@ int dv3d_decoder_head(const float* x, long long n_pts, int n_hyp, int rows_per_p
                       const float* weight, float bias, double offset, float* prob_out, float* offset_out,
                       void* stream);
 
+/* The whole decoder stack of a PointFlow pass as ONE tcgen05 kernel (csrc/decoder_fused.cu): the three
+ * Conv1d(k=3)+BN+ReLU layers, the 1-channel Conv1d head, the softmax over the 7 hypotheses and the expected
+ * offset (refinement.py:17-25,42-44; lightningmodel.py:238-241).  A 128-row tile is 16 whole points, so the
+ * activations never leave the SM between layers.  x [n_pts*8, ldx] as for dv3d_conv1d_bn_relu (the 8th row of a
+ * point is treated as zero, whatever it holds); hidden width must be 128.
+ *   dv3d_decoder_pack_weights: weight_tkn [3, Cin, 128] -> the tap-stationary shared-memory images
+ *   (dv3d_decoder_pack_bytes(Cin) bytes; Cin % 16 == 0).
+ *   W_packed / scale / shift: HOST arrays of 3 device pointers (layer 1..3); precision 1 = 3xTF32, 2 = TF32.
+ *   prob_out [n_pts,7], offset_out [n_pts] optional; depth_accum [n_pts] optional: depth += offset
+ *   (eval-3dvnet.py:99) in the same kernel. */
+size_t dv3d_decoder_pack_bytes(int Cin);
+int dv3d_decoder_pack_weights(const float* weight_tkn, int Cin, int Cout, void* packed, void* stream);
+int dv3d_decoder_fused(const float* x, long long n_pts, int rows_per_point, int Cin, int ldx,
+                       const void* const* W_packed, const float* const* scale, const float* const* shift,
+                       int hidden, const float* head_weight, float head_bias, double offset, int precision,
+                       float* prob_out, float* offset_out, float* depth_accum, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * Coarse-to-fine depth upsampling: the step right after the hot path.
  * PropagationNet (upsampling.py:14-36): four Conv2d(3x3, pad 1, no bias)+BN+ReLU, softmax over
@@ -395,6 +412,8 @@ typedef struct dv3d_net_params_t {
     dv3d_dense_params_t dec[3];
     const float* dec_head_weight;  /* [1,Cin,3] torch layout */
     float dec_head_bias;
+    /* dv3d_decoder_pack_weights images of the three layers: all set -> the engine runs dv3d_decoder_fused */
+    const void* dec_fused[3];
 } dv3d_net_params_t;
 
 /* Optional stage timing of dv3d_hot_path: CUDA events recorded on the launching stream around
@@ -411,8 +430,8 @@ typedef struct dv3d_net_params_t {
 #define DV3D_STAGE_UNET 7         /* kernel maps + sparse convolutions */
 #define DV3D_STAGE_FLOW_WARP 8    /* points_var_kernel, 7 hypotheses */
 #define DV3D_STAGE_FLOW_INTERP 9
-#define DV3D_STAGE_DEC_GEMM0 10   /* first decoder Conv1d (K = 3*352) as one gather-GEMM launch */
-#define DV3D_STAGE_DEC_REST 11    /* two more Conv1d GEMMs + head + depth update */
+#define DV3D_STAGE_DEC_GEMM0 10   /* dv3d_decoder_fused (whole decoder + depth update); per-layer path: first Conv1d */
+#define DV3D_STAGE_DEC_REST 11    /* per-layer path only: two more Conv1d GEMMs + head + depth update */
 int dv3d_engine_profile(int enable);
 int dv3d_engine_profile_read(int* ids, float* ms, int cap);
 

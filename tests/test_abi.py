@@ -31,7 +31,7 @@ def test_header_parses_and_every_symbol_is_exported(L):
 
 
 def test_abi_version_and_error_reporting(L):
-    assert L.cdll.dv3d_abi_version() == 3
+    assert L.cdll.dv3d_abi_version() == 4
     # argument validation happens before any CUDA call: safe without a GPU
     rc = L.cdll.dv3d_planesweep_var(None, 1, 16, 4, 4, None, None, None, None, 1, 0.5, 0.05, 8, 8, 8, 16, 16, None,
                                     None)
