@@ -120,7 +120,7 @@ def run_reference(args, rank):
                    'l2': 'n/a (CPU)', 'timing': 'host wall clock around the timed steps'},
         'cpu_baseline': {'value': value, 'unit': 'ref-views/s', 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': value, 'unit': 'ref-views/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-        'gpu_launches': 0}))
+        'gpu_launches': 0}), flush=True)
 
 
 def run_c4(args, rank, world, dev, dist, ops, lm):
@@ -405,10 +405,11 @@ def main():
     tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
     if os.path.exists(tpath):
         traffic = json.load(open(tpath))
-    # first decoder Conv1d as one launch of the dominant kernel (tcgen05 gather-GEMM): useful FLOPs
-    # 2 M K N with M = n_ref * 3136 points * 7 hypothesis rows (the 8th row of a point is all-zero padding and
-    # is NOT counted), K = 3 * 352, N = 128
-    gemm_flops = 2.0 * (n_ref * PLANE[0] * PLANE[1] * 7) * (3 * 352) * 128
+    # the dominant kernel: the one-kernel PointFlow decoder (csrc/decoder_fused.cu, tcgen05), one launch per
+    # PointFlow pass. Useful FLOPs 2 M (K N) summed over its layers, with M = n_ref * 3136 points * 7 hypothesis
+    # rows (the 8th row of a point is zero padding and is NOT counted): Conv1d k=3 352->128, 128->128, 128->128,
+    # 128->1 (refinement.py:17-25)
+    gemm_flops = 2.0 * (n_ref * PLANE[0] * PLANE[1] * 7) * (3 * (352 + 128 + 128) * 128 + 3 * 128)
     g_achieved = gemm_flops / (g_ms * 1e-3) / 1e12
 
     line = {
@@ -427,13 +428,14 @@ def main():
                                           + edges.numel() * 4 + 64),
                 'd2h_bytes_per_step': int(out_host.numel() * 4), 'ms_per_step': ms_e2e / args.steps},
         'gpu_launches': launches,
-        'roofline': {'kernel': 'gather_gemm_tc_kernel<128> (first decoder Conv1d, M=%d K=1056 N=128; full rounds + '
-                               'tap-split tail launch, timed together)' % (n_ref * 25088),
+        'roofline': {'kernel': 'decoder_fused_kernel (whole PointFlow decoder of %d points x 7 hypotheses in one tcgen05 '
+                               'launch: 3 x Conv1d+BN+ReLU, head, softmax, depth update)' % (n_ref * PLANE[0] * PLANE[1]),
                      'bound': 'tensor', 'achieved': g_achieved, 'peak': tpeak, 'unit': 'TFLOP/s',
-                     'frac': g_achieved / tpeak, 'traffic': traffic.get('gather_gemm_tc_decoder0'),
+                     'frac': g_achieved / tpeak, 'traffic': traffic.get('decoder_fused_kernel'),
                      'peak_source': tpeak_src, 'algorithmic_flops_per_launch': gemm_flops, 'kernel_ms': g_ms,
                      'note': 'useful fp32-grade FLOPs; the kernel issues 3 TF32 MMAs per useful one (3xTF32 split) and '
-                             'TF32 runs at half the bf16 rate, so 1/6 of the bf16 peak is its ceiling'},
+                             'TF32 runs at half the bf16 rate, so 1/6 of the bf16 peak is its ceiling; at 1 ref view the '
+                             '196 row tiles take 2 rounds on 148 SMs (1.32 rounds of work)'},
         'roofline_warp': {'kernel': 'planesweep_var_kernel', 'bound': 'hbm', 'achieved': achieved, 'peak': peak,
                           'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic.get('planesweep_var_kernel'),
                           'peak_source': peak_src, 'algorithmic_bytes_per_launch': ALGO_BYTES * n_ref,
@@ -472,7 +474,7 @@ def main():
         except Exception as exc:  # the headline line must survive a failure of the supplementary block
             line['c4'] = {'error': '%s: %s' % (type(exc).__name__, exc)}
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
