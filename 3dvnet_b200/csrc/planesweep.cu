@@ -344,6 +344,246 @@ points_var_kernel(const float4* __restrict__ feats, SampleGeom geom, const float
     }
 }
 
+// ------------------------------------------------------------------------ backward (w.r.t. the feature maps)
+// The reference trains through F.grid_sample + the two scatter means (mvsnet.py:209-216, lightningmodel.py:165-169;
+// the sampling grid itself is built under no_grad, mvsnet.py:187 / lightningmodel.py:147,190):
+//     x_var = mean_e(x_e^2) - mean_e(x_e)^2   =>   d x_var / d x_e = (2/n) (x_e - mean),
+//     d x_e / d F[src_e, tap] = bilinear weight of the tap.
+// The backward kernels recompute the sample records and the samples exactly as the forward kernels do (nothing is
+// saved but the inputs), form g * (2/n) (x_e - mean) per (pixel, plane, edge, channel) and add w_tap times that to
+// the four taps of the NHWC gradient map with 16-byte vector atomics.  Consecutive planes that fall into the same
+// 2x2 footprint are summed in registers first (one flush per footprint instead of one per plane).  Like ATen's own
+// CUDA grid_sampler backward, the accumulation order of the atomics is not fixed: results are reproducible to
+// fp32 rounding, not bit for bit.
+__device__ __forceinline__ void red_add4(float* addr, const float4& v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void fma4(float4& a, float w, const float4& g) {
+    a.x = fmaf(w, g.x, a.x); a.y = fmaf(w, g.y, a.y); a.z = fmaf(w, g.z, a.z); a.w = fmaf(w, g.w, a.w);
+}
+
+// sum over a staged pass of edges of the sampled feature (4 channels of group g) for NK planes
+template <int NK>
+__device__ __forceinline__ void sum_edges(const float4* __restrict__ feats, const int* __restrict__ esrc, int e_begin,
+                                          int n_e, int img_stride4, int Wf, int v, int g, const int (*s_rec)[KD][TP],
+                                          const float4 (*s_wt)[KD][TP], float4 (&sum)[KD]) {
+    for (int e = 0; e < n_e; ++e) {
+        const float4* base = feats + (size_t)__ldg(esrc + e_begin + e) * img_stride4 + g;
+#pragma unroll
+        for (int k = 0; k < NK; ++k) {
+            const int rec = s_rec[e][k][v];
+            const float4 wt = s_wt[e][k][v];
+            const float4* p = base + (size_t)(rec >> 2) * 8;
+            const int dx = (rec & 1) * 8, dy = ((rec >> 1) & 1) * Wf * 8;
+            const float4 t00 = ldg4(p), t01 = ldg4(p + dx), t10 = ldg4(p + dy), t11 = ldg4(p + dy + dx);
+            float4 x = make_float4(t00.x * wt.x, t00.y * wt.x, t00.z * wt.x, t00.w * wt.x);
+            fma4(x, wt.y, t01);
+            fma4(x, wt.z, t10);
+            fma4(x, wt.w, t11);
+            sum[k].x += x.x; sum[k].y += x.y; sum[k].z += x.z; sum[k].w += x.w;
+        }
+    }
+}
+
+// scatter pass: grad_x_e = gsc[k] * (x_e - mean[k]) with gsc = g * 2/n, pushed to the four taps
+template <int NK>
+__device__ __forceinline__ void scatter_edges(const float4* __restrict__ feats, float* __restrict__ grad_feats,
+                                              const int* __restrict__ esrc, int e_begin, int n_e, int img_stride4, int Wf,
+                                              int v, int g, const int (*s_rec)[KD][TP], const float4 (*s_wt)[KD][TP],
+                                              const float4 (&mean)[KD], const float4 (&gsc)[KD]) {
+    for (int e = 0; e < n_e; ++e) {
+        const int src = __ldg(esrc + e_begin + e);
+        const float4* base = feats + (size_t)src * img_stride4 + g;
+        float* gbase = grad_feats + ((size_t)src * img_stride4 + g) * 4;
+        int prev = -1;
+        float4 a00 = make_float4(0, 0, 0, 0), a01 = a00, a10 = a00, a11 = a00;
+        auto flush = [&]() {
+            if (prev < 0) return;
+            float* p = gbase + (size_t)(prev >> 2) * 32;
+            const int dx = (prev & 1) * 32, dy = ((prev >> 1) & 1) * Wf * 32;
+            // clamped (out-of-bounds) taps alias a live one with weight 0: their sums are exactly 0 unless aliased
+            red_add4(p, a00);
+            if (dx) red_add4(p + dx, a01); else red_add4(p, a01);
+            if (dy) red_add4(p + dy, a10); else red_add4(p, a10);
+            red_add4(p + dy + dx, a11);
+            a00 = a01 = a10 = a11 = make_float4(0, 0, 0, 0);
+        };
+#pragma unroll
+        for (int k = 0; k < NK; ++k) {
+            const int rec = s_rec[e][k][v];
+            const float4 wt = s_wt[e][k][v];
+            if (rec != prev) {
+                flush();
+                prev = rec;
+            }
+            const float4* p = base + (size_t)(rec >> 2) * 8;
+            const int dx = (rec & 1) * 8, dy = ((rec >> 1) & 1) * Wf * 8;
+            const float4 t00 = ldg4(p), t01 = ldg4(p + dx), t10 = ldg4(p + dy), t11 = ldg4(p + dy + dx);
+            float4 x = make_float4(t00.x * wt.x, t00.y * wt.x, t00.z * wt.x, t00.w * wt.x);
+            fma4(x, wt.y, t01);
+            fma4(x, wt.z, t10);
+            fma4(x, wt.w, t11);
+            const float4 gx = make_float4(gsc[k].x * (x.x - mean[k].x), gsc[k].y * (x.y - mean[k].y),
+                                          gsc[k].z * (x.z - mean[k].z), gsc[k].w * (x.w - mean[k].w));
+            fma4(a00, wt.x, gx);
+            fma4(a01, wt.y, gx);
+            fma4(a10, wt.z, gx);
+            fma4(a11, wt.w, gx);
+        }
+        flush();
+    }
+}
+
+__global__ void __launch_bounds__(256, 1)
+planesweep_var_bwd_kernel(const float4* __restrict__ feats, SampleGeom geom, const float* __restrict__ cams,
+                          const int* __restrict__ ref_img, const int* __restrict__ rowptr, const int* __restrict__ esrc,
+                          double d0, double d1, int D, int h, int w, int H, int W, int chunks_per_cta,
+                          const float* __restrict__ grad_out, float* __restrict__ grad_feats) {
+    pdl_wait();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4 (*s_wt)[KD][TP] = reinterpret_cast<float4 (*)[KD][TP]>(smem_raw);
+    int (*s_rec)[KD][TP] = reinterpret_cast<int (*)[KD][TP]>(smem_raw + sizeof(float4) * EMAX * KD * TP);
+    float* s_g = reinterpret_cast<float*>(smem_raw + (sizeof(float4) + sizeof(int)) * EMAX * KD * TP);
+    __shared__ float s_P[EMAX][12];
+
+    const int tid = threadIdx.x;
+    const int r = blockIdx.y;
+    const int P = h * w;
+    const int p0 = blockIdx.x * TP;
+    const int e0 = rowptr[r], e1 = rowptr[r + 1];
+    const float inv_n = 1.f / (float)(e1 - e0);
+    const int img_stride4 = geom.Hf * geom.Wf * 8;
+    const int pv = tid & 31, pk = tid >> 5;
+    const int v = tid >> 3, g = tid & 7;
+    const int p = min(p0 + pv, P - 1);
+    const float u = linspace_np(0.0, (double)(W - 1), w, p % w);
+    const float vv = linspace_np(0.0, (double)(H - 1), h, p / w);
+
+    const int chunk_begin = blockIdx.z * chunks_per_cta;
+    const int n_chunks = (D + KD - 1) / KD;
+    for (int ch = chunk_begin; ch < min(chunk_begin + chunks_per_cta, n_chunks); ++ch) {
+        const int dbase = ch * KD;
+        __syncthreads();
+        {   // the gradient tile [c][k][pixel] of this chunk, 128-byte rows
+            const int warp = tid >> 5, lane = tid & 31;
+            const bool ok = p0 + lane < P;
+            for (int row = warp; row < 32 * KD; row += 8) {
+                const int c = row >> 3, k = row & 7, d = dbase + k;
+                s_g[c * CS + k * TP + lane] = (ok && d < D) ? __ldg(grad_out + (((size_t)r * 32 + c) * D + d) * P + p0 + lane) : 0.f;
+            }
+        }
+        const float z = linspace_np(d0, d1, D, min(dbase + pk, D - 1));
+        float X0, X1, X2;
+        backproject(cams + (size_t)__ldg(ref_img + r) * CAM_STRIDE, (float)((double)u * (double)z),
+                    (float)((double)vv * (double)z), z, X0, X1, X2);
+        float4 mean[KD], gsc[KD];
+#pragma unroll
+        for (int k = 0; k < KD; ++k) mean[k] = make_float4(0, 0, 0, 0);
+        for (int pass = 0; pass < 2; ++pass) {
+            for (int eb = e0; eb < e1; eb += EMAX) {
+                const int n_e = min(EMAX, e1 - eb);
+                __syncthreads();
+                if (tid < n_e * 12) s_P[tid / 12][tid % 12] = __ldg(cams + (size_t)__ldg(esrc + eb + tid / 12) * CAM_STRIDE + CAM_P + tid % 12);
+                __syncthreads();
+                for (int e = 0; e < n_e; ++e) {
+                    int rec;
+                    float4 wt;
+                    make_record(s_P[e], X0, X1, X2, geom, rec, wt);
+                    s_rec[e][pk][pv] = rec;
+                    s_wt[e][pk][pv] = wt;
+                }
+                __syncthreads();
+                if (pass == 0)
+                    sum_edges<KD>(feats, esrc, eb, n_e, img_stride4, geom.Wf, v, g, s_rec, s_wt, mean);
+                else
+                    scatter_edges<KD>(feats, grad_feats, esrc, eb, n_e, img_stride4, geom.Wf, v, g, s_rec, s_wt, mean, gsc);
+            }
+            if (pass == 0) {
+#pragma unroll
+                for (int k = 0; k < KD; ++k) {
+                    mean[k].x *= inv_n; mean[k].y *= inv_n; mean[k].z *= inv_n; mean[k].w *= inv_n;
+                    const float* gp = s_g + (4 * g) * CS + k * TP + v;
+                    const float f = 2.f * inv_n;
+                    gsc[k] = make_float4(gp[0] * f, gp[CS] * f, gp[2 * CS] * f, gp[3 * CS] * f);
+                }
+            }
+        }
+    }
+}
+
+// point-level backward: grad of the variance features [n_pts, rows, ld] (channels feat_off..+32) w.r.t. the maps
+__global__ void __launch_bounds__(256, 1)
+points_var_bwd_kernel(const float4* __restrict__ feats, SampleGeom geom, const float* __restrict__ cams,
+                      const int* __restrict__ ref_img, const int* __restrict__ rowptr, const int* __restrict__ esrc,
+                      const float* __restrict__ depth, int h, int w, int H, int W, int n_side, double offset,
+                      const float* __restrict__ grad_feat, int rows_per_point, int feat_stride, int feat_off,
+                      float* __restrict__ grad_feats) {
+    pdl_wait();
+    __shared__ int s_rec[EMAX][KD][TP];
+    __shared__ float4 s_wt[EMAX][KD][TP];
+    __shared__ float s_P[EMAX][12];
+    const int tid = threadIdx.x;
+    const int r = blockIdx.y;
+    const int P = h * w;
+    const int p0 = blockIdx.x * TP;
+    const int e0 = rowptr[r], e1 = rowptr[r + 1];
+    const float inv_n = 1.f / (float)(e1 - e0);
+    const int img_stride4 = geom.Hf * geom.Wf * 8;
+    const int n_hyp = 2 * n_side + 1;
+    const int pv = tid & 31, pk = tid >> 5;
+    const int v = tid >> 3, g = tid & 7;
+    const int p = min(p0 + pv, P - 1);
+    const float u = linspace_np(0.0, (double)(W - 1), w, p % w);
+    const float vv = linspace_np(0.0, (double)(H - 1), h, p / w);
+    const float dpt = __ldg(depth + (size_t)r * P + p);
+    const float z = __fadd_rn(dpt, (float)((double)(pk - n_side) * offset));
+    float X0, X1, X2;
+    backproject(cams + (size_t)__ldg(ref_img + r) * CAM_STRIDE, __fmul_rn(u, z), __fmul_rn(vv, z), z, X0, X1, X2);
+
+    float4 mean[KD], gsc[KD];
+#pragma unroll
+    for (int k = 0; k < KD; ++k) mean[k] = gsc[k] = make_float4(0, 0, 0, 0);
+    const bool live = p0 + v < P;
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int eb = e0; eb < e1; eb += EMAX) {
+            const int n_e = min(EMAX, e1 - eb);
+            __syncthreads();
+            if (tid < n_e * 12) s_P[tid / 12][tid % 12] = __ldg(cams + (size_t)__ldg(esrc + eb + tid / 12) * CAM_STRIDE + CAM_P + tid % 12);
+            __syncthreads();
+            if (pk < n_hyp) {
+                for (int e = 0; e < n_e; ++e) {
+                    int rec;
+                    float4 wt;
+                    make_record(s_P[e], X0, X1, X2, geom, rec, wt);
+                    s_rec[e][pk][pv] = rec;
+                    s_wt[e][pk][pv] = wt;
+                }
+            }
+            __syncthreads();
+            if (pass == 0) {
+                if (n_hyp == 1) sum_edges<1>(feats, esrc, eb, n_e, img_stride4, geom.Wf, v, g, s_rec, s_wt, mean);
+                else sum_edges<7>(feats, esrc, eb, n_e, img_stride4, geom.Wf, v, g, s_rec, s_wt, mean);
+            } else if (live) {
+                if (n_hyp == 1) scatter_edges<1>(feats, grad_feats, esrc, eb, n_e, img_stride4, geom.Wf, v, g, s_rec, s_wt, mean, gsc);
+                else scatter_edges<7>(feats, grad_feats, esrc, eb, n_e, img_stride4, geom.Wf, v, g, s_rec, s_wt, mean, gsc);
+            }
+        }
+        if (pass == 0) {
+#pragma unroll
+            for (int k = 0; k < 7; ++k) {
+                if (k < n_hyp) {
+                    mean[k].x *= inv_n; mean[k].y *= inv_n; mean[k].z *= inv_n; mean[k].w *= inv_n;
+                    float4 gv = make_float4(0, 0, 0, 0);
+                    if (live)
+                        gv = __ldg(reinterpret_cast<const float4*>(grad_feat + (((size_t)r * P + p0 + v) * rows_per_point + k) * feat_stride + feat_off + 4 * g));
+                    const float f = 2.f * inv_n;
+                    gsc[k] = make_float4(gv.x * f, gv.y * f, gv.z * f, gv.w * f);
+                }
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------ camera algebra
 __device__ void inv3(const double* m, double* o) {
     double a = m[0], b = m[1], c = m[2], d = m[3], e = m[4], f = m[5], g = m[6], h = m[7], i = m[8];
@@ -486,6 +726,51 @@ extern "C" int dv3d_points_var(const float* feats_nhwc, int n_imgs, int C, int H
     if (n_ref == 0) return DV3D_OK;
     dim3 grid(cdiv(h * w, TP), n_ref);
     DV3D_LAUNCH((points_var_kernel), grid, 256, 0, (cudaStream_t)stream, reinterpret_cast<const float4*>(feats_nhwc), make_geom(Hf, Wf, H, W), cams, ref_img, edge_rowptr, edge_src, depth, h, w, H, W, n_side, offset, pts_out, feat_out, rows_per_point, feat_stride, feat_off);
+    DV3D_LAUNCHED();
+    return DV3D_OK;
+}
+
+extern "C" int dv3d_planesweep_var_backward(const float* feats_nhwc, int n_imgs, int C, int Hf, int Wf, const float* cams,
+                                            const int* ref_img, const int* edge_rowptr, const int* edge_src, int n_ref,
+                                            double depth_start, double depth_interval, int D, int h, int w, int H, int W,
+                                            const float* grad_x_var, float* grad_feats_nhwc, void* stream) {
+    DV3D_REQUIRE(C == 32, "planesweep_var_backward: C must be 32, got %d", C);
+    DV3D_REQUIRE(feats_nhwc && cams && ref_img && edge_rowptr && edge_src && grad_x_var && grad_feats_nhwc,
+                 "planesweep_var_backward: null pointer");
+    DV3D_REQUIRE(n_imgs > 0 && Hf > 1 && Wf > 1 && D > 0 && h > 0 && w > 0 && H > 1 && W > 1 && n_ref >= 0 && n_ref <= 65535,
+                 "planesweep_var_backward: bad shape");
+    DV3D_REQUIRE((long long)Hf * Wf < (1 << 29), "planesweep_var_backward: feature map too large for the record encoding");
+    if (n_ref == 0) return DV3D_OK;
+    const int P = h * w, tiles = cdiv(P, TP), n_chunks = cdiv(D, KD);
+    int dsplit = cdiv(4 * kNumSMs, (long long)tiles * n_ref);
+    dsplit = dsplit < 1 ? 1 : (dsplit > n_chunks ? n_chunks : dsplit);
+    const int chunks_per_cta = cdiv(n_chunks, dsplit);
+    dim3 grid(tiles, n_ref, cdiv(n_chunks, chunks_per_cta));
+    const double d1 = depth_start + depth_interval * (D - 1);
+    const size_t smem = (sizeof(float4) + sizeof(int)) * EMAX * KD * TP + sizeof(float) * 32 * CS;
+    static std::atomic<unsigned long long> attr{0};
+    DV3D_FUNC_SMEM_ONCE(attr, (planesweep_var_bwd_kernel), (int)smem);
+    DV3D_LAUNCH((planesweep_var_bwd_kernel), grid, 256, smem, (cudaStream_t)stream, reinterpret_cast<const float4*>(feats_nhwc), make_geom(Hf, Wf, H, W), cams, ref_img, edge_rowptr, edge_src, depth_start, d1, D, h, w, H, W, chunks_per_cta, grad_x_var, grad_feats_nhwc);
+    DV3D_LAUNCHED();
+    return DV3D_OK;
+}
+
+extern "C" int dv3d_points_var_backward(const float* feats_nhwc, int n_imgs, int C, int Hf, int Wf, const float* cams,
+                                        const int* ref_img, const int* edge_rowptr, const int* edge_src,
+                                        const float* depth, int n_ref, int h, int w, int H, int W, int n_side, double offset,
+                                        const float* grad_feat, int rows_per_point, int feat_stride, int feat_off,
+                                        float* grad_feats_nhwc, void* stream) {
+    DV3D_REQUIRE(C == 32, "points_var_backward: C must be 32, got %d", C);
+    DV3D_REQUIRE(n_side == 0 || n_side == 3, "points_var_backward: n_side must be 0 or 3, got %d", n_side);
+    DV3D_REQUIRE(feats_nhwc && cams && ref_img && edge_rowptr && edge_src && depth && grad_feat && grad_feats_nhwc,
+                 "points_var_backward: null pointer");
+    DV3D_REQUIRE(rows_per_point >= 2 * n_side + 1 && feat_stride % 4 == 0 && feat_off % 4 == 0 && feat_off + C <= feat_stride &&
+                     ((uintptr_t)grad_feat & 15) == 0,
+                 "points_var_backward: bad gradient layout");
+    DV3D_REQUIRE(n_imgs > 0 && Hf > 1 && Wf > 1 && h > 0 && w > 0 && n_ref >= 0 && n_ref <= 65535, "points_var_backward: bad shape");
+    if (n_ref == 0) return DV3D_OK;
+    dim3 grid(cdiv(h * w, TP), n_ref);
+    DV3D_LAUNCH((points_var_bwd_kernel), grid, 256, 0, (cudaStream_t)stream, reinterpret_cast<const float4*>(feats_nhwc), make_geom(Hf, Wf, H, W), cams, ref_img, edge_rowptr, edge_src, depth, h, w, H, W, n_side, offset, grad_feat, rows_per_point, feat_stride, feat_off, grad_feats_nhwc);
     DV3D_LAUNCHED();
     return DV3D_OK;
 }

@@ -27,5 +27,6 @@ def fold_bn(bn):
 def require_eval(module):
     if module.training:
         raise NotImplementedError(
-            '%s: the B200 kernels implement the inference path (eval mode, BatchNorm running statistics); '
-            'call .eval() — the autograd/backward path is not built yet' % type(module).__name__)
+            '%s: this module has a forward (inference) kernel only - call .eval(). The differentiable pieces are '
+            'MVSNet (warp + variance as torch.autograd.Function, mv3d/functional.py, regulariser through cuDNN) and '
+            'the point-level variance features' % type(module).__name__)

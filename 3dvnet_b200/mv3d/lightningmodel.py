@@ -11,6 +11,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
+from . import functional
 from ._pack import PackCache, fold_bn, require_eval
 from .subnetworks.mvsnet import MVSNet
 from .subnetworks.scenemodeling import PointNet, SparseUNet, SparseScene
@@ -100,9 +101,15 @@ class PL3DVNet(nn.Module):
 
     def construct_feature_rich_pointcloud(self, depth_pred, depth_batch, img_feats, rotmats, tvecs, K, ref_src_edges):
         """-> pts [n_ref*P,3], pts_feat [n_ref*P,C], pts_batch [n_ref*P] (lightningmodel.py:132-174)"""
-        plan, nhwc, cams = self._geometry(img_feats, rotmats, tvecs, K, ref_src_edges)
         depth = depth_pred.detach().float().contiguous()
-        pts, feat = ops.points_var(nhwc, cams, plan, depth, self.hparams.img_size, 0, 0.0)
+        if torch.is_grad_enabled() and img_feats.requires_grad:
+            # training: the variance features carry a gradient to the feature maps (mv3d/functional.py); the
+            # points do not (the reference builds the re-projection under no_grad, lightningmodel.py:147)
+            pts, feat = functional.point_variance(img_feats, rotmats, tvecs, K, ref_src_edges, depth,
+                                                  self.hparams.img_size, 0, 0.0)
+        else:
+            plan, nhwc, cams = self._geometry(img_feats, rotmats, tvecs, K, ref_src_edges)
+            pts, feat = ops.points_var(nhwc, cams, plan, depth, self.hparams.img_size, 0, 0.0)
         n, P = depth.shape[0], depth.shape[1] * depth.shape[2]
         pts_batch = depth_batch.unsqueeze(1).expand(n, P).reshape(-1)
         return pts.view(-1, 3), feat.view(-1, feat.shape[2]), pts_batch

@@ -7,11 +7,20 @@ from collections import OrderedDict
 
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 import torchvision
 
 from ... import ops
-from .. import utils
+from .. import functional, utils
 from .._pack import PackCache, fold_bn, require_eval
+
+
+def _autograd_path(module, *tensors):
+    """True when the call must be differentiable (training mode, or an input that carries a gradient): the 3D
+    convolutions then run through torch / cuDNN so that autograd sees them (library work, like the 2D backbone);
+    the warp + variance in front of them stays ours in both directions (mv3d/functional.py). Inference never
+    takes this path."""
+    return module.training or (torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors))
 
 
 class ConvBnRelu3d(nn.Module):
@@ -26,7 +35,9 @@ class ConvBnRelu3d(nn.Module):
         self._pack = PackCache()
 
     def forward(self, x, skip=None):
-        require_eval(self)
+        if _autograd_path(self, x, skip):
+            y = F.relu(self.bn(self.conv(x)))           # mvsnet.py:24-25
+            return y if skip is None else skip + y      # mvsnet.py:159-161
         scale, shift = self._pack.get([self.bn.weight, self.bn.bias, self.bn.running_mean, self.bn.running_var],
                                       lambda: fold_bn(self.bn))
         return ops.conv3d_bn_relu(x, self.conv.weight.detach(), scale, shift, self.stride, skip)
@@ -43,7 +54,9 @@ class DeconvBnRelu3d(nn.Module):
         self._pack = PackCache()
 
     def forward(self, x, skip=None):
-        require_eval(self)
+        if _autograd_path(self, x, skip):
+            y = F.relu(self.bn(self.deconv(x)))         # mvsnet.py:35-36
+            return y if skip is None else skip + y
         scale, shift = self._pack.get([self.bn.weight, self.bn.bias, self.bn.running_mean, self.bn.running_var],
                                       lambda: fold_bn(self.bn))
         return ops.deconv3d_bn_relu(x, self.deconv.weight.detach(), scale, shift, skip)
@@ -87,12 +100,20 @@ class CostRegNet(nn.Module):
     def forward(self, x):
         """[n,C,D,h,w] -> x_reg [n,1,D,h,w]"""
         f = self.features(x)
+        if _autograd_path(self, f):
+            return self.prob(f)
         _, reg = ops.prob_softargmin(f, self.prob.weight.detach(), self._prob_bias(), 0.0, 1.0, want_reg=True)
         return reg.unsqueeze(1)
 
     def depth(self, x, depth_start, depth_end, want_reg=False):
         """fused prob conv + softmax(-x) + expectation (mvsnet.py:219-227)"""
         f = self.features(x)
+        if _autograd_path(self, f):
+            x_reg = self.prob(f).squeeze(1)
+            prob = F.softmax(-x_reg, dim=1)
+            vals = torch.linspace(depth_start, depth_end, x_reg.shape[1]).type_as(x_reg).view(1, -1, 1, 1)
+            depth = torch.sum(vals * prob, dim=1)
+            return depth, (x_reg if want_reg else None)
         return ops.prob_softargmin(f, self.prob.weight.detach(), self._prob_bias(), depth_start, depth_end, want_reg)
 
 
@@ -145,8 +166,13 @@ class MVSNet(nn.Module):
 
     def cost_volume(self, features_quarter, batch, depth_start, depth_interval, n_planes, depth_img_size,
                     feats_nhwc=None, plan=None):
-        """x_var [n_ref,C,D,h,w] (mvsnet.py:187-216) without materialising x_vox."""
+        """x_var [n_ref,C,D,h,w] (mvsnet.py:187-216) without materialising x_vox. Differentiable w.r.t. the feature
+        maps (autograd.Function of mv3d/functional.py) whenever they carry a gradient."""
         plan = ops.edge_plan(batch.ref_src_edges, features_quarter.device) if plan is None else plan
+        if torch.is_grad_enabled() and features_quarter.requires_grad:
+            return functional.PlaneSweepVariance.apply(features_quarter, batch.rotmats, batch.tvecs, batch.K, plan,
+                                                       depth_start, depth_interval, n_planes, tuple(depth_img_size),
+                                                       tuple(self.img_size))
         if feats_nhwc is None:
             fq = features_quarter.detach().float()
             if fq.is_contiguous(memory_format=torch.channels_last) and not fq.is_contiguous():
@@ -167,8 +193,9 @@ class MVSNet(nn.Module):
         return depth
 
     def forward(self, batch, depth_start, depth_interval, n_planes, depth_img_size):
-        """-> depth_img [n_ref,h,w], features_half, features_quarter, features_eighth (mvsnet.py:176-229)"""
-        require_eval(self)
+        """-> depth_img [n_ref,h,w], features_half, features_quarter, features_eighth (mvsnet.py:176-229).
+        Works in training mode too: warp + variance forward/backward are the CUDA kernels of csrc/planesweep.cu,
+        the 2D backbone and the 3D regulariser train through torch / cuDNN."""
         # channels-last through the cuDNN backbone: the FPN then emits NHWC feature maps, which the warp
         # kernels consume without a transposition pass (SURVEY.md §8f.2)
         images = batch.images.contiguous(memory_format=torch.channels_last)

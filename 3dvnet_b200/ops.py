@@ -172,6 +172,36 @@ def points_var(feats_nhwc, cams, plan, depth, img_size, n_side, offset, feat_out
     return pts, feat_out
 
 
+def planesweep_var_backward(feats_nhwc, cams, plan, depth_start, depth_interval, n_planes, plane_size, img_size, grad_x_var):
+    """gradient of planesweep_var w.r.t. feats_nhwc (mvsnet.py:209-216 trained through grid_sample + scatter mean)"""
+    _chk(feats_nhwc, torch.float32, 'feats_nhwc', 4), _chk(grad_x_var, torch.float32, 'grad_x_var', 5)
+    n_imgs, Hf, Wf, C = feats_nhwc.shape
+    h, w = plane_size
+    if tuple(grad_x_var.shape) != (plan.n_ref, C, n_planes, h, w):
+        raise RuntimeError('grad_x_var must be %s, got %s' % ((plan.n_ref, C, n_planes, h, w), tuple(grad_x_var.shape)))
+    grad = torch.zeros_like(feats_nhwc, memory_format=torch.contiguous_format)
+    lib().call('dv3d_planesweep_var_backward', _p(feats_nhwc), n_imgs, C, Hf, Wf, _p(cams), _p(plan.ref_img), _p(plan.rowptr),
+               _p(plan.edge_src), plan.n_ref, float(depth_start), float(depth_interval), int(n_planes), h, w, img_size[0],
+               img_size[1], _p(grad_x_var), _p(grad), _stream())
+    return grad
+
+
+def points_var_backward(feats_nhwc, cams, plan, depth, img_size, n_side, offset, grad_feat, feat_off=0):
+    """gradient of points_var's variance features [n_pts, rows, ld] (channels feat_off..) w.r.t. feats_nhwc"""
+    _chk(feats_nhwc, torch.float32, 'feats_nhwc', 4), _chk(depth, torch.float32, 'depth', 3)
+    _chk(grad_feat, torch.float32, 'grad_feat', 3)
+    n_imgs, Hf, Wf, C = feats_nhwc.shape
+    n_ref, h, w = depth.shape
+    rows, ld = grad_feat.shape[1], grad_feat.shape[2]
+    if grad_feat.shape[0] != n_ref * h * w:
+        raise RuntimeError('grad_feat must have %d rows, got %d' % (n_ref * h * w, grad_feat.shape[0]))
+    grad = torch.zeros_like(feats_nhwc, memory_format=torch.contiguous_format)
+    lib().call('dv3d_points_var_backward', _p(feats_nhwc), n_imgs, C, Hf, Wf, _p(cams), _p(plan.ref_img), _p(plan.rowptr),
+               _p(plan.edge_src), _p(depth), n_ref, h, w, img_size[0], img_size[1], int(n_side), float(offset),
+               _p(grad_feat), rows, ld, int(feat_off), _p(grad), _stream())
+    return grad
+
+
 def conv3d_bn_relu(x, weight, scale, shift, stride=1, skip=None):
     _chk(x, torch.float32, 'x', 5), _chk(weight, torch.float32, 'weight', 5)
     n, Cin, D, H, W = x.shape

@@ -92,6 +92,21 @@ int dv3d_points_var(const float* feats_nhwc, int n_imgs, int C, int Hf, int Wf, 
                     const int* ref_img, const int* edge_rowptr, const int* edge_src, const float* depth, int n_ref,
                     int h, int w, int H, int W, int n_side, double offset, float* pts_out, float* feat_out,
                     int rows_per_point, int feat_stride, int feat_off, void* stream);
+/* Backward of the two warp + variance entry points above w.r.t. the source feature maps (the reference trains
+ * through F.grid_sample + two scatter means, mvsnet.py:209-216 / lightningmodel.py:165-169; its sampling grid is
+ * built under no_grad): grad_feats_nhwc [n_imgs,Hf,Wf,32] must be ZERO on entry and receives
+ * sum over (pixel, plane, edge) of g * (2/n_edges) (x_e - mean) * bilinear tap weight, accumulated with vector
+ * atomics (reproducible to fp32 rounding, like ATen's CUDA grid_sampler backward).  Everything but the gradient
+ * arguments is as in the forward call. */
+int dv3d_planesweep_var_backward(const float* feats_nhwc, int n_imgs, int C, int Hf, int Wf, const float* cams,
+                                 const int* ref_img, const int* edge_rowptr, const int* edge_src, int n_ref,
+                                 double depth_start, double depth_interval, int D, int h, int w, int H, int W,
+                                 const float* grad_x_var, float* grad_feats_nhwc, void* stream);
+int dv3d_points_var_backward(const float* feats_nhwc, int n_imgs, int C, int Hf, int Wf, const float* cams,
+                             const int* ref_img, const int* edge_rowptr, const int* edge_src, const float* depth,
+                             int n_ref, int h, int w, int H, int W, int n_side, double offset, const float* grad_feat,
+                             int rows_per_point, int feat_stride, int feat_off, float* grad_feats_nhwc, void* stream);
+
 
 /* ------------------------------------------------------------------------------------
  * CostRegNet layers, inference mode (mvsnet.py:18-36,133-163).  NCDHW fp32.

@@ -57,12 +57,15 @@ def test_ops_refuse_cpu_tensors():
         ops.nchw_to_nhwc(torch.zeros(1, 32, 4, 4))
 
 
-def test_modules_refuse_training_mode():
+def test_forward_only_modules_refuse_training_mode():
+    """the sparse scene model and the decoder have inference kernels only: training mode must raise, not fall back
+    (MVSNet is differentiable: tests/test_gpu_autograd.py)"""
     import torch
-    m = importlib.import_module('3dvnet_b200.mv3d.subnetworks.mvsnet')
-    net = m.CostRegNet(32, 8)
+    m = importlib.import_module('3dvnet_b200.mv3d.subnetworks.refinement')
+    dec = m.HypothesisDecoder(352, 128)
+    assert dec.training
     with pytest.raises(NotImplementedError, match='inference'):
-        net.conv0(torch.zeros(1, 32, 8, 8, 8))
+        dec(None, torch.zeros(4, 7, 3), torch.zeros(4, 7, 32), torch.zeros(4, dtype=torch.long))
 
 
 def test_edge_plan_matches_reference_grouping():
