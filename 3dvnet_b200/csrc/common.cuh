@@ -71,6 +71,20 @@ static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 b
 #define DV3D_LAUNCH(kernel, grid, block, smem, stream, ...) \
     (void)dv3d::launch_pdl(kernel, grid, block, smem, stream, __VA_ARGS__)
 
+// ---------------------------------------------------------------- small device -> host read-backs
+// The data-dependent sizes of the path (bounding box, voxel / level / tile counts) are a few bytes each.  A
+// cudaMemcpyAsync + cudaStreamSynchronize round trip costs 25-40 us of idle GPU per read on this path; read_back
+// instead enqueues one tiny kernel that copies the items into a pinned, mapped host "mailbox" and raises a
+// sequence flag, and the host spins on that flag (a PCIe write + a cache miss, ~5 us).  Up to 16 items of at
+// most 64 bytes per call, bytes multiples of 4; every calling host thread owns its mailbox.  DV3D_MAILBOX=0
+// selects the memcpy + synchronize path (A/B measurements).  Returns DV3D_OK / DV3D_ECUDA (error text set).
+struct ReadItem {
+    const void* src;  // device
+    void* dst;        // host
+    int bytes;
+};
+int read_back(const ReadItem* items, int n_items, cudaStream_t st);
+
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 

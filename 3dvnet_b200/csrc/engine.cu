@@ -319,11 +319,13 @@ static int model_scene(const dv3d_net_params_t& net, const float* pts, const flo
             TRY(dv3d_coarsen_enqueue_batch(sc.lv[0].coords, nv, strides + 1, nl - 1, gx, gy, gz, gb, cws + 1, cws_bytes + 1, nv,
                                            ccoords + 1, sst));
         }
-        for (int l = 1; l < nl; ++l) {
-            long long n_out = 0;
-            TRY(dv3d_coarsen_finish(cws[l], 1 << l, gx, gy, gz, gb, nv, &n_out, sst));
-            sc.lv[l].n = n_out;
-            sc.lv[l].stride = 1 << l;
+        if (nl > 1) {
+            long long n_out[DV3D_MAX_LEVELS] = {};
+            TRY(dv3d_coarsen_finish_batch(cws + 1, strides + 1, nl - 1, gx, gy, gz, gb, nv, n_out, sst));
+            for (int l = 1; l < nl; ++l) {
+                sc.lv[l].n = n_out[l - 1];
+                sc.lv[l].stride = 1 << l;
+            }
         }
         if (nl > 1) {
             const int* hc[DV3D_MAX_LEVELS];

@@ -270,9 +270,13 @@ extern "C" int dv3d_pair_plan_counts(const void* const* plans, int n_plans, long
     DV3D_REQUIRE(plans && n_plans >= 0 && n_plans <= 64 && n_tiles_host, "pair_plan_counts: bad arguments");
     int tmp[64][2];
     cudaStream_t st = (cudaStream_t)stream;
-    for (int i = 0; i < n_plans; ++i)
-        DV3D_CUDA(cudaMemcpyAsync(tmp[i], (const int*)plans[i] + PP_NTILES, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
-    DV3D_CUDA(cudaStreamSynchronize(st));
+    for (int i0 = 0; i0 < n_plans; i0 += 16) {   // one mailbox message per 16 plans
+        ReadItem items[16];
+        const int n = n_plans - i0 < 16 ? n_plans - i0 : 16;
+        for (int i = 0; i < n; ++i) items[i] = ReadItem{(const int*)plans[i0 + i] + PP_NTILES, tmp[i0 + i], 2 * (int)sizeof(int)};
+        int rc = read_back(items, n, st);
+        if (rc) return rc;
+    }
     for (int i = 0; i < n_plans; ++i) {
         n_tiles_host[i] = tmp[i][0];
         if (n_pairs_host) n_pairs_host[i] = tmp[i][1];

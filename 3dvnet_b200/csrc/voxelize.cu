@@ -455,8 +455,11 @@ extern "C" int dv3d_voxel_grid(const float* pts, const long long* batch, long lo
     DV3D_LAUNCH((bbox_decode_kernel), 1, 32, 0, st, h, out8);
     DV3D_LAUNCHED();
     float host8[8];
-    DV3D_CUDA(cudaMemcpyAsync(host8, out8, sizeof(host8), cudaMemcpyDeviceToHost, st));
-    DV3D_CUDA(cudaStreamSynchronize(st));
+    {
+        ReadItem it = {out8, host8, (int)sizeof(host8)};
+        int rc = read_back(&it, 1, st);
+        if (rc) return rc;
+    }
     dv3d_voxel_grid_t g;
     memset(&g, 0, sizeof(g));
     g.edge_len = edge_len;
@@ -524,8 +527,11 @@ extern "C" int dv3d_voxelize(const float* pts, const long long* batch, long long
     DV3D_LAUNCH((emit_anchors_kernel), cdiv(n_words, 256), 256, 0, st, s.bitmap, s.prefix, s.block_sums, n_words, G, (float)(grid->edge_len / 2.0), cap, anchor_pts, anchor_idx3d, anchor_batch, min_idx);
     DV3D_LAUNCHED();
     long long host[2] = {0, 0};
-    DV3D_CUDA(cudaMemcpyAsync(host, s.total, 16, cudaMemcpyDeviceToHost, st));
-    DV3D_CUDA(cudaStreamSynchronize(st));
+    {
+        ReadItem it = {s.total, host, 16};
+        int rc = read_back(&it, 1, st);
+        if (rc) return rc;
+    }
     *n_anchors_host = host[0];
     DV3D_REQUIRE((int)(host[1] & 0xffffffff) == 0, "voxelize: a point fell outside the bounding-box grid (NaN input?)");
     if (host[0] > cap) {
@@ -636,13 +642,44 @@ extern "C" int dv3d_coarsen_finish(const void* workspace, int new_stride, int di
     const long long n_words = ((long long)L.X * L.Y * L.Z * n_batch + 31) / 32;
     ScanSpace s = carve(const_cast<void*>(workspace), n_words);
     long long host[2] = {0, 0};
-    DV3D_CUDA(cudaMemcpyAsync(host, s.total, 16, cudaMemcpyDeviceToHost, st));
-    DV3D_CUDA(cudaStreamSynchronize(st));
+    {
+        ReadItem it = {s.total, host, 16};
+        int rc = read_back(&it, 1, st);
+        if (rc) return rc;
+    }
     *n_coarse_host = host[0];
     DV3D_REQUIRE((int)(host[1] & 0xffffffff) == 0, "coarsen: a coordinate lies outside the declared lattice");
     if (host[0] > cap) {
         set_error("coarsen: %lld coarse voxels exceed the output capacity %lld", host[0], cap);
         return DV3D_ENOSPC;
+    }
+    return DV3D_OK;
+}
+
+// the counts of several enqueued coarsening steps with ONE read-back
+extern "C" int dv3d_coarsen_finish_batch(const void* const* workspaces, const int* new_strides, int n_levels, int dim_x,
+                                         int dim_y, int dim_z, int n_batch, long long cap, long long* n_coarse_host,
+                                         void* stream) {
+    DV3D_REQUIRE(workspaces && new_strides && n_coarse_host && n_levels >= 1 && n_levels <= CB_MAX,
+                 "coarsen_finish_batch: bad arguments (1..%d levels)", CB_MAX);
+    long long host[CB_MAX][2] = {};
+    ReadItem items[CB_MAX];
+    for (int l = 0; l < n_levels; ++l) {
+        DV3D_REQUIRE(workspaces[l] && new_strides[l] > 0, "coarsen_finish_batch: bad level %d", l);
+        LevelDims L = {cdiv(dim_x, new_strides[l]), cdiv(dim_y, new_strides[l]), cdiv(dim_z, new_strides[l]), new_strides[l]};
+        const long long n_words = ((long long)L.X * L.Y * L.Z * n_batch + 31) / 32;
+        ScanSpace s = carve(const_cast<void*>(workspaces[l]), n_words);
+        items[l] = ReadItem{s.total, host[l], 16};
+    }
+    int rc = read_back(items, n_levels, (cudaStream_t)stream);
+    if (rc) return rc;
+    for (int l = 0; l < n_levels; ++l) {
+        n_coarse_host[l] = host[l][0];
+        DV3D_REQUIRE((int)(host[l][1] & 0xffffffff) == 0, "coarsen: a coordinate lies outside the declared lattice");
+        if (host[l][0] > cap) {
+            set_error("coarsen: %lld coarse voxels exceed the output capacity %lld", host[l][0], cap);
+            return DV3D_ENOSPC;
+        }
     }
     return DV3D_OK;
 }

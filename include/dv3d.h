@@ -225,6 +225,9 @@ int dv3d_coarsen_enqueue_batch(const int* coords, long long n, const int* new_st
                                long long cap, int* const* coarse_coords, void* stream);
 int dv3d_coarsen_finish(const void* workspace, int new_stride, int dim_x, int dim_y, int dim_z, int n_batch,
                         long long cap, long long* n_coarse_host, void* stream);
+/* the counts of several levels enqueued by dv3d_coarsen_enqueue_batch with ONE read-back (HOST arrays) */
+int dv3d_coarsen_finish_batch(const void* const* workspaces, const int* new_strides, int n_levels, int dim_x, int dim_y,
+                              int dim_z, int n_batch, long long cap, long long* n_coarse_host, void* stream);
 /* kernel map: nbr[o*27+k] = row of coords_out[o] + offset_k*step in the input level, or -1
  * (offset_k x fastest).  k3s1: same level, step = ts.  k3s2: out = coarse, in = fine table,
  * step = ts_fine.  transposed k3s2: out = fine, in = coarse table, step = -ts_fine
