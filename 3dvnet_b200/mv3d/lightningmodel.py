@@ -61,6 +61,7 @@ class PL3DVNet(nn.Module):
         self._nhwc = _FeatureCache()
         self._engine_pack = PackCache()
         self._engine_tensors = None
+        self._graphs = {}
 
     @property
     def device(self):
@@ -276,6 +277,56 @@ class PL3DVNet(nn.Module):
         d = self.refine_quarter.forward_from(feats_quarter[ref_idx], depth)
         d = self.refine_half.forward_from(feats_half[ref_idx], d)
         return self.refine_full.forward_from(images[ref_idx], d)
+
+    def _backbone(self, images):
+        """feats_half, feats_quarter of the 2D backbone + FPN (mvsnet.py:183-185), channels-last. The ~200 cuDNN /
+        elementwise launches of MnasNet are host-bound in eager mode (2.5 ms for 8 images), so they are captured once
+        per input shape into a CUDA graph and replayed (DV3D_BACKBONE_GRAPH=0: eager). The returned tensors are the
+        graph's static outputs: valid until the next call with the same shape."""
+        import os
+        m = self.mvsnet
+
+        def run(x):
+            fh, fq, _, _, _ = m.feat_shrinker(*m.feat_extractor(x))
+            return fh, fq
+        if os.environ.get('DV3D_BACKBONE_GRAPH', '1') == '0' or not images.is_cuda:
+            return run(images.contiguous(memory_format=torch.channels_last))
+        first = next(m.feat_extractor.parameters())
+        key = (tuple(images.shape), images.dtype, images.device, first.data_ptr(), first._version)
+        g = self._graphs.get(key)
+        if g is None:
+            if len(self._graphs) > 4:
+                self._graphs.clear()
+            static_in = torch.empty_like(images, memory_format=torch.channels_last)
+            static_in.copy_(images)
+            side = torch.cuda.Stream(device=images.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):      # warm-up outside capture: cuDNN algorithm selection, lazy init
+                for _ in range(2):
+                    run(static_in)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                outs = run(static_in)
+            g = self._graphs[key] = (graph, static_in, outs)
+        graph, static_in, outs = g
+        static_in.copy_(images)
+        graph.replay()
+        return outs
+
+    def full_pass(self, images, rotmats, tvecs, K, ref_src_edges, images_batch, offsets_list, depth_config=None):
+        """SURVEY.md section 8d's full pipeline of one batch, the loop body of process_scene
+        (eval-3dvnet.py:58-125): 2D backbone + FPN (torchvision / cuDNN, channels-last so that the NHWC feature maps
+        feed the warp kernels without a transposition pass) -> the hot path through the native engine (one C-ABI
+        call) -> nearest upsampling + the three PropagationNets. -> dict(ref [n_ref,h,w], final [n_ref,H,W])."""
+        require_eval(self)
+        with torch.no_grad():
+            cfg = self.hparams.depth_test if depth_config is None else depth_config
+            fh, fq = self._backbone(images)
+            plan = ops.edge_plan(ref_src_edges, images.device)
+            depth = self.hot_path(fq, rotmats, tvecs, K, plan, images_batch, cfg, offsets_list)
+            return {'ref': depth, 'final': self.upsample(depth, plan.ref_idx, fq, fh, images), 'feats_quarter': fq,
+                    'feats_half': fh}
 
     def forward(self, batch, offsets, n_iters):
         """Inference-only counterpart of lightningmodel.py:48-122: returns the depth maps of every

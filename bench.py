@@ -93,6 +93,35 @@ def cpu_step(b, params):
                                  DEPTH_CFG, EDGE_LEN, IMG_SIZE, params)
 
 
+def cpu_full_step(net_cpu, b, images, params):
+    """SURVEY.md section 8d's full pipeline on the CPU: the backbone / FPN modules themselves (torchvision, fp32)
+    -> the oracle's hot path -> the oracle's upsampling cascade (oracle/upsample.py)"""
+    from oracle import pipeline, upsample
+    with torch.no_grad():
+        fh, fq, _, _, _ = net_cpu.mvsnet.feat_shrinker(*net_cpu.mvsnet.feat_extractor(images))
+        depth = pipeline.hot_path(fq, b.rotmats, b.tvecs, b.K, b.ref_src_edges, b.images_batch, DEPTH_CFG, EDGE_LEN,
+                                  IMG_SIZE, params)
+        ref_idx = torch.unique(b.ref_src_edges[0])
+        sd = net_cpu.state_dict()
+        return depth, upsample.upsample_cascade(depth, fq[ref_idx], fh[ref_idx], images[ref_idx],
+                                                pipeline.sub(sd, 'refine_quarter.'), pipeline.sub(sd, 'refine_half.'),
+                                                pipeline.sub(sd, 'refine_full.')), fq
+
+
+def full_model(params, device):
+    """PL3DVNet with seeded random backbone / PropagationNet weights (no checkpoint exists offline) + the
+    synthetic hot-path weights; identical on every call"""
+    lm = importlib.import_module('3dvnet_b200.mv3d.lightningmodel')
+    torch.manual_seed(1234)
+    net = lm.PL3DVNet(DEPTH_CFG, DEPTH_CFG, EDGE_LEN, feat_dim=32, img_size=IMG_SIZE)
+    net.load_state_dict(params, strict=False)
+    return net.to(device).eval()
+
+
+def synth_images(seed, n_imgs):
+    return torch.randn(n_imgs, 3, *IMG_SIZE, generator=torch.Generator().manual_seed(9000 + seed))
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -106,6 +135,15 @@ def run_reference(args, rank):
         cpu_step(b, params)
     dt = time.perf_counter() - t0
     value = args.steps * args.refs_per_step / dt
+    # supplementary: SURVEY section 8d's FULL pipeline (backbone + FPN -> hot path -> 3 PropagationNets) on the CPU
+    net_cpu = full_model(params, 'cpu')
+    images = synth_images(0, args.refs_per_step + N_SRC)
+    cpu_full_step(net_cpu, b, images, params)
+    t0 = time.perf_counter()
+    n_full = max(1, min(args.steps, 3))
+    for _ in range(n_full):
+        cpu_full_step(net_cpu, b, images, params)
+    dt_full = (time.perf_counter() - t0) / n_full
     sample = '%d step(s) of the full workload (each %d ref view(s)), torch CPU threads=%d' % (
         args.steps, args.refs_per_step, cores)
     print(json.dumps({
@@ -120,6 +158,9 @@ def run_reference(args, rank):
                    'l2': 'n/a (CPU)', 'timing': 'host wall clock around the timed steps'},
         'cpu_baseline': {'value': value, 'unit': 'ref-views/s', 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': value, 'unit': 'ref-views/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'e2e_full': {'value': args.refs_per_step / dt_full, 'unit': 'ref-views/s', 'ms_per_step': 1e3 * dt_full,
+                     'pipeline': 'images -> MnasNet + FPN (torch CPU) -> oracle hot path -> oracle PropagationNet x3 -> '
+                                 'full-resolution depth (eval-3dvnet.py:58-125)', 'steps': n_full},
         'gpu_launches': 0}), flush=True)
 
 
@@ -171,11 +212,21 @@ def run_c4(args, rank, world, dev, dist, ops, lm):
         # that every rank voxelises the same points in the sharded scene model
         h, w = PLANE
         d_init = torch.empty((refs, h, w), dtype=torch.float32, device=dev)
-        abs_rel = None
+        abs_rel, ms_one = None, None
         if rank == 0:
             d_one, d0 = net.hot_path(fq, R, t, K, e, ib, DEPTH_CFG, OFFSETS_LIST, return_init=True)
             d_init.copy_(d0)
             abs_rel = float((torch.abs(full.view_as(d_one) - d_one) / (d_one + 1e-7)).mean().item())
+            # the same scene on ONE GPU (rank 0, the other ranks idle), same timing rules: the strong-scaling base
+            ev1 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+            torch.cuda.synchronize()
+            for a, z in ev1:
+                flush.zero_()
+                a.record()
+                net.hot_path(fq, R, t, K, e, ib, DEPTH_CFG, OFFSETS_LIST)
+                z.record()
+            torch.cuda.synchronize()
+            ms_one = sum(a.elapsed_time(z) for a, z in ev1) / steps
         dist.broadcast(d_init, 0)
         start, end = par.shard_range(refs, world, rank)
         xs_sh = par.model_scene_sharded(net, d_init[start:end].contiguous(), ib, fq, R, t, K, e, heap=heap)
@@ -193,7 +244,12 @@ def run_c4(args, rank, world, dev, dist, ops, lm):
     return {'workload': 'C4: 1 scene, %d refs + 7 halo keyframes, 256x320, D=96, 7 src, 4cm voxels, 2x(scene model + '
                         '3 PointFlow), reference views sharded over %d ranks' % (refs, world),
             'value': steps * refs / sec, 'unit': 'ref-views/s', 'scaling': 'strong', 'steps': steps, 'warmup': warm,
-            'ms_per_step': 1e3 * sec / steps, 'abs_rel_vs_single_gpu': abs_rel, 'voxel_idx_equal': idx_equal,
+            'ms_per_step': 1e3 * sec / steps,
+            'single_gpu': None if ms_one is None else {
+                'ms_per_step': ms_one, 'value': refs / (ms_one * 1e-3),
+                'note': 'the same 64-view scene through PL3DVNet.hot_path on rank 0 alone (engine, one native call)'},
+            'speedup_vs_single_gpu': None if ms_one is None else ms_one / (1e3 * sec / steps),
+            'abs_rel_vs_single_gpu': abs_rel, 'voxel_idx_equal': idx_equal,
             'sparse_feat_max_rel_err_vs_single_gpu': feat_err,
             'all_gather_bytes': 2 * refs * PLANE[0] * PLANE[1] * 35 * 4, 'all_gathers': 2, 'barriers': barriers,
             'gpu_launches_per_rank': launches // steps,
@@ -344,6 +400,41 @@ def main():
     ms_e2e = timed(step_e2e, args.steps)
     copy_stream.synchronize()
 
+    # Supplementary: SURVEY section 8d's FULL pipeline, end to end through the public API (PL3DVNet.full_pass):
+    # images + cameras uploaded from pinned host memory, backbone + FPN (cuDNN, channels-last, fp32 - TF32
+    # convolutions switched off), the hot path (engine), the three PropagationNets, full-resolution depth read back
+    full = None
+    if world == 1:
+        tf32_was = torch.backends.cudnn.allow_tf32
+        torch.backends.cudnn.allow_tf32 = False
+        net_full = full_model(params, dev)
+        img_host = synth_images(rank, n_ref + N_SRC).pin_memory()
+        img_dev = torch.empty_like(img_host, device=dev)
+        full_host = torch.empty((n_ref,) + IMG_SIZE, dtype=torch.float32).pin_memory()
+        small = {k: torch.empty_like(v, device=dev) for k, v in host.items() if k != 'feats_quarter'}
+
+        def step_full():
+            img_dev.copy_(img_host, non_blocking=True)
+            for k in small:
+                small[k].copy_(host[k], non_blocking=True)
+            out = net_full.full_pass(img_dev, small['rotmats'], small['tvecs'], small['K'], edges.clone(),
+                                     small['images_batch'], OFFSETS_LIST)
+            full_host.copy_(out['final'], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return out
+
+        for _ in range(3):
+            step_full()
+        ms_full = timed(step_full, args.steps)
+        torch.backends.cudnn.allow_tf32 = tf32_was
+        full = {'value': args.steps * n_ref / (ms_full * 1e-3), 'unit': 'ref-views/s', 'ms_per_step': ms_full / args.steps,
+                'h2d_bytes_per_step': int(img_host.numel() * 4 + sum(host[k].numel() * host[k].element_size() for k in small)
+                                          + edges.numel() * 4 + 64),
+                'd2h_bytes_per_step': int(full_host.numel() * 4),
+                'pipeline': 'images -> MnasNet + FPN (torchvision / cuDNN, channels-last, fp32) -> dv3d_hot_path -> '
+                            'PropagationNet x3 (tcgen05 gather-GEMM) -> full-resolution depth (eval-3dvnet.py:58-125)'}
+        del net_full
+
     # Supplementary: S independent steps in flight (one host thread + CUDA stream each). A single C2
     # step is ~240 short dependent kernels that leave most SMs idle; a server fills the GPU this way.
     ms_multi = None
@@ -427,6 +518,7 @@ def main():
                 'h2d_bytes_per_step': int(sum(v.numel() * v.element_size() for v in host.values())
                                           + edges.numel() * 4 + 64),
                 'd2h_bytes_per_step': int(out_host.numel() * 4), 'ms_per_step': ms_e2e / args.steps},
+        'e2e_full': full,
         'gpu_launches': launches,
         'roofline': {'kernel': 'decoder_fused_kernel (whole PointFlow decoder of %d points x 7 hypotheses in one tcgen05 '
                                'launch: 3 x Conv1d+BN+ReLU, head, softmax, depth update)' % (n_ref * PLANE[0] * PLANE[1]),
