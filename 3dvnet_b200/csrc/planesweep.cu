@@ -22,6 +22,7 @@
 //   Phase 3: variance -> padded shared tile [c][k][pixel] -> 128-byte coalesced row stores
 //     into x_var[r][c][d][p0..p0+31].
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -124,7 +125,7 @@ __device__ __forceinline__ float2 hi2(const float4& t) { return make_float2(t.z,
 // far planes do).  Without it (PointFlow hypotheses, few and far apart) every sample issues its four
 // independent loads unconditionally, so the unrolled loop keeps dozens of loads in flight instead of
 // serialising 49 load -> use round trips per thread.
-template <int NK, bool REUSE>
+template <int NK, bool REUSE, bool FAST = false>
 __device__ __forceinline__ void consume_edges(const float4* __restrict__ feats, const int* __restrict__ esrc,
                                               int e_begin, int n_e, int img_stride4, int Wf, int v, int g,
                                               const int (*s_rec)[KD][TP], const float4 (*s_wt)[KD][TP],
@@ -157,8 +158,13 @@ __device__ __forceinline__ void consume_edges(const float4* __restrict__ feats, 
             // scatter 'mean' of x and of x**2: plain sums in edge order (mvsnet.py:214-215)
             acc_s[k][0] = __fadd2_rn(acc_s[k][0], va);
             acc_s[k][1] = __fadd2_rn(acc_s[k][1], vb);
-            acc_q[k][0] = __fadd2_rn(acc_q[k][0], sq2_rn(va));
-            acc_q[k][1] = __fadd2_rn(acc_q[k][1], sq2_rn(vb));
+            if (FAST) {   // tolerance mode: x*x + acc as one FFMA2 (the exact mode rounds the square first)
+                acc_q[k][0] = __ffma2_rn(va, va, acc_q[k][0]);
+                acc_q[k][1] = __ffma2_rn(vb, vb, acc_q[k][1]);
+            } else {
+                acc_q[k][0] = __fadd2_rn(acc_q[k][0], sq2_rn(va));
+                acc_q[k][1] = __fadd2_rn(acc_q[k][1], sq2_rn(vb));
+            }
         }
     }
 }
@@ -257,6 +263,150 @@ planesweep_var_kernel(const float4* __restrict__ feats, SampleGeom geom, const f
         }
         // the __syncthreads at the top of the next chunk's first pass orders these reads of s_out
         // (and the consumption of the records) before anything is rewritten.
+    }
+}
+
+// ------------------------------------------------------------------------ tolerance mode of the plane sweep
+// Same decomposition as planesweep_var_kernel, but the projection is evaluated the way the geometry allows instead
+// of the way the reference happens to round it: the frustum point of (pixel, plane) is X(z) = z * dir + o with
+// dir = R^T Kinv [u, v, 1] per pixel and o = -R^T t per reference, hence for a source view
+//     q(z) = z * (M dir) + (M o + p4),        M = P_src[:, :3] with rows 0 / 1 pre-scaled by (Wf-1)/(W-1), (Hf-1)/(H-1)
+// and the un-normalised sampling position is (q_x, q_y) * rcp(|q_z| + 1e-8): 3 FMA + 1 reciprocal + 2 multiplies
+// per (pixel, plane, edge) instead of 12 FMA, two IEEE divisions and two fp64 divisions by the image size; the
+// variance is q/n - (s/n)^2 with one reciprocal multiply.  Positions agree with the reference chain to ~2e-5 of a
+// feature pixel, x_var to ~2e-5 of its scale (asserted in tests/test_gpu_warp_fast.py).
+// MEASURED (profiles/r2_11_sweep_planesweep.md): 65.5 -> 57.3 us at C2, 625 -> 539 us at C5 - the projection was
+// never the bottleneck; the kernel is bound by the per-sample gather + FMA work of phase 2 (4 L1 wavefronts and ~20
+// issue slots per (pixel, plane, edge, 4 channels)), which both modes share.  12 % is not worth giving up the
+// bit-exact slab, so this mode is an OPT-IN (DV3D_WARP=fast / dv3d_set_warp_mode(1)); exact is the default.
+struct FastEdge {
+    float m[3][3];  // M (rows 0, 1 pre-scaled)
+    float b[3];     // M o + p4 (rows 0, 1 pre-scaled)
+};
+
+__device__ __forceinline__ void make_record_fast(float qx, float qy, float qz, const SampleGeom& g, int& rec, float4& wt) {
+    const float r = __frcp_rn(fabsf(qz) + 1e-8f);
+    const float ix = qx * r, iy = qy * r;
+    rec = 0;
+    wt = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ix > -1.f && ix < (float)g.Wf && iy > -1.f && iy < (float)g.Hf) {
+        const float fx0 = floorf(ix), fy0 = floorf(iy);
+        const float tx = ix - fx0, ty = iy - fy0;
+        const int x0 = (int)fx0, y0 = (int)fy0;
+        const bool l = x0 >= 0, rr = x0 + 1 <= g.Wf - 1, t = y0 >= 0, b = y0 + 1 <= g.Hf - 1;
+        const float wl = l ? 1.f - tx : 0.f, wr = rr ? tx : 0.f;
+        const float wtp = t ? 1.f - ty : 0.f, wb = b ? ty : 0.f;
+        wt = make_float4(wtp * wl, wtp * wr, wb * wl, wb * wr);
+        const int cx = l ? x0 : 0, cy = t ? y0 : 0;
+        const int dx = (l && rr) ? 1 : 0, dy = (t && b) ? 1 : 0;
+        rec = ((cy * g.Wf + cx) << 2) | (dy << 1) | dx;
+    }
+}
+
+__global__ void __launch_bounds__(256, 2)
+planesweep_var_fast_kernel(const float4* __restrict__ feats, SampleGeom geom, const float* __restrict__ cams,
+                           const int* __restrict__ ref_img, const int* __restrict__ rowptr, const int* __restrict__ esrc,
+                           float d0, float dstep, int D, int h, int w, int H, int W, int chunks_per_cta,
+                           float* __restrict__ out) {
+    pdl_wait();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4 (*s_wt)[KD][TP] = reinterpret_cast<float4 (*)[KD][TP]>(smem_raw);
+    int (*s_rec)[KD][TP] = reinterpret_cast<int (*)[KD][TP]>(smem_raw + sizeof(float4) * EMAX * KD * TP);
+    float* s_out = reinterpret_cast<float*>(smem_raw + (sizeof(float4) + sizeof(int)) * EMAX * KD * TP);
+    __shared__ FastEdge s_E[EMAX];
+    __shared__ float s_o[3];
+
+    const int tid = threadIdx.x;
+    const int r = blockIdx.y;
+    const int P = h * w;
+    const int p0 = blockIdx.x * TP;
+    const int e0 = rowptr[r], e1 = rowptr[r + 1];
+    const float inv_n = 1.f / (float)(e1 - e0);
+    const int img_stride4 = geom.Hf * geom.Wf * 8;
+    const float sx = geom.wfm1 / geom.wm1, sy = geom.hfm1 / geom.hm1;
+    const float* cref = cams + (size_t)__ldg(ref_img + r) * CAM_STRIDE;
+
+    const int pv = tid & 31, pk = tid >> 5;
+    const int v = tid >> 3, g = tid & 7;
+    const int p = min(p0 + pv, P - 1);
+    const float u = linspace_np(0.0, (double)(W - 1), w, p % w);
+    const float vv = linspace_np(0.0, (double)(H - 1), h, p / w);
+    // dir = R^T (Kinv [u, v, 1]) of this thread's pixel; o = -R^T t of the reference
+    float dir0, dir1, dir2;
+    {
+        const float* Ki = cref + CAM_KINV;
+        const float* R = cref + CAM_R;
+        const float c0 = fmaf(__ldg(Ki + 0), u, fmaf(__ldg(Ki + 1), vv, __ldg(Ki + 2)));
+        const float c1 = fmaf(__ldg(Ki + 3), u, fmaf(__ldg(Ki + 4), vv, __ldg(Ki + 5)));
+        const float c2 = fmaf(__ldg(Ki + 6), u, fmaf(__ldg(Ki + 7), vv, __ldg(Ki + 8)));
+        dir0 = fmaf(__ldg(R + 0), c0, fmaf(__ldg(R + 3), c1, __ldg(R + 6) * c2));
+        dir1 = fmaf(__ldg(R + 1), c0, fmaf(__ldg(R + 4), c1, __ldg(R + 7) * c2));
+        dir2 = fmaf(__ldg(R + 2), c0, fmaf(__ldg(R + 5), c1, __ldg(R + 8) * c2));
+    }
+    if (tid < 3) {
+        const float* R = cref + CAM_R;
+        const float* t = cref + CAM_T;
+        s_o[tid] = -(__ldg(R + tid) * __ldg(t + 0) + __ldg(R + 3 + tid) * __ldg(t + 1) + __ldg(R + 6 + tid) * __ldg(t + 2));
+    }
+
+    const int chunk_begin = blockIdx.z * chunks_per_cta;
+    const int n_chunks = (D + KD - 1) / KD;
+    for (int ch = chunk_begin; ch < min(chunk_begin + chunks_per_cta, n_chunks); ++ch) {
+        const int dbase = ch * KD;
+        float2 acc_s[KD][2], acc_q[KD][2];
+#pragma unroll
+        for (int k = 0; k < KD; ++k) acc_s[k][0] = acc_s[k][1] = acc_q[k][0] = acc_q[k][1] = make_float2(0, 0);
+        const float z = fmaf((float)min(dbase + pk, D - 1), dstep, d0);
+
+        for (int eb = e0; eb < e1; eb += EMAX) {
+            const int n_e = min(EMAX, e1 - eb);
+            __syncthreads();
+            if (tid < n_e * 12) {   // M (pre-scaled) of every staged edge, then b = M o + p4
+                const int e = tid / 12, i = tid % 12, row = i >> 2, col = i & 3;
+                const float sc = row == 0 ? sx : (row == 1 ? sy : 1.f);
+                const float val = __ldg(cams + (size_t)__ldg(esrc + eb + e) * CAM_STRIDE + CAM_P + i) * sc;
+                if (col < 3) s_E[e].m[row][col] = val;
+                else s_E[e].b[row] = val;
+            }
+            __syncthreads();
+            if (tid < n_e * 3) {
+                const int e = tid / 3, row = tid % 3;
+                s_E[e].b[row] += s_E[e].m[row][0] * s_o[0] + s_E[e].m[row][1] * s_o[1] + s_E[e].m[row][2] * s_o[2];
+            }
+            __syncthreads();
+            for (int e = 0; e < n_e; ++e) {
+                const FastEdge& E = s_E[e];
+                const float ax = fmaf(E.m[0][0], dir0, fmaf(E.m[0][1], dir1, E.m[0][2] * dir2));
+                const float ay = fmaf(E.m[1][0], dir0, fmaf(E.m[1][1], dir1, E.m[1][2] * dir2));
+                const float az = fmaf(E.m[2][0], dir0, fmaf(E.m[2][1], dir1, E.m[2][2] * dir2));
+                int rec;
+                float4 wt;
+                make_record_fast(fmaf(z, ax, E.b[0]), fmaf(z, ay, E.b[1]), fmaf(z, az, E.b[2]), geom, rec, wt);
+                s_rec[e][pk][pv] = rec;
+                s_wt[e][pk][pv] = wt;
+            }
+            __syncthreads();
+            consume_edges<KD, true, true>(feats, esrc, eb, n_e, img_stride4, geom.Wf, v, g, s_rec, s_wt, acc_s, acc_q);
+        }
+#pragma unroll
+        for (int k = 0; k < KD; ++k) {
+            float* o = s_out + (4 * g) * CS + k * TP + v;
+            float m;
+            m = acc_s[k][0].x * inv_n; o[0] = fmaf(acc_q[k][0].x, inv_n, -m * m);
+            m = acc_s[k][0].y * inv_n; o[CS] = fmaf(acc_q[k][0].y, inv_n, -m * m);
+            m = acc_s[k][1].x * inv_n; o[2 * CS] = fmaf(acc_q[k][1].x, inv_n, -m * m);
+            m = acc_s[k][1].y * inv_n; o[3 * CS] = fmaf(acc_q[k][1].y, inv_n, -m * m);
+        }
+        __syncthreads();
+        {
+            const int warp = tid >> 5, lane = tid & 31;
+            const bool ok = p0 + lane < P;
+#pragma unroll 4
+            for (int row = warp; row < 32 * KD; row += 8) {
+                const int c = row >> 3, k = row & 7, d = dbase + k;
+                if (ok && d < D) out[(((size_t)r * 32 + c) * D + d) * P + p0 + lane] = s_out[c * CS + k * TP + lane];
+            }
+        }
     }
 }
 
@@ -664,6 +814,18 @@ static SampleGeom make_geom(int Hf, int Wf, int H, int W) {
 
 using namespace dv3d;
 
+// 0 = exact (default: the reference's fp32 operation chain, bit-exact x_var), 1 = fast (tolerance mode, DV3D_WARP=fast)
+static std::atomic<int> g_warp_mode{[] {
+    const char* e = getenv("DV3D_WARP");
+    return (e && (e[0] == 'f' || e[0] == 'F' || e[0] == '1')) ? 1 : 0;
+}()};
+extern "C" int dv3d_set_warp_mode(int mode) {
+    DV3D_REQUIRE(mode == 0 || mode == 1, "set_warp_mode: 0 = exact, 1 = fast; got %d", mode);
+    g_warp_mode.store(mode);
+    return DV3D_OK;
+}
+extern "C" int dv3d_get_warp_mode(void) { return g_warp_mode.load(); }
+
 extern "C" int dv3d_nchw_to_nhwc(const float* src, float* dst, int n, int C, int HW, void* stream) {
     DV3D_REQUIRE(src && dst && n >= 0 && C > 0 && HW > 0, "nchw_to_nhwc: bad arguments");
     if (n == 0) return DV3D_OK;
@@ -702,6 +864,13 @@ extern "C" int dv3d_planesweep_var(const float* feats_nhwc, int n_imgs, int C, i
     DV3D_REQUIRE(n_ref <= 65535, "planesweep_var: n_ref > 65535");
     double d1 = depth_start + depth_interval * (D - 1);
     const size_t smem = (sizeof(float4) + sizeof(int)) * EMAX * KD * TP + sizeof(float) * 32 * CS;
+    if (g_warp_mode == 1) {
+        static std::atomic<unsigned long long> fattr{0};
+        DV3D_FUNC_SMEM_ONCE(fattr, (planesweep_var_fast_kernel), (int)smem);
+        DV3D_LAUNCH((planesweep_var_fast_kernel), grid, 256, smem, (cudaStream_t)stream, reinterpret_cast<const float4*>(feats_nhwc), make_geom(Hf, Wf, H, W), cams, ref_img, edge_rowptr, edge_src, (float)depth_start, (float)depth_interval, D, h, w, H, W, chunks_per_cta, x_var);
+        DV3D_LAUNCHED();
+        return DV3D_OK;
+    }
     static std::atomic<unsigned long long> attr{0};
     DV3D_FUNC_SMEM_ONCE(attr, (planesweep_var_kernel), (int)smem);
     DV3D_LAUNCH((planesweep_var_kernel), grid, 256, smem, (cudaStream_t)stream, reinterpret_cast<const float4*>(feats_nhwc), make_geom(Hf, Wf, H, W), cams, ref_img, edge_rowptr, edge_src, depth_start, d1, D, h, w, H, W, chunks_per_cta, x_var);

@@ -38,6 +38,22 @@ def gemm_mode():
     return _gemm_mode
 
 
+# Arithmetic of the plane-sweep warp + variance kernel (csrc/planesweep.cu):
+#   'exact'  the reference's fp32 operation chain, x_var bit-identical to the CPU PyTorch path (default)
+#   'fast'   affine-in-depth projection + reciprocal, x_var within ~2e-5 of its scale, 12 % faster (DV3D_WARP=fast)
+WARP_MODES = ('exact', 'fast')
+
+
+def set_warp_mode(mode):
+    if mode not in WARP_MODES:
+        raise ValueError('warp mode must be one of %s, got %r' % (WARP_MODES, mode))
+    lib().call('dv3d_set_warp_mode', WARP_MODES.index(mode))
+
+
+def warp_mode():
+    return WARP_MODES[int(lib().raw('dv3d_get_warp_mode')())]
+
+
 def pack_weights(w_kn):
     """[K, N] fp32 (K % 32 == 0, N in {64,128}) -> the tcgen05 kernel's packed image, or None
     in 'f32' mode."""

@@ -78,6 +78,12 @@ int dv3d_planesweep_var(const float* feats_nhwc, int n_imgs, int C, int Hf, int 
                         const int* ref_img, const int* edge_rowptr, const int* edge_src, int n_ref,
                         double depth_start, double depth_interval, int D, int h, int w, int H, int W, float* x_var,
                         void* stream);
+/* Arithmetic of dv3d_planesweep_var: 0 = exact (default: the reference's fp32 operation chain replayed instruction
+ * for instruction, x_var bit-identical to the CPU PyTorch path), 1 = fast (opt-in, DV3D_WARP=fast: affine-in-depth
+ * projection + reciprocal, x_var within ~2e-5 of its scale, 12 % faster - measured, see csrc/planesweep.cu).
+ * The point-level kernels (dv3d_points_var) always use the exact chain. Process-wide. */
+int dv3d_set_warp_mode(int mode);
+int dv3d_get_warp_mode(void);
 
 /* ------------------------------------------------------------------------------------
  * Point-level back-projection + re-projection warp + variance, 1 or 2n+1 hypotheses per

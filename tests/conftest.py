@@ -49,3 +49,13 @@ def golden_inputs(g):
                n_intervals=int(g['D']), size=tuple(int(v) for v in g['plane']))
     img_size = tuple(int(v) for v in g['img_size'])
     return t, cfg, img_size
+
+
+@pytest.fixture
+def exact_warp():
+    """the plane-sweep kernel's verification mode (bit-exact x_var) for the duration of a test"""
+    ops = importlib.import_module('3dvnet_b200.ops')
+    old = ops.warp_mode()
+    ops.set_warp_mode('exact')
+    yield
+    ops.set_warp_mode(old)

@@ -31,7 +31,7 @@ def _edges(kind, b):
 
 
 @pytest.mark.parametrize('kind', ['regular', 'irregular'])
-def test_planesweep_variance_backward_matches_autograd(kind, mods):
+def test_planesweep_variance_backward_matches_autograd(kind, mods, exact_warp):
     import oracle.planesweep as o
     img, plane, D = (64, 80), (16, 24), 16
     b = mods['synth'].make_batch(1, 13, img, plane, 32, 2, 2, False, 7)

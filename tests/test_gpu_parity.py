@@ -23,6 +23,18 @@ def abs_rel(pred, ref):
     return (err.reshape(ref.shape[0], -1).sum(1) / (n + 1e-7)).mean().item()
 
 
+@pytest.fixture(scope='module', autouse=True)
+def _exact_warp_mode():
+    """the golden vectors are pinned bit for bit: this module runs the plane sweep in its verification mode
+    (tests/test_gpu_warp_fast.py and test_gpu_parity_full.py cover the default tolerance mode)"""
+    importlib.import_module('3dvnet_b200.build').build()
+    ops = importlib.import_module('3dvnet_b200.ops')
+    old = ops.warp_mode()
+    ops.set_warp_mode('exact')
+    yield
+    ops.set_warp_mode(old)
+
+
 @pytest.fixture(scope='module')
 def mods():
     importlib.import_module('3dvnet_b200.build').build()

@@ -8,7 +8,8 @@ Pass criteria (north_star: depth within 1e-3 abs-rel, voxel indices bit-exact):
 
 * TEACHER-FORCED (every stage started from the oracle's input of that stage - the map stage -> stage is continuous
   except at the voxelisation, so these bounds are tight and hold for EVERY seed):
-    x_var bit-exact | initial depth <= 2e-5 abs-rel, <= 2e-4 m max | voxel tables bit-exact |
+    x_var bit-exact (default mode) and within 3e-5 (mean, of its scale) in the kernel's opt-in fast mode |
+    initial depth <= 2e-5 abs-rel, <= 2e-4 m max | voxel tables bit-exact |
     sparse features <= 5e-4 of the level's max | PointFlow offsets <= 5e-5 m max per pass.
 * FREE-RUNNING (2 x (scene model + 3 PointFlow passes) on its own depth): the schedule is NOT a continuous map - a
   1e-6 depth difference can move a point across a voxel face, which changes that voxel's PointNet input by up to
@@ -37,6 +38,7 @@ OFFSETS = [[0.05, 0.05, 0.025], [0.05, 0.05, 0.025]]  # eval-3dvnet.py:23
 # only these may exceed 1e-3 free-running, and only up to that self-sensitivity
 CHAOTIC_SEEDS = (1, 2, 5, 6)
 
+TF_XVAR_MEAN, TF_XVAR_MAX = 3e-5, 1e-3   # fast-mode x_var: mean error / mean |x_var|, max error / max |x_var|
 TF_DEPTH0_ABSREL, TF_DEPTH0_MAX = 2e-5, 2e-4
 TF_FEAT_REL = 5e-4
 TF_OFFSET_MAX = 5e-5
@@ -94,7 +96,7 @@ def abs_rel(got, ref):
     return (torch.abs(got - ref) / (ref + 1e-7)).mean().item()
 
 
-def check_teacher_forced(net, b, tr, cfg, check_xvar=True):
+def check_teacher_forced(net, b, tr, cfg):
     """every stage of the CUDA path on the ORACLE's input of that stage"""
     g = NS()
     g.feats_quarter, g.rotmats, g.tvecs, g.K = (b.feats_quarter.to(DEV), b.rotmats.to(DEV), b.tvecs.to(DEV),
@@ -102,10 +104,23 @@ def check_teacher_forced(net, b, tr, cfg, check_xvar=True):
     g.ref_src_edges = b.ref_src_edges
     gargs = (g.feats_quarter, g.rotmats, g.tvecs, g.K, g.ref_src_edges)
     db = tr.db.to(DEV)
+    ops = importlib.import_module('3dvnet_b200.ops')
     with torch.no_grad():
-        x_var = net.mvsnet.cost_volume(g.feats_quarter, g, cfg['depth_start'], cfg['depth_interval'],
-                                       cfg['n_intervals'], cfg['size'])
-        if check_xvar:
+        cv = lambda: net.mvsnet.cost_volume(g.feats_quarter, g, cfg['depth_start'], cfg['depth_interval'],
+                                            cfg['n_intervals'], cfg['size'])
+        mode = ops.warp_mode()
+        ops.set_warp_mode('fast')       # the opt-in tolerance mode of the warp kernel (DV3D_WARP=fast)
+        try:
+            x_fast = cv()
+        finally:
+            ops.set_warp_mode(mode)
+        err = (x_fast.cpu() - tr.x_var).abs()
+        scale = tr.x_var.abs().mean().item()
+        assert err.mean().item() <= TF_XVAR_MEAN * scale and err.max().item() <= TF_XVAR_MAX * tr.x_var.abs().max().item(), \
+            (err.mean().item() / scale, err.max().item() / tr.x_var.abs().max().item())
+        del x_fast
+        x_var = cv()                    # default mode: the reference's operation chain, bit for bit
+        if mode == 'exact':
             assert torch.equal(x_var.cpu().view(torch.int32), tr.x_var.view(torch.int32)), 'x_var is not bit-exact'
         d_end = cfg['depth_start'] + cfg['depth_interval'] * (cfg['n_intervals'] - 1)
         d0, _ = net.mvsnet.cnn_3d.depth(x_var, cfg['depth_start'], d_end)
@@ -218,7 +233,7 @@ def test_c3_scene_of_8_reference_views(mods):
     assert abs_rel(got, tr.final) <= max(FREE_ABSREL, abs_rel(refp, tr.final))
 
 
-def test_c5_variance_slab_crop_is_bit_exact(mods):
+def test_c5_variance_slab_crop_is_bit_exact(mods, exact_warp):
     """BASELINE configs[4] (512x640, D=192, 10 src): depth planes 88..95 and 184..191 of the CUDA slab against the
     oracle evaluated on exactly those planes of the full 192-plane linspace"""
     import oracle.planesweep as ops_a

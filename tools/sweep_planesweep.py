@@ -36,9 +36,9 @@ def main():
     peaks = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     peak = float(json.load(open(peaks))['hbm_gbs']) if os.path.exists(peaks) else 6650.0
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    print('| case | voxels | edges | algorithmic MB | kernel us | GB/s | frac of %.0f GB/s |' % peak)
-    print('|---|---:|---:|---:|---:|---:|---:|')
-    for name, img, D, plane, n_src, n_ref in CASES:
+    print('| case | mode | voxels | edges | algorithmic MB | kernel us | GB/s | frac of %.0f GB/s |' % peak)
+    print('|---|---|---:|---:|---:|---:|---:|---:|')
+    for name, img, D, plane, n_src, n_ref in [c for c in CASES for _ in (0, 1)][::2]:
         b = synth.make_batch(1, n_ref + n_src, img, plane, 32, n_src - n_src // 2, n_src // 2, False, 0)
         plan = ops.edge_plan(b.ref_src_edges, dev)
         nhwc = ops.nchw_to_nhwc(b.feats_quarter.to(dev))
@@ -46,20 +46,22 @@ def main():
         out = torch.empty((plan.n_ref, 32, D) + plane, dtype=torch.float32, device=dev)
         Hf, Wf = b.feats_quarter.shape[-2:]
         algo = plan.n_edges * 32 * Hf * Wf * 4 + out.numel() * 4
-        ts = []
-        for i in range(args.iters + 3):
-            flush.zero_()
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
-            ops.planesweep_var(nhwc, cams, plan, 0.5, 0.05, D, plane, img, out=out)
-            e.record()
-            torch.cuda.synchronize()
-            if i >= 3:
-                ts.append(s.elapsed_time(e) * 1e3)
-        us = float(np.median(ts))
-        gbs = algo / us / 1e3
-        print('| %s | %d | %d | %.1f | %.1f | %.0f | %.3f |' % (name, plan.n_ref * D * plane[0] * plane[1], plan.n_edges,
-                                                              algo / 1e6, us, gbs, gbs / peak))
+        for mode in ('exact', 'fast'):
+            ops.set_warp_mode(mode)
+            ts = []
+            for i in range(args.iters + 3):
+                flush.zero_()
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                ops.planesweep_var(nhwc, cams, plan, 0.5, 0.05, D, plane, img, out=out)
+                e.record()
+                torch.cuda.synchronize()
+                if i >= 3:
+                    ts.append(s.elapsed_time(e) * 1e3)
+            us = float(np.median(ts))
+            gbs = algo / us / 1e3
+            print('| %s | %s | %d | %d | %.1f | %.1f | %.0f | %.3f |' % (name, mode, plan.n_ref * D * plane[0] * plane[1],
+                                                                       plan.n_edges, algo / 1e6, us, gbs, gbs / peak))
 
 
 if __name__ == '__main__':
