@@ -412,7 +412,10 @@ planesweep_var_fast_kernel(const float4* __restrict__ feats, SampleGeom geom, co
 
 // Point-level variant: the "planes" of a pixel are its 2n+1 depth hypotheses around the
 // current depth estimate (lightningmodel.py:201-205); outputs are point-major.
-__global__ void __launch_bounds__(256, 1)  // 98 CTAs at C2: registers are better spent on loads in flight
+// MINB = 1: up to 255 registers, dozens of tap loads in flight per thread - best while the grid does not fill the
+// GPU (98 CTAs at C2); MINB = 2: two CTAs per SM once there are more CTAs than SMs (8+ reference views per call)
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB)
 points_var_kernel(const float4* __restrict__ feats, SampleGeom geom, const float* __restrict__ cams,
                   const int* __restrict__ ref_img, const int* __restrict__ rowptr, const int* __restrict__ esrc,
                   const float* __restrict__ depth, int h, int w, int H, int W, int n_side, double offset,
@@ -894,7 +897,10 @@ extern "C" int dv3d_points_var(const float* feats_nhwc, int n_imgs, int C, int H
     DV3D_REQUIRE(n_imgs > 0 && Hf > 1 && Wf > 1 && h > 0 && w > 0 && n_ref >= 0 && n_ref <= 65535, "points_var: bad shape");
     if (n_ref == 0) return DV3D_OK;
     dim3 grid(cdiv(h * w, TP), n_ref);
-    DV3D_LAUNCH((points_var_kernel), grid, 256, 0, (cudaStream_t)stream, reinterpret_cast<const float4*>(feats_nhwc), make_geom(Hf, Wf, H, W), cams, ref_img, edge_rowptr, edge_src, depth, h, w, H, W, n_side, offset, pts_out, feat_out, rows_per_point, feat_stride, feat_off);
+    if ((long long)grid.x * grid.y > kNumSMs)
+        DV3D_LAUNCH((points_var_kernel<2>), grid, 256, 0, (cudaStream_t)stream, reinterpret_cast<const float4*>(feats_nhwc), make_geom(Hf, Wf, H, W), cams, ref_img, edge_rowptr, edge_src, depth, h, w, H, W, n_side, offset, pts_out, feat_out, rows_per_point, feat_stride, feat_off);
+    else
+        DV3D_LAUNCH((points_var_kernel<1>), grid, 256, 0, (cudaStream_t)stream, reinterpret_cast<const float4*>(feats_nhwc), make_geom(Hf, Wf, H, W), cams, ref_img, edge_rowptr, edge_src, depth, h, w, H, W, n_side, offset, pts_out, feat_out, rows_per_point, feat_stride, feat_off);
     DV3D_LAUNCHED();
     return DV3D_OK;
 }

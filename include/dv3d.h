@@ -334,6 +334,9 @@ int dv3d_decoder_head(const float* x, long long n_pts, int n_hyp, int rows_per_p
  *   prob_out [n_pts,7], offset_out [n_pts] optional; depth_accum [n_pts] optional: depth += offset
  *   (eval-3dvnet.py:99) in the same kernel. */
 size_t dv3d_decoder_pack_bytes(int Cin);
+/* profiling aid: device buffer of n_tiles * 8 int64 clock stamps written by every dv3d_decoder_fused launch
+ * (NULL switches it off; tools/decoder_phases.py) */
+int dv3d_decoder_set_timing_buffer(void* device_buffer);
 int dv3d_decoder_pack_weights(const float* weight_tkn, int Cin, int Cout, void* packed, void* stream);
 int dv3d_decoder_fused(const float* x, long long n_pts, int rows_per_point, int Cin, int ldx,
                        const void* const* W_packed, const float* const* scale, const float* const* shift,
