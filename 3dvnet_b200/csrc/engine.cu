@@ -259,26 +259,28 @@ static int model_scene(const dv3d_net_params_t& net, const float* pts, const flo
     float* x0 = ar.get<float>((size_t)N * in_pad);
     float* xa = ar.get<float>((size_t)N * Hd);
     float* xb = ar.get<float>((size_t)N * Hd);
-    float* pool = ar.get<float>((size_t)nv * Hd);
+    // the four per-voxel max pools are produced by the epilogues of fc1..fc4 (dv3d_linear_pool): one 0xFF fill for all
+    float* pools = ar.get<float>((size_t)4 * nv * Hd);
     float* F = ar.get<float>((size_t)nv * net.pointnet[5].N);
     ARENA_CHECK(ar);
+    DV3D_CUDA(cudaMemsetAsync(pools, 0xFF, sizeof(float) * 4 * (size_t)nv * Hd, cs));
     TRY(dv3d_pointnet_input(pts, pts_feat, 32, a_pts, seg, N, 32, in_pad, x0, st));
     TRY(dv3d_linear(x0, in_pad, in_pad, nullptr, nullptr, 0, N, net.pointnet[0].W, net.pointnet[0].Wp, net.pointnet[0].b, Hd,
                     0, xa, st));
-    TRY(dv3d_linear(xa, Hd, Hd, nullptr, nullptr, 0, N, net.pointnet[1].W, net.pointnet[1].Wp, net.pointnet[1].b, Hd, 1, xb,
-                    st));
+    TRY(dv3d_linear_pool(xa, Hd, Hd, nullptr, nullptr, 0, N, net.pointnet[1].W, net.pointnet[1].Wp, net.pointnet[1].b, Hd, 1,
+                         xb, pools, seg, st));
     float *cur = xb, *nxt = xa;
     for (int i = 2; i <= 4; ++i) {
-        TRY(dv3d_segment_max(cur, seg, N, Hd, nv, pool, st));
-        TRY(dv3d_linear(cur, Hd, Hd, pool, seg, Hd, N, net.pointnet[i].W, net.pointnet[i].Wp, net.pointnet[i].b, Hd, 1, nxt,
-                        st));
+        float* pool_in = pools + (size_t)(i - 2) * nv * Hd;
+        float* pool_out = pools + (size_t)(i - 1) * nv * Hd;
+        TRY(dv3d_linear_pool(cur, Hd, Hd, pool_in, seg, Hd, N, net.pointnet[i].W, net.pointnet[i].Wp, net.pointnet[i].b, Hd, 1,
+                             nxt, pool_out, seg, st));
         float* t = cur;
         cur = nxt;
         nxt = t;
     }
-    TRY(dv3d_segment_max(cur, seg, N, Hd, nv, pool, st));
-    TRY(dv3d_linear(pool, Hd, Hd, nullptr, nullptr, 0, nv, net.pointnet[5].W, net.pointnet[5].Wp, net.pointnet[5].b,
-                    net.pointnet[5].N, 1, F, st));
+    TRY(dv3d_linear(pools + (size_t)3 * nv * Hd, Hd, Hd, nullptr, nullptr, 0, nv, net.pointnet[5].W, net.pointnet[5].Wp,
+                    net.pointnet[5].b, net.pointnet[5].N, 1, F, st));
 
     // ---- coordinate levels, hash tables, kernel maps (what ME keeps in its coordinate manager)
     next_stage(DV3D_STAGE_LEVELS, side->stream);
@@ -494,7 +496,7 @@ extern "C" size_t dv3d_hot_path_workspace_bytes(const dv3d_net_params_t* net, in
     size_t per_outer = 0;
     per_outer += Np * (3 + 32 + 2);                               // pts, feat, pts_batch (int64)
     per_outer += Np * (3 + 3 + 2 + 1);                            // anchors
-    per_outer += Np * (net->pointnet_in_pad + 3 * 128 + 64);      // PointNet
+    per_outer += Np * (net->pointnet_in_pad + 6 * 128 + 64);      // PointNet (x0, xa, xb, 4 pools, F)
     // levels: coords 4, table <= 12 * 4 n + 768, kernel maps 27 x (3 same + 2 down + 2 up) per voxel
     per_outer += Np * 3 * (4 + 12) + Np * 27 * 7 + 3 * 1024;
     // pair-major plans (7 maps: pair_in <= 27 n + 27*128, pair_slot 27 n, tile ids) and the P buffer of

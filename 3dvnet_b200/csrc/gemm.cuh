@@ -61,7 +61,20 @@ struct GemmDesc {
     // the registered symmetric regions (symm_attach); callers leave it zero.
     float* peer_out[kMaxPeers];
     int n_peers;
+    // Optional fused segment max (PointNet, scenemodeling.py:129): every finished row m is also max-reduced into
+    // pool_out[pool_seg[m], :] (row pitch = out_ld).  pool_out must be filled with 0xFF bytes beforehand (see
+    // atomic_max_f32) and every segment must own at least one row.
+    float* pool_out;
+    const int* pool_seg;
 };
+
+// max(*addr, v) on a float slot initialised to 0xFFFFFFFF (a negative NaN: the smallest int, the largest unsigned):
+// non-negative floats order like ints, negative floats like unsigned ints reversed.  Exact and order independent.
+__device__ __forceinline__ void atomic_max_f32(float* addr, float v) {
+    v += 0.f;  // -0 -> +0
+    if (v >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+    else atomicMin(reinterpret_cast<unsigned*>(addr), __float_as_uint(v));
+}
 
 // Epilogue of one 16-byte unit (4 channels c0..c0+3 of output row m).  The 4 lanes that hold
 // the 16 channels of a GroupNorm group are consecutive and aligned, so the group statistics are
@@ -103,6 +116,13 @@ __device__ __forceinline__ void epilogue4(const GemmDesc& d, float4 y, long long
     if (zero_row) y = make_float4(0.f, 0.f, 0.f, 0.f);
     const size_t at = (size_t)m * d.out_ld + c0;
     *reinterpret_cast<float4*>(d.out + at) = y;
+    if (d.pool_out) {
+        float* o = d.pool_out + (size_t)__ldg(d.pool_seg + m) * d.out_ld + c0;
+        atomic_max_f32(o, y.x);
+        atomic_max_f32(o + 1, y.y);
+        atomic_max_f32(o + 2, y.z);
+        atomic_max_f32(o + 3, y.w);
+    }
     for (int p = 0; p < d.n_peers; ++p) *reinterpret_cast<float4*>(d.peer_out[p] + at) = y;
 }
 

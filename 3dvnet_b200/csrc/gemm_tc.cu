@@ -45,6 +45,8 @@ __host__ __device__ constexpr size_t tc_smem_bytes(int N) {
 }
 
 static int g_gemm_precision = 1;  // 1 = 3xTF32, 2 = TF32
+// profiling aid (tools/gemm_phases.py): 8 clock64 stamps per CTA of every launch, or nullptr
+__device__ long long* g_gemm_stamps = nullptr;
 
 // ------------------------------------------------------------------ weight packing
 // W [Ktot, N] row-major -> per 32-row chunk the shared-memory image of B as a K-major
@@ -121,12 +123,7 @@ __device__ __forceinline__ void walk_enter(ChunkWalk& c, const GemmDesc& d, int 
 // that arrives last adds the partials in split order (deterministic) and runs the epilogue.
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-gather_gemm_tc_kernel(const __grid_constant__ GemmDesc d, int precision_and_flags) {
-    // bits 8.. of the precision word are TIMING EXPERIMENT switches (tools/bench_gemm.py): they
-    // remove one pipeline stage's work at a time and make the result meaningless
-    const int precision = precision_and_flags & 0xff;
-    const bool dbg_no_a_store = (precision_and_flags >> 8) & 1, dbg_no_a_load = (precision_and_flags >> 9) & 1,
-               dbg_no_b_copy = (precision_and_flags >> 10) & 1, dbg_no_mma = (precision_and_flags >> 11) & 1;
+gather_gemm_tc_kernel(const __grid_constant__ GemmDesc d, int precision) {
     const float* __restrict__ Wp = d.Wp;
     extern __shared__ unsigned char smem_raw[];
     // SWIZZLE_128B operands need 1024-byte alignment
@@ -148,9 +145,11 @@ gather_gemm_tc_kernel(const __grid_constant__ GemmDesc d, int precision_and_flag
     const int per_split = (d.n_slices + n_split - 1) / n_split;
     const int s_begin = min((int)blockIdx.y * per_split, d.n_slices), s_end = min(s_begin + per_split, d.n_slices);
 
+    long long* stamp = g_gemm_stamps ? g_gemm_stamps + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 12 : nullptr;
+    if (stamp && tid == 0) stamp[0] = clock64();
     if (tid == 0) {
         for (int s = 0; s < TC_STAGES; ++s) {
-            mbar_init(bar_full + 8 * s, TC_PRODUCERS + 1);  // 256 producers + the copy thread's arrive.expect_tx
+            mbar_init(bar_full + 8 * s, TC_PRODUCERS / 32 + 1);  // one elected arrive per producer warp + the copy thread's expect_tx
             mbar_init(bar_empty + 8 * s, 1);
         }
         mbar_init(bar_accum, 1);
@@ -163,8 +162,19 @@ gather_gemm_tc_kernel(const __grid_constant__ GemmDesc d, int precision_and_flag
     constexpr uint32_t TMEM_COLS = BN == 128 ? 512 : 256;
     if (warp == 8) tmem_alloc(smem_u32(s_misc), TMEM_COLS);
     // everything above is independent of the previous kernel in the stream (PDL prologue)
+    if (stamp && tid == 0) stamp[1] = clock64();   // prologue (barriers, TMEM) done
     pdl_wait();
     __syncthreads();
+    if (stamp && tid == 0) stamp[2] = clock64();   // dependency resolved
+    // epilogue column parameters of this thread (it keeps one 4-channel column, see the epilogue): requested now,
+    // consumed after the main loop - their L2 round trip (~480 cycles) disappears behind the gathers
+    constexpr int EPI_UNITS = BN / 4;
+    const int epi_c0 = (tid % EPI_UNITS) * 4;
+    const float4 epi_one = make_float4(1.f, 1.f, 1.f, 1.f), epi_zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 p_scale = d.scale ? __ldg(reinterpret_cast<const float4*>(d.scale + epi_c0)) : epi_one;
+    const float4 p_shift = d.shift ? __ldg(reinterpret_cast<const float4*>(d.shift + epi_c0)) : epi_zero;
+    const float4 p_gw = d.gn_weight ? __ldg(reinterpret_cast<const float4*>(d.gn_weight + epi_c0)) : epi_one;
+    const float4 p_gb = d.gn_weight ? __ldg(reinterpret_cast<const float4*>(d.gn_bias + epi_c0)) : epi_zero;
 
     // stage the row table of the tile and flag the slices that have at least one live row
     if (tid < TC_PRODUCERS) {
@@ -197,6 +207,7 @@ gather_gemm_tc_kernel(const __grid_constant__ GemmDesc d, int precision_and_flag
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    if (stamp && tid == 0) stamp[3] = clock64();   // row table staged
     const uint32_t tmem_base = s_misc[0];
     const uint32_t active = s_misc[1];
     int n_it = 0;
@@ -224,10 +235,6 @@ gather_gemm_tc_kernel(const __grid_constant__ GemmDesc d, int precision_and_flag
             const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
             mbar_wait(bar_empty + 8 * st, ph ^ 1u);
             unsigned char* stage = smem + st * STAGE;
-            if (dbg_no_a_store) {
-                mbar_arrive(bar_full + 8 * st);
-                return;
-            }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 float4 a = v[i];
@@ -244,8 +251,11 @@ gather_gemm_tc_kernel(const __grid_constant__ GemmDesc d, int precision_and_flag
                 *reinterpret_cast<float4*>(stage + off) = big;
                 *reinterpret_cast<float4*>(stage + TC_A_BYTES + off) = small;
             }
+            // every lane makes its stores visible to the async proxy, then ONE arrive per warp (256 serialised
+            // arrivals per stage were ~1000 cycles of a 4-chunk tile)
             fence_proxy_async_smem();
-            mbar_arrive(bar_full + 8 * st);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_full + 8 * st);
         };
         for (int it0 = 0; it0 < n_it; it0 += TC_PREFETCH) {
 #pragma unroll
@@ -254,7 +264,7 @@ gather_gemm_tc_kernel(const __grid_constant__ GemmDesc d, int precision_and_flag
                 if (it < n_it) {
                     store_chunk(it, buf[p]);
                     if (it + TC_PREFETCH < n_it) {
-                        if (!dbg_no_a_load) cursor_load(ld, buf[p]);
+                        cursor_load(ld, buf[p]);
                         cursor_next(ld, d, s_end, active, s_rows, r0, j);
                     }
                 }
@@ -279,7 +289,6 @@ gather_gemm_tc_kernel(const __grid_constant__ GemmDesc d, int precision_and_flag
                 for (int kk = 0; kk < TC_KC / 8; ++kk) {
                     const uint32_t ko = kk * 32;  // 8 tf32 = 32 bytes inside the swizzle row
                     const uint32_t acc = (it | kk) ? 1u : 0u;
-                    if (dbg_no_mma) continue;
                     if (precision == 1) {
                         umma_tf32(tmem_base, umma_desc_sw128(a_big + ko), umma_desc_sw128(b_big + ko), idesc_pair, acc);
                         umma_tf32(tmem_base + 2 * BN, umma_desc_sw128(a_small + ko), umma_desc_sw128(b_big + ko), idesc, acc);
@@ -305,15 +314,6 @@ gather_gemm_tc_kernel(const __grid_constant__ GemmDesc d, int precision_and_flag
                 const int st = it % TC_STAGES;
                 const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
                 mbar_wait(bar_empty + 8 * st, ph ^ 1u);
-                if (dbg_no_b_copy) {
-                    mbar_arrive(bar_full + 8 * st);
-                    ++w.wchunk;
-                    if (++w.kc == w.nk) {
-                        ++w.s;
-                        walk_enter(w, d, s_end, active);
-                    }
-                    continue;
-                }
                 mbar_arrive_expect_tx(bar_full + 8 * st, 2 * B_IMG);
                 bulk_g2s(smem_u32(smem + st * STAGE + 2 * TC_A_BYTES), Wp + (size_t)w.wchunk * (2 * BN * 32), 2 * B_IMG,
                          bar_full + 8 * st);
@@ -329,21 +329,28 @@ gather_gemm_tc_kernel(const __grid_constant__ GemmDesc d, int precision_and_flag
 
     // ===================== accumulator tile TMEM -> shared memory: warps 0..3, thread = row = TMEM lane
     if (warp < 4) {
+        if (stamp && tid == 0) stamp[4] = clock64();   // this producer's last chunk stored
         if (n_it > 0) mbar_wait(bar_accum, 0);  // all MMAs done: the stages are free to be overwritten
         tc_fence_after();
+        if (stamp && tid == 0) stamp[5] = clock64();   // accumulator complete
         const int row = warp * 32 + lane;
         const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 16) {
             float y[16];
             if (n_it > 0) {
-                tmem_ld16(trow + (uint32_t)c0, y);
+                uint32_t ry[16], rz[16], rw[16];   // the three loads are in flight together, one wait
+                tmem_ld16_nowait(trow + (uint32_t)c0, ry);
                 if (precision == 1) {
-                    float z[16], w[16];
-                    tmem_ld16(trow + (uint32_t)(BN + c0), z);
-                    tmem_ld16(trow + (uint32_t)(2 * BN + c0), w);
+                    tmem_ld16_nowait(trow + (uint32_t)(BN + c0), rz);
+                    tmem_ld16_nowait(trow + (uint32_t)(2 * BN + c0), rw);
+                }
+                tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) y[i] += z[i] + w[i];
+                for (int i = 0; i < 16; ++i) y[i] = __uint_as_float(ry[i]);
+                if (precision == 1) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) y[i] += __uint_as_float(rz[i]) + __uint_as_float(rw[i]);
                 }
             } else {
 #pragma unroll
@@ -356,6 +363,7 @@ gather_gemm_tc_kernel(const __grid_constant__ GemmDesc d, int precision_and_flag
     }
     tc_fence_before();
     __syncthreads();
+    if (stamp && tid == 0) stamp[6] = clock64();   // tile in shared memory
     if (warp == 8) tmem_dealloc(tmem_base, TMEM_COLS);
 
     // ===================== epilogue on 16-byte units, all warps
@@ -380,27 +388,138 @@ gather_gemm_tc_kernel(const __grid_constant__ GemmDesc d, int precision_and_flag
         __threadfence();
         ws_tile4 = ws_base;
     }
-    for (int i = tid; i < ITEMS; i += TC_THREADS) {
-        const int row = i / UNITS, c0 = (i % UNITS) * 4;
-        float4 y;
-        if (ws_tile4) {
-            // partials in split order; every load is issued before the first add
-            float4 v[TC_MAX_SPLIT];
-#pragma unroll
-            for (int sp = 0; sp < TC_MAX_SPLIT; ++sp)
-                v[sp] = sp < n_split ? __ldcg(ws_tile4 + (size_t)sp * ITEMS + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-            y = v[0];
-#pragma unroll
-            for (int sp = 1; sp < TC_MAX_SPLIT; ++sp) {
-                y.x += v[sp].x; y.y += v[sp].y; y.z += v[sp].z; y.w += v[sp].w;
+    // A thread keeps ONE 4-channel column for all its rows (TC_THREADS is a multiple of UNITS): the per-channel
+    // parameters are loaded once, row addresses advance by a constant, and a warp still covers whole rows, so the 4
+    // lanes of a 16-channel GroupNorm group stay adjacent.
+    // The loop is SPECIALISED: measured with in-kernel clock stamps (tools/gemm_phases.py), the generic loop spent
+    // ~480 cycles per row iteration although it issues ~100 instructions - with 2.5 warps per scheduler the fetch
+    // bubbles of its ~15 taken branches per iteration (feature tests, reconvergence points) are not hidden.  The three
+    // common shapes (plain store for the pair-major partial rows, affine for Linear / Conv1d / Conv2d, GroupNorm for
+    // the sparse layers) get straight-line bodies; split partials, peer stores, pooling and zero rows take the
+    // general loop.
+    {
+        constexpr int ROWS_PER_IT = TC_THREADS / UNITS;
+        static_assert(TC_THREADS % UNITS == 0, "a thread must keep its column");
+        const int c0 = epi_c0, row0 = tid / UNITS;
+        const float4 zero4 = epi_zero;
+        const bool gn = d.gn_weight != nullptr;
+        const bool relu = d.relu_out != 0;
+        float* out0 = d.out + (size_t)m0 * d.out_ld + c0;
+        const float* res0 = d.residual ? d.residual + (size_t)m0 * d.res_ld + c0 : nullptr;
+        const int rows_live = (int)(d.M - m0 < TC_BM ? d.M - m0 : TC_BM);
+        const int zmod = d.zero_row_mod, zphase = zmod ? (int)(m0 % zmod) : 0;
+        const float* tile0 = s_tile + c0;
+        const int out_ld = d.out_ld, res_ld = d.res_ld;
+        if (stamp && tid == 0) stamp[8] = stamp[9] = clock64();   // column parameters loaded
+        const bool general = ws_tile4 || d.n_peers || zmod || (d.pool_out && gn);
+        auto group_norm = [&](float4& y) {   // same operation order as epilogue4 (gemm.cuh): identical bits
+            float sum = (y.x + y.y) + (y.z + y.w);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+            const float mean = sum * (1.f / 16.f);
+            const float dx = y.x - mean, dy = y.y - mean, dz = y.z - mean, dw = y.w - mean;
+            float q = fmaf(dx, dx, dy * dy) + fmaf(dz, dz, dw * dw);
+            q += __shfl_xor_sync(0xffffffffu, q, 1);
+            q += __shfl_xor_sync(0xffffffffu, q, 2);
+            const float rstd = 1.f / sqrtf(q * (1.f / 16.f) + 1e-5f);
+            y.x = fmaf(dx * rstd, p_gw.x, p_gb.x);
+            y.y = fmaf(dy * rstd, p_gw.y, p_gb.y);
+            y.z = fmaf(dz * rstd, p_gw.z, p_gb.z);
+            y.w = fmaf(dw * rstd, p_gw.w, p_gb.w);
+        };
+        if (!general && !gn && !d.scale && !d.shift && !res0 && !relu) {
+            // ---- plain store (pair-major partial rows)
+#pragma unroll 4
+            for (int row = row0; row < TC_BM; row += ROWS_PER_IT) {
+                const float4 y = *reinterpret_cast<const float4*>(tile0 + row * TILE_LD);
+                if (row < rows_live) *reinterpret_cast<float4*>(out0 + (size_t)row * out_ld) = y;
+            }
+        } else if (!general && !gn) {
+            // ---- y * scale + shift (+ residual) (+ ReLU) (+ fused segment max of the PointNet layers)
+            const bool has_scale = d.scale != nullptr, has_shift = d.shift != nullptr, has_pool = d.pool_out != nullptr;
+#pragma unroll 2
+            for (int row = row0; row < TC_BM; row += ROWS_PER_IT) {
+                float4 y = *reinterpret_cast<const float4*>(tile0 + row * TILE_LD);
+                if (has_scale) { y.x *= p_scale.x; y.y *= p_scale.y; y.z *= p_scale.z; y.w *= p_scale.w; }
+                if (has_shift) { y.x += p_shift.x; y.y += p_shift.y; y.z += p_shift.z; y.w += p_shift.w; }
+                if (row < rows_live) {
+                    if (res0) {
+                        const float4 rv = __ldg(reinterpret_cast<const float4*>(res0 + (size_t)row * res_ld));
+                        y.x += rv.x; y.y += rv.y; y.z += rv.z; y.w += rv.w;
+                    }
+                    if (relu) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
+                    *reinterpret_cast<float4*>(out0 + (size_t)row * out_ld) = y;
+                    if (has_pool) {
+                        float* o = d.pool_out + (size_t)__ldg(d.pool_seg + m0 + row) * out_ld + c0;
+                        atomic_max_f32(o, y.x);
+                        atomic_max_f32(o + 1, y.y);
+                        atomic_max_f32(o + 2, y.z);
+                        atomic_max_f32(o + 3, y.w);
+                    }
+                }
+            }
+        } else if (!general) {
+            // ---- GroupNorm (+ residual) (+ ReLU)
+#pragma unroll 2
+            for (int row = row0; row < TC_BM; row += ROWS_PER_IT) {
+                float4 y = *reinterpret_cast<const float4*>(tile0 + row * TILE_LD);
+                if (d.scale) { y.x *= p_scale.x; y.y *= p_scale.y; y.z *= p_scale.z; y.w *= p_scale.w; }
+                if (d.shift) { y.x += p_shift.x; y.y += p_shift.y; y.z += p_shift.z; y.w += p_shift.w; }
+                group_norm(y);
+                if (row < rows_live) {
+                    if (res0) {
+                        const float4 rv = __ldg(reinterpret_cast<const float4*>(res0 + (size_t)row * res_ld));
+                        y.x += rv.x; y.y += rv.y; y.z += rv.z; y.w += rv.w;
+                    }
+                    if (relu) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
+                    *reinterpret_cast<float4*>(out0 + (size_t)row * out_ld) = y;
+                }
             }
         } else {
-            y = *reinterpret_cast<const float4*>(s_tile + row * TILE_LD + c0);
+            // ---- general loop: K-split partials, peer stores (symmetric heap), fused segment max, zero rows
+            for (int row = row0; row < TC_BM; row += ROWS_PER_IT) {
+                float4 y;
+                if (ws_tile4) {
+                    const int i = row * UNITS + (tid % UNITS);
+                    // partials in split order; every load is issued before the first add
+                    float4 v[TC_MAX_SPLIT];
+#pragma unroll
+                    for (int sp = 0; sp < TC_MAX_SPLIT; ++sp)
+                        v[sp] = sp < n_split ? __ldcg(ws_tile4 + (size_t)sp * ITEMS + i) : zero4;
+                    y = v[0];
+#pragma unroll
+                    for (int sp = 1; sp < TC_MAX_SPLIT; ++sp) {
+                        y.x += v[sp].x; y.y += v[sp].y; y.z += v[sp].z; y.w += v[sp].w;
+                    }
+                } else {
+                    y = *reinterpret_cast<const float4*>(tile0 + row * TILE_LD);
+                }
+                if (d.scale) { y.x *= p_scale.x; y.y *= p_scale.y; y.z *= p_scale.z; y.w *= p_scale.w; }
+                if (d.shift) { y.x += p_shift.x; y.y += p_shift.y; y.z += p_shift.z; y.w += p_shift.w; }
+                if (gn) group_norm(y);
+                if (row < rows_live) {
+                    if (res0) {
+                        const float4 rv = __ldg(reinterpret_cast<const float4*>(res0 + (size_t)row * res_ld));
+                        y.x += rv.x; y.y += rv.y; y.z += rv.z; y.w += rv.w;
+                    }
+                    if (relu) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
+                    if (zmod && (zphase + row) % zmod == d.zero_row_val) y = zero4;
+                    const size_t at = (size_t)row * out_ld;
+                    *reinterpret_cast<float4*>(out0 + at) = y;
+                    for (int p = 0; p < d.n_peers; ++p)
+                        *reinterpret_cast<float4*>(d.peer_out[p] + (size_t)m0 * out_ld + c0 + at) = y;
+                    if (d.pool_out) {
+                        float* o = d.pool_out + (size_t)__ldg(d.pool_seg + m0 + row) * out_ld + c0;
+                        atomic_max_f32(o, y.x);
+                        atomic_max_f32(o + 1, y.y);
+                        atomic_max_f32(o + 2, y.z);
+                        atomic_max_f32(o + 3, y.w);
+                    }
+                }
+            }
         }
-        const long long m = m0 + row;
-        const bool zero_row = d.zero_row_mod && (int)(m % d.zero_row_mod) == d.zero_row_val;
-        epilogue4(d, y, m, c0, m < d.M, zero_row);
     }
+    if (stamp && tid == 0) stamp[7] = clock64();
 }
 
 int validate_gather_gemm(const GemmDesc& d, int k_multiple);
@@ -465,9 +584,14 @@ extern "C" int dv3d_gemm_pack_weights(const float* W, int Ktot, int N, void* pac
 }
 
 extern "C" int dv3d_set_gemm_precision(int mode) {
-    DV3D_REQUIRE((mode & 0xff) == 1 || (mode & 0xff) == 2, "set_gemm_precision: 1 = 3xTF32 (fp32-grade), 2 = TF32; got %d",
-                 mode);  // bits 8..11: timing-experiment switches, see gather_gemm_tc_kernel
+    DV3D_REQUIRE(mode == 1 || mode == 2, "set_gemm_precision: 1 = 3xTF32 (fp32-grade), 2 = TF32; got %d", mode);
     g_gemm_precision = mode;
     return DV3D_OK;
 }
 extern "C" int dv3d_get_gemm_precision(void) { return g_gemm_precision; }
+
+extern "C" int dv3d_gemm_set_timing_buffer(void* device_buffer) {
+    long long* p = (long long*)device_buffer;
+    DV3D_CUDA(cudaMemcpyToSymbol(g_gemm_stamps, &p, sizeof(p)));
+    return DV3D_OK;
+}

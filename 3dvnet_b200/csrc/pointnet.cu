@@ -92,6 +92,30 @@ extern "C" int dv3d_linear(const float* x_a, int Ca, int lda, const float* pool,
     return launch_gather_gemm(d, (cudaStream_t)stream);
 }
 
+extern "C" int dv3d_linear_pool(const float* x_a, int Ca, int lda, const float* pool, const int* seg, int Cb, long long N,
+                                const float* weight_kn, const void* W_packed, const float* bias, int Cout, int relu_input,
+                                float* y, float* pool_out, const int* pool_seg, void* stream) {
+    DV3D_REQUIRE(x_a && (weight_kn || W_packed) && y && N >= 0 && Ca > 0 && Cb >= 0, "linear_pool: bad arguments");
+    DV3D_REQUIRE(Cb == 0 || (pool && seg), "linear_pool: the pooled half needs pool and seg");
+    DV3D_REQUIRE(pool_out && pool_seg, "linear_pool: pool_out (0xFF-filled) and pool_seg are required");
+    GemmDesc d = {};
+    d.n_slices = Cb ? 2 : 1;
+    d.slice[0] = GemmSlice{x_a, nullptr, 0, 0, lda, Ca};
+    if (Cb) d.slice[1] = GemmSlice{pool, seg, 1, 0, Cb, Cb};
+    d.M = N;
+    d.n_src_rows = N;
+    d.N = Cout;
+    d.W = weight_kn;
+    d.Wp = (const float*)W_packed;
+    d.shift = bias;
+    d.relu_in = relu_input;
+    d.out = y;
+    d.out_ld = Cout;
+    d.pool_out = pool_out;
+    d.pool_seg = pool_seg;
+    return launch_gather_gemm(d, (cudaStream_t)stream);
+}
+
 extern "C" int dv3d_segment_max(const float* x, const int* seg, long long N, int C, long long n_seg, float* out,
                                 void* stream) {
     DV3D_REQUIRE(x && seg && out && N >= 0 && n_seg >= 0 && C > 0 && C % 4 == 0, "segment_max: bad arguments");

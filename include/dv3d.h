@@ -179,6 +179,9 @@ size_t dv3d_gemm_pack_bytes(int Ktot, int N);
 int dv3d_gemm_pack_weights(const float* W, int Ktot, int N, void* packed, void* stream);
 int dv3d_set_gemm_precision(int mode);
 int dv3d_get_gemm_precision(void);
+/* profiling aid (tools/gemm_phases.py): device buffer of (grid.x * grid.y) * 8 int64 clock stamps written by every
+ * tcgen05 gather-GEMM launch on the current device; NULL switches it off */
+int dv3d_gemm_set_timing_buffer(void* device_buffer);
 
 /* ------------------------------------------------------------------------------------
  * PointNet (scenemodeling.py:116-144).
@@ -195,6 +198,13 @@ int dv3d_linear(const float* x_a, int Ca, int lda, const float* pool, const int*
                 const float* weight_kn, const void* W_packed, const float* bias, int Cout, int relu_input, float* y,
                 void* stream);
 /* segment max with empty segments = 0 (torch_scatter 'max'): out [n_seg,C] */
+/* dv3d_linear whose epilogue also max-pools the output rows per segment (scatter max of scenemodeling.py:129 fused
+ * into the layer that produces its operand): pool_out[pool_seg[m], :] = max(pool_out[...], y[m, :]), row pitch Cout.
+ * pool_out must be pre-filled with 0xFF bytes (cudaMemsetAsync) and every segment must own at least one row; the
+ * result is the exact maximum (order independent), identical to dv3d_segment_max on y. */
+int dv3d_linear_pool(const float* x_a, int Ca, int lda, const float* pool, const int* seg, int Cb, long long N,
+                     const float* weight_kn, const void* W_packed, const float* bias, int Cout, int relu_input, float* y,
+                     float* pool_out, const int* pool_seg, void* stream);
 int dv3d_segment_max(const float* x, const int* seg, long long N, int C, long long n_seg, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------

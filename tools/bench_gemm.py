@@ -76,31 +76,9 @@ def main():
         packed = ops.pack_weights(wk)
         us = timeit(lambda: ops.linear(x, wk, b, True, packed=packed))
         rows.append((mode, 'linear M=3136 K=128 N=128', us, 2.0 * 3136 * 128 * 128 / us / 1e6))
-    # pipeline-stage ablations on the two main shapes (results are garbage, only the time matters)
-    lib = importlib.import_module('3dvnet_b200._lib').lib()
-    n_pts, Cin = 3136, 352
-    x = rnd(n_pts, 8, Cin)
-    w = rnd(3, Cin, 128)
-    sc, sh = rnd(128), rnd(128)
-    packed = ops.pack_weights(w.reshape(-1, 128).contiguous())
-    out = torch.empty((n_pts, 8, 128), device=dev)
-    n = 50000
-    nbr = torch.randint(0, n, (n, 27), generator=g)
-    nbr[torch.rand(n, 27, generator=g) >= 0.3] = -1
-    nbr = nbr.int().to(dev)
-    feat = rnd(n, 128)
-    W = rnd(27, 128, 128)
-    gw, gb = rnd(128), rnd(128)
-    packedW = ops.pack_weights(W.reshape(-1, 128).contiguous())
-    for name, flags in (('full', 0), ('no A store', 1), ('no A load+store', 3), ('no B copy', 4), ('no MMA', 8),
-                        ('no A, no B', 7), ('no A, no MMA', 11), ('no B, no MMA', 12), ('nothing (barriers only)', 15)):
-        for prec, pname in ((1, 'tf32x3'), (2, 'tf32')):
-            lib.call('dv3d_set_gemm_precision', prec | (flags << 8))
-            us = timeit(lambda: ops.conv1d_bn_relu(x, w, sc, sh, out=out, packed=packed))
-            us2 = timeit(lambda: ops.sparse_conv(feat, nbr, W, gw, gb, feat, True, packed=packedW))
-            rows.append((pname, 'ABLATION %s: conv1d K=1056 | sparse n=50000' % name, us, us2))
-    lib.call('dv3d_set_gemm_precision', 1)
-    print('| mode | shape | us / launch | dense-equivalent TFLOP/s (ablation rows: second shape us) |')
+    # (the pipeline-stage ablation switches of round 1 were removed from the product kernel; the per-phase cost of a
+    # tile is now read from in-kernel clock stamps: tools/gemm_phases.py, tools/decoder_phases.py)
+    print('| mode | shape | us / launch | dense-equivalent TFLOP/s |')
     print('|---|---|---:|---:|')
     for r in rows:
         print('| %s | %s | %.1f | %.1f |' % r)
