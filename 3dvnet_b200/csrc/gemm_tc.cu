@@ -164,7 +164,9 @@ gather_gemm_tc_kernel(const __grid_constant__ GemmDesc d, int precision) {
     // everything above is independent of the previous kernel in the stream (PDL prologue)
     if (stamp && tid == 0) stamp[1] = clock64();   // prologue (barriers, TMEM) done
     pdl_wait();
+    tc_fence_before();
     __syncthreads();
+    tc_fence_after();
     if (stamp && tid == 0) stamp[2] = clock64();   // dependency resolved
     // epilogue column parameters of this thread (it keeps one 4-channel column, see the epilogue): requested now,
     // consumed after the main loop - their L2 round trip (~480 cycles) disappears behind the gathers
@@ -176,6 +178,26 @@ gather_gemm_tc_kernel(const __grid_constant__ GemmDesc d, int precision) {
     const float4 p_gw = d.gn_weight ? __ldg(reinterpret_cast<const float4*>(d.gn_weight + epi_c0)) : epi_one;
     const float4 p_gb = d.gn_weight ? __ldg(reinterpret_cast<const float4*>(d.gn_bias + epi_c0)) : epi_zero;
 
+    // Single-slice launches (pair-major sparse convolution, Linear, Conv2d rows...): every producer thread derives
+    // the 4 row numbers it gathers itself (the 8 threads of a row write the same value and each reads back its own),
+    // so no block-wide staging pass and no second barrier stand between the dependency wait and the first gather.
+    const bool fast_rows = d.n_slices == 1 && !d.kmap;
+    if (fast_rows) {
+        if (tid < TC_PRODUCERS) {
+            const GemmSlice& sl = d.slice[0];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int r = (tid >> 3) + 32 * i;
+                const long long m = m0 + r;
+                long long rr = -1;
+                if (m < d.M) {
+                    rr = sl.idx ? (long long)__ldg(sl.idx + m * sl.idx_stride) : m + sl.shift;
+                    if (!sl.idx && rr >= d.n_src_rows) rr = -1;
+                }
+                s_rows[r] = rr < 0 ? -1 : (int)rr;
+            }
+        }
+    } else {
     // stage the row table of the tile and flag the slices that have at least one live row
     if (tid < TC_PRODUCERS) {
         unsigned my_active = 0;
@@ -207,9 +229,10 @@ gather_gemm_tc_kernel(const __grid_constant__ GemmDesc d, int precision) {
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    }
     if (stamp && tid == 0) stamp[3] = clock64();   // row table staged
     const uint32_t tmem_base = s_misc[0];
-    const uint32_t active = s_misc[1];
+    const uint32_t active = fast_rows ? 1u : s_misc[1];
     int n_it = 0;
     for (int s = s_begin; s < s_end; ++s)
         if ((active >> s) & 1u) n_it += d.slice[s].K / TC_KC;
@@ -327,16 +350,18 @@ gather_gemm_tc_kernel(const __grid_constant__ GemmDesc d, int precision) {
         __syncwarp();
     }
 
-    // ===================== accumulator tile TMEM -> shared memory: warps 0..3, thread = row = TMEM lane
-    if (warp < 4) {
+    // ===================== accumulator tile TMEM -> shared memory: all 8 producer warps, thread = row = TMEM lane
+    // (warp w may touch lanes 32 (w % 4) .. +31: warps 0-3 drain the first half of the columns, warps 4-7 the second)
+    if (warp < 8) {
         if (stamp && tid == 0) stamp[4] = clock64();   // this producer's last chunk stored
         if (n_it > 0) mbar_wait(bar_accum, 0);  // all MMAs done: the stages are free to be overwritten
         tc_fence_after();
         if (stamp && tid == 0) stamp[5] = clock64();   // accumulator complete
-        const int row = warp * 32 + lane;
-        const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+        const int row = (warp & 3) * 32 + lane;
+        const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        const int c_begin = (warp >> 2) * (BN / 2);
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 16) {
+        for (int c0 = c_begin; c0 < c_begin + BN / 2; c0 += 16) {
             float y[16];
             if (n_it > 0) {
                 uint32_t ry[16], rz[16], rw[16];   // the three loads are in flight together, one wait
