@@ -45,6 +45,7 @@ __host__ __device__ constexpr size_t tc_smem_bytes(int N) {
 }
 
 static int g_gemm_precision = 1;  // 1 = 3xTF32, 2 = TF32
+static int g_gemm_persistent = 0;  // 0 = automatic (more tiles than SMs), 1 = whenever possible, -1 = never (tests / A-B runs)
 // profiling aid (tools/gemm_phases.py): 8 clock64 stamps per CTA of every launch, or nullptr
 __device__ long long* g_gemm_stamps = nullptr;
 
@@ -118,6 +119,160 @@ __device__ __forceinline__ void walk_enter(ChunkWalk& c, const GemmDesc& d, int 
     c.nk = c.s < s_end ? d.slice[c.s].K / TC_KC : 0;
 }
 
+// ------------------------------------------------------------------ tile epilogue (shared by both kernels)
+struct EpiParams {
+    float4 scale, shift, gw, gb;   // this thread's 4-channel column of the per-channel parameters
+};
+template <int BN>
+__device__ __forceinline__ EpiParams load_epi_params(const GemmDesc& d, int tid) {
+    const int c0 = (tid % (BN / 4)) * 4;
+    const float4 one = make_float4(1.f, 1.f, 1.f, 1.f), zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    EpiParams ep;
+    ep.scale = d.scale ? __ldg(reinterpret_cast<const float4*>(d.scale + c0)) : one;
+    ep.shift = d.shift ? __ldg(reinterpret_cast<const float4*>(d.shift + c0)) : zero;
+    ep.gw = d.gn_weight ? __ldg(reinterpret_cast<const float4*>(d.gn_weight + c0)) : one;
+    ep.gb = d.gn_weight ? __ldg(reinterpret_cast<const float4*>(d.gn_bias + c0)) : zero;
+    return ep;
+}
+
+// s_tile: the 128 x BN accumulator tile in shared memory (row pitch BN + 4); NT threads (a multiple of BN / 4) take part
+template <int BN, int NT>
+__device__ __forceinline__ void tile_epilogue(const GemmDesc& d, const float* s_tile, long long m0, int tid,
+                                              const EpiParams& ep, const float4* ws_tile4, int n_split, long long* stamp) {
+    constexpr int UNITS = BN / 4, ITEMS = TC_BM * UNITS, TILE_LD = BN + 4;
+    // A thread keeps ONE 4-channel column for all its rows (NT is a multiple of UNITS): the per-channel
+    // parameters are loaded once, row addresses advance by a constant, and a warp still covers whole rows, so the 4
+    // lanes of a 16-channel GroupNorm group stay adjacent.
+    // The loop is SPECIALISED: measured with in-kernel clock stamps (tools/gemm_phases.py), the generic loop spent
+    // ~480 cycles per row iteration although it issues ~100 instructions - with 2.5 warps per scheduler the fetch
+    // bubbles of its ~15 taken branches per iteration (feature tests, reconvergence points) are not hidden.  The three
+    // common shapes (plain store for the pair-major partial rows, affine for Linear / Conv1d / Conv2d, GroupNorm for
+    // the sparse layers) get straight-line bodies; split partials, peer stores, pooling and zero rows take the
+    // general loop.
+    {
+        constexpr int ROWS_PER_IT = NT / UNITS;
+        static_assert(NT % UNITS == 0, "a thread must keep its column");
+        const int c0 = (tid % UNITS) * 4, row0 = tid / UNITS;
+        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        const bool gn = d.gn_weight != nullptr;
+        const bool relu = d.relu_out != 0;
+        float* out0 = d.out + (size_t)m0 * d.out_ld + c0;
+        const float* res0 = d.residual ? d.residual + (size_t)m0 * d.res_ld + c0 : nullptr;
+        const int rows_live = (int)(d.M - m0 < TC_BM ? d.M - m0 : TC_BM);
+        const int zmod = d.zero_row_mod, zphase = zmod ? (int)(m0 % zmod) : 0;
+        const float* tile0 = s_tile + c0;
+        const int out_ld = d.out_ld, res_ld = d.res_ld;
+        if (stamp && tid == 0) stamp[8] = stamp[9] = clock64();   // column parameters loaded
+        const bool general = ws_tile4 || d.n_peers || zmod || (d.pool_out && gn);
+        auto group_norm = [&](float4& y) {   // same operation order as epilogue4 (gemm.cuh): identical bits
+            float sum = (y.x + y.y) + (y.z + y.w);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+            const float mean = sum * (1.f / 16.f);
+            const float dx = y.x - mean, dy = y.y - mean, dz = y.z - mean, dw = y.w - mean;
+            float q = fmaf(dx, dx, dy * dy) + fmaf(dz, dz, dw * dw);
+            q += __shfl_xor_sync(0xffffffffu, q, 1);
+            q += __shfl_xor_sync(0xffffffffu, q, 2);
+            const float rstd = 1.f / sqrtf(q * (1.f / 16.f) + 1e-5f);
+            y.x = fmaf(dx * rstd, ep.gw.x, ep.gb.x);
+            y.y = fmaf(dy * rstd, ep.gw.y, ep.gb.y);
+            y.z = fmaf(dz * rstd, ep.gw.z, ep.gb.z);
+            y.w = fmaf(dw * rstd, ep.gw.w, ep.gb.w);
+        };
+        if (!general && !gn && !d.scale && !d.shift && !res0 && !relu) {
+            // ---- plain store (pair-major partial rows)
+#pragma unroll 4
+            for (int row = row0; row < TC_BM; row += ROWS_PER_IT) {
+                const float4 y = *reinterpret_cast<const float4*>(tile0 + row * TILE_LD);
+                if (row < rows_live) *reinterpret_cast<float4*>(out0 + (size_t)row * out_ld) = y;
+            }
+        } else if (!general && !gn) {
+            // ---- y * scale + shift (+ residual) (+ ReLU) (+ fused segment max of the PointNet layers)
+            const bool has_scale = d.scale != nullptr, has_shift = d.shift != nullptr, has_pool = d.pool_out != nullptr;
+#pragma unroll 2
+            for (int row = row0; row < TC_BM; row += ROWS_PER_IT) {
+                float4 y = *reinterpret_cast<const float4*>(tile0 + row * TILE_LD);
+                if (has_scale) { y.x *= ep.scale.x; y.y *= ep.scale.y; y.z *= ep.scale.z; y.w *= ep.scale.w; }
+                if (has_shift) { y.x += ep.shift.x; y.y += ep.shift.y; y.z += ep.shift.z; y.w += ep.shift.w; }
+                if (row < rows_live) {
+                    if (res0) {
+                        const float4 rv = __ldg(reinterpret_cast<const float4*>(res0 + (size_t)row * res_ld));
+                        y.x += rv.x; y.y += rv.y; y.z += rv.z; y.w += rv.w;
+                    }
+                    if (relu) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
+                    *reinterpret_cast<float4*>(out0 + (size_t)row * out_ld) = y;
+                    if (has_pool) {
+                        float* o = d.pool_out + (size_t)__ldg(d.pool_seg + m0 + row) * out_ld + c0;
+                        atomic_max_f32(o, y.x);
+                        atomic_max_f32(o + 1, y.y);
+                        atomic_max_f32(o + 2, y.z);
+                        atomic_max_f32(o + 3, y.w);
+                    }
+                }
+            }
+        } else if (!general) {
+            // ---- GroupNorm (+ residual) (+ ReLU)
+#pragma unroll 2
+            for (int row = row0; row < TC_BM; row += ROWS_PER_IT) {
+                float4 y = *reinterpret_cast<const float4*>(tile0 + row * TILE_LD);
+                if (d.scale) { y.x *= ep.scale.x; y.y *= ep.scale.y; y.z *= ep.scale.z; y.w *= ep.scale.w; }
+                if (d.shift) { y.x += ep.shift.x; y.y += ep.shift.y; y.z += ep.shift.z; y.w += ep.shift.w; }
+                group_norm(y);
+                if (row < rows_live) {
+                    if (res0) {
+                        const float4 rv = __ldg(reinterpret_cast<const float4*>(res0 + (size_t)row * res_ld));
+                        y.x += rv.x; y.y += rv.y; y.z += rv.z; y.w += rv.w;
+                    }
+                    if (relu) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
+                    *reinterpret_cast<float4*>(out0 + (size_t)row * out_ld) = y;
+                }
+            }
+        } else {
+            // ---- general loop: K-split partials, peer stores (symmetric heap), fused segment max, zero rows
+            for (int row = row0; row < TC_BM; row += ROWS_PER_IT) {
+                float4 y;
+                if (ws_tile4) {
+                    const int i = row * UNITS + (tid % UNITS);
+                    // partials in split order; every load is issued before the first add
+                    float4 v[TC_MAX_SPLIT];
+#pragma unroll
+                    for (int sp = 0; sp < TC_MAX_SPLIT; ++sp)
+                        v[sp] = sp < n_split ? __ldcg(ws_tile4 + (size_t)sp * ITEMS + i) : zero4;
+                    y = v[0];
+#pragma unroll
+                    for (int sp = 1; sp < TC_MAX_SPLIT; ++sp) {
+                        y.x += v[sp].x; y.y += v[sp].y; y.z += v[sp].z; y.w += v[sp].w;
+                    }
+                } else {
+                    y = *reinterpret_cast<const float4*>(tile0 + row * TILE_LD);
+                }
+                if (d.scale) { y.x *= ep.scale.x; y.y *= ep.scale.y; y.z *= ep.scale.z; y.w *= ep.scale.w; }
+                if (d.shift) { y.x += ep.shift.x; y.y += ep.shift.y; y.z += ep.shift.z; y.w += ep.shift.w; }
+                if (gn) group_norm(y);
+                if (row < rows_live) {
+                    if (res0) {
+                        const float4 rv = __ldg(reinterpret_cast<const float4*>(res0 + (size_t)row * res_ld));
+                        y.x += rv.x; y.y += rv.y; y.z += rv.z; y.w += rv.w;
+                    }
+                    if (relu) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
+                    if (zmod && (zphase + row) % zmod == d.zero_row_val) y = zero4;
+                    const size_t at = (size_t)row * out_ld;
+                    *reinterpret_cast<float4*>(out0 + at) = y;
+                    for (int p = 0; p < d.n_peers; ++p)
+                        *reinterpret_cast<float4*>(d.peer_out[p] + (size_t)m0 * out_ld + c0 + at) = y;
+                    if (d.pool_out) {
+                        float* o = d.pool_out + (size_t)__ldg(d.pool_seg + m0 + row) * out_ld + c0;
+                        atomic_max_f32(o, y.x);
+                        atomic_max_f32(o + 1, y.y);
+                        atomic_max_f32(o + 2, y.z);
+                        atomic_max_f32(o + 3, y.w);
+                    }
+                }
+            }
+        }
+    }
+}
+
 // grid = (row tiles, K splits).  With K splits > 1 every CTA contracts a contiguous range of
 // slices, parks its raw 128 x N partial in d.split_ws and bumps the tile's counter; the CTA
 // that arrives last adds the partials in split order (deterministic) and runs the epilogue.
@@ -168,15 +323,9 @@ gather_gemm_tc_kernel(const __grid_constant__ GemmDesc d, int precision) {
     __syncthreads();
     tc_fence_after();
     if (stamp && tid == 0) stamp[2] = clock64();   // dependency resolved
-    // epilogue column parameters of this thread (it keeps one 4-channel column, see the epilogue): requested now,
+    // epilogue column parameters of this thread (it keeps one 4-channel column, see tile_epilogue): requested now,
     // consumed after the main loop - their L2 round trip (~480 cycles) disappears behind the gathers
-    constexpr int EPI_UNITS = BN / 4;
-    const int epi_c0 = (tid % EPI_UNITS) * 4;
-    const float4 epi_one = make_float4(1.f, 1.f, 1.f, 1.f), epi_zero = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4 p_scale = d.scale ? __ldg(reinterpret_cast<const float4*>(d.scale + epi_c0)) : epi_one;
-    const float4 p_shift = d.shift ? __ldg(reinterpret_cast<const float4*>(d.shift + epi_c0)) : epi_zero;
-    const float4 p_gw = d.gn_weight ? __ldg(reinterpret_cast<const float4*>(d.gn_weight + epi_c0)) : epi_one;
-    const float4 p_gb = d.gn_weight ? __ldg(reinterpret_cast<const float4*>(d.gn_bias + epi_c0)) : epi_zero;
+    const EpiParams epi = load_epi_params<BN>(d, tid);
 
     // Single-slice launches (pair-major sparse convolution, Linear, Conv2d rows...): every producer thread derives
     // the 4 row numbers it gathers itself (the 8 threads of a row write the same value and each reads back its own),
@@ -413,138 +562,215 @@ gather_gemm_tc_kernel(const __grid_constant__ GemmDesc d, int precision) {
         __threadfence();
         ws_tile4 = ws_base;
     }
-    // A thread keeps ONE 4-channel column for all its rows (TC_THREADS is a multiple of UNITS): the per-channel
-    // parameters are loaded once, row addresses advance by a constant, and a warp still covers whole rows, so the 4
-    // lanes of a 16-channel GroupNorm group stay adjacent.
-    // The loop is SPECIALISED: measured with in-kernel clock stamps (tools/gemm_phases.py), the generic loop spent
-    // ~480 cycles per row iteration although it issues ~100 instructions - with 2.5 warps per scheduler the fetch
-    // bubbles of its ~15 taken branches per iteration (feature tests, reconvergence points) are not hidden.  The three
-    // common shapes (plain store for the pair-major partial rows, affine for Linear / Conv1d / Conv2d, GroupNorm for
-    // the sparse layers) get straight-line bodies; split partials, peer stores, pooling and zero rows take the
-    // general loop.
-    {
-        constexpr int ROWS_PER_IT = TC_THREADS / UNITS;
-        static_assert(TC_THREADS % UNITS == 0, "a thread must keep its column");
-        const int c0 = epi_c0, row0 = tid / UNITS;
-        const float4 zero4 = epi_zero;
-        const bool gn = d.gn_weight != nullptr;
-        const bool relu = d.relu_out != 0;
-        float* out0 = d.out + (size_t)m0 * d.out_ld + c0;
-        const float* res0 = d.residual ? d.residual + (size_t)m0 * d.res_ld + c0 : nullptr;
-        const int rows_live = (int)(d.M - m0 < TC_BM ? d.M - m0 : TC_BM);
-        const int zmod = d.zero_row_mod, zphase = zmod ? (int)(m0 % zmod) : 0;
-        const float* tile0 = s_tile + c0;
-        const int out_ld = d.out_ld, res_ld = d.res_ld;
-        if (stamp && tid == 0) stamp[8] = stamp[9] = clock64();   // column parameters loaded
-        const bool general = ws_tile4 || d.n_peers || zmod || (d.pool_out && gn);
-        auto group_norm = [&](float4& y) {   // same operation order as epilogue4 (gemm.cuh): identical bits
-            float sum = (y.x + y.y) + (y.z + y.w);
-            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-            sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-            const float mean = sum * (1.f / 16.f);
-            const float dx = y.x - mean, dy = y.y - mean, dz = y.z - mean, dw = y.w - mean;
-            float q = fmaf(dx, dx, dy * dy) + fmaf(dz, dz, dw * dw);
-            q += __shfl_xor_sync(0xffffffffu, q, 1);
-            q += __shfl_xor_sync(0xffffffffu, q, 2);
-            const float rstd = 1.f / sqrtf(q * (1.f / 16.f) + 1e-5f);
-            y.x = fmaf(dx * rstd, p_gw.x, p_gb.x);
-            y.y = fmaf(dy * rstd, p_gw.y, p_gb.y);
-            y.z = fmaf(dz * rstd, p_gw.z, p_gb.z);
-            y.w = fmaf(dw * rstd, p_gw.w, p_gb.w);
-        };
-        if (!general && !gn && !d.scale && !d.shift && !res0 && !relu) {
-            // ---- plain store (pair-major partial rows)
-#pragma unroll 4
-            for (int row = row0; row < TC_BM; row += ROWS_PER_IT) {
-                const float4 y = *reinterpret_cast<const float4*>(tile0 + row * TILE_LD);
-                if (row < rows_live) *reinterpret_cast<float4*>(out0 + (size_t)row * out_ld) = y;
+    tile_epilogue<BN, TC_THREADS>(d, s_tile, m0, tid, epi, ws_tile4, n_split, stamp);
+    if (stamp && tid == 0) stamp[7] = clock64();
+}
+
+// ------------------------------------------------------------------ persistent variant (single-slice launches)
+// Pair-major sparse convolutions, Linear layers and Conv2d rows are ONE slice with K = 64..256: a tile is 2..8 K chunks,
+// i.e. ~0.4-1.5 us of MMA inside a ~6.5 us chain of dependent latencies (row numbers -> gather -> split/store -> MMA ->
+// TMEM drain -> epilogue, tools/gemm_phases.py).  With more tiles than SMs that chain used to be paid once per tile and
+// per wave.  Here grid = min(tiles, 148) CTAs loop over their tiles: the mbarrier rings and the weight copies keep
+// running across tiles, the accumulator tile gets its own shared-memory region (so the weight copies of the next tile
+// never wait for this tile's epilogue), and the producers request the NEXT tile's row numbers and first chunks right
+// after storing the last chunk of this one - that round trip overlaps the MMA wait, the drain and the epilogue.
+template <int BN>
+__host__ __device__ constexpr int tcp_stages() { return BN == 128 ? 2 : 3; }
+template <int BN>
+__host__ __device__ constexpr size_t tcp_smem_bytes() {
+    return 1024 + (size_t)tcp_stages<BN>() * tc_stage_bytes(BN) + (size_t)TC_BM * (BN + 4) * sizeof(float) + 512;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gather_gemm_tc_persistent_kernel(const __grid_constant__ GemmDesc d, int precision) {
+    constexpr int PS = tcp_stages<BN>();
+    constexpr int STAGE = tc_stage_bytes(BN), B_IMG = BN * 128, TILE_LD = BN + 4;
+    constexpr uint32_t TMEM_COLS = BN == 128 ? 512 : 256;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    float* s_tile = reinterpret_cast<float*>(smem + PS * STAGE);
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_tile + TC_BM * TILE_LD);   // full[PS] empty[PS] accum tmem_free
+    uint32_t* s_misc = reinterpret_cast<uint32_t*>(s_bar + 2 * PS + 2);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t bar_full = smem_u32(s_bar), bar_empty = smem_u32(s_bar + PS), bar_accum = smem_u32(s_bar + 2 * PS),
+                   bar_free = smem_u32(s_bar + 2 * PS + 1);
+    const GemmSlice& sl = d.slice[0];
+    const int nk = sl.K / TC_KC;
+    const long long n_tiles = (d.M + TC_BM - 1) / TC_BM;
+    const float* __restrict__ Wp = d.Wp;
+
+    if (tid == 0) {
+        for (int s = 0; s < PS; ++s) {
+            mbar_init(bar_full + 8 * s, TC_PRODUCERS / 32 + 1);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        mbar_init(bar_accum, 1);
+        mbar_init(bar_free, 1);
+        fence_mbar_init();
+    }
+    if (warp == 8) tmem_alloc(smem_u32(s_misc), TMEM_COLS);
+    pdl_wait();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = s_misc[0];
+
+    if (warp == 8) {
+        // ===================== MMA issuer (uniform control flow, one elected lane)
+        constexpr uint32_t idesc = umma_idesc_tf32(TC_BM, BN), idesc_pair = umma_idesc_tf32(TC_BM, 2 * BN);
+        int j = 0;
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
+            if (j > 0) {   // the previous tile has left TMEM
+                mbar_wait(bar_free, (uint32_t)(j - 1) & 1u);
+                tc_fence_after();
             }
-        } else if (!general && !gn) {
-            // ---- y * scale + shift (+ residual) (+ ReLU) (+ fused segment max of the PointNet layers)
-            const bool has_scale = d.scale != nullptr, has_shift = d.shift != nullptr, has_pool = d.pool_out != nullptr;
-#pragma unroll 2
-            for (int row = row0; row < TC_BM; row += ROWS_PER_IT) {
-                float4 y = *reinterpret_cast<const float4*>(tile0 + row * TILE_LD);
-                if (has_scale) { y.x *= p_scale.x; y.y *= p_scale.y; y.z *= p_scale.z; y.w *= p_scale.w; }
-                if (has_shift) { y.x += p_shift.x; y.y += p_shift.y; y.z += p_shift.z; y.w += p_shift.w; }
-                if (row < rows_live) {
-                    if (res0) {
-                        const float4 rv = __ldg(reinterpret_cast<const float4*>(res0 + (size_t)row * res_ld));
-                        y.x += rv.x; y.y += rv.y; y.z += rv.z; y.w += rv.w;
-                    }
-                    if (relu) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
-                    *reinterpret_cast<float4*>(out0 + (size_t)row * out_ld) = y;
-                    if (has_pool) {
-                        float* o = d.pool_out + (size_t)__ldg(d.pool_seg + m0 + row) * out_ld + c0;
-                        atomic_max_f32(o, y.x);
-                        atomic_max_f32(o + 1, y.y);
-                        atomic_max_f32(o + 2, y.z);
-                        atomic_max_f32(o + 3, y.w);
-                    }
-                }
-            }
-        } else if (!general) {
-            // ---- GroupNorm (+ residual) (+ ReLU)
-#pragma unroll 2
-            for (int row = row0; row < TC_BM; row += ROWS_PER_IT) {
-                float4 y = *reinterpret_cast<const float4*>(tile0 + row * TILE_LD);
-                if (d.scale) { y.x *= p_scale.x; y.y *= p_scale.y; y.z *= p_scale.z; y.w *= p_scale.w; }
-                if (d.shift) { y.x += p_shift.x; y.y += p_shift.y; y.z += p_shift.z; y.w += p_shift.w; }
-                group_norm(y);
-                if (row < rows_live) {
-                    if (res0) {
-                        const float4 rv = __ldg(reinterpret_cast<const float4*>(res0 + (size_t)row * res_ld));
-                        y.x += rv.x; y.y += rv.y; y.z += rv.z; y.w += rv.w;
-                    }
-                    if (relu) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
-                    *reinterpret_cast<float4*>(out0 + (size_t)row * out_ld) = y;
-                }
-            }
-        } else {
-            // ---- general loop: K-split partials, peer stores (symmetric heap), fused segment max, zero rows
-            for (int row = row0; row < TC_BM; row += ROWS_PER_IT) {
-                float4 y;
-                if (ws_tile4) {
-                    const int i = row * UNITS + (tid % UNITS);
-                    // partials in split order; every load is issued before the first add
-                    float4 v[TC_MAX_SPLIT];
+            for (int it = 0; it < nk; ++it) {
+                const int g = j * nk + it, st = g % PS;
+                mbar_wait(bar_full + 8 * st, (uint32_t)(g / PS) & 1u);
+                tc_fence_after();
+                const uint32_t a_big = smem_u32(smem + st * STAGE), a_small = a_big + TC_A_BYTES, b_big = a_big + 2 * TC_A_BYTES;
+                if (elect_one()) {
 #pragma unroll
-                    for (int sp = 0; sp < TC_MAX_SPLIT; ++sp)
-                        v[sp] = sp < n_split ? __ldcg(ws_tile4 + (size_t)sp * ITEMS + i) : zero4;
-                    y = v[0];
-#pragma unroll
-                    for (int sp = 1; sp < TC_MAX_SPLIT; ++sp) {
-                        y.x += v[sp].x; y.y += v[sp].y; y.z += v[sp].z; y.w += v[sp].w;
+                    for (int kk = 0; kk < TC_KC / 8; ++kk) {
+                        const uint32_t ko = kk * 32, acc = (it | kk) ? 1u : 0u;
+                        if (precision == 1) {
+                            umma_tf32(tmem_base, umma_desc_sw128(a_big + ko), umma_desc_sw128(b_big + ko), idesc_pair, acc);
+                            umma_tf32(tmem_base + 2 * BN, umma_desc_sw128(a_small + ko), umma_desc_sw128(b_big + ko), idesc, acc);
+                        } else {
+                            umma_tf32(tmem_base, umma_desc_sw128(a_big + ko), umma_desc_sw128(b_big + ko), idesc, acc);
+                        }
                     }
-                } else {
-                    y = *reinterpret_cast<const float4*>(tile0 + row * TILE_LD);
+                    umma_commit(bar_empty + 8 * st);
                 }
-                if (d.scale) { y.x *= p_scale.x; y.y *= p_scale.y; y.z *= p_scale.z; y.w *= p_scale.w; }
-                if (d.shift) { y.x += p_shift.x; y.y += p_shift.y; y.z += p_shift.z; y.w += p_shift.w; }
-                if (gn) group_norm(y);
-                if (row < rows_live) {
-                    if (res0) {
-                        const float4 rv = __ldg(reinterpret_cast<const float4*>(res0 + (size_t)row * res_ld));
-                        y.x += rv.x; y.y += rv.y; y.z += rv.z; y.w += rv.w;
-                    }
-                    if (relu) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
-                    if (zmod && (zphase + row) % zmod == d.zero_row_val) y = zero4;
-                    const size_t at = (size_t)row * out_ld;
-                    *reinterpret_cast<float4*>(out0 + at) = y;
-                    for (int p = 0; p < d.n_peers; ++p)
-                        *reinterpret_cast<float4*>(d.peer_out[p] + (size_t)m0 * out_ld + c0 + at) = y;
-                    if (d.pool_out) {
-                        float* o = d.pool_out + (size_t)__ldg(d.pool_seg + m0 + row) * out_ld + c0;
-                        atomic_max_f32(o, y.x);
-                        atomic_max_f32(o + 1, y.y);
-                        atomic_max_f32(o + 2, y.z);
-                        atomic_max_f32(o + 3, y.w);
-                    }
+                __syncwarp();
+            }
+            if (elect_one()) umma_commit(bar_accum);
+            __syncwarp();
+        }
+    } else if (warp == 9) {
+        if (lane == 0) {
+            // ===================== weight copies: run ahead across tiles, bounded by the stage ring only
+            int j = 0;
+            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
+                const size_t wchunk0 = d.tile_wslice ? (size_t)__ldg(d.tile_wslice + tile) * nk : 0;
+                for (int it = 0; it < nk; ++it) {
+                    const int g = j * nk + it, st = g % PS;
+                    mbar_wait(bar_empty + 8 * st, ((uint32_t)(g / PS) & 1u) ^ 1u);
+                    mbar_arrive_expect_tx(bar_full + 8 * st, 2 * B_IMG);
+                    bulk_g2s(smem_u32(smem + st * STAGE + 2 * TC_A_BYTES), Wp + (wchunk0 + it) * (2 * BN * 32), 2 * B_IMG,
+                             bar_full + 8 * st);
                 }
             }
         }
+        __syncwarp();
+    } else {
+        // ===================== producers + epilogue (warps 0..7)
+        const EpiParams epi = load_epi_params<BN>(d, tid);
+        const int pj = tid & 7, r0 = tid >> 3;   // 16-byte unit of the 128-byte chunk row; rows r0 + 32 i
+        const float* src[4];
+        float4 buf[TC_PREFETCH][4];
+        auto request_tile = [&](long long tile) {   // row numbers of the tile, then its first chunks
+            const long long m0 = tile * TC_BM;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const long long m = m0 + r0 + 32 * i;
+                long long rr = -1;
+                if (m < d.M) {
+                    rr = sl.idx ? (long long)__ldg(sl.idx + m * sl.idx_stride) : m + sl.shift;
+                    if (!sl.idx && rr >= d.n_src_rows) rr = -1;
+                }
+                src[i] = rr >= 0 ? sl.src + (size_t)rr * sl.ld + pj * 4 : nullptr;
+            }
+#pragma unroll
+            for (int p = 0; p < TC_PREFETCH; ++p)
+                if (p < nk) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        buf[p][i] = src[i] ? __ldg(reinterpret_cast<const float4*>(src[i] + p * TC_KC)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+        };
+        if ((long long)blockIdx.x < n_tiles) request_tile(blockIdx.x);
+        int j = 0;
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
+            const long long m0 = tile * TC_BM;
+            for (int it0 = 0; it0 < nk; it0 += TC_PREFETCH) {
+#pragma unroll
+                for (int p = 0; p < TC_PREFETCH; ++p) {
+                    const int it = it0 + p;
+                    if (it < nk) {
+                        const int g = j * nk + it, st = g % PS;
+                        mbar_wait(bar_empty + 8 * st, ((uint32_t)(g / PS) & 1u) ^ 1u);
+                        unsigned char* stage = smem + st * STAGE;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            float4 a = buf[p][i];
+                            if (d.relu_in) {
+                                a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
+                            }
+                            float4 big, small;
+                            split_tf32(a.x, big.x, small.x);
+                            split_tf32(a.y, big.y, small.y);
+                            split_tf32(a.z, big.z, small.z);
+                            split_tf32(a.w, big.w, small.w);
+                            const int r = r0 + 32 * i;
+                            const int off = r * 128 + ((pj ^ (r & 7)) << 4);
+                            *reinterpret_cast<float4*>(stage + off) = big;
+                            *reinterpret_cast<float4*>(stage + TC_A_BYTES + off) = small;
+                        }
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_full + 8 * st);
+                        if (it + TC_PREFETCH < nk) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                buf[p][i] = src[i] ? __ldg(reinterpret_cast<const float4*>(src[i] + (it + TC_PREFETCH) * TC_KC))
+                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                    }
+                }
+            }
+            // the next tile's rows and first chunks travel while this tile finishes
+            if (tile + gridDim.x < n_tiles) request_tile(tile + gridDim.x);
+
+            mbar_wait(bar_accum, (uint32_t)j & 1u);
+            tc_fence_after();
+            // every warp is done reading the previous tile from s_tile
+            asm volatile("bar.sync 1, %0;" ::"n"(TC_PRODUCERS) : "memory");
+            {
+                const int row = (warp & 3) * 32 + lane;
+                const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+                const int c_begin = (warp >> 2) * (BN / 2);
+#pragma unroll 1
+                for (int c0 = c_begin; c0 < c_begin + BN / 2; c0 += 16) {
+                    uint32_t ry[16], rz[16], rw[16];
+                    tmem_ld16_nowait(trow + (uint32_t)c0, ry);
+                    if (precision == 1) {
+                        tmem_ld16_nowait(trow + (uint32_t)(BN + c0), rz);
+                        tmem_ld16_nowait(trow + (uint32_t)(2 * BN + c0), rw);
+                    }
+                    tmem_ld_wait();
+                    float y[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) y[i] = __uint_as_float(ry[i]);
+                    if (precision == 1) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) y[i] += __uint_as_float(rz[i]) + __uint_as_float(rw[i]);
+                    }
+                    float4* tp = reinterpret_cast<float4*>(s_tile + row * TILE_LD + c0);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) tp[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+                }
+            }
+            tc_fence_before();
+            asm volatile("bar.sync 1, %0;" ::"n"(TC_PRODUCERS) : "memory");
+            if (tid == 0) mbar_arrive(bar_free);   // TMEM may be overwritten by the next tile's first MMA
+            tile_epilogue<BN, TC_PRODUCERS>(d, s_tile, m0, tid, epi, nullptr, 1, nullptr);
+        }
     }
-    if (stamp && tid == 0) stamp[7] = clock64();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
 int validate_gather_gemm(const GemmDesc& d, int k_multiple);
@@ -576,6 +802,22 @@ int launch_gather_gemm_tc(const GemmDesc& d_in, cudaStream_t st) {
         if (split > TC_MAX_SPLIT) split = TC_MAX_SPLIT;
         const size_t need = (size_t)tiles * split * TC_BM * d.N * sizeof(float);
         if (d.split_ws_bytes < need) split = 1;  // tiles * split <= 148 partials fit a dv3d_sparse_conv_workspace_bytes buffer
+    }
+    // persistent variant: one slice, no kernel map, no K split, more tiles than SMs (or forced for tests)
+    const bool persist_ok = d.n_slices == 1 && !d.kmap && split == 1;
+    if (persist_ok && (g_gemm_persistent > 0 || (g_gemm_persistent == 0 && tiles > kNumSMs))) {
+        const int grid_p = tiles < kNumSMs ? tiles : kNumSMs;
+        if (d.N == 128) {
+            static std::atomic<unsigned long long> attr{0};
+            DV3D_FUNC_SMEM_ONCE(attr, (gather_gemm_tc_persistent_kernel<128>), (int)tcp_smem_bytes<128>());
+            DV3D_LAUNCH((gather_gemm_tc_persistent_kernel<128>), grid_p, TC_THREADS, tcp_smem_bytes<128>(), st, d, g_gemm_precision);
+        } else {
+            static std::atomic<unsigned long long> attr{0};
+            DV3D_FUNC_SMEM_ONCE(attr, (gather_gemm_tc_persistent_kernel<64>), (int)tcp_smem_bytes<64>());
+            DV3D_LAUNCH((gather_gemm_tc_persistent_kernel<64>), grid_p, TC_THREADS, tcp_smem_bytes<64>(), st, d, g_gemm_precision);
+        }
+        DV3D_LAUNCHED();
+        return DV3D_OK;
     }
     dim3 grid(tiles, split);
     if (d.N == 128) {
@@ -614,6 +856,12 @@ extern "C" int dv3d_set_gemm_precision(int mode) {
     return DV3D_OK;
 }
 extern "C" int dv3d_get_gemm_precision(void) { return g_gemm_precision; }
+
+extern "C" int dv3d_set_gemm_persistent(int mode) {
+    DV3D_REQUIRE(mode >= -1 && mode <= 1, "set_gemm_persistent: -1 = never, 0 = automatic, 1 = whenever possible; got %d", mode);
+    g_gemm_persistent = mode;
+    return DV3D_OK;
+}
 
 extern "C" int dv3d_gemm_set_timing_buffer(void* device_buffer) {
     long long* p = (long long*)device_buffer;

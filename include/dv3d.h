@@ -179,6 +179,10 @@ size_t dv3d_gemm_pack_bytes(int Ktot, int N);
 int dv3d_gemm_pack_weights(const float* W, int Ktot, int N, void* packed, void* stream);
 int dv3d_set_gemm_precision(int mode);
 int dv3d_get_gemm_precision(void);
+/* Persistent variant of the tcgen05 gather-GEMM for single-slice launches (pair-major sparse convolution, Linear,
+ * Conv2d rows): -1 = never, 0 = automatic (more 128-row tiles than SMs; default), 1 = whenever the launch qualifies.
+ * Results are bit-identical in all modes. Process-wide; for tests and A/B measurements. */
+int dv3d_set_gemm_persistent(int mode);
 /* profiling aid (tools/gemm_phases.py): device buffer of (grid.x * grid.y) * 8 int64 clock stamps written by every
  * tcgen05 gather-GEMM launch on the current device; NULL switches it off */
 int dv3d_gemm_set_timing_buffer(void* device_buffer);
