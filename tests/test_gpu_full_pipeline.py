@@ -86,3 +86,24 @@ def test_full_pass_matches_cpu_pipeline(setup):
     assert out['final'].shape == final.shape == (len(ref_idx),) + s['img']
     rel = (out['final'].cpu() - final).abs() / (final.abs() + 1e-7)
     assert torch.median(rel).item() <= 1e-4 and rel.mean().item() <= 2e-3, (torch.median(rel).item(), rel.mean().item())
+
+
+def test_process_scene_plugin_equals_full_pass(setup):
+    """the reference's pred_func plugin (eval-3dvnet.py:26-127): same signature / return, same depth as full_pass
+    whatever the backbone chunking"""
+    from argparse import Namespace
+    ev = importlib.import_module('3dvnet_b200.mv3d.eval_3dvnet')
+    s = setup
+    b = s['b']
+    offsets = [[0.05, 0.025]]
+    want = _run_gpu(s, offsets)['final'].cpu().numpy()
+    batch = Namespace(images=b.images, rotmats=b.rotmats, tvecs=b.tvecs, K=b.K, ref_src_edges=b.ref_src_edges)
+    old = ev.BACKBONE_BATCH
+    try:
+        for chunk in (64, 2):
+            ev.BACKBONE_BATCH = chunk
+            got, a, c = ev.process_scene(batch, None, None, s['net'], depth_config=s['cfg'], offsets_list=offsets)
+            assert a is None and c is None and got.shape == want.shape
+            np.testing.assert_allclose(got, want, rtol=0, atol=1e-5)
+    finally:
+        ev.BACKBONE_BATCH = old
