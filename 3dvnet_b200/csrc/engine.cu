@@ -152,12 +152,29 @@ struct KMap {
     size_t plan_bytes;
     long long n_tiles;
     bool use_pairs;
+    long long row0;              // first output row of this map (sharded scene: the rank's range), n_out rows from there
     const struct Level* out_lv;
     const struct Level* in_lv;
     int step;
 };
 
+// A scene that spans GPUs (BASELINE config C4): this rank's share of the sparse U-Net.  Rank r owns rows
+// [r m, min((r+1) m, n)) of every level, m = ceil(n / world).  Layer outputs live in the symmetric heap (same offset
+// on every rank; the convolution epilogues store finished rows into every peer's copy, csrc/symm.cu) and one flag
+// barrier follows every layer whose output the next layer gathers through a kernel map.
+struct Shard {
+    int rank, world;
+    char* heap;                 // local symmetric block, registered with dv3d_symm_register
+    size_t heap_bytes, heap_off;
+    void* const* peer_heaps;    // ascending rank order, this rank left out
+    int n_peers;
+    int* err_flag;
+    int epoch;                  // last barrier epoch used (strictly increasing over the life of the heap)
+};
+
 struct Scene {
+    Shard* shard;                    // nullptr: single GPU
+    long long r0[DV3D_MAX_LEVELS], r1[DV3D_MAX_LEVELS];  // this rank's row range per level (whole level when !shard)
     Level lv[DV3D_MAX_LEVELS];
     int n_levels;
     KMap same[DV3D_MAX_LEVELS];      // k3 s1 kernel map of level l
@@ -172,24 +189,55 @@ struct Scene {
     size_t split_ws_bytes;
 };
 
-static int sparse_conv(const dv3d_dense_params_t& p, const float* feat, long long n_in, const KMap& km, long long n_out,
-                       const float* residual, Scene& sc, float* out, void* st) {
-    if (km.use_pairs && p.Wp)
-        return dv3d_sparse_conv_pairs(feat, n_in, p.K / 27, km.plan, km.n_tiles, n_out, p.Wp, p.N, p.a, p.b, residual, 1,
-                                      sc.pair_ws, sc.pair_ws_bytes, out, st);
-    return dv3d_sparse_conv(feat, n_in, p.K / 27, km.nbr, n_out, p.W, p.Wp, p.N, p.a, p.b, residual, 1, sc.split_ws,
-                            sc.split_ws_bytes, out, st);
+// rows of a layer output: the arena, or - sharded scene - the symmetric heap (same offset on every rank, because every
+// rank allocates the same sizes in the same order: the coordinate levels are identical everywhere)
+static float* layer_rows(Scene& sc, Arena& ar, long long n, int C) {
+    if (!sc.shard) return ar.get<float>((size_t)n * C);
+    Shard& sh = *sc.shard;
+    const size_t bytes = align_up((size_t)n * C * sizeof(float), 256);
+    if (sh.heap_off + bytes > sh.heap_bytes) {
+        ar.failed = true;  // reported as ENOSPC by ARENA_CHECK
+        return nullptr;
+    }
+    float* p = reinterpret_cast<float*>(sh.heap + sh.heap_off);
+    sh.heap_off += bytes;
+    return p;
+}
+
+// cross-GPU barrier behind a layer whose output the next layer gathers through a kernel map
+static int layer_barrier(Scene& sc, void* st) {
+    if (!sc.shard) return DV3D_OK;
+    Shard& sh = *sc.shard;
+    return dv3d_symm_barrier(sh.heap, sh.peer_heaps, sh.n_peers, sh.rank, ++sh.epoch, sh.err_flag, st);
+}
+
+// One sparse convolution + GroupNorm + ReLU for the rows the kernel map covers (all rows, or this rank's range):
+// `feat` and `out` are full [n, C] arrays, `residual` too.  Sharded: the epilogue stores the rows into every rank's
+// copy of `out` (csrc/symm.cu) and the barrier follows.
+static int sparse_conv(const dv3d_dense_params_t& p, const float* feat, long long n_in, const KMap& km, const float* residual,
+                       Scene& sc, float* out, void* st) {
+    if (km.n_out > 0) {
+        const float* res = residual ? residual + km.row0 * p.N : nullptr;
+        float* o = out + km.row0 * p.N;
+        if (km.use_pairs && p.Wp)
+            TRY(dv3d_sparse_conv_pairs(feat, n_in, p.K / 27, km.plan, km.n_tiles, km.n_out, p.Wp, p.N, p.a, p.b, res, 1,
+                                       sc.pair_ws, sc.pair_ws_bytes, o, st));
+        else
+            TRY(dv3d_sparse_conv(feat, n_in, p.K / 27, km.nbr, km.n_out, p.W, p.Wp, p.N, p.a, p.b, res, 1, sc.split_ws,
+                                 sc.split_ws_bytes, o, st));
+    }
+    return layer_barrier(sc, st);
 }
 
 // relu(x + GN2(conv2(relu(GN1(conv1(x))))))  (scenemodeling.py:16-44)
 static int res_block(const dv3d_dense_params_t (&p)[2], const float* x, long long n, const KMap& nbr, Scene& sc, Arena& ar,
                      float** out, void* st) {
     const int C = p[0].N;
-    float* h = ar.get<float>((size_t)n * C);
-    float* y = ar.get<float>((size_t)n * C);
+    float* h = layer_rows(sc, ar, n, C);
+    float* y = layer_rows(sc, ar, n, C);
     ARENA_CHECK(ar);
-    TRY(sparse_conv(p[0], x, n, nbr, n, nullptr, sc, h, st));
-    TRY(sparse_conv(p[1], h, n, nbr, n, x, sc, y, st));
+    TRY(sparse_conv(p[0], x, n, nbr, nullptr, sc, h, st));
+    TRY(sparse_conv(p[1], h, n, nbr, x, sc, y, st));
     *out = y;
     return DV3D_OK;
 }
@@ -202,13 +250,15 @@ static int build_level(Level& L, int* err_flag, Arena& ar, void* st) {
 }
 
 // kernel map and, on the tensor-core path, its pair-major plan (counts are read back later, once)
-static int kernel_map(const Level& out_lv, const Level& in_lv, int step, bool want_plan, Arena& ar, KMap* km, void* st) {
-    km->n_out = out_lv.n;
-    km->nbr = ar.get<int>((size_t)out_lv.n * 27);
+static int kernel_map(const Level& out_lv, long long row0, long long row1, const Level& in_lv, int step, bool want_plan,
+                      Arena& ar, KMap* km, void* st) {
+    km->row0 = row0;
+    km->n_out = row1 - row0;
+    km->nbr = ar.get<int>((size_t)(km->n_out > 0 ? km->n_out : 1) * 27);
     km->plan = nullptr;
     km->n_tiles = 0;
     km->use_pairs = false;
-    const size_t pb = want_plan ? dv3d_pair_plan_bytes(out_lv.n) : 0;
+    const size_t pb = want_plan ? dv3d_pair_plan_bytes(km->n_out) : 0;
     if (want_plan) km->plan = ar.get<char>(pb);
     ARENA_CHECK(ar);
     km->plan_bytes = pb;
@@ -220,8 +270,8 @@ static int kernel_map(const Level& out_lv, const Level& in_lv, int step, bool wa
 }
 
 // voxelise -> PointNet -> sparse 3D-UNet on the feature-rich point cloud (lightningmodel.py:176-185)
-static int model_scene(const dv3d_net_params_t& net, const float* pts, const float* pts_feat, const long long* pts_batch,
-                       long long N, double edge_len, Scene& sc, Arena& ar, void* st) {
+static int model_scene(const dv3d_net_params_t& net, const float* pts, const float* pts_feat, int feat_ld,
+                       const long long* pts_batch, long long N, double edge_len, Scene& sc, Arena& ar, void* st) {
     cudaStream_t cs = (cudaStream_t)st;
     SideStream* side = side_stream(cs);
     DV3D_REQUIRE(side, "hot_path: cannot create the side stream (more than 32 caller streams?)");
@@ -264,7 +314,7 @@ static int model_scene(const dv3d_net_params_t& net, const float* pts, const flo
     float* F = ar.get<float>((size_t)nv * net.pointnet[5].N);
     ARENA_CHECK(ar);
     DV3D_CUDA(cudaMemsetAsync(pools, 0xFF, sizeof(float) * 4 * (size_t)nv * Hd, cs));
-    TRY(dv3d_pointnet_input(pts, pts_feat, 32, a_pts, seg, N, 32, in_pad, x0, st));
+    TRY(dv3d_pointnet_input(pts, pts_feat, feat_ld, a_pts, seg, N, 32, in_pad, x0, st));
     TRY(dv3d_linear(x0, in_pad, in_pad, nullptr, nullptr, 0, N, net.pointnet[0].W, net.pointnet[0].Wp, net.pointnet[0].b, Hd,
                     0, xa, st));
     TRY(dv3d_linear_pool(xa, Hd, Hd, nullptr, nullptr, 0, N, net.pointnet[1].W, net.pointnet[1].Wp, net.pointnet[1].b, Hd, 1,
@@ -351,19 +401,31 @@ static int model_scene(const dv3d_net_params_t& net, const float* pts, const flo
     // every kernel map of the U-Net and its pair-major plan, then ONE sync for the counts
     {
         const bool want_plan = net.res_down[0][0][0].Wp != nullptr;
+        DV3D_REQUIRE(!sc.shard || want_plan, "hot_path: the row-sharded U-Net needs a tensor-core GEMM mode (packed weights)");
+        for (int l = 0; l < nl; ++l) {   // this rank's rows of every level
+            const long long n = sc.lv[l].n;
+            if (sc.shard) {
+                const long long m = (n + sc.shard->world - 1) / sc.shard->world;
+                sc.r0[l] = std::min((long long)sc.shard->rank * m, n);
+                sc.r1[l] = std::min((long long)(sc.shard->rank + 1) * m, n);
+            } else {
+                sc.r0[l] = 0;
+                sc.r1[l] = n;
+            }
+        }
         KMap* maps[3 * DV3D_MAX_LEVELS];
         int n_maps = 0;
         for (int l = 0; l < nl; ++l) {
-            TRY(kernel_map(sc.lv[l], sc.lv[l], sc.lv[l].stride, want_plan, ar, &sc.same[l], sst));
-            maps[n_maps++] = &sc.same[l];
+            TRY(kernel_map(sc.lv[l], sc.r0[l], sc.r1[l], sc.lv[l], sc.lv[l].stride, want_plan, ar, &sc.same[l], sst));
+            if (sc.same[l].n_out > 0) maps[n_maps++] = &sc.same[l];  // a tail rank may own no row of a small level
         }
         for (int l = 0; l + 1 < nl; ++l) {
-            TRY(kernel_map(sc.lv[l + 1], sc.lv[l], sc.lv[l].stride, want_plan, ar, &sc.down[l], sst));
-            maps[n_maps++] = &sc.down[l];
+            TRY(kernel_map(sc.lv[l + 1], sc.r0[l + 1], sc.r1[l + 1], sc.lv[l], sc.lv[l].stride, want_plan, ar, &sc.down[l], sst));
+            if (sc.down[l].n_out > 0) maps[n_maps++] = &sc.down[l];
         }
         for (int l = 0; l + 1 < nl; ++l) {
-            TRY(kernel_map(sc.lv[l], sc.lv[l + 1], -sc.lv[l].stride, want_plan, ar, &sc.up[l], sst));
-            maps[n_maps++] = &sc.up[l];
+            TRY(kernel_map(sc.lv[l], sc.r0[l], sc.r1[l], sc.lv[l + 1], -sc.lv[l].stride, want_plan, ar, &sc.up[l], sst));
+            if (sc.up[l].n_out > 0) maps[n_maps++] = &sc.up[l];
         }
         {
             const int* co[3 * DV3D_MAX_LEVELS];
@@ -373,8 +435,8 @@ static int model_scene(const dv3d_net_params_t& net, const float* pts, const flo
             int stp[3 * DV3D_MAX_LEVELS];
             int* nb[3 * DV3D_MAX_LEVELS];
             for (int i = 0; i < n_maps; ++i) {
-                co[i] = maps[i]->out_lv->coords;
-                no[i] = maps[i]->out_lv->n;
+                co[i] = maps[i]->out_lv->coords + 4 * maps[i]->row0;
+                no[i] = maps[i]->n_out;
                 tb[i] = maps[i]->in_lv->table;
                 tbb[i] = maps[i]->in_lv->table_bytes;
                 stp[i] = maps[i]->step;
@@ -418,12 +480,14 @@ static int model_scene(const dv3d_net_params_t& net, const float* pts, const flo
     next_stage(DV3D_STAGE_UNET, cs);
     float* xs[DV3D_MAX_LEVELS];
     float* x = F;
+    // sharded: no rank may store into a peer's heap before that peer has left the previous use of it
+    TRY(layer_barrier(sc, st));
     for (int b = 0; b < net.n_res[0]; ++b) TRY(res_block(net.res_down[0][b], x, sc.lv[0].n, sc.same[0], sc, ar, &x, st));
     xs[0] = x;
     for (int i = 1; i < nl; ++i) {
-        float* y = ar.get<float>((size_t)sc.lv[i].n * net.down[i - 1].N);
+        float* y = layer_rows(sc, ar, sc.lv[i].n, net.down[i - 1].N);
         ARENA_CHECK(ar);
-        TRY(sparse_conv(net.down[i - 1], x, sc.lv[i - 1].n, sc.down[i - 1], sc.lv[i].n, nullptr, sc, y, st));
+        TRY(sparse_conv(net.down[i - 1], x, sc.lv[i - 1].n, sc.down[i - 1], nullptr, sc, y, st));
         x = y;
         for (int b = 0; b < net.n_res[i]; ++b) TRY(res_block(net.res_down[i][b], x, sc.lv[i].n, sc.same[i], sc, ar, &x, st));
         xs[i] = x;
@@ -432,24 +496,128 @@ static int model_scene(const dv3d_net_params_t& net, const float* pts, const flo
     sc.dims[nl - 1] = net.res_down[nl - 1][0][0].N;
     for (int i = 0; i < nl - 1; ++i) {
         const int l = nl - 2 - i;  // target (finer) level
-        const int Cu = net.up[i].N;
-        float* up = ar.get<float>((size_t)sc.lv[l].n * Cu);
-        float* adj = ar.get<float>((size_t)sc.lv[l].n * net.feat_adj[i].N);
+        const int Cu = net.up[i].N, Cx = net.feat_adj[i].K - Cu, Ca = net.feat_adj[i].N;
+        const long long r0 = sc.r0[l], n_loc = sc.r1[l] - sc.r0[l];
+        // the transposed convolution feeds the 1x1 'feature adjust' row by row: its output stays local to the rank
+        float* up = ar.get<float>((size_t)(n_loc > 0 ? n_loc : 1) * Cu);
+        float* adj = layer_rows(sc, ar, sc.lv[l].n, Ca);
         ARENA_CHECK(ar);
-        TRY(sparse_conv(net.up[i], x, sc.lv[l + 1].n, sc.up[l], sc.lv[l].n, nullptr, sc, up, st));
-        TRY(dv3d_concat_linear_gn_relu(up, Cu, xs[l], net.feat_adj[i].K - Cu, sc.lv[l].n, net.feat_adj[i].W, net.feat_adj[i].Wp,
-                                       net.feat_adj[i].N, net.feat_adj[i].a, net.feat_adj[i].b, adj, st));
+        if (n_loc > 0) {
+            const KMap& km = sc.up[l];
+            const dv3d_dense_params_t& p = net.up[i];
+            if (km.use_pairs && p.Wp)
+                TRY(dv3d_sparse_conv_pairs(x, sc.lv[l + 1].n, p.K / 27, km.plan, km.n_tiles, n_loc, p.Wp, p.N, p.a, p.b, nullptr, 1,
+                                           sc.pair_ws, sc.pair_ws_bytes, up, st));
+            else
+                TRY(dv3d_sparse_conv(x, sc.lv[l + 1].n, p.K / 27, km.nbr, n_loc, p.W, p.Wp, p.N, p.a, p.b, nullptr, 1, sc.split_ws,
+                                     sc.split_ws_bytes, up, st));
+            TRY(dv3d_concat_linear_gn_relu(up, Cu, xs[l] + r0 * Cx, Cx, n_loc, net.feat_adj[i].W, net.feat_adj[i].Wp, Ca,
+                                           net.feat_adj[i].a, net.feat_adj[i].b, adj + r0 * Ca, st));
+        }
+        TRY(layer_barrier(sc, st));
         x = adj;
         // the reversed n_res list: res_up[i] has n_res[nl-2-i] blocks (scenemodeling.py:168-175)
         for (int b = 0; b < net.n_res[l]; ++b) TRY(res_block(net.res_up[i][b], x, sc.lv[l].n, sc.same[l], sc, ar, &x, st));
         sc.feats[l] = x;
-        sc.dims[l] = net.feat_adj[i].N;
+        sc.dims[l] = Ca;
     }
     // position of index (0,0,0) of every batch (scenemodeling.py:211-226 / refinement.py:33)
     sc.origin = ar.get<float>((size_t)grid.n_batch * 3);
     ARENA_CHECK(ar);
     DV3D_CUDA(cudaMemsetAsync(sc.origin, 0, sizeof(float) * grid.n_batch * 3, cs));
     TRY(dv3d_batch_origin(a_pts, a_idx, a_batch, nv, (float)edge_len, sc.origin, st));
+    return DV3D_OK;
+}
+
+
+// everything a PointFlow pass needs besides the scene model (lightningmodel.py:187-242)
+struct PassCtx {
+    const float* feats_nhwc;
+    int n_imgs, Hf, Wf;
+    const float* cams;
+    const int *ref_img, *edge_rowptr, *edge_src;
+    float* depth;            // [n_ref, h, w], updated in place
+    int n_ref, h, w, H, W;
+    long long Np;
+    int in_dim, var_off;
+    float *operand, *dec_a, *dec_b, *pts_hyp, *offs;
+    const long long* pts_batch;
+    void* split_ws;
+    size_t split_ws_bytes;
+    double edge_len;
+    void* stream;
+};
+
+static int pointflow_pass(const dv3d_net_params_t& net, const PassCtx& c, const Scene& sc, double offset) {
+    cudaStream_t cs = (cudaStream_t)c.stream;
+    const float* feats_nhwc = c.feats_nhwc;
+    const int n_imgs = c.n_imgs, Hf = c.Hf, Wf = c.Wf, n_ref = c.n_ref, h = c.h, w = c.w, H = c.H, W = c.W;
+    const float* cams = c.cams;
+    const int *ref_img = c.ref_img, *edge_rowptr = c.edge_rowptr, *edge_src = c.edge_src;
+    float *depth = c.depth, *operand = c.operand, *dec_a = c.dec_a, *dec_b = c.dec_b, *pts_hyp = c.pts_hyp, *offs = c.offs;
+    const long long* pts_batch = c.pts_batch;
+    const long long Np = c.Np;
+    const int in_dim = c.in_dim, var_off = c.var_off;
+    void* split_ws = c.split_ws;
+    const size_t split_ws_bytes = c.split_ws_bytes;
+    const double edge_len = c.edge_len;
+    void* stream = c.stream;
+    // PointFlow pass (lightningmodel.py:187-242)
+    {
+        Prof pr(DV3D_STAGE_FLOW_WARP, cs);
+        TRY(dv3d_points_var(feats_nhwc, n_imgs, 32, Hf, Wf, cams, ref_img, edge_rowptr, edge_src, depth, n_ref, h, w,
+                            H, W, 3, offset, pts_hyp, operand, 8, in_dim, var_off, stream));
+    }
+    int off_c = 0;
+    {
+        Prof pr(DV3D_STAGE_FLOW_INTERP, cs);
+        // all levels with one launch, finest level first in the operand (refinement.py:41 prepends)
+        float res_l[DV3D_MAX_LEVELS];
+        int stride_l[DV3D_MAX_LEVELS], C_l[DV3D_MAX_LEVELS], off_l[DV3D_MAX_LEVELS];
+        const void* tab_l[DV3D_MAX_LEVELS];
+        size_t tabb_l[DV3D_MAX_LEVELS];
+        const float* feat_l[DV3D_MAX_LEVELS];
+        for (int l = 0; l < sc.n_levels; ++l) {
+            res_l[l] = (float)(sc.lv[l].stride * edge_len);
+            stride_l[l] = sc.lv[l].stride;
+            tab_l[l] = sc.lv[l].table;
+            tabb_l[l] = sc.lv[l].table_bytes;
+            feat_l[l] = sc.feats[l];
+            C_l[l] = sc.dims[l];
+            off_l[l] = off_c;
+            off_c += sc.dims[l];
+        }
+        TRY(dv3d_sparse_interp_batch(pts_hyp, pts_batch, Np, 7, 8, sc.origin, sc.n_levels, res_l, stride_l, tab_l,
+                                     tabb_l, feat_l, C_l, off_l, operand, in_dim, stream));
+    }
+    DV3D_REQUIRE(off_c == var_off, "hot_path: decoder input width %d != level widths %d + 32", in_dim, off_c);
+    if (net.dec_fused[0] && net.dec_fused[1] && net.dec_fused[2]) {
+        // the whole decoder + `depth += offset` as one tcgen05 kernel (csrc/decoder_fused.cu)
+        Prof pr(DV3D_STAGE_DEC_GEMM0, cs);
+        const void* wp[3] = {net.dec_fused[0], net.dec_fused[1], net.dec_fused[2]};
+        const float* sc[3] = {net.dec[0].a, net.dec[1].a, net.dec[2].a};
+        const float* sh[3] = {net.dec[0].b, net.dec[1].b, net.dec[2].b};
+        TRY(dv3d_decoder_fused(operand, Np, 8, in_dim, in_dim, wp, sc, sh, net.dec[0].N, net.dec_head_weight,
+                               net.dec_head_bias, offset, dv3d_get_gemm_precision() & 0xff, nullptr, nullptr, depth,
+                               stream));
+    } else {
+        {
+            Prof pr(DV3D_STAGE_DEC_GEMM0, cs);
+            TRY(dv3d_conv1d_bn_relu(operand, Np, 8, in_dim, in_dim, net.dec[0].W, net.dec[0].Wp, net.dec[0].a,
+                                    net.dec[0].b, net.dec[0].N, dec_a, net.dec[0].N, split_ws, split_ws_bytes, stream));
+        }
+        {
+            Prof pr(DV3D_STAGE_DEC_REST, cs);
+            TRY(dv3d_conv1d_bn_relu(dec_a, Np, 8, net.dec[1].K / 3, net.dec[0].N, net.dec[1].W, net.dec[1].Wp,
+                                    net.dec[1].a, net.dec[1].b, net.dec[1].N, dec_b, net.dec[1].N, split_ws, split_ws_bytes, stream));
+            TRY(dv3d_conv1d_bn_relu(dec_b, Np, 8, net.dec[2].K / 3, net.dec[1].N, net.dec[2].W, net.dec[2].Wp,
+                                    net.dec[2].a, net.dec[2].b, net.dec[2].N, dec_a, net.dec[2].N, split_ws, split_ws_bytes, stream));
+            TRY(dv3d_decoder_head(dec_a, Np, 7, 8, net.dec[2].N, net.dec[2].N, net.dec_head_weight, net.dec_head_bias,
+                                  offset, nullptr, offs, stream));
+            DV3D_LAUNCH((add_inplace_kernel), cdiv(Np, 256), 256, 0, cs, depth, offs, Np);
+            DV3D_LAUNCHED();
+        }
+    }
     return DV3D_OK;
 }
 
@@ -511,6 +679,154 @@ extern "C" size_t dv3d_hot_path_workspace_bytes(const dv3d_net_params_t* net, in
     return floats * sizeof(float) + kBitmapShare + dv3d_sparse_conv_workspace_bytes(128) + (64 << 10) /* alignment slack */;
 }
 
+// The whole pass for `n_ref` reference views.  With a Shard these are the rank's contiguous range
+// [ref_start, ref_start + n_ref) of the scene's `n_ref_total` references (depth_batch then holds all n_ref_total
+// entries): the rank's point rows go into the symmetric heap of every rank (peer copies over NVLink + one flag
+// barrier - the exchange step of SURVEY.md section 8e), every rank voxelises the whole cloud, and the sparse U-Net runs
+// row-sharded (model_scene).
+static int hot_path_impl(const dv3d_net_params_t& net, const float* feats_nhwc, int n_imgs, int Hf, int Wf,
+                         const float* rotmats, const float* tvecs, const float* K, const int* ref_img,
+                         const int* edge_rowptr, const int* edge_src, int n_ref, const long long* depth_batch,
+                         double depth_start, double depth_interval, int D, int h, int w, int H, int W, double edge_len,
+                         const double* offsets_host, int n_outer, int n_inner, void* workspace, size_t workspace_bytes,
+                         Shard* sh, int n_ref_total, int ref_start, float* depth_init_out, float* depth_out, void* stream) {
+    cudaStream_t cs = (cudaStream_t)stream;
+    Arena ar{(char*)workspace, workspace_bytes, 0, false};
+    const long long P = (long long)h * w, Np = (long long)n_ref * P;
+    const long long Ng = (long long)n_ref_total * P, row0 = (long long)ref_start * P;  // the whole cloud, this rank's first row
+
+    // ================= path A: cost volume -> CostRegNet -> soft-argmin (mvsnet.py:176-229)
+    float* cams = ar.get<float>((size_t)n_imgs * 36);
+    ARENA_CHECK(ar);
+    TRY(dv3d_camera_tables(rotmats, tvecs, K, n_imgs, cams, stream));
+    float* depth = nullptr;
+    float* offs = nullptr;
+    if (n_ref > 0) {
+        float* x_var = ar.get<float>((size_t)n_ref * 32 * D * P);
+        ARENA_CHECK(ar);
+        {
+            Prof pr(DV3D_STAGE_PLANESWEEP, cs);
+            TRY(dv3d_planesweep_var(feats_nhwc, n_imgs, 32, Hf, Wf, cams, ref_img, edge_rowptr, edge_src, n_ref, depth_start,
+                                    depth_interval, D, h, w, H, W, x_var, stream));
+        }
+        float* act[10];
+        int aD[10], aH[10], aW[10];
+        {
+            Prof pr(DV3D_STAGE_COSTREG, cs);
+            const float* in = x_var;
+            int cd = D, ch = h, cw = w;
+            for (int i = 0; i < 10; ++i) {
+                const dv3d_conv3d_params_t& c = net.costreg[i];
+                int od = cd, oh = ch, ow = cw;
+                if (c.kind == 1) od = (cd + 1) / 2, oh = (ch + 1) / 2, ow = (cw + 1) / 2;
+                if (c.kind == 2) od = 2 * cd, oh = 2 * ch, ow = 2 * cw;
+                act[i] = ar.get<float>((size_t)n_ref * c.Cout * od * oh * ow);
+                ARENA_CHECK(ar);
+                // skips: x = conv4 + conv7(x); x = conv2 + conv8(x); x = conv0 + conv9(x)  (mvsnet.py:159-161)
+                const float* skip = i == 7 ? act[4] : i == 8 ? act[2] : i == 9 ? act[0] : nullptr;
+                if (c.kind == 2)
+                    TRY(dv3d_deconv3d_bn_relu(in, n_ref, c.Cin, cd, ch, cw, c.weight, c.scale, c.shift, c.Cout, skip, act[i], stream));
+                else
+                    TRY(dv3d_conv3d_bn_relu(in, n_ref, c.Cin, cd, ch, cw, c.weight, c.scale, c.shift, c.Cout, c.kind == 1 ? 2 : 1,
+                                            skip, act[i], stream));
+                aD[i] = od, aH[i] = oh, aW[i] = ow;
+                in = act[i];
+                cd = od, ch = oh, cw = ow;
+            }
+            DV3D_REQUIRE(aD[9] == D && aH[9] == h && aW[9] == w, "hot_path: CostRegNet does not return to full resolution");
+        }
+        depth = ar.get<float>((size_t)Np);
+        offs = ar.get<float>((size_t)Np);
+        ARENA_CHECK(ar);
+        const double depth_end = depth_start + depth_interval * (D - 1);
+        {
+            Prof pr(DV3D_STAGE_SOFTARGMIN, cs);
+            TRY(dv3d_prob_softargmin(act[9], n_ref, net.costreg[9].Cout, D, h, w, net.prob_weight, net.prob_bias,
+                                     (float)depth_start, (float)depth_end, nullptr, depth, stream));
+        }
+        if (depth_init_out) DV3D_CUDA(cudaMemcpyAsync(depth_init_out, depth, sizeof(float) * Np, cudaMemcpyDeviceToDevice, cs));
+    }
+
+    // ================= path B: volumetric refinement (eval-3dvnet.py:73-99)
+    if (n_outer * n_inner > 0) {
+        ar.off = 0;  // path A's volumes are dead; keep only cams / depth / offs by re-reserving them first
+        float* cams2 = ar.get<float>((size_t)n_imgs * 36);
+        (void)cams2;  // same address as cams
+        // depth / offs live behind the volumes: move them to the front of the arena
+        float* depth_f = ar.get<float>((size_t)Np);
+        float* offs_f = ar.get<float>((size_t)Np);
+        if (Np > 0) DV3D_CUDA(cudaMemcpyAsync(depth_f, depth, sizeof(float) * Np, cudaMemcpyDeviceToDevice, cs));
+        depth = depth_f;
+        offs = offs_f;
+        const int in_dim = net.dec[0].K / 3, var_off = in_dim - 32;
+        float* operand = ar.get<float>((size_t)Np * 8 * in_dim);  // [n_pts, 8, in_dim], padding row stays zero
+        const bool fused_dec = net.dec_fused[0] && net.dec_fused[1] && net.dec_fused[2];
+        float* dec_a = fused_dec ? nullptr : ar.get<float>((size_t)Np * 8 * net.dec[0].N);
+        float* dec_b = fused_dec ? nullptr : ar.get<float>((size_t)Np * 8 * net.dec[1].N);
+        float* pts_hyp = ar.get<float>((size_t)Np * 7 * 3);
+        long long* pts_batch_all = ar.get<long long>((size_t)Ng);  // batch index of every point of the cloud
+        const size_t split_ws_bytes = dv3d_sparse_conv_workspace_bytes(128);
+        void* split_ws = ar.get<char>(split_ws_bytes);
+        ARENA_CHECK(ar);
+        const PassCtx pc = {feats_nhwc, n_imgs, Hf, Wf, cams, ref_img, edge_rowptr, edge_src, depth, n_ref, h, w, H, W, Np, in_dim,
+                            var_off, operand, dec_a, dec_b, pts_hyp, offs, pts_batch_all + row0, split_ws, split_ws_bytes, edge_len,
+                            stream};
+        if (Np > 0) DV3D_CUDA(cudaMemsetAsync(operand, 0, sizeof(float) * Np * 8 * in_dim, cs));
+        DV3D_CUDA(cudaMemsetAsync(split_ws, 0, dv3d_sparse_conv_workspace_bytes(128), cs));
+        DV3D_LAUNCH((expand_batch_kernel), cdiv(Ng, 256), 256, 0, cs, depth_batch, (int)P, Ng, pts_batch_all);
+        DV3D_LAUNCHED();
+        // sharded: the cloud lives at fixed offsets of the symmetric heap, the layer outputs behind it
+        float *pts_sym = nullptr, *feat_sym = nullptr;
+        size_t layers_off = 0;
+        if (sh) {
+            const size_t pts_bytes = align_up((size_t)Ng * 3 * sizeof(float), 256), feat_bytes = align_up((size_t)Ng * 32 * sizeof(float), 256);
+            DV3D_REQUIRE(256 + pts_bytes + feat_bytes <= sh->heap_bytes, "hot_path_sharded: the symmetric heap is too small for the point cloud");
+            pts_sym = reinterpret_cast<float*>(sh->heap + 256);
+            feat_sym = reinterpret_cast<float*>(sh->heap + 256 + pts_bytes);
+            layers_off = 256 + pts_bytes + feat_bytes;
+        }
+        const size_t mark = ar.off;
+        for (int o = 0; o < n_outer; ++o) {
+            ar.off = mark;
+            // feature-rich point cloud (lightningmodel.py:132-174)
+            float* pts = sh ? pts_sym : ar.get<float>((size_t)Np * 3);
+            float* pfeat = sh ? feat_sym : ar.get<float>((size_t)Np * 32);
+            ARENA_CHECK(ar);
+            if (Np > 0) {
+                Prof pr(DV3D_STAGE_POINTCLOUD, cs);
+                TRY(dv3d_points_var(feats_nhwc, n_imgs, 32, Hf, Wf, cams, ref_img, edge_rowptr, edge_src, depth, n_ref, h, w, H,
+                                    W, 0, 0.0, pts + 3 * row0, pfeat + 32 * row0, 1, 32, 0, stream));
+            }
+            if (sh) {
+                // all-gather of the point rows: this rank's rows into every peer's copy, then the barrier.  A peer is
+                // past every reader of its copy of the cloud: it has arrived at the last barrier of the previous
+                // scene model, which follows its voxelisation and PointNet in stream order.
+                Prof pr(DV3D_STAGE_EXCHANGE, cs);
+                for (int p = 0; p < sh->n_peers && Np > 0; ++p) {
+                    char* peer = reinterpret_cast<char*>(sh->peer_heaps[p]);
+                    DV3D_CUDA(cudaMemcpyAsync(peer + ((char*)(pts + 3 * row0) - sh->heap), pts + 3 * row0, sizeof(float) * 3 * Np,
+                                              cudaMemcpyDeviceToDevice, cs));
+                    DV3D_CUDA(cudaMemcpyAsync(peer + ((char*)(pfeat + 32 * row0) - sh->heap), pfeat + 32 * row0, sizeof(float) * 32 * Np,
+                                              cudaMemcpyDeviceToDevice, cs));
+                }
+                TRY(dv3d_symm_barrier(sh->heap, sh->peer_heaps, sh->n_peers, sh->rank, ++sh->epoch, sh->err_flag, stream));
+                sh->heap_off = layers_off;
+            }
+            Scene sc;
+            memset(&sc, 0, sizeof(sc));
+            sc.shard = sh;
+            sc.split_ws = split_ws;
+            sc.split_ws_bytes = dv3d_sparse_conv_workspace_bytes(128);
+            TRY(model_scene(net, pts, pfeat, 32, pts_batch_all, Ng, edge_len, sc, ar, stream));
+            for (int it = 0; it < n_inner && Np > 0; ++it) {
+                TRY(pointflow_pass(net, pc, sc, offsets_host[o * n_inner + it]));
+            }
+        }
+    }
+    if (Np > 0) DV3D_CUDA(cudaMemcpyAsync(depth_out, depth, sizeof(float) * Np, cudaMemcpyDeviceToDevice, cs));
+    return DV3D_OK;
+}
+
 extern "C" int dv3d_hot_path(const dv3d_net_params_t* netp, const float* feats_nhwc, int n_imgs, int Hf, int Wf,
                              const float* rotmats, const float* tvecs, const float* K, const int* ref_img,
                              const int* edge_rowptr, const int* edge_src, int n_ref, const long long* depth_batch,
@@ -523,162 +839,51 @@ extern "C" int dv3d_hot_path(const dv3d_net_params_t* netp, const float* feats_n
     DV3D_REQUIRE(n_outer >= 0 && n_inner >= 0 && (n_outer * n_inner == 0 || offsets_host), "hot_path: bad refinement schedule");
     DV3D_REQUIRE(D % 8 == 0 && h % 8 == 0 && w % 8 == 0,
                  "hot_path: D, h, w must be multiples of 8 (three stride-2 levels of CostRegNet), got %d %d %d", D, h, w);
-    const dv3d_net_params_t& net = *netp;
-    DV3D_REQUIRE(net.n_levels >= 1 && net.n_levels <= DV3D_MAX_LEVELS, "hot_path: n_levels out of range");
+    DV3D_REQUIRE(netp->n_levels >= 1 && netp->n_levels <= DV3D_MAX_LEVELS, "hot_path: n_levels out of range");
     if (n_ref == 0) return DV3D_OK;
-    cudaStream_t cs = (cudaStream_t)stream;
-    Arena ar{(char*)workspace, workspace_bytes, 0, false};
-    const long long P = (long long)h * w, Np = (long long)n_ref * P;
+    return hot_path_impl(*netp, feats_nhwc, n_imgs, Hf, Wf, rotmats, tvecs, K, ref_img, edge_rowptr, edge_src, n_ref, depth_batch,
+                         depth_start, depth_interval, D, h, w, H, W, edge_len, offsets_host, n_outer, n_inner, workspace,
+                         workspace_bytes, nullptr, n_ref, 0, depth_init_out, depth_out, stream);
+}
 
-    // ================= path A: cost volume -> CostRegNet -> soft-argmin (mvsnet.py:176-229)
-    float* cams = ar.get<float>((size_t)n_imgs * 36);
-    float* x_var = ar.get<float>((size_t)n_ref * 32 * D * P);
-    ARENA_CHECK(ar);
-    TRY(dv3d_camera_tables(rotmats, tvecs, K, n_imgs, cams, stream));
-    {
-        Prof pr(DV3D_STAGE_PLANESWEEP, cs);
-        TRY(dv3d_planesweep_var(feats_nhwc, n_imgs, 32, Hf, Wf, cams, ref_img, edge_rowptr, edge_src, n_ref, depth_start,
-                                depth_interval, D, h, w, H, W, x_var, stream));
-    }
-    float* act[10];
-    int aD[10], aH[10], aW[10];
-    {
-        Prof pr(DV3D_STAGE_COSTREG, cs);
-        const float* in = x_var;
-        int cd = D, ch = h, cw = w;
-        for (int i = 0; i < 10; ++i) {
-            const dv3d_conv3d_params_t& c = net.costreg[i];
-            int od = cd, oh = ch, ow = cw;
-            if (c.kind == 1) od = (cd + 1) / 2, oh = (ch + 1) / 2, ow = (cw + 1) / 2;
-            if (c.kind == 2) od = 2 * cd, oh = 2 * ch, ow = 2 * cw;
-            act[i] = ar.get<float>((size_t)n_ref * c.Cout * od * oh * ow);
-            ARENA_CHECK(ar);
-            // skips: x = conv4 + conv7(x); x = conv2 + conv8(x); x = conv0 + conv9(x)  (mvsnet.py:159-161)
-            const float* skip = i == 7 ? act[4] : i == 8 ? act[2] : i == 9 ? act[0] : nullptr;
-            if (c.kind == 2)
-                TRY(dv3d_deconv3d_bn_relu(in, n_ref, c.Cin, cd, ch, cw, c.weight, c.scale, c.shift, c.Cout, skip, act[i], stream));
-            else
-                TRY(dv3d_conv3d_bn_relu(in, n_ref, c.Cin, cd, ch, cw, c.weight, c.scale, c.shift, c.Cout, c.kind == 1 ? 2 : 1,
-                                        skip, act[i], stream));
-            aD[i] = od, aH[i] = oh, aW[i] = ow;
-            in = act[i];
-            cd = od, ch = oh, cw = ow;
-        }
-        DV3D_REQUIRE(aD[9] == D && aH[9] == h && aW[9] == w, "hot_path: CostRegNet does not return to full resolution");
-    }
-    float* depth = ar.get<float>((size_t)Np);
-    float* offs = ar.get<float>((size_t)Np);
-    ARENA_CHECK(ar);
-    const double depth_end = depth_start + depth_interval * (D - 1);
-    {
-        Prof pr(DV3D_STAGE_SOFTARGMIN, cs);
-        TRY(dv3d_prob_softargmin(act[9], n_ref, net.costreg[9].Cout, D, h, w, net.prob_weight, net.prob_bias,
-                                 (float)depth_start, (float)depth_end, nullptr, depth, stream));
-    }
-    if (depth_init_out) DV3D_CUDA(cudaMemcpyAsync(depth_init_out, depth, sizeof(float) * Np, cudaMemcpyDeviceToDevice, cs));
+extern "C" size_t dv3d_hot_path_sharded_heap_bytes(const dv3d_net_params_t* net, int n_ref_total, int h, int w) {
+    if (!net || n_ref_total <= 0 || h <= 0 || w <= 0) return 0;
+    const size_t Ng = (size_t)n_ref_total * h * w;
+    int blocks = 0;
+    for (int l = 0; l < net->n_levels; ++l) blocks += net->n_res[l] * (l == net->n_levels - 1 ? 1 : 2);
+    // flags, the cloud (3 + 32 floats per point), every layer output of the U-Net (at most one voxel per point and
+    // 128 channels: two per residual block, one per down / feature-adjust layer), 256 bytes of alignment each
+    const size_t layers = (size_t)(2 * blocks + 2 * (net->n_levels - 1));
+    return 256 + Ng * 35 * 4 + 512 + (Ng * 128 * 4 + 256) * layers;
+}
 
-    // ================= path B: volumetric refinement (eval-3dvnet.py:73-99)
-    if (n_outer * n_inner > 0) {
-        ar.off = 0;  // path A's volumes are dead; keep only cams / depth / offs by re-reserving them first
-        float* cams2 = ar.get<float>((size_t)n_imgs * 36);
-        (void)cams2;  // same address as cams
-        // depth / offs live behind the volumes: move them to the front of the arena
-        float* depth_f = ar.get<float>((size_t)Np);
-        float* offs_f = ar.get<float>((size_t)Np);
-        DV3D_CUDA(cudaMemcpyAsync(depth_f, depth, sizeof(float) * Np, cudaMemcpyDeviceToDevice, cs));
-        depth = depth_f;
-        offs = offs_f;
-        const int in_dim = net.dec[0].K / 3, var_off = in_dim - 32;
-        float* operand = ar.get<float>((size_t)Np * 8 * in_dim);  // [n_pts, 8, in_dim], padding row stays zero
-        float* dec_a = ar.get<float>((size_t)Np * 8 * net.dec[0].N);
-        float* dec_b = ar.get<float>((size_t)Np * 8 * net.dec[1].N);
-        float* pts_hyp = ar.get<float>((size_t)Np * 7 * 3);
-        long long* pts_batch = ar.get<long long>((size_t)Np);
-        const size_t split_ws_bytes = dv3d_sparse_conv_workspace_bytes(128);
-        void* split_ws = ar.get<char>(split_ws_bytes);
-        ARENA_CHECK(ar);
-        DV3D_CUDA(cudaMemsetAsync(operand, 0, sizeof(float) * Np * 8 * in_dim, cs));
-        DV3D_CUDA(cudaMemsetAsync(split_ws, 0, dv3d_sparse_conv_workspace_bytes(128), cs));
-        DV3D_LAUNCH((expand_batch_kernel), cdiv(Np, 256), 256, 0, cs, depth_batch, (int)P, Np, pts_batch);
-        DV3D_LAUNCHED();
-        const size_t mark = ar.off;
-        for (int o = 0; o < n_outer; ++o) {
-            ar.off = mark;
-            // feature-rich point cloud (lightningmodel.py:132-174)
-            float* pts = ar.get<float>((size_t)Np * 3);
-            float* pfeat = ar.get<float>((size_t)Np * 32);
-            ARENA_CHECK(ar);
-            {
-                Prof pr(DV3D_STAGE_POINTCLOUD, cs);
-                TRY(dv3d_points_var(feats_nhwc, n_imgs, 32, Hf, Wf, cams, ref_img, edge_rowptr, edge_src, depth, n_ref, h, w, H,
-                                    W, 0, 0.0, pts, pfeat, 1, 32, 0, stream));
-            }
-            Scene sc;
-            memset(&sc, 0, sizeof(sc));
-            sc.split_ws = split_ws;
-            sc.split_ws_bytes = dv3d_sparse_conv_workspace_bytes(128);
-            TRY(model_scene(net, pts, pfeat, pts_batch, Np, edge_len, sc, ar, stream));
-            for (int it = 0; it < n_inner; ++it) {
-                const double offset = offsets_host[o * n_inner + it];
-                // PointFlow pass (lightningmodel.py:187-242)
-                {
-                    Prof pr(DV3D_STAGE_FLOW_WARP, cs);
-                    TRY(dv3d_points_var(feats_nhwc, n_imgs, 32, Hf, Wf, cams, ref_img, edge_rowptr, edge_src, depth, n_ref, h, w,
-                                        H, W, 3, offset, pts_hyp, operand, 8, in_dim, var_off, stream));
-                }
-                int off_c = 0;
-                {
-                    Prof pr(DV3D_STAGE_FLOW_INTERP, cs);
-                    // all levels with one launch, finest level first in the operand (refinement.py:41 prepends)
-                    float res_l[DV3D_MAX_LEVELS];
-                    int stride_l[DV3D_MAX_LEVELS], C_l[DV3D_MAX_LEVELS], off_l[DV3D_MAX_LEVELS];
-                    const void* tab_l[DV3D_MAX_LEVELS];
-                    size_t tabb_l[DV3D_MAX_LEVELS];
-                    const float* feat_l[DV3D_MAX_LEVELS];
-                    for (int l = 0; l < sc.n_levels; ++l) {
-                        res_l[l] = (float)(sc.lv[l].stride * edge_len);
-                        stride_l[l] = sc.lv[l].stride;
-                        tab_l[l] = sc.lv[l].table;
-                        tabb_l[l] = sc.lv[l].table_bytes;
-                        feat_l[l] = sc.feats[l];
-                        C_l[l] = sc.dims[l];
-                        off_l[l] = off_c;
-                        off_c += sc.dims[l];
-                    }
-                    TRY(dv3d_sparse_interp_batch(pts_hyp, pts_batch, Np, 7, 8, sc.origin, sc.n_levels, res_l, stride_l, tab_l,
-                                                 tabb_l, feat_l, C_l, off_l, operand, in_dim, stream));
-                }
-                DV3D_REQUIRE(off_c == var_off, "hot_path: decoder input width %d != level widths %d + 32", in_dim, off_c);
-                if (net.dec_fused[0] && net.dec_fused[1] && net.dec_fused[2]) {
-                    // the whole decoder + `depth += offset` as one tcgen05 kernel (csrc/decoder_fused.cu)
-                    Prof pr(DV3D_STAGE_DEC_GEMM0, cs);
-                    const void* wp[3] = {net.dec_fused[0], net.dec_fused[1], net.dec_fused[2]};
-                    const float* sc[3] = {net.dec[0].a, net.dec[1].a, net.dec[2].a};
-                    const float* sh[3] = {net.dec[0].b, net.dec[1].b, net.dec[2].b};
-                    TRY(dv3d_decoder_fused(operand, Np, 8, in_dim, in_dim, wp, sc, sh, net.dec[0].N, net.dec_head_weight,
-                                           net.dec_head_bias, offset, dv3d_get_gemm_precision() & 0xff, nullptr, nullptr, depth,
-                                           stream));
-                } else {
-                    {
-                        Prof pr(DV3D_STAGE_DEC_GEMM0, cs);
-                        TRY(dv3d_conv1d_bn_relu(operand, Np, 8, in_dim, in_dim, net.dec[0].W, net.dec[0].Wp, net.dec[0].a,
-                                                net.dec[0].b, net.dec[0].N, dec_a, net.dec[0].N, split_ws, split_ws_bytes, stream));
-                    }
-                    {
-                        Prof pr(DV3D_STAGE_DEC_REST, cs);
-                        TRY(dv3d_conv1d_bn_relu(dec_a, Np, 8, net.dec[1].K / 3, net.dec[0].N, net.dec[1].W, net.dec[1].Wp,
-                                                net.dec[1].a, net.dec[1].b, net.dec[1].N, dec_b, net.dec[1].N, split_ws, split_ws_bytes, stream));
-                        TRY(dv3d_conv1d_bn_relu(dec_b, Np, 8, net.dec[2].K / 3, net.dec[1].N, net.dec[2].W, net.dec[2].Wp,
-                                                net.dec[2].a, net.dec[2].b, net.dec[2].N, dec_a, net.dec[2].N, split_ws, split_ws_bytes, stream));
-                        TRY(dv3d_decoder_head(dec_a, Np, 7, 8, net.dec[2].N, net.dec[2].N, net.dec_head_weight, net.dec_head_bias,
-                                              offset, nullptr, offs, stream));
-                        DV3D_LAUNCH((add_inplace_kernel), cdiv(Np, 256), 256, 0, cs, depth, offs, Np);
-                        DV3D_LAUNCHED();
-                    }
-                }
-            }
-        }
-    }
-    DV3D_CUDA(cudaMemcpyAsync(depth_out, depth, sizeof(float) * Np, cudaMemcpyDeviceToDevice, cs));
-    return DV3D_OK;
+extern "C" int dv3d_hot_path_sharded(const dv3d_net_params_t* netp, const float* feats_nhwc, int n_imgs, int Hf, int Wf,
+                                     const float* rotmats, const float* tvecs, const float* K, const int* ref_img,
+                                     const int* edge_rowptr, const int* edge_src, int n_ref_local, int ref_start,
+                                     int n_ref_total, const long long* depth_batch_all, double depth_start,
+                                     double depth_interval, int D, int h, int w, int H, int W, double edge_len,
+                                     const double* offsets_host, int n_outer, int n_inner, void* workspace,
+                                     size_t workspace_bytes, int rank, int world, void* heap, size_t heap_bytes,
+                                     void* const* peer_heaps, int* epoch, int* err_flag, float* depth_init_out,
+                                     float* depth_out, void* stream) {
+    DV3D_REQUIRE(netp && feats_nhwc && rotmats && tvecs && K && depth_batch_all, "hot_path_sharded: null pointer");
+    DV3D_REQUIRE(n_ref_local >= 0 && ref_start >= 0 && ref_start + n_ref_local <= n_ref_total && n_ref_total > 0,
+                 "hot_path_sharded: reference range [%d, %d) outside 0..%d", ref_start, ref_start + n_ref_local, n_ref_total);
+    DV3D_REQUIRE(n_ref_local == 0 || (ref_img && edge_rowptr && edge_src && depth_out), "hot_path_sharded: null pointer");
+    DV3D_REQUIRE(workspace && ((uintptr_t)workspace & 255) == 0, "hot_path_sharded: workspace must be a 256-byte aligned device arena");
+    DV3D_REQUIRE(n_outer >= 0 && n_inner >= 0 && (n_outer * n_inner == 0 || offsets_host), "hot_path_sharded: bad refinement schedule");
+    DV3D_REQUIRE(D % 8 == 0 && h % 8 == 0 && w % 8 == 0,
+                 "hot_path_sharded: D, h, w must be multiples of 8 (three stride-2 levels of CostRegNet), got %d %d %d", D, h, w);
+    DV3D_REQUIRE(netp->n_levels >= 1 && netp->n_levels <= DV3D_MAX_LEVELS, "hot_path_sharded: n_levels out of range");
+    DV3D_REQUIRE(world >= 2 && world <= 8 && rank >= 0 && rank < world, "hot_path_sharded: rank %d of %d (2..8 ranks)", rank, world);
+    DV3D_REQUIRE(heap && peer_heaps && epoch && err_flag && ((uintptr_t)heap & 255) == 0,
+                 "hot_path_sharded: the symmetric heap (dv3d_symm_alloc + dv3d_symm_register), its peers, epoch and error flag are required");
+    DV3D_REQUIRE(netp->res_down[0][0][0].Wp,
+                 "hot_path_sharded: needs a tensor-core GEMM mode with packed weights (only those epilogues store into peer memory)");
+    Shard sh = {rank, world, (char*)heap, heap_bytes, 256, peer_heaps, world - 1, err_flag, *epoch};
+    const int rc = hot_path_impl(*netp, feats_nhwc, n_imgs, Hf, Wf, rotmats, tvecs, K, ref_img, edge_rowptr, edge_src, n_ref_local,
+                                 depth_batch_all, depth_start, depth_interval, D, h, w, H, W, edge_len, offsets_host, n_outer,
+                                 n_inner, workspace, workspace_bytes, &sh, n_ref_total, ref_start, depth_init_out, depth_out, stream);
+    *epoch = sh.epoch;  // also on failure: epochs already used must not be reused
+    return rc;
 }

@@ -647,10 +647,55 @@ def hot_path_engine(net_params, feats_nhwc, rotmats, tvecs, K, plan, depth_batch
     return (depth, init) if want_init else depth
 
 
+def hot_path_engine_sharded(net_params, feats_nhwc, rotmats, tvecs, K, plan_local, ref_start, depth_batch_all, depth_cfg,
+                            img_size, edge_len, offsets_list, heap, want_init=False):
+    """dv3d_hot_path_sharded (csrc/engine.cu): this rank's share of a scene spanning the ranks of `heap`
+    (parallel.SymmHeap). `plan_local` is the EdgePlan of the rank's contiguous range of reference views (None when
+    the rank has none), `ref_start` its first view among the sorted references, `depth_batch_all` [n_ref_total].
+    -> depth [n_local,h,w] (and the initial soft-argmin depth when want_init)."""
+    _chk(feats_nhwc, torch.float32, 'feats_nhwc', 4), _chk(depth_batch_all, torch.int64, 'depth_batch_all', 1)
+    _chk(rotmats, torch.float32, 'rotmats', 3), _chk(tvecs, torch.float32, 'tvecs', 2), _chk(K, torch.float32, 'K', 3)
+    n_imgs, Hf, Wf, C = feats_nhwc.shape
+    h, w = depth_cfg['size']
+    D = int(depth_cfg['n_intervals'])
+    dev = feats_nhwc.device
+    L = lib()
+    n_total = int(depth_batch_all.shape[0])
+    n_local = plan_local.n_ref if plan_local is not None else 0
+    need = L.raw('dv3d_hot_path_workspace_bytes')(ctypes.byref(net_params), n_imgs, n_total, D, h, w)
+    akey = (dev, torch.cuda.current_stream().cuda_stream)
+    arena = _arena.get(akey)
+    if arena is None or arena.numel() < need:
+        arena = _arena[akey] = torch.empty(need, dtype=torch.uint8, device=dev)
+    heap_need = L.raw('dv3d_hot_path_sharded_heap_bytes')(ctypes.byref(net_params), n_total, h, w)
+    if heap.nbytes < heap_need:
+        raise RuntimeError('hot_path_sharded: the symmetric heap has %d bytes, %d reference views of %dx%d need %d'
+                           % (heap.nbytes, n_total, h, w, heap_need))
+    n_outer = len(offsets_list)
+    n_inner = len(offsets_list[0]) if n_outer else 0
+    if any(len(o) != n_inner for o in offsets_list):
+        raise RuntimeError('hot_path: every refinement iteration must have the same number of PointFlow passes')
+    offs = (ctypes.c_double * max(1, n_outer * n_inner))(*[float(v) for o in offsets_list for v in o])
+    depth = torch.empty((n_local, h, w), dtype=torch.float32, device=dev)
+    init = torch.empty_like(depth) if want_init else None
+    epoch = ctypes.c_int(heap.epoch)
+    pl = plan_local
+    try:
+        L.call('dv3d_hot_path_sharded', ctypes.byref(net_params), _p(feats_nhwc), n_imgs, Hf, Wf, _p(rotmats), _p(tvecs),
+               _p(K), _p(pl.ref_img) if pl else None, _p(pl.rowptr) if pl else None, _p(pl.edge_src) if pl else None,
+               n_local, int(ref_start), n_total, _p(depth_batch_all), float(depth_cfg['depth_start']),
+               float(depth_cfg['depth_interval']), D, h, w, img_size[0], img_size[1], float(edge_len), offs, n_outer,
+               n_inner, _p(arena), arena.numel(), heap.rank, heap.world, heap.ptr, heap.nbytes, heap._peer_ptrs,
+               ctypes.byref(epoch), heap.err.data_ptr(), _p(init), _p(depth), _stream())
+    finally:
+        heap.epoch = epoch.value
+    return (depth, init) if want_init else depth
+
+
 (STAGE_PLANESWEEP, STAGE_COSTREG, STAGE_SOFTARGMIN, STAGE_POINTCLOUD, STAGE_VOXELIZE, STAGE_POINTNET, STAGE_LEVELS,
- STAGE_UNET, STAGE_FLOW_WARP, STAGE_FLOW_INTERP, STAGE_DEC_GEMM0, STAGE_DEC_REST) = range(12)
+ STAGE_UNET, STAGE_FLOW_WARP, STAGE_FLOW_INTERP, STAGE_DEC_GEMM0, STAGE_DEC_REST, STAGE_EXCHANGE) = range(13)
 STAGE_NAMES = ('planesweep_var', 'costreg', 'softargmin', 'pointcloud', 'voxelize', 'pointnet', 'levels', 'unet',
-               'flow_warp', 'flow_interp', 'dec_gemm0', 'dec_rest')
+               'flow_warp', 'flow_interp', 'dec_gemm0', 'dec_rest', 'exchange')
 
 
 def engine_profile(enable):

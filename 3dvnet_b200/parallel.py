@@ -129,6 +129,53 @@ def hot_path_sharded(net, feats_quarter, rotmats, tvecs, K, ref_src_edges, image
     return depth, (start, end)
 
 
+class ShardPlan(object):
+    """What does not change between steps of `hot_path_sharded_native` for one edge list: this rank's range of the
+    sorted reference views, the CSR edge plan of that range (resident on the device) and the view -> scene map."""
+
+    def __init__(self, ref_src_edges, images_batch, device, world, rank):
+        from . import ops
+        ref_idx = torch.unique(ref_src_edges[0])
+        self.n_ref = int(ref_idx.shape[0])
+        self.start, self.end = shard_range(self.n_ref, world, rank)
+        edges_local, _ = local_edges(ref_src_edges, self.start, self.end)
+        self.plan = ops.edge_plan(edges_local, device) if self.end > self.start else None
+        self.depth_batch_all = images_batch.to(device)[ref_idx.to(device)].long().contiguous()
+
+
+def hot_path_sharded_native(net, feats_quarter, rotmats, tvecs, K, ref_src_edges, images_batch, depth_config,
+                            offsets_list, heap, plan=None, return_init=False):
+    """`hot_path_sharded` from ONE native call per rank (csrc/engine.cu dv3d_hot_path_sharded): no Python between
+    the kernels, the point rows travel as peer copies into the symmetric heap instead of an NCCL all-gather, and
+    the sparse U-Net runs row-sharded with epilogue stores into peer memory. `heap` is this group's `SymmHeap`
+    (at least `native_heap_bytes` large); `plan` a `ShardPlan` to reuse across steps.
+    Returns this rank's depth maps [n_local, h, w] and its range (start, end) of the sorted reference views."""
+    from . import ops
+    from .mv3d._pack import require_eval
+    require_eval(net)
+    _require_peer_store_gemm(ops)
+    dev = feats_quarter.device
+    if plan is None:
+        plan = ShardPlan(ref_src_edges, images_batch, dev, heap.world, heap.rank)
+    fq = feats_quarter.detach().float()
+    if fq.dim() == 4 and fq.is_contiguous(memory_format=torch.channels_last) and not fq.is_contiguous():
+        nhwc = fq.permute(0, 2, 3, 1)
+    else:
+        nhwc = ops.nchw_to_nhwc(fq.contiguous())
+    out = ops.hot_path_engine_sharded(net.engine_params(), nhwc, rotmats.float().contiguous(), tvecs.float().contiguous(),
+                                      K.float().contiguous(), plan.plan, plan.start, plan.depth_batch_all, depth_config,
+                                      net.hparams.img_size, net.edge_len, offsets_list, heap, want_init=return_init)
+    return out, (plan.start, plan.end)
+
+
+def native_heap_bytes(net, n_ref_total, size):
+    """size of the `SymmHeap` `hot_path_sharded_native` needs for `n_ref_total` reference views of `size` (h, w)"""
+    import ctypes
+    from . import ops
+    return int(ops.lib().raw('dv3d_hot_path_sharded_heap_bytes')(ctypes.byref(net.engine_params()), int(n_ref_total),
+                                                                  int(size[0]), int(size[1])))
+
+
 # ----------------------------------------------------------------------------- sparse U-Net sharded by voxel rows
 def _require_peer_store_gemm(ops):
     """Only the tcgen05 gather-GEMM and the pair-reduce kernel store their epilogue into the peers' copies of a

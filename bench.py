@@ -180,14 +180,18 @@ def run_c4(args, rank, world, dev, dist, ops, lm):
     fq, R, t, K = b.feats_quarter.to(dev), b.rotmats.to(dev), b.tvecs.to(dev), b.K.to(dev)
     e, ib = b.ref_src_edges, b.images_batch.to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    heap = par.SymmHeap(2048 << 20)
+    heap = par.SymmHeap(max(2048 << 20, par.native_heap_bytes(net, refs, PLANE)))
+    splan = par.ShardPlan(e, ib, dev, world, rank)
 
-    def step():
+    def step():   # one native call per rank (csrc/engine.cu dv3d_hot_path_sharded)
+        return par.hot_path_sharded_native(net, fq, R, t, K, e, ib, DEPTH_CFG, OFFSETS_LIST, heap, plan=splan)
+
+    def step_composed():   # round 1's path: the same schedule composed op by op from Python, NCCL all-gather
         return par.hot_path_sharded(net, fq, R, t, K, e, ib, DEPTH_CFG, OFFSETS_LIST, heap=heap)
 
-    with torch.no_grad():
+    def timed(fn):
         for _ in range(warm):
-            depth, rng = step()
+            out = fn()
         torch.cuda.synchronize()
         dist.barrier()
         torch.cuda.synchronize()
@@ -196,7 +200,7 @@ def run_c4(args, rank, world, dev, dist, ops, lm):
         for a, z in ev:
             flush.zero_()
             a.record()
-            depth, rng = step()
+            out = fn()
             z.record()
         torch.cuda.synchronize()
         dist.barrier()
@@ -205,6 +209,24 @@ def run_c4(args, rank, world, dev, dist, ops, lm):
         heap.check()
         ms = torch.tensor([sum(a.elapsed_time(z) for a, z in ev)], dtype=torch.float64, device=dev)
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return out, ms, launches, barriers
+
+    with torch.no_grad():
+        (depth_c, _), ms_c, _, _ = timed(step_composed)
+        (depth, rng), ms, launches, barriers = timed(step)
+        native_equals_composed = bool(torch.equal(depth, depth_c))
+        stage_ms = None
+        if rank == 0:   # where the step goes: one more (untimed) step with the engine's stage events
+            ops.engine_profile(True)
+        dist.barrier()
+        step()
+        torch.cuda.synchronize()
+        if rank == 0:
+            acc = {}
+            for sid, v in ops.engine_profile_read():
+                acc[ops.STAGE_NAMES[sid]] = acc.get(ops.STAGE_NAMES[sid], 0.0) + v
+            ops.engine_profile(False)
+            stage_ms = {k: round(v, 3) for k, v in acc.items()}
         counts = par.shard_counts(refs, world)
         full = par.all_gather_rows(depth.reshape(depth.shape[0], -1).contiguous(), counts)
 
@@ -212,7 +234,7 @@ def run_c4(args, rank, world, dev, dist, ops, lm):
         # that every rank voxelises the same points in the sharded scene model
         h, w = PLANE
         d_init = torch.empty((refs, h, w), dtype=torch.float32, device=dev)
-        abs_rel, ms_one = None, None
+        abs_rel, ms_one, stage_one = None, None, None
         if rank == 0:
             d_one, d0 = net.hot_path(fq, R, t, K, e, ib, DEPTH_CFG, OFFSETS_LIST, return_init=True)
             d_init.copy_(d0)
@@ -227,6 +249,14 @@ def run_c4(args, rank, world, dev, dist, ops, lm):
                 z.record()
             torch.cuda.synchronize()
             ms_one = sum(a.elapsed_time(z) for a, z in ev1) / steps
+            ops.engine_profile(True)
+            net.hot_path(fq, R, t, K, e, ib, DEPTH_CFG, OFFSETS_LIST)
+            torch.cuda.synchronize()
+            acc = {}
+            for sid, v in ops.engine_profile_read():
+                acc[ops.STAGE_NAMES[sid]] = acc.get(ops.STAGE_NAMES[sid], 0.0) + v
+            ops.engine_profile(False)
+            stage_one = {k: round(v, 3) for k, v in acc.items()}
         dist.broadcast(d_init, 0)
         start, end = par.shard_range(refs, world, rank)
         xs_sh = par.model_scene_sharded(net, d_init[start:end].contiguous(), ib, fq, R, t, K, e, heap=heap)
@@ -246,15 +276,20 @@ def run_c4(args, rank, world, dev, dist, ops, lm):
             'value': steps * refs / sec, 'unit': 'ref-views/s', 'scaling': 'strong', 'steps': steps, 'warmup': warm,
             'ms_per_step': 1e3 * sec / steps,
             'single_gpu': None if ms_one is None else {
-                'ms_per_step': ms_one, 'value': refs / (ms_one * 1e-3),
+                'ms_per_step': ms_one, 'value': refs / (ms_one * 1e-3), 'stage_ms': stage_one,
                 'note': 'the same 64-view scene through PL3DVNet.hot_path on rank 0 alone (engine, one native call)'},
             'speedup_vs_single_gpu': None if ms_one is None else ms_one / (1e3 * sec / steps),
             'abs_rel_vs_single_gpu': abs_rel, 'voxel_idx_equal': idx_equal,
             'sparse_feat_max_rel_err_vs_single_gpu': feat_err,
-            'all_gather_bytes': 2 * refs * PLANE[0] * PLANE[1] * 35 * 4, 'all_gathers': 2, 'barriers': barriers,
+            'composed_from_python': {'ms_per_step': float(ms_c.item()) / steps,
+                                     'note': 'the same schedule op by op from Python with an NCCL all-gather (round 1)',
+                                     'depth_bit_identical_to_native': native_equals_composed},
+            'stage_ms_rank0': stage_ms,
+            'exchange_bytes': 2 * refs * PLANE[0] * PLANE[1] * 35 * 4, 'exchanges': 2, 'barriers': barriers,
             'gpu_launches_per_rank': launches // steps,
-            'collective': 'all_gather_into_tensor of [N_g,35] fp32 point rows, once per scene-model call; sparse U-Net '
-                          'layers exchange rows by epilogue stores into peer memory + one flag barrier per layer',
+            'collective': 'point rows [N_local,3]+[N_local,32] fp32 copied into every peer heap (NVLink peer copies) + one '
+                          'flag barrier, once per scene-model call; sparse U-Net layers exchange rows by epilogue stores '
+                          'into peer memory + one flag barrier per layer; no NCCL call inside the step',
             'timing': 'CUDA events on the launching stream, L2 flushed per step, barrier both sides, max over ranks'}
 
 

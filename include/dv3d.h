@@ -473,6 +473,7 @@ typedef struct dv3d_net_params_t {
 #define DV3D_STAGE_FLOW_INTERP 9
 #define DV3D_STAGE_DEC_GEMM0 10   /* dv3d_decoder_fused (whole decoder + depth update); per-layer path: first Conv1d */
 #define DV3D_STAGE_DEC_REST 11    /* per-layer path only: two more Conv1d GEMMs + head + depth update */
+#define DV3D_STAGE_EXCHANGE 12    /* dv3d_hot_path_sharded only: point rows into the peers' heaps + the barrier */
 int dv3d_engine_profile(int enable);
 int dv3d_engine_profile_read(int* ids, float* ms, int cap);
 
@@ -509,6 +510,31 @@ int dv3d_symm_register(const void* base, size_t bytes, void* const* peer_bases, 
 int dv3d_symm_unregister(const void* base);
 int dv3d_symm_barrier(void* local_flags, void* const* peer_flags, int n_peers, int rank, int epoch, int* err_flag,
                       void* stream);
+
+/* BASELINE config C4 from one native call per rank: the hot path of a scene whose reference views are sharded over
+ * `world` GPUs (one process each).  This rank computes the cost volumes, depths and PointFlow passes of the
+ * contiguous range [ref_start, ref_start + n_ref_local) of the scene's n_ref_total sorted reference views
+ * (eval-3dvnet.py:60-99 for those views); ref_img / edge_rowptr / edge_src describe that range only, depth_batch_all
+ * [n_ref_total] all views.  Per refinement iteration the rank's point rows are copied into every peer's heap and one
+ * flag barrier follows (the all-gather utils.voxelize needs, mv3d/utils.py:39-48), every rank voxelises the whole
+ * cloud (identical tables everywhere), and the sparse U-Net runs for this rank's rows of every level with its
+ * epilogues storing into all heaps and one barrier per layer (scenemodeling.py:191-237).
+ *   heap / peer_heaps: dv3d_symm_alloc + dv3d_symm_open blocks of heap_bytes >= dv3d_hot_path_sharded_heap_bytes,
+ *   registered with dv3d_symm_register; peers in ascending rank order with this rank left out; the first 256 bytes
+ *   are the barrier flags.  *epoch: last barrier epoch used on this heap (0 at first), updated on return; every
+ *   rank must make the same sequence of calls.  err_flag: device int, set if a peer misses a barrier (the kernel
+ *   traps).  workspace: dv3d_hot_path_workspace_bytes(net, n_imgs, n_ref_total, D, h, w).
+ *   n_ref_local may be 0 (more ranks than views): the rank still takes part in the scene model.
+ * Results are those of dv3d_hot_path on the whole scene, rows [ref_start, ref_start + n_ref_local). */
+size_t dv3d_hot_path_sharded_heap_bytes(const dv3d_net_params_t* net, int n_ref_total, int h, int w);
+int dv3d_hot_path_sharded(const dv3d_net_params_t* net, const float* feats_nhwc, int n_imgs, int Hf, int Wf,
+                          const float* rotmats, const float* tvecs, const float* K, const int* ref_img,
+                          const int* edge_rowptr, const int* edge_src, int n_ref_local, int ref_start, int n_ref_total,
+                          const long long* depth_batch_all, double depth_start, double depth_interval, int D, int h,
+                          int w, int H, int W, double edge_len, const double* offsets_host, int n_outer, int n_inner,
+                          void* workspace, size_t workspace_bytes, int rank, int world, void* heap, size_t heap_bytes,
+                          void* const* peer_heaps, int* epoch, int* err_flag, float* depth_init_out, float* depth_out,
+                          void* stream);
 
 #ifdef __cplusplus
 }

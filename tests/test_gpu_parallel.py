@@ -56,12 +56,23 @@ def _worker(rank, world, port, out_dir):
         xs_sh = par.model_scene_sharded(net, depth[start:end].contiguous(), b.images_batch, fq, R, t, K, e, heap=heap)
         d_sh, _ = par.hot_path_sharded(net, fq, R, t, K, e, b.images_batch.to(dev), cfg, offs, heap=heap)
         heap.check()
+        # the same from ONE native call per rank (dv3d_hot_path_sharded): peer copies of the point rows instead of
+        # the NCCL all-gather, twice in a row (the heap is reused behind its barriers)
+        heap2 = par.SymmHeap(max(64 << 20, par.native_heap_bytes(net, len(ref_idx), plane)))
+        d_nat, rng_nat = par.hot_path_sharded_native(net, fq, R, t, K, e, b.images_batch.to(dev), cfg, offs, heap2)
+        d_nat2, _ = par.hot_path_sharded_native(net, fq, R, t, K, e, b.images_batch.to(dev), cfg, offs, heap2)
+        torch.cuda.synchronize()
+        heap2.check()
+    assert rng_nat == (s0, s1)
+    rel_nat = float(((d_nat - d_one).abs() / (d_one.abs() + 1e-7)).mean()) if s1 > s0 else 0.0
+    nat_same = bool(torch.equal(d_nat, d_sh)) and bool(torch.equal(d_nat, d_nat2))
     feat_err = max(float((a['feats'] - r['feats']).abs().max() / r['feats'].abs().max()) for a, r in zip(xs_sh, xs_ref))
     idx_same = all(torch.equal(a['idx'], r['idx']) and a['feats'].shape == r['feats'].shape for a, r in zip(xs_sh, xs_ref))
     rel_sh = float(((d_sh - d_one).abs() / (d_one.abs() + 1e-7)).mean()) if s1 > s0 else 0.0
     same = all(torch.equal(a['feats'], r['feats']) and torch.equal(a['idx'], r['idx']) for a, r in zip(xs, xs_ref))
     rel = float(((d_loc - d_one).abs() / (d_one.abs() + 1e-7)).mean()) if s1 > s0 else 0.0
-    np.save(os.path.join(out_dir, 'r%d.npy' % rank), np.array([same, xs[-1]['feats'].shape[0], rel, s1 - s0, feat_err, idx_same, rel_sh]))
+    np.save(os.path.join(out_dir, 'r%d.npy' % rank), np.array([same, xs[-1]['feats'].shape[0], rel, s1 - s0, feat_err, idx_same, rel_sh, rel_nat, nat_same]))
+    heap2.close()
     heap.close()
     dist.barrier()
     dist.destroy_process_group()
@@ -73,13 +84,15 @@ def test_model_scene_sharded_equals_single_gpu(tmp_path):
     importlib.import_module('3dvnet_b200.build').build()
     mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
     for r in range(2):
-        same, n, rel, n_loc, feat_err, idx_same, rel_sh = np.load(tmp_path / ('r%d.npy' % r))
+        same, n, rel, n_loc, feat_err, idx_same, rel_sh, rel_nat, nat_same = np.load(tmp_path / ('r%d.npy' % r))
         assert same == 1 and n > 0
         assert n_loc > 0 and rel < 1e-3, rel    # BASELINE tolerance (abs-rel depth)
         # row-sharded U-Net: same voxel sets; features to fp32 rounding (the pair-major / output-stationary choice
         # and the K-split depend on the number of local rows, so the summation order differs from one GPU)
         assert idx_same == 1 and feat_err < 1e-4, feat_err
         assert rel_sh < 1e-3, rel_sh
+        # the native entry runs the same kernels on the same rows as the composed sharded path: bit-identical depth
+        assert rel_nat < 1e-3 and nat_same == 1, (rel_nat, nat_same)
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
