@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "gemm.cuh"
 
 namespace dv3d {
 
@@ -136,6 +137,52 @@ __global__ void add_inplace_kernel(float* __restrict__ x, const float* __restric
 }
 
 
+// Halo exchange of the row-sharded U-Net.  Rows are sorted by voxel id, so the rows of level l a rank gathers through
+// its kernel maps (its own rows' 3x3x3 neighbours, parents and children) form a band around its own range: each rank
+// takes the min / max input row over its maps per level ...
+struct HaloMaps {
+    const int* nbr[3 * DV3D_MAX_LEVELS];
+    long long n[3 * DV3D_MAX_LEVELS];   // entries (rows x 27)
+    int level[3 * DV3D_MAX_LEVELS];     // level of the map's INPUT rows
+};
+__global__ void __launch_bounds__(256)
+halo_needs_kernel(HaloMaps hm, int* __restrict__ lo, int* __restrict__ hi) {
+    pdl_wait();
+    const int* nbr = hm.nbr[blockIdx.y];
+    const long long n = hm.n[blockIdx.y];
+    int mn = 0x7fffffff, mx = -1;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int v = __ldg(nbr + i);
+        if (v >= 0) mn = min(mn, v), mx = max(mx, v);
+    }
+    mn = __reduce_min_sync(0xffffffffu, mn);
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if ((threadIdx.x & 31) == 0 && mx >= 0) {
+        atomicMin(lo + hm.level[blockIdx.y], mn);
+        atomicMax(hi + hm.level[blockIdx.y], mx + 1);
+    }
+}
+// ... and writes them into every peer's table (first 256 bytes of the heap, behind the barrier flags): entry
+// [level][index of this rank among the destination's peers] = (lo, hi).  The barrier in front of the first layer
+// publishes them.  A producer then stores row g of a level-l output into peer p only when lo <= g < hi.
+constexpr int kHaloTabOff = 64;   // bytes; 3 levels x 7 peers x 2 ints = 168 bytes
+struct PeerPtrs {
+    char* p[kMaxPeers];
+};
+__global__ void halo_publish_kernel(const int* __restrict__ lo, const int* __restrict__ hi, int n_levels, int rank, int n_peers,
+                                    PeerPtrs peers) {
+    pdl_wait();
+    const int p = threadIdx.x;
+    if (p >= n_peers) return;
+    const int dest_rank = p < rank ? p : p + 1;
+    const int my_idx = rank < dest_rank ? rank : rank - 1;
+    int* tab = reinterpret_cast<int*>(peers.p[p] + kHaloTabOff);
+    for (int l = 0; l < n_levels; ++l) {
+        tab[(l * kMaxPeers + my_idx) * 2 + 0] = lo[l];
+        tab[(l * kMaxPeers + my_idx) * 2 + 1] = hi[l];
+    }
+}
+
 struct Level {
     int* coords;
     long long n;
@@ -174,6 +221,7 @@ struct Shard {
 
 struct Scene {
     Shard* shard;                    // nullptr: single GPU
+    const int* halo_tab;             // sharded: [level][peer][lo, hi) rows each peer needs (device, in the heap header)
     long long r0[DV3D_MAX_LEVELS], r1[DV3D_MAX_LEVELS];  // this rank's row range per level (whole level when !shard)
     Level lv[DV3D_MAX_LEVELS];
     int n_levels;
@@ -214,9 +262,16 @@ static int layer_barrier(Scene& sc, void* st) {
 // One sparse convolution + GroupNorm + ReLU for the rows the kernel map covers (all rows, or this rank's range):
 // `feat` and `out` are full [n, C] arrays, `residual` too.  Sharded: the epilogue stores the rows into every rank's
 // copy of `out` (csrc/symm.cu) and the barrier follows.
+static void set_halo(const Scene& sc, int out_level, bool to_all, long long row0) {
+    if (sc.shard) symm_set_halo(to_all ? nullptr : sc.halo_tab + out_level * kMaxPeers * 2, row0);
+}
+
 static int sparse_conv(const dv3d_dense_params_t& p, const float* feat, long long n_in, const KMap& km, const float* residual,
-                       Scene& sc, float* out, void* st) {
+                       Scene& sc, float* out, int out_level, bool to_all, void* st) {
     if (km.n_out > 0) {
+        // to_all: the level's final features, which every rank samples in its PointFlow passes; otherwise only the
+        // ranks whose kernel maps reach a row receive it
+        set_halo(sc, out_level, to_all, km.row0);
         const float* res = residual ? residual + km.row0 * p.N : nullptr;
         float* o = out + km.row0 * p.N;
         if (km.use_pairs && p.Wp)
@@ -225,19 +280,20 @@ static int sparse_conv(const dv3d_dense_params_t& p, const float* feat, long lon
         else
             TRY(dv3d_sparse_conv(feat, n_in, p.K / 27, km.nbr, km.n_out, p.W, p.Wp, p.N, p.a, p.b, res, 1, sc.split_ws,
                                  sc.split_ws_bytes, o, st));
+        if (sc.shard) symm_set_halo(nullptr, 0);
     }
     return layer_barrier(sc, st);
 }
 
 // relu(x + GN2(conv2(relu(GN1(conv1(x))))))  (scenemodeling.py:16-44)
 static int res_block(const dv3d_dense_params_t (&p)[2], const float* x, long long n, const KMap& nbr, Scene& sc, Arena& ar,
-                     float** out, void* st) {
+                     float** out, int level, bool to_all, void* st) {
     const int C = p[0].N;
     float* h = layer_rows(sc, ar, n, C);
     float* y = layer_rows(sc, ar, n, C);
     ARENA_CHECK(ar);
-    TRY(sparse_conv(p[0], x, n, nbr, nullptr, sc, h, st));
-    TRY(sparse_conv(p[1], h, n, nbr, x, sc, y, st));
+    TRY(sparse_conv(p[0], x, n, nbr, nullptr, sc, h, level, false, st));
+    TRY(sparse_conv(p[1], h, n, nbr, x, sc, y, level, to_all, st));
     *out = y;
     return DV3D_OK;
 }
@@ -444,6 +500,34 @@ static int model_scene(const dv3d_net_params_t& net, const float* pts, const flo
             }
             TRY(dv3d_kernel_map_batch(co, no, tb, tbb, stp, nb, n_maps, sst));
         }
+        if (sc.shard) {
+            // the rows of every level this rank gathers, into every peer's halo table (published by the barrier in
+            // front of the first layer)
+            Shard& sh = *sc.shard;
+            int* lohi = ar.get<int>(2 * DV3D_MAX_LEVELS);
+            ARENA_CHECK(ar);
+            int *lo = lohi, *hi = lohi + DV3D_MAX_LEVELS;
+            DV3D_CUDA(cudaMemsetAsync(lo, 0x7f, sizeof(int) * DV3D_MAX_LEVELS, side->stream));
+            DV3D_CUDA(cudaMemsetAsync(hi, 0, sizeof(int) * DV3D_MAX_LEVELS, side->stream));
+            if (n_maps > 0) {
+                HaloMaps hm = {};
+                long long max_n = 0;
+                for (int i = 0; i < n_maps; ++i) {
+                    hm.nbr[i] = maps[i]->nbr;
+                    hm.n[i] = maps[i]->n_out * 27;
+                    hm.level[i] = (int)(maps[i]->in_lv - sc.lv);
+                    max_n = std::max(max_n, hm.n[i]);
+                }
+                const unsigned gx = (unsigned)std::min<long long>(cdiv(max_n, 256 * 8), 148 * 4);
+                DV3D_LAUNCH((halo_needs_kernel), dim3(gx, n_maps), 256, 0, side->stream, hm, lo, hi);
+                DV3D_LAUNCHED();
+            }
+            PeerPtrs pp = {};
+            for (int p = 0; p < sh.n_peers; ++p) pp.p[p] = reinterpret_cast<char*>(sh.peer_heaps[p]);
+            DV3D_LAUNCH((halo_publish_kernel), 1, 32, 0, side->stream, (const int*)lo, (const int*)hi, nl, sh.rank, sh.n_peers, pp);
+            DV3D_LAUNCHED();
+            sc.halo_tab = reinterpret_cast<const int*>(sh.heap + kHaloTabOff);
+        }
         sc.pair_ws = nullptr;
         sc.pair_ws_bytes = 0;
         if (want_plan) {
@@ -482,14 +566,17 @@ static int model_scene(const dv3d_net_params_t& net, const float* pts, const flo
     float* x = F;
     // sharded: no rank may store into a peer's heap before that peer has left the previous use of it
     TRY(layer_barrier(sc, st));
-    for (int b = 0; b < net.n_res[0]; ++b) TRY(res_block(net.res_down[0][b], x, sc.lv[0].n, sc.same[0], sc, ar, &x, st));
+    for (int b = 0; b < net.n_res[0]; ++b)
+        TRY(res_block(net.res_down[0][b], x, sc.lv[0].n, sc.same[0], sc, ar, &x, 0, nl == 1 && b == net.n_res[0] - 1, st));
     xs[0] = x;
     for (int i = 1; i < nl; ++i) {
         float* y = layer_rows(sc, ar, sc.lv[i].n, net.down[i - 1].N);
         ARENA_CHECK(ar);
-        TRY(sparse_conv(net.down[i - 1], x, sc.lv[i - 1].n, sc.down[i - 1], nullptr, sc, y, st));
+        const bool deepest = i == nl - 1;
+        TRY(sparse_conv(net.down[i - 1], x, sc.lv[i - 1].n, sc.down[i - 1], nullptr, sc, y, i, deepest && net.n_res[i] == 0, st));
         x = y;
-        for (int b = 0; b < net.n_res[i]; ++b) TRY(res_block(net.res_down[i][b], x, sc.lv[i].n, sc.same[i], sc, ar, &x, st));
+        for (int b = 0; b < net.n_res[i]; ++b)
+            TRY(res_block(net.res_down[i][b], x, sc.lv[i].n, sc.same[i], sc, ar, &x, i, deepest && b == net.n_res[i] - 1, st));
         xs[i] = x;
     }
     sc.feats[nl - 1] = xs[nl - 1];
@@ -511,13 +598,16 @@ static int model_scene(const dv3d_net_params_t& net, const float* pts, const flo
             else
                 TRY(dv3d_sparse_conv(x, sc.lv[l + 1].n, p.K / 27, km.nbr, n_loc, p.W, p.Wp, p.N, p.a, p.b, nullptr, 1, sc.split_ws,
                                      sc.split_ws_bytes, up, st));
+            set_halo(sc, l, net.n_res[l] == 0, r0);
             TRY(dv3d_concat_linear_gn_relu(up, Cu, xs[l] + r0 * Cx, Cx, n_loc, net.feat_adj[i].W, net.feat_adj[i].Wp, Ca,
                                            net.feat_adj[i].a, net.feat_adj[i].b, adj + r0 * Ca, st));
+            if (sc.shard) symm_set_halo(nullptr, 0);
         }
         TRY(layer_barrier(sc, st));
         x = adj;
         // the reversed n_res list: res_up[i] has n_res[nl-2-i] blocks (scenemodeling.py:168-175)
-        for (int b = 0; b < net.n_res[l]; ++b) TRY(res_block(net.res_up[i][b], x, sc.lv[l].n, sc.same[l], sc, ar, &x, st));
+        for (int b = 0; b < net.n_res[l]; ++b)
+            TRY(res_block(net.res_up[i][b], x, sc.lv[l].n, sc.same[l], sc, ar, &x, l, b == net.n_res[l] - 1, st));
         sc.feats[l] = x;
         sc.dims[l] = Ca;
     }

@@ -61,6 +61,11 @@ struct GemmDesc {
     // the registered symmetric regions (symm_attach); callers leave it zero.
     float* peer_out[kMaxPeers];
     int n_peers;
+    // Halo exchange: when set, peer p only receives the rows lo <= row_base + m < hi with lo = peer_rows[2 p],
+    // hi = peer_rows[2 p + 1] (device ints: the rows of this level that rank gathers through its kernel maps).
+    // nullptr: every row goes to every peer.  Set by symm_set_halo for the launches that follow.
+    const int* peer_rows;
+    long long row_base;     // global row index of out row 0
     // Optional fused segment max (PointNet, scenemodeling.py:129): every finished row m is also max-reduced into
     // pool_out[pool_seg[m], :] (row pitch = out_ld).  pool_out must be filled with 0xFF bytes beforehand (see
     // atomic_max_f32) and every segment must own at least one row.
@@ -123,13 +128,20 @@ __device__ __forceinline__ void epilogue4(const GemmDesc& d, float4 y, long long
         atomic_max_f32(o + 2, y.z);
         atomic_max_f32(o + 3, y.w);
     }
-    for (int p = 0; p < d.n_peers; ++p) *reinterpret_cast<float4*>(d.peer_out[p] + at) = y;
+    if (d.n_peers) {
+        const long long g = d.row_base + m;
+        for (int p = 0; p < d.n_peers; ++p)
+            if (!d.peer_rows || (g >= __ldg(d.peer_rows + 2 * p) && g < __ldg(d.peer_rows + 2 * p + 1)))
+                *reinterpret_cast<float4*>(d.peer_out[p] + at) = y;
+    }
 }
 
 // d.Wp == nullptr: fp32 CUDA-core kernel (gemm.cu); otherwise the tcgen05 kernel (gemm_tc.cu),
 // 3xTF32 or TF32 according to dv3d_set_gemm_precision.
 // fills d.peer_out / d.n_peers when d.out lies inside a region registered with dv3d_symm_register
 void symm_attach(GemmDesc& d);
+// rows that go to each peer for the launches that follow on this host thread (nullptr: all rows); see GemmDesc
+void symm_set_halo(const int* peer_rows, long long row_base);
 int launch_gather_gemm(const GemmDesc& d, cudaStream_t st);
 int launch_gather_gemm_tc(const GemmDesc& d, cudaStream_t st);
 int gather_gemm_tc_splits(long long M, int n_slices);

@@ -229,6 +229,23 @@ __device__ __forceinline__ void tile_epilogue(const GemmDesc& d, const float* s_
             }
         } else {
             // ---- general loop: K-split partials, peer stores (symmetric heap), fused segment max, zero rows
+            // rows of this tile that go to peer p: [lo, hi) packed as lo | hi << 16 (halo exchange, GemmDesc::peer_rows)
+            unsigned peer_iv[kMaxPeers];
+#pragma unroll
+            for (int p = 0; p < kMaxPeers; ++p) {
+                peer_iv[p] = 0u;
+                if (p < d.n_peers) {
+                    long long lo = 0, hi = TC_BM;
+                    if (d.peer_rows) {
+                        const long long g0 = d.row_base + m0;
+                        lo = (long long)__ldg(d.peer_rows + 2 * p) - g0;
+                        hi = (long long)__ldg(d.peer_rows + 2 * p + 1) - g0;
+                        lo = lo < 0 ? 0 : (lo > TC_BM ? TC_BM : lo);
+                        hi = hi < 0 ? 0 : (hi > TC_BM ? TC_BM : hi);
+                    }
+                    peer_iv[p] = (unsigned)lo | ((unsigned)hi << 16);
+                }
+            }
             for (int row = row0; row < TC_BM; row += ROWS_PER_IT) {
                 float4 y;
                 if (ws_tile4) {
@@ -258,8 +275,10 @@ __device__ __forceinline__ void tile_epilogue(const GemmDesc& d, const float* s_
                     if (zmod && (zphase + row) % zmod == d.zero_row_val) y = zero4;
                     const size_t at = (size_t)row * out_ld;
                     *reinterpret_cast<float4*>(out0 + at) = y;
-                    for (int p = 0; p < d.n_peers; ++p)
-                        *reinterpret_cast<float4*>(d.peer_out[p] + (size_t)m0 * out_ld + c0 + at) = y;
+#pragma unroll
+                    for (int p = 0; p < kMaxPeers; ++p)
+                        if ((unsigned)row >= (peer_iv[p] & 0xffffu) && (unsigned)row < (peer_iv[p] >> 16))
+                            *reinterpret_cast<float4*>(d.peer_out[p] + (size_t)m0 * out_ld + c0 + at) = y;
                     if (d.pool_out) {
                         float* o = d.pool_out + (size_t)__ldg(d.pool_seg + m0 + row) * out_ld + c0;
                         atomic_max_f32(o, y.x);

@@ -22,8 +22,18 @@ static SymmRegion g_regions[16];
 static int g_n_regions = 0;
 static std::mutex g_symm_mu;
 
+static thread_local const int* t_halo_rows = nullptr;
+static thread_local long long t_halo_base = 0;
+
+void symm_set_halo(const int* peer_rows, long long row_base) {
+    t_halo_rows = peer_rows;
+    t_halo_base = row_base;
+}
+
 void symm_attach(GemmDesc& d) {
     d.n_peers = 0;
+    d.peer_rows = nullptr;
+    d.row_base = 0;
     if (g_n_regions == 0) return;
     std::lock_guard<std::mutex> lock(g_symm_mu);
     const char* o = reinterpret_cast<const char*>(d.out);
@@ -32,6 +42,8 @@ void symm_attach(GemmDesc& d) {
         if (o >= r.base && o < r.base + r.bytes) {
             for (int p = 0; p < r.n_peers; ++p) d.peer_out[p] = reinterpret_cast<float*>(r.peers[p] + (o - r.base));
             d.n_peers = r.n_peers;
+            d.peer_rows = t_halo_rows;
+            d.row_base = t_halo_base;
             return;
         }
     }

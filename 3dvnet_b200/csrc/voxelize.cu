@@ -189,45 +189,95 @@ __device__ __forceinline__ unsigned rank_of(long long id, const unsigned* bitmap
     return block_offs[w / SCAN_BLK] + prefix[w] + __popc(bits);
 }
 
-// one thread per bitmap word: emit the anchors of its set bits in ascending id order
+// one thread per bitmap word: emit the anchors of its set bits in ascending id order.
+// min_idx (utils.py:61, the per-batch minimum index) is reduced per warp and per block before it reaches global memory:
+// one atomicMin per anchor and axis on the same three addresses cost 380 us for the 194 k anchors of a 64-view scene.
 __global__ void __launch_bounds__(256)
 emit_anchors_kernel(const unsigned* __restrict__ bitmap, const unsigned* __restrict__ prefix,
                     const unsigned* __restrict__ block_offs, long long n_words, GridDev G, float half_e,
                     long long cap, float* __restrict__ anchor_pts, int* __restrict__ anchor_idx3d,
                     long long* __restrict__ anchor_batch, int* __restrict__ min_idx) {
     pdl_wait();
-    long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= n_words) return;
-    unsigned bits = bitmap[w];
-    if (!bits) return;
-    long long rank = (long long)block_offs[w / SCAN_BLK] + prefix[w];
-    const long long cells = G.n[0] * G.n[1] * G.n[2];
-    const long long max_grid_idx = G.g[0] * G.g[1] * G.g[2];
-    const long long gxy = G.g[0] * G.g[1];
-    while (bits) {
-        int bit = __ffs(bits) - 1;
-        bits &= bits - 1;
-        if (rank < cap) {
-            long long id = (w << 5) + bit;
-            long long b = id / cells;                 // == scatter-min of the batch ids of its points
-            long long a = id - b * max_grid_idx;      // utils.py:53
-            int z = (int)(a / gxy);                   // utils.py:55
-            long long rem = a - (long long)z * gxy;
-            int y = (int)(rem / G.g[0]);              // utils.py:56
-            int x = (int)(rem % G.g[0]);              // utils.py:57
-            // utils.py:58: (idx * e + bbox_min) + e/2, separate roundings
-            anchor_pts[3 * rank + 0] = __fadd_rn(__fadd_rn(__fmul_rn((float)x, G.e), G.bmin[0]), half_e);
-            anchor_pts[3 * rank + 1] = __fadd_rn(__fadd_rn(__fmul_rn((float)y, G.e), G.bmin[1]), half_e);
-            anchor_pts[3 * rank + 2] = __fadd_rn(__fadd_rn(__fmul_rn((float)z, G.e), G.bmin[2]), half_e);
-            anchor_idx3d[3 * rank + 0] = x;
-            anchor_idx3d[3 * rank + 1] = y;
-            anchor_idx3d[3 * rank + 2] = z;
-            anchor_batch[rank] = b;
-            atomicMin(min_idx + 3 * b + 0, x);
-            atomicMin(min_idx + 3 * b + 1, y);
-            atomicMin(min_idx + 3 * b + 2, z);
+    __shared__ long long s_b[8];
+    __shared__ int s_min[8][3];
+    const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned bits = w < n_words ? bitmap[w] : 0u;
+    long long b0 = -1;                      // batch of this word's first anchor
+    int mx = 0x7fffffff, my = 0x7fffffff, mz = 0x7fffffff;
+    if (bits) {
+        long long rank = (long long)block_offs[w / SCAN_BLK] + prefix[w];
+        const long long cells = G.n[0] * G.n[1] * G.n[2];
+        const long long max_grid_idx = G.g[0] * G.g[1] * G.g[2];
+        const long long gxy = G.g[0] * G.g[1];
+        while (bits) {
+            int bit = __ffs(bits) - 1;
+            bits &= bits - 1;
+            if (rank < cap) {
+                long long id = (w << 5) + bit;
+                long long b = id / cells;                 // == scatter-min of the batch ids of its points
+                long long a = id - b * max_grid_idx;      // utils.py:53
+                int z = (int)(a / gxy);                   // utils.py:55
+                long long rem = a - (long long)z * gxy;
+                int y = (int)(rem / G.g[0]);              // utils.py:56
+                int x = (int)(rem % G.g[0]);              // utils.py:57
+                // utils.py:58: (idx * e + bbox_min) + e/2, separate roundings
+                anchor_pts[3 * rank + 0] = __fadd_rn(__fadd_rn(__fmul_rn((float)x, G.e), G.bmin[0]), half_e);
+                anchor_pts[3 * rank + 1] = __fadd_rn(__fadd_rn(__fmul_rn((float)y, G.e), G.bmin[1]), half_e);
+                anchor_pts[3 * rank + 2] = __fadd_rn(__fadd_rn(__fmul_rn((float)z, G.e), G.bmin[2]), half_e);
+                anchor_idx3d[3 * rank + 0] = x;
+                anchor_idx3d[3 * rank + 1] = y;
+                anchor_idx3d[3 * rank + 2] = z;
+                anchor_batch[rank] = b;
+                if (b0 < 0) b0 = b;
+                if (b == b0) {
+                    mx = min(mx, x), my = min(my, y), mz = min(mz, z);
+                } else {                                  // a word that straddles two batches (one per batch boundary)
+                    atomicMin(min_idx + 3 * b + 0, x);
+                    atomicMin(min_idx + 3 * b + 1, y);
+                    atomicMin(min_idx + 3 * b + 2, z);
+                }
+            }
+            ++rank;
         }
-        ++rank;
+    }
+    // warp: lanes that share the batch of the warp's first occupied word reduce together, the others go direct
+    const unsigned occ = __ballot_sync(0xffffffffu, b0 >= 0);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    long long wb = -1;
+    if (occ) {
+        wb = __shfl_sync(0xffffffffu, b0, __ffs(occ) - 1);
+        const bool join = b0 == wb;
+        if (b0 >= 0 && !join) {
+            atomicMin(min_idx + 3 * b0 + 0, mx);
+            atomicMin(min_idx + 3 * b0 + 1, my);
+            atomicMin(min_idx + 3 * b0 + 2, mz);
+        }
+        mx = __reduce_min_sync(0xffffffffu, join ? mx : 0x7fffffff);
+        my = __reduce_min_sync(0xffffffffu, join ? my : 0x7fffffff);
+        mz = __reduce_min_sync(0xffffffffu, join ? mz : 0x7fffffff);
+    }
+    if (lane == 0) {
+        s_b[wid] = wb;
+        s_min[wid][0] = mx, s_min[wid][1] = my, s_min[wid][2] = mz;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {   // block: merge runs of equal batch ids (ids ascend with the word index)
+        long long cur = -1;
+        int cx = 0x7fffffff, cy = 0x7fffffff, cz = 0x7fffffff;
+        for (int i = 0; i <= 8; ++i) {
+            const long long bi = i < 8 ? s_b[i] : -2;
+            if (i < 8 && bi < 0) continue;    // a warp without anchors
+            if (bi != cur) {
+                if (cur >= 0) {
+                    atomicMin(min_idx + 3 * cur + 0, cx);
+                    atomicMin(min_idx + 3 * cur + 1, cy);
+                    atomicMin(min_idx + 3 * cur + 2, cz);
+                }
+                cur = bi;
+                cx = cy = cz = 0x7fffffff;
+            }
+            if (i < 8) cx = min(cx, s_min[i][0]), cy = min(cy, s_min[i][1]), cz = min(cz, s_min[i][2]);
+        }
     }
 }
 
