@@ -183,6 +183,40 @@ __global__ void halo_publish_kernel(const int* __restrict__ lo, const int* __res
     }
 }
 
+// Sharded PointNet: every rank max-pools ITS points into a partial pool in its heap; a rank then needs the pooled
+// value only for the voxels its own points fall into (next layer's input, scenemodeling.py:129-131) or, behind the last
+// layer, for its own voxel rows.  One thread per (item, 4 channels): the max over all ranks' partial pools, read in place
+// over NVLink.  Slots nobody touched still hold the 0xFFFFFFFF fill of atomic_max_f32.
+struct PoolSrcs {
+    const float* part[kMaxPeers + 1];
+    int n;
+};
+__global__ void __launch_bounds__(256)
+pool_pull_max_kernel(PoolSrcs src, const int* __restrict__ seg, long long n_items, long long row_off, int C,
+                     float* __restrict__ red) {
+    pdl_wait();
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int units = C / 4;
+    if (i >= n_items * units) return;
+    const long long item = i / units;
+    const int c4 = (int)(i - item * units);
+    const long long v = seg ? (long long)__ldg(seg + item) : row_off + item;
+    uint4 u[kMaxPeers + 1];
+#pragma unroll
+    for (int r = 0; r <= kMaxPeers; ++r)   // every load in flight before the first compare
+        if (r < src.n) u[r] = __ldcg(reinterpret_cast<const uint4*>(src.part[r] + v * C) + c4);
+    uint4 m = u[0];
+    auto mx = [](unsigned a, unsigned b) {
+        if (a == 0xffffffffu) return b;
+        if (b == 0xffffffffu) return a;
+        return __float_as_uint(fmaxf(__uint_as_float(a), __uint_as_float(b)));
+    };
+#pragma unroll
+    for (int r = 1; r <= kMaxPeers; ++r)
+        if (r < src.n) m.x = mx(m.x, u[r].x), m.y = mx(m.y, u[r].y), m.z = mx(m.z, u[r].z), m.w = mx(m.w, u[r].w);
+    reinterpret_cast<uint4*>(red + v * C)[c4] = m;
+}
+
 struct Level {
     int* coords;
     long long n;
@@ -222,6 +256,7 @@ struct Shard {
 struct Scene {
     Shard* shard;                    // nullptr: single GPU
     const int* halo_tab;             // sharded: [level][peer][lo, hi) rows each peer needs (device, in the heap header)
+    long long pt_row0, pt_n;         // sharded: this rank's rows of the point cloud (its reference views' points)
     long long r0[DV3D_MAX_LEVELS], r1[DV3D_MAX_LEVELS];  // this rank's row range per level (whole level when !shard)
     Level lv[DV3D_MAX_LEVELS];
     int n_levels;
@@ -362,31 +397,63 @@ static int model_scene(const dv3d_net_params_t& net, const float* pts, const flo
     // ---- PointNet (scenemodeling.py:127-144), main stream
     next_stage(DV3D_STAGE_POINTNET, cs);
     const int in_pad = net.pointnet_in_pad, Hd = net.pointnet[0].N;
-    float* x0 = ar.get<float>((size_t)N * in_pad);
-    float* xa = ar.get<float>((size_t)N * Hd);
-    float* xb = ar.get<float>((size_t)N * Hd);
-    // the four per-voxel max pools are produced by the epilogues of fc1..fc4 (dv3d_linear_pool): one 0xFF fill for all
-    float* pools = ar.get<float>((size_t)4 * nv * Hd);
-    float* F = ar.get<float>((size_t)nv * net.pointnet[5].N);
+    // single GPU: all points; sharded: the points of this rank's reference views, pooled across ranks (below)
+    const long long p0 = sc.shard ? sc.pt_row0 : 0, Npl = sc.shard ? sc.pt_n : N;
+    const int* seg_l = seg + p0;
+    float* x0 = ar.get<float>((size_t)Npl * in_pad);
+    float* xa = ar.get<float>((size_t)Npl * Hd);
+    float* xb = ar.get<float>((size_t)Npl * Hd);
+    // the four per-voxel max pools are produced by the epilogues of fc2..fc5 (dv3d_linear_pool): one 0xFF fill for all.
+    // Sharded: these are the rank's PARTIAL pools (in the heap, peers read them) and `red` holds the pooled values
+    float* pools = sc.shard ? layer_rows(sc, ar, 4 * nv, Hd) : ar.get<float>((size_t)4 * nv * Hd);
+    float* red = sc.shard ? ar.get<float>((size_t)4 * nv * Hd) : pools;
+    float* F = sc.shard ? nullptr : ar.get<float>((size_t)nv * net.pointnet[5].N);
     ARENA_CHECK(ar);
+    PoolSrcs srcs[4] = {};
+    if (sc.shard)
+        for (int k = 0; k < 4; ++k) {
+            const float* part = pools + (size_t)k * nv * Hd;
+            srcs[k].n = sc.shard->n_peers + 1;
+            srcs[k].part[0] = part;
+            for (int p = 0; p < sc.shard->n_peers; ++p)
+                srcs[k].part[p + 1] = reinterpret_cast<const float*>(reinterpret_cast<const char*>(sc.shard->peer_heaps[p]) +
+                                                                     ((const char*)part - sc.shard->heap));
+        }
+    // pooled values of pool k for the voxels of this rank's points (behind a barrier: every rank's partial pool is complete)
+    auto pull_for_points = [&](int k) -> int {
+        if (!sc.shard) return DV3D_OK;
+        TRY(layer_barrier(sc, st));
+        if (Npl > 0) {
+            DV3D_LAUNCH((pool_pull_max_kernel), cdiv(Npl * (Hd / 4), 256), 256, 0, cs, srcs[k], seg_l, Npl, 0ll, Hd,
+                        red + (size_t)k * nv * Hd);
+            DV3D_LAUNCHED();
+        }
+        return DV3D_OK;
+    };
     DV3D_CUDA(cudaMemsetAsync(pools, 0xFF, sizeof(float) * 4 * (size_t)nv * Hd, cs));
-    TRY(dv3d_pointnet_input(pts, pts_feat, feat_ld, a_pts, seg, N, 32, in_pad, x0, st));
-    TRY(dv3d_linear(x0, in_pad, in_pad, nullptr, nullptr, 0, N, net.pointnet[0].W, net.pointnet[0].Wp, net.pointnet[0].b, Hd,
-                    0, xa, st));
-    TRY(dv3d_linear_pool(xa, Hd, Hd, nullptr, nullptr, 0, N, net.pointnet[1].W, net.pointnet[1].Wp, net.pointnet[1].b, Hd, 1,
-                         xb, pools, seg, st));
+    if (Npl > 0) {
+        TRY(dv3d_pointnet_input(pts + 3 * p0, pts_feat + (size_t)feat_ld * p0, feat_ld, a_pts, seg_l, Npl, 32, in_pad, x0, st));
+        TRY(dv3d_linear(x0, in_pad, in_pad, nullptr, nullptr, 0, Npl, net.pointnet[0].W, net.pointnet[0].Wp, net.pointnet[0].b,
+                        Hd, 0, xa, st));
+        TRY(dv3d_linear_pool(xa, Hd, Hd, nullptr, nullptr, 0, Npl, net.pointnet[1].W, net.pointnet[1].Wp, net.pointnet[1].b, Hd,
+                             1, xb, pools, seg_l, st));
+    }
     float *cur = xb, *nxt = xa;
     for (int i = 2; i <= 4; ++i) {
-        float* pool_in = pools + (size_t)(i - 2) * nv * Hd;
+        TRY(pull_for_points(i - 2));
+        float* pool_in = red + (size_t)(i - 2) * nv * Hd;
         float* pool_out = pools + (size_t)(i - 1) * nv * Hd;
-        TRY(dv3d_linear_pool(cur, Hd, Hd, pool_in, seg, Hd, N, net.pointnet[i].W, net.pointnet[i].Wp, net.pointnet[i].b, Hd, 1,
-                             nxt, pool_out, seg, st));
+        if (Npl > 0)
+            TRY(dv3d_linear_pool(cur, Hd, Hd, pool_in, seg_l, Hd, Npl, net.pointnet[i].W, net.pointnet[i].Wp, net.pointnet[i].b,
+                                 Hd, 1, nxt, pool_out, seg_l, st));
         float* t = cur;
         cur = nxt;
         nxt = t;
     }
-    TRY(dv3d_linear(pools + (size_t)3 * nv * Hd, Hd, Hd, nullptr, nullptr, 0, nv, net.pointnet[5].W, net.pointnet[5].Wp,
-                    net.pointnet[5].b, net.pointnet[5].N, 1, F, st));
+    if (!sc.shard)
+        TRY(dv3d_linear(pools + (size_t)3 * nv * Hd, Hd, Hd, nullptr, nullptr, 0, nv, net.pointnet[5].W, net.pointnet[5].Wp,
+                        net.pointnet[5].b, net.pointnet[5].N, 1, F, st));
+    // sharded: the last layer runs per voxel row range behind the join (it stores its rows through the halo table)
 
     // ---- coordinate levels, hash tables, kernel maps (what ME keeps in its coordinate manager)
     next_stage(DV3D_STAGE_LEVELS, side->stream);
@@ -564,8 +631,27 @@ static int model_scene(const dv3d_net_params_t& net, const float* pts, const flo
     next_stage(DV3D_STAGE_UNET, cs);
     float* xs[DV3D_MAX_LEVELS];
     float* x = F;
-    // sharded: no rank may store into a peer's heap before that peer has left the previous use of it
-    TRY(layer_barrier(sc, st));
+    if (sc.shard) {
+        // this barrier publishes the halo tables and completes every rank's last partial pool; PointNet's output layer
+        // (scenemodeling.py:141-144) for this rank's voxel rows, delivered like any level-0 layer
+        TRY(layer_barrier(sc, st));
+        const long long r0 = sc.r0[0], n_loc = sc.r1[0] - sc.r0[0];
+        const int Cf = net.pointnet[5].N;
+        F = layer_rows(sc, ar, nv, Cf);
+        ARENA_CHECK(ar);
+        if (n_loc > 0) {
+            float* red3 = red + (size_t)3 * nv * Hd;
+            DV3D_LAUNCH((pool_pull_max_kernel), cdiv(n_loc * (Hd / 4), 256), 256, 0, cs, srcs[3], (const int*)nullptr, n_loc,
+                        r0, Hd, red3);
+            DV3D_LAUNCHED();
+            set_halo(sc, 0, nl == 1 && net.n_res[0] == 0, r0);
+            TRY(dv3d_linear(red3 + r0 * Hd, Hd, Hd, nullptr, nullptr, 0, n_loc, net.pointnet[5].W, net.pointnet[5].Wp,
+                            net.pointnet[5].b, Cf, 1, F + r0 * Cf, st));
+            symm_set_halo(nullptr, 0);
+        }
+        TRY(layer_barrier(sc, st));
+        x = F;
+    }
     for (int b = 0; b < net.n_res[0]; ++b)
         TRY(res_block(net.res_down[0][b], x, sc.lv[0].n, sc.same[0], sc, ar, &x, 0, nl == 1 && b == net.n_res[0] - 1, st));
     xs[0] = x;
@@ -905,6 +991,8 @@ static int hot_path_impl(const dv3d_net_params_t& net, const float* feats_nhwc, 
             Scene sc;
             memset(&sc, 0, sizeof(sc));
             sc.shard = sh;
+            sc.pt_row0 = row0;
+            sc.pt_n = Np;
             sc.split_ws = split_ws;
             sc.split_ws_bytes = dv3d_sparse_conv_workspace_bytes(128);
             TRY(model_scene(net, pts, pfeat, 32, pts_batch_all, Ng, edge_len, sc, ar, stream));
@@ -944,7 +1032,8 @@ extern "C" size_t dv3d_hot_path_sharded_heap_bytes(const dv3d_net_params_t* net,
     // flags, the cloud (3 + 32 floats per point), every layer output of the U-Net (at most one voxel per point and
     // 128 channels: two per residual block, one per down / feature-adjust layer), 256 bytes of alignment each
     const size_t layers = (size_t)(2 * blocks + 2 * (net->n_levels - 1));
-    return 256 + Ng * 35 * 4 + 512 + (Ng * 128 * 4 + 256) * layers;
+    // + PointNet: four partial pools and the output layer, at most 128 channels each
+    return 256 + Ng * 35 * 4 + 512 + (Ng * 128 * 4 + 256) * (layers + 5);
 }
 
 extern "C" int dv3d_hot_path_sharded(const dv3d_net_params_t* netp, const float* feats_nhwc, int n_imgs, int Hf, int Wf,
