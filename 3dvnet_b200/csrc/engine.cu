@@ -183,38 +183,42 @@ __global__ void halo_publish_kernel(const int* __restrict__ lo, const int* __res
     }
 }
 
-// Sharded PointNet: every rank max-pools ITS points into a partial pool in its heap; a rank then needs the pooled
-// value only for the voxels its own points fall into (next layer's input, scenemodeling.py:129-131) or, behind the last
-// layer, for its own voxel rows.  One thread per (item, 4 channels): the max over all ranks' partial pools, read in place
-// over NVLink.  Slots nobody touched still hold the 0xFFFFFFFF fill of atomic_max_f32.
-struct PoolSrcs {
-    const float* part[kMaxPeers + 1];
-    int n;
-};
+// Sharded PointNet: a rank runs the per-point layers for the points that fall into ITS voxel rows [r0, r1) - whichever
+// rank back-projected them; every rank holds the whole cloud - so the per-voxel max pools (scenemodeling.py:129) are
+// complete locally and nothing is exchanged.  The order of the selected points is arbitrary (atomic append): it only
+// permutes rows of private activations, and max pooling is order independent.
 __global__ void __launch_bounds__(256)
-pool_pull_max_kernel(PoolSrcs src, const int* __restrict__ seg, long long n_items, long long row_off, int C,
-                     float* __restrict__ red) {
+select_points_kernel(const int* __restrict__ seg, long long N, int r0, int r1, int* __restrict__ sel, int* __restrict__ count) {
     pdl_wait();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int units = C / 4;
-    if (i >= n_items * units) return;
-    const long long item = i / units;
-    const int c4 = (int)(i - item * units);
-    const long long v = seg ? (long long)__ldg(seg + item) : row_off + item;
-    uint4 u[kMaxPeers + 1];
-#pragma unroll
-    for (int r = 0; r <= kMaxPeers; ++r)   // every load in flight before the first compare
-        if (r < src.n) u[r] = __ldcg(reinterpret_cast<const uint4*>(src.part[r] + v * C) + c4);
-    uint4 m = u[0];
-    auto mx = [](unsigned a, unsigned b) {
-        if (a == 0xffffffffu) return b;
-        if (b == 0xffffffffu) return a;
-        return __float_as_uint(fmaxf(__uint_as_float(a), __uint_as_float(b)));
-    };
-#pragma unroll
-    for (int r = 1; r <= kMaxPeers; ++r)
-        if (r < src.n) m.x = mx(m.x, u[r].x), m.y = mx(m.y, u[r].y), m.z = mx(m.z, u[r].z), m.w = mx(m.w, u[r].w);
-    reinterpret_cast<uint4*>(red + v * C)[c4] = m;
+    const bool mine = i < N && __ldg(seg + i) >= r0 && __ldg(seg + i) < r1;
+    const unsigned m = __ballot_sync(0xffffffffu, mine);
+    if (!m) return;
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == __ffs(m) - 1) base = atomicAdd(count, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+    if (mine) sel[base + __popc(m & ((1u << lane) - 1u))] = (int)i;
+}
+// rows [pts - anchor | feat | 0-padding] of the selected points (as pointnet_input_kernel) and their LOCAL voxel row
+__global__ void __launch_bounds__(256)
+pointnet_input_sel_kernel(const float* __restrict__ pts, const float* __restrict__ pts_feat, int feat_ld,
+                          const float* __restrict__ anchor_pts, const int* __restrict__ seg, const int* __restrict__ sel,
+                          long long M, int C, int ld, int r0, float* __restrict__ out, int* __restrict__ seg_sel) {
+    pdl_wait();
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M * ld) return;
+    const long long j = i / ld;
+    const int c = (int)(i - j * ld);
+    const long long p = __ldg(sel + j);
+    const int v = __ldg(seg + p);
+    float x = 0.f;
+    if (c < 3)
+        x = __fsub_rn(__ldg(pts + 3 * p + c), __ldg(anchor_pts + 3 * (long long)v + c));
+    else if (c < 3 + C)
+        x = __ldg(pts_feat + p * feat_ld + (c - 3));
+    out[i] = x;
+    if (c == 0) seg_sel[j] = v - r0;
 }
 
 struct Level {
@@ -256,7 +260,6 @@ struct Shard {
 struct Scene {
     Shard* shard;                    // nullptr: single GPU
     const int* halo_tab;             // sharded: [level][peer][lo, hi) rows each peer needs (device, in the heap header)
-    long long pt_row0, pt_n;         // sharded: this rank's rows of the point cloud (its reference views' points)
     long long r0[DV3D_MAX_LEVELS], r1[DV3D_MAX_LEVELS];  // this rank's row range per level (whole level when !shard)
     Level lv[DV3D_MAX_LEVELS];
     int n_levels;
@@ -291,6 +294,7 @@ static float* layer_rows(Scene& sc, Arena& ar, long long n, int C) {
 static int layer_barrier(Scene& sc, void* st) {
     if (!sc.shard) return DV3D_OK;
     Shard& sh = *sc.shard;
+    Prof pr(DV3D_STAGE_BARRIER, (cudaStream_t)st);
     return dv3d_symm_barrier(sh.heap, sh.peer_heaps, sh.n_peers, sh.rank, ++sh.epoch, sh.err_flag, st);
 }
 
@@ -397,63 +401,64 @@ static int model_scene(const dv3d_net_params_t& net, const float* pts, const flo
     // ---- PointNet (scenemodeling.py:127-144), main stream
     next_stage(DV3D_STAGE_POINTNET, cs);
     const int in_pad = net.pointnet_in_pad, Hd = net.pointnet[0].N;
-    // single GPU: all points; sharded: the points of this rank's reference views, pooled across ranks (below)
-    const long long p0 = sc.shard ? sc.pt_row0 : 0, Npl = sc.shard ? sc.pt_n : N;
-    const int* seg_l = seg + p0;
+    // single GPU: all points and voxels; sharded: this rank's voxel rows [v0, v1) and the points inside them
+    long long v0 = 0, v1 = nv, Npl = N;
+    const int* seg_l = seg;
+    int* sel = nullptr;
+    if (sc.shard) {
+        const long long m = (nv + sc.shard->world - 1) / sc.shard->world;   // as sc.r0 / sc.r1 of level 0 below
+        v0 = std::min((long long)sc.shard->rank * m, nv);
+        v1 = std::min((long long)(sc.shard->rank + 1) * m, nv);
+        sel = ar.get<int>((size_t)N);
+        int* count = ar.get<int>(1);
+        ARENA_CHECK(ar);
+        DV3D_CUDA(cudaMemsetAsync(count, 0, sizeof(int), cs));
+        DV3D_LAUNCH((select_points_kernel), cdiv(N, 256), 256, 0, cs, (const int*)seg, N, (int)v0, (int)v1, sel, count);
+        DV3D_LAUNCHED();
+        int host_count = 0;
+        ReadItem it = {count, &host_count, 4};
+        TRY(read_back(&it, 1, cs));
+        Npl = host_count;
+    }
+    const long long nvl = v1 - v0;
     float* x0 = ar.get<float>((size_t)Npl * in_pad);
     float* xa = ar.get<float>((size_t)Npl * Hd);
     float* xb = ar.get<float>((size_t)Npl * Hd);
-    // the four per-voxel max pools are produced by the epilogues of fc2..fc5 (dv3d_linear_pool): one 0xFF fill for all.
-    // Sharded: these are the rank's PARTIAL pools (in the heap, peers read them) and `red` holds the pooled values
-    float* pools = sc.shard ? layer_rows(sc, ar, 4 * nv, Hd) : ar.get<float>((size_t)4 * nv * Hd);
-    float* red = sc.shard ? ar.get<float>((size_t)4 * nv * Hd) : pools;
+    // the four per-voxel max pools are produced by the epilogues of fc2..fc5 (dv3d_linear_pool): one 0xFF fill for all
+    float* pools = ar.get<float>((size_t)4 * nvl * Hd);
     float* F = sc.shard ? nullptr : ar.get<float>((size_t)nv * net.pointnet[5].N);
     ARENA_CHECK(ar);
-    PoolSrcs srcs[4] = {};
-    if (sc.shard)
-        for (int k = 0; k < 4; ++k) {
-            const float* part = pools + (size_t)k * nv * Hd;
-            srcs[k].n = sc.shard->n_peers + 1;
-            srcs[k].part[0] = part;
-            for (int p = 0; p < sc.shard->n_peers; ++p)
-                srcs[k].part[p + 1] = reinterpret_cast<const float*>(reinterpret_cast<const char*>(sc.shard->peer_heaps[p]) +
-                                                                     ((const char*)part - sc.shard->heap));
-        }
-    // pooled values of pool k for the voxels of this rank's points (behind a barrier: every rank's partial pool is complete)
-    auto pull_for_points = [&](int k) -> int {
-        if (!sc.shard) return DV3D_OK;
-        TRY(layer_barrier(sc, st));
-        if (Npl > 0) {
-            DV3D_LAUNCH((pool_pull_max_kernel), cdiv(Npl * (Hd / 4), 256), 256, 0, cs, srcs[k], seg_l, Npl, 0ll, Hd,
-                        red + (size_t)k * nv * Hd);
-            DV3D_LAUNCHED();
-        }
-        return DV3D_OK;
-    };
-    DV3D_CUDA(cudaMemsetAsync(pools, 0xFF, sizeof(float) * 4 * (size_t)nv * Hd, cs));
+    if (nvl > 0) DV3D_CUDA(cudaMemsetAsync(pools, 0xFF, sizeof(float) * 4 * (size_t)nvl * Hd, cs));
+    if (sc.shard && Npl > 0) {
+        int* seg_sel = ar.get<int>((size_t)Npl);
+        ARENA_CHECK(ar);
+        DV3D_LAUNCH((pointnet_input_sel_kernel), cdiv(Npl * in_pad, 256), 256, 0, cs, pts, pts_feat, feat_ld, (const float*)a_pts,
+                    (const int*)seg, (const int*)sel, Npl, 32, in_pad, (int)v0, x0, seg_sel);
+        DV3D_LAUNCHED();
+        seg_l = seg_sel;
+    } else if (Npl > 0) {
+        TRY(dv3d_pointnet_input(pts, pts_feat, feat_ld, a_pts, seg, N, 32, in_pad, x0, st));
+    }
     if (Npl > 0) {
-        TRY(dv3d_pointnet_input(pts + 3 * p0, pts_feat + (size_t)feat_ld * p0, feat_ld, a_pts, seg_l, Npl, 32, in_pad, x0, st));
         TRY(dv3d_linear(x0, in_pad, in_pad, nullptr, nullptr, 0, Npl, net.pointnet[0].W, net.pointnet[0].Wp, net.pointnet[0].b,
                         Hd, 0, xa, st));
         TRY(dv3d_linear_pool(xa, Hd, Hd, nullptr, nullptr, 0, Npl, net.pointnet[1].W, net.pointnet[1].Wp, net.pointnet[1].b, Hd,
                              1, xb, pools, seg_l, st));
-    }
-    float *cur = xb, *nxt = xa;
-    for (int i = 2; i <= 4; ++i) {
-        TRY(pull_for_points(i - 2));
-        float* pool_in = red + (size_t)(i - 2) * nv * Hd;
-        float* pool_out = pools + (size_t)(i - 1) * nv * Hd;
-        if (Npl > 0)
+        float *cur = xb, *nxt = xa;
+        for (int i = 2; i <= 4; ++i) {
+            float* pool_in = pools + (size_t)(i - 2) * nvl * Hd;
+            float* pool_out = pools + (size_t)(i - 1) * nvl * Hd;
             TRY(dv3d_linear_pool(cur, Hd, Hd, pool_in, seg_l, Hd, Npl, net.pointnet[i].W, net.pointnet[i].Wp, net.pointnet[i].b,
                                  Hd, 1, nxt, pool_out, seg_l, st));
-        float* t = cur;
-        cur = nxt;
-        nxt = t;
+            float* t = cur;
+            cur = nxt;
+            nxt = t;
+        }
     }
     if (!sc.shard)
         TRY(dv3d_linear(pools + (size_t)3 * nv * Hd, Hd, Hd, nullptr, nullptr, 0, nv, net.pointnet[5].W, net.pointnet[5].Wp,
                         net.pointnet[5].b, net.pointnet[5].N, 1, F, st));
-    // sharded: the last layer runs per voxel row range behind the join (it stores its rows through the halo table)
+    // sharded: the output layer runs behind the join (it stores its rows through the halo table)
 
     // ---- coordinate levels, hash tables, kernel maps (what ME keeps in its coordinate manager)
     next_stage(DV3D_STAGE_LEVELS, side->stream);
@@ -632,21 +637,17 @@ static int model_scene(const dv3d_net_params_t& net, const float* pts, const flo
     float* xs[DV3D_MAX_LEVELS];
     float* x = F;
     if (sc.shard) {
-        // this barrier publishes the halo tables and completes every rank's last partial pool; PointNet's output layer
-        // (scenemodeling.py:141-144) for this rank's voxel rows, delivered like any level-0 layer
+        // this barrier publishes the halo tables (and no rank stores into a heap its owner still reads); then PointNet's
+        // output layer (scenemodeling.py:141-144) for this rank's voxel rows, delivered like any level-0 layer
         TRY(layer_barrier(sc, st));
-        const long long r0 = sc.r0[0], n_loc = sc.r1[0] - sc.r0[0];
         const int Cf = net.pointnet[5].N;
         F = layer_rows(sc, ar, nv, Cf);
         ARENA_CHECK(ar);
-        if (n_loc > 0) {
-            float* red3 = red + (size_t)3 * nv * Hd;
-            DV3D_LAUNCH((pool_pull_max_kernel), cdiv(n_loc * (Hd / 4), 256), 256, 0, cs, srcs[3], (const int*)nullptr, n_loc,
-                        r0, Hd, red3);
-            DV3D_LAUNCHED();
-            set_halo(sc, 0, nl == 1 && net.n_res[0] == 0, r0);
-            TRY(dv3d_linear(red3 + r0 * Hd, Hd, Hd, nullptr, nullptr, 0, n_loc, net.pointnet[5].W, net.pointnet[5].Wp,
-                            net.pointnet[5].b, Cf, 1, F + r0 * Cf, st));
+        DV3D_REQUIRE(sc.r0[0] == v0 && sc.r1[0] == v1, "hot_path_sharded: PointNet and U-Net disagree on the rank's voxel rows");
+        if (nvl > 0) {
+            set_halo(sc, 0, nl == 1 && net.n_res[0] == 0, v0);
+            TRY(dv3d_linear(pools + (size_t)3 * nvl * Hd, Hd, Hd, nullptr, nullptr, 0, nvl, net.pointnet[5].W, net.pointnet[5].Wp,
+                            net.pointnet[5].b, Cf, 1, F + v0 * Cf, st));
             symm_set_halo(nullptr, 0);
         }
         TRY(layer_barrier(sc, st));
@@ -991,8 +992,6 @@ static int hot_path_impl(const dv3d_net_params_t& net, const float* feats_nhwc, 
             Scene sc;
             memset(&sc, 0, sizeof(sc));
             sc.shard = sh;
-            sc.pt_row0 = row0;
-            sc.pt_n = Np;
             sc.split_ws = split_ws;
             sc.split_ws_bytes = dv3d_sparse_conv_workspace_bytes(128);
             TRY(model_scene(net, pts, pfeat, 32, pts_batch_all, Ng, edge_len, sc, ar, stream));
@@ -1032,8 +1031,8 @@ extern "C" size_t dv3d_hot_path_sharded_heap_bytes(const dv3d_net_params_t* net,
     // flags, the cloud (3 + 32 floats per point), every layer output of the U-Net (at most one voxel per point and
     // 128 channels: two per residual block, one per down / feature-adjust layer), 256 bytes of alignment each
     const size_t layers = (size_t)(2 * blocks + 2 * (net->n_levels - 1));
-    // + PointNet: four partial pools and the output layer, at most 128 channels each
-    return 256 + Ng * 35 * 4 + 512 + (Ng * 128 * 4 + 256) * (layers + 5);
+    // + PointNet's output layer
+    return 256 + Ng * 35 * 4 + 512 + (Ng * 128 * 4 + 256) * (layers + 1);
 }
 
 extern "C" int dv3d_hot_path_sharded(const dv3d_net_params_t* netp, const float* feats_nhwc, int n_imgs, int Hf, int Wf,

@@ -693,9 +693,10 @@ def hot_path_engine_sharded(net_params, feats_nhwc, rotmats, tvecs, K, plan_loca
 
 
 (STAGE_PLANESWEEP, STAGE_COSTREG, STAGE_SOFTARGMIN, STAGE_POINTCLOUD, STAGE_VOXELIZE, STAGE_POINTNET, STAGE_LEVELS,
- STAGE_UNET, STAGE_FLOW_WARP, STAGE_FLOW_INTERP, STAGE_DEC_GEMM0, STAGE_DEC_REST, STAGE_EXCHANGE) = range(13)
+ STAGE_UNET, STAGE_FLOW_WARP, STAGE_FLOW_INTERP, STAGE_DEC_GEMM0, STAGE_DEC_REST, STAGE_EXCHANGE,
+ STAGE_BARRIER) = range(14)
 STAGE_NAMES = ('planesweep_var', 'costreg', 'softargmin', 'pointcloud', 'voxelize', 'pointnet', 'levels', 'unet',
-               'flow_warp', 'flow_interp', 'dec_gemm0', 'dec_rest', 'exchange')
+               'flow_warp', 'flow_interp', 'dec_gemm0', 'dec_rest', 'exchange', 'barrier')
 
 
 def engine_profile(enable):

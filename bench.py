@@ -215,18 +215,19 @@ def run_c4(args, rank, world, dev, dist, ops, lm):
         (depth_c, _), ms_c, _, _ = timed(step_composed)
         (depth, rng), ms, launches, barriers = timed(step)
         native_equals_composed = bool(torch.equal(depth, depth_c))
-        stage_ms = None
-        if rank == 0:   # where the step goes: one more (untimed) step with the engine's stage events
-            ops.engine_profile(True)
+        # where the step goes: one more (untimed) step with the engine's stage events, on every rank
+        ops.engine_profile(True)
         dist.barrier()
         step()
         torch.cuda.synchronize()
-        if rank == 0:
-            acc = {}
-            for sid, v in ops.engine_profile_read():
-                acc[ops.STAGE_NAMES[sid]] = acc.get(ops.STAGE_NAMES[sid], 0.0) + v
-            ops.engine_profile(False)
-            stage_ms = {k: round(v, 3) for k, v in acc.items()}
+        acc = {}
+        for sid, v in ops.engine_profile_read():
+            acc[ops.STAGE_NAMES[sid]] = acc.get(ops.STAGE_NAMES[sid], 0.0) + v
+        ops.engine_profile(False)
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, {k: round(v, 3) for k, v in acc.items()})
+        stage_ms = per_rank[0]
+        stage_minmax = {k: [min(r.get(k, 0.0) for r in per_rank), max(r.get(k, 0.0) for r in per_rank)] for k in per_rank[0]}
         counts = par.shard_counts(refs, world)
         full = par.all_gather_rows(depth.reshape(depth.shape[0], -1).contiguous(), counts)
 
@@ -284,7 +285,8 @@ def run_c4(args, rank, world, dev, dist, ops, lm):
             'composed_from_python': {'ms_per_step': float(ms_c.item()) / steps,
                                      'note': 'the same schedule op by op from Python with an NCCL all-gather (round 1)',
                                      'depth_bit_identical_to_native': native_equals_composed},
-            'stage_ms_rank0': stage_ms,
+            'stage_ms_rank0': stage_ms, 'stage_ms_min_max_over_ranks': stage_minmax,
+            'stage_note': "'barrier' is part of 'unet'; 'levels' runs on a side stream beside 'pointnet'",
             'exchange_bytes': 2 * refs * PLANE[0] * PLANE[1] * 35 * 4, 'exchanges': 2, 'barriers': barriers,
             'gpu_launches_per_rank': launches // steps,
             'collective': 'point rows [N_local,3]+[N_local,32] fp32 copied into every peer heap (NVLink peer copies) + one '

@@ -474,6 +474,7 @@ typedef struct dv3d_net_params_t {
 #define DV3D_STAGE_DEC_GEMM0 10   /* dv3d_decoder_fused (whole decoder + depth update); per-layer path: first Conv1d */
 #define DV3D_STAGE_DEC_REST 11    /* per-layer path only: two more Conv1d GEMMs + head + depth update */
 #define DV3D_STAGE_EXCHANGE 12    /* dv3d_hot_path_sharded only: point rows into the peers' heaps + the barrier */
+#define DV3D_STAGE_BARRIER 13     /* sharded only: every cross-GPU barrier (time inside the pointnet / unet stages) */
 int dv3d_engine_profile(int enable);
 int dv3d_engine_profile_read(int* ids, float* ms, int cap);
 
