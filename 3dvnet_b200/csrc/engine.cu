@@ -7,6 +7,7 @@
 // allocator over a caller-provided arena.  The sequence below mirrors, call for call, the
 // Python-composed path in 3dvnet_b200/mv3d (which stays as the reference-shaped interface and
 // as the parity cross-check: tests assert bit-identical depth).
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -275,6 +276,12 @@ struct Scene {
     size_t split_ws_bytes;
 };
 
+// DV3D_SHARD_BALANCE=0: equal row counts on every level (A/B measurements; the composed Python path shards that way)
+static bool shard_balance() {   // read per call: every rank of a job must see the same value
+    const char* e = getenv("DV3D_SHARD_BALANCE");
+    return !(e && e[0] == '0');
+}
+
 // rows of a layer output: the arena, or - sharded scene - the symmetric heap (same offset on every rank, because every
 // rank allocates the same sizes in the same order: the coordinate levels are identical everywhere)
 static float* layer_rows(Scene& sc, Arena& ar, long long n, int C) {
@@ -539,6 +546,27 @@ static int model_scene(const dv3d_net_params_t& net, const float* pts, const flo
             } else {
                 sc.r0[l] = 0;
                 sc.r1[l] = n;
+            }
+        }
+        if (sc.shard && nl > 1 && shard_balance()) {
+            // coarser levels: equal WORK per rank instead (level 0 keeps equal rows: PointNet, which runs beside this
+            // on the main stream, already works on that range, and its finest-level layers are balanced as they are)
+            const int world = sc.shard->world;
+            int* bounds = ar.get<int>((size_t)(nl - 1) * 16);
+            char* scratch[DV3D_MAX_LEVELS] = {};
+            for (int l = 1; l < nl; ++l) scratch[l] = ar.get<char>(dv3d_balanced_row_bounds_scratch_bytes(sc.lv[l].n, 8));
+            ARENA_CHECK(ar);
+            for (int l = 1; l < nl; ++l)
+                TRY(dv3d_balanced_row_bounds(sc.lv[l].coords, sc.lv[l].n, sc.lv[l].table, sc.lv[l].table_bytes, sc.lv[l].stride,
+                                             world, 8, scratch[l], bounds + (l - 1) * 16, sst));
+            int host_bounds[DV3D_MAX_LEVELS][16];
+            ReadItem items[DV3D_MAX_LEVELS];
+            for (int l = 1; l < nl; ++l) items[l - 1] = ReadItem{bounds + (l - 1) * 16, host_bounds[l], (int)sizeof(int) * (world + 1)};
+            TRY(read_back(items, nl - 1, side->stream));
+            for (int l = 1; l < nl; ++l) {
+                sc.r0[l] = host_bounds[l][sc.shard->rank];
+                sc.r1[l] = host_bounds[l][sc.shard->rank + 1];
+                DV3D_REQUIRE(sc.r0[l] >= 0 && sc.r0[l] <= sc.r1[l] && sc.r1[l] <= sc.lv[l].n, "hot_path_sharded: bad row bounds");
             }
         }
         KMap* maps[3 * DV3D_MAX_LEVELS];

@@ -126,6 +126,93 @@ kernel_map_batch_kernel(const __grid_constant__ KernelMapBatch b) {
     }
 }
 
+// ---- work-balanced row ranges for a level sharded over GPUs (csrc/engine.cu, Shard) -----------------------------
+// The cost of a sparse convolution over a row range follows its number of (row, neighbour) pairs, and rows are sorted
+// by voxel id: equal row counts give the ranks that own the dense middle of a scene up to 1.5x the work of the edge
+// ranks.  One warp counts the occupied neighbours of every `stride`-th row ...
+__global__ void __launch_bounds__(256)
+sample_neighbours_kernel(const int* __restrict__ coords, long long n_samples, int stride, HashView t, int step,
+                         int* __restrict__ cnt) {
+    pdl_wait();
+    const long long s = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (s >= n_samples) return;
+    const int k = threadIdx.x & 31;
+    const long long o = s * stride;
+    bool hit = false;
+    if (k < 27) {
+        const int dx = k % 3 - 1, dy = (k / 3) % 3 - 1, dz = k / 9 - 1;
+        const int b = coords[4 * o], x = coords[4 * o + 1] + dx * step, y = coords[4 * o + 2] + dy * step,
+                  z = coords[4 * o + 3] + dz * step;
+        hit = coord_in_range(b, x, y, z) && hash_find(t, coord_key(b, x, y, z)) >= 0;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (k == 0) cnt[s] = __popc(m);
+}
+// ... and one block cuts the prefix sum of the samples into `world` equal parts: bounds[k] = first row of rank k
+// (a multiple of 128, the GEMM row tile, except bounds[world] = n).  Integer arithmetic only: every rank derives the
+// same bounds from its identical copy of the level.
+__global__ void __launch_bounds__(1024)
+balanced_bounds_kernel(const int* __restrict__ cnt, long long n_samples, int stride, long long n, int world,
+                       int* __restrict__ bounds) {
+    pdl_wait();
+    __shared__ long long s_warp[32];
+    __shared__ long long s_total, s_carry;
+    __shared__ int s_b[17];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    long long sum = 0;
+    for (long long i = tid; i < n_samples; i += 1024) sum += cnt[i];
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) s_warp[wid] = sum;
+    if (tid <= world) s_b[tid] = tid == world ? (int)n : 0;
+    __syncthreads();
+    if (tid == 0) {
+        long long t = 0;
+        for (int w = 0; w < 32; ++w) t += s_warp[w];
+        s_total = t;
+        s_carry = 0;
+    }
+    __syncthreads();
+    const long long total = s_total;
+    for (long long base = 0; base < n_samples; base += 1024) {
+        const long long i = base + tid;
+        const long long v = i < n_samples ? cnt[i] : 0;
+        long long incl = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += up;
+        }
+        __syncthreads();   // s_warp / s_carry of the previous chunk are consumed
+        if (lane == 31) s_warp[wid] = incl;
+        __syncthreads();
+        long long off = s_carry;
+        for (int w = 0; w < wid; ++w) off += s_warp[w];
+        incl += off;
+        const long long excl = incl - v;
+        if (i < n_samples)
+            for (int k = 1; k < world; ++k) {
+                const long long target = total * k / world;
+                if (excl < target && target <= incl) {   // the sample where the running sum crosses k / world of the work
+                    long long row = (i + 1) * stride;
+                    row = (row + 64) / 128 * 128;
+                    s_b[k] = (int)(row > n ? n : row);
+                }
+            }
+        __syncthreads();
+        if (tid == 1023) s_carry = incl;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (total == 0) {   // fewer rows than one sample: equal row counts
+            const long long m = (n + world - 1) / world;
+            for (int k = 1; k < world; ++k) s_b[k] = (int)(k * m < n ? k * m : n);
+        }
+        s_b[world] = (int)n;
+        for (int k = 1; k <= world; ++k)   // monotone: a level too small to cut leaves some ranks without rows
+            if (s_b[k] < s_b[k - 1]) s_b[k] = s_b[k - 1];
+        for (int k = 0; k <= world; ++k) bounds[k] = s_b[k];
+    }
+}
+
 // One warp per query point.  q = ((p - origin[b]) / res) * stride in base-voxel units
 // (refinement.py:34-35); lanes 0..7 probe the 8 corners, all lanes accumulate C channels.
 template <int C>
@@ -406,6 +493,29 @@ extern "C" int dv3d_sparse_interp(const float* pts, const long long* pts_batch, 
         DV3D_LAUNCH((sparse_interp_kernel<64>), cdiv(Nq, 8), 256, 0, st, pts, pts_batch, Nq, n_hyp, rows_per_point, origin, res, stride, t, feat, out, out_ld, out_off);
     else
         DV3D_LAUNCH((sparse_interp_kernel<128>), cdiv(Nq, 8), 256, 0, st, pts, pts_batch, Nq, n_hyp, rows_per_point, origin, res, stride, t, feat, out, out_ld, out_off);
+    DV3D_LAUNCHED();
+    return DV3D_OK;
+}
+
+extern "C" size_t dv3d_balanced_row_bounds_scratch_bytes(long long n, int sample_stride) {
+    if (n < 0 || sample_stride <= 0) return 0;
+    return align_up((size_t)((n + sample_stride - 1) / sample_stride + 1) * sizeof(int), 256);
+}
+
+extern "C" int dv3d_balanced_row_bounds(const int* coords, long long n, const void* table, size_t table_bytes, int step,
+                                        int world, int sample_stride, void* scratch, int* bounds_dev, void* stream) {
+    HashView t;
+    DV3D_REQUIRE(coords && table && scratch && bounds_dev && n >= 0 && world >= 1 && world <= 16 && sample_stride >= 1,
+                 "balanced_row_bounds: bad arguments");
+    DV3D_REQUIRE(hash_view(const_cast<void*>(table), table_bytes, &t), "balanced_row_bounds: bad table size");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long n_samples = n / sample_stride;   // rows 0, s, 2 s, ... < n
+    int* cnt = reinterpret_cast<int*>(scratch);
+    if (n_samples > 0) {
+        DV3D_LAUNCH((sample_neighbours_kernel), cdiv(n_samples, 8), 256, 0, st, coords, n_samples, sample_stride, t, step, cnt);
+        DV3D_LAUNCHED();
+    }
+    DV3D_LAUNCH((balanced_bounds_kernel), 1, 1024, 0, st, (const int*)cnt, n_samples, sample_stride, n, world, bounds_dev);
     DV3D_LAUNCHED();
     return DV3D_OK;
 }

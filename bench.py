@@ -213,8 +213,11 @@ def run_c4(args, rank, world, dev, dist, ops, lm):
 
     with torch.no_grad():
         (depth_c, _), ms_c, _, _ = timed(step_composed)
+        os.environ['DV3D_SHARD_BALANCE'] = '0'      # equal row counts on every level, as the composed path shards
+        (depth_e, _), ms_e, _, _ = timed(step)
+        native_equals_composed = bool(torch.equal(depth_e, depth_c))
+        os.environ['DV3D_SHARD_BALANCE'] = '1'      # the default: coarse levels cut by work (csrc/sparse.cu)
         (depth, rng), ms, launches, barriers = timed(step)
-        native_equals_composed = bool(torch.equal(depth, depth_c))
         # where the step goes: one more (untimed) step with the engine's stage events, on every rank
         ops.engine_profile(True)
         dist.barrier()
@@ -284,7 +287,8 @@ def run_c4(args, rank, world, dev, dist, ops, lm):
             'sparse_feat_max_rel_err_vs_single_gpu': feat_err,
             'composed_from_python': {'ms_per_step': float(ms_c.item()) / steps,
                                      'note': 'the same schedule op by op from Python with an NCCL all-gather (round 1)',
-                                     'depth_bit_identical_to_native': native_equals_composed},
+                                     'depth_bit_identical_to_native_with_equal_rows': native_equals_composed},
+            'native_equal_rows_ms_per_step': float(ms_e.item()) / steps,
             'stage_ms_rank0': stage_ms, 'stage_ms_min_max_over_ranks': stage_minmax,
             'stage_note': "'barrier' is part of 'unet'; 'levels' runs on a side stream beside 'pointnet'",
             'exchange_bytes': 2 * refs * PLANE[0] * PLANE[1] * 35 * 4, 'exchanges': 2, 'barriers': barriers,

@@ -257,6 +257,14 @@ int dv3d_kernel_map(const int* coords_out, long long n_out, const void* table_in
 /* up to 16 kernel maps (all the maps of a scene) with one launch; HOST arrays of device pointers / sizes */
 int dv3d_kernel_map_batch(const int* const* coords_out, const long long* n_out, const void* const* table_in,
                           const size_t* table_bytes, const int* step, int* const* nbr, int n_maps, void* stream);
+/* Row ranges of one sparse level for `world` GPUs with equal WORK instead of equal row counts: the occupied 3x3x3
+ * neighbours (offset `step`) of every sample_stride-th row are counted through the level's own hash table and the
+ * prefix sum is cut into `world` parts.  bounds_dev[0..world] (device ints): rank k owns rows
+ * [bounds[k], bounds[k+1]); interior bounds are multiples of 128.  Deterministic: identical on every rank that holds
+ * the same level.  scratch: dv3d_balanced_row_bounds_scratch_bytes(n, sample_stride). */
+size_t dv3d_balanced_row_bounds_scratch_bytes(long long n, int sample_stride);
+int dv3d_balanced_row_bounds(const int* coords, long long n, const void* table, size_t table_bytes, int step, int world,
+                             int sample_stride, void* scratch, int* bounds_dev, void* stream);
 /* out[o] = sum_k feat[nbr[o,k]] @ W[k]   (W [27,Cin,Cout], ME layout); optional fused per-row
  * GroupNorm (gn_weight/gn_bias [Cout], 16 channels per group, eps 1e-5), optional residual
  * add (before the ReLU) and ReLU — the SparseResidual3d / down / up blocks.  Cin % 16 == 0
