@@ -77,6 +77,28 @@ def test_shard_plan_and_local_edges():
     assert seen == e.shape[1]
 
 
+def test_native_shard_plans_tile_the_reference_views():
+    """ShardPlan (the per-rank input of dv3d_hot_path_sharded): the ranks' ranges tile the sorted reference views,
+    each rank's CSR plan holds exactly its edges, more ranks than views leaves the tail ranks empty"""
+    par = importlib.import_module('3dvnet_b200.parallel')
+    synth = importlib.import_module('3dvnet_b200.synth')
+    e = torch.from_numpy(synth.make_edges(7, 2, 2, include_self=True))
+    ib = torch.zeros(int(e.max()) + 1, dtype=torch.long)
+    n_ref = len(torch.unique(e[0]))
+    for world in (2, 3, 8, n_ref + 2):
+        at, edges = 0, 0
+        for rank in range(world):
+            sp = par.ShardPlan(e, ib, 'cpu', world, rank)
+            assert sp.n_ref == n_ref and sp.start == at and sp.depth_batch_all.shape[0] == n_ref
+            at = sp.end
+            if sp.end == sp.start:
+                assert sp.plan is None
+            else:
+                assert sp.plan.n_ref == sp.end - sp.start
+                edges += sp.plan.n_edges
+        assert at == n_ref and edges == e.shape[1]
+
+
 def test_row_ranges_partition_every_level():
     par = importlib.import_module('3dvnet_b200.parallel')
     for n in (0, 1, 7, 8, 9, 1000, 200_704):
