@@ -602,6 +602,13 @@ static int launch_s1_tiled(const float* x, int n, int Cin, int D, int H, int W, 
     return DV3D_OK;
 }
 
+namespace dv3d {
+// csrc/conv3d_tc.cu: the 32 -> 8 first layer on tcgen05
+int conv3d_tc_mode();
+int launch_conv3d_c32_c8_tc(const float* x, int n, int D, int H, int W, const float* weight, const float* scale,
+                            const float* shift, float* y, cudaStream_t st);
+}  // namespace dv3d
+
 extern "C" int dv3d_conv3d_bn_relu(const float* x, int n, int Cin, int D, int H, int W, const float* weight,
                                    const float* scale, const float* shift, int Cout, int stride, const float* skip,
                                    float* y, void* stream) {
@@ -611,6 +618,8 @@ extern "C" int dv3d_conv3d_bn_relu(const float* x, int n, int Cin, int D, int H,
     DV3D_REQUIRE(Cin <= 128, "conv3d: Cin > 128 unsupported");
     if (n == 0) return DV3D_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    if (stride == 1 && Cin == 32 && Cout == 8 && !skip && conv3d_tc_mode() == 0)
+        return launch_conv3d_c32_c8_tc(x, n, D, H, W, weight, scale, shift, y, st);
     if (stride == 1 && Cin % CIC == 0 && (long long)D * H * W >= 100000) {
         // depth of the CTA tile: fewest rounds of 2 CTAs per SM, weighted by the planes per CTA
         const long long per_plane = (long long)cdiv(W, TX) * cdiv(H, TY) * n * (Cout / COT);

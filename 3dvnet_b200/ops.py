@@ -44,6 +44,21 @@ def gemm_mode():
 WARP_MODES = ('exact', 'fast')
 
 
+CONV3D_MODES = ('tc', 'ffma')
+
+
+def set_conv3d_mode(mode):
+    """'tc': the first CostRegNet layer (32 -> 8) on tcgen05 with 3xTF32 arithmetic (csrc/conv3d_tc.cu, default);
+    'ffma': every layer on the fp32 CUDA-core kernels (DV3D_CONV3D=ffma)"""
+    if mode not in CONV3D_MODES:
+        raise ValueError('conv3d mode must be one of %s, got %r' % (CONV3D_MODES, mode))
+    lib().call('dv3d_set_conv3d_mode', CONV3D_MODES.index(mode))
+
+
+def conv3d_mode():
+    return CONV3D_MODES[int(lib().raw('dv3d_get_conv3d_mode')())]
+
+
 def set_warp_mode(mode):
     if mode not in WARP_MODES:
         raise ValueError('warp mode must be one of %s, got %r' % (WARP_MODES, mode))

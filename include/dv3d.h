@@ -124,6 +124,10 @@ int dv3d_points_var_backward(const float* feats_nhwc, int n_imgs, int C, int Hf,
 int dv3d_conv3d_bn_relu(const float* x, int n, int Cin, int D, int H, int W, const float* weight,
                         const float* scale, const float* shift, int Cout, int stride, const float* skip,
                         float* y, void* stream);
+/* The first CostRegNet layer (Cin 32, Cout 8, stride 1, no skip) runs on tcgen05 with 3xTF32 arithmetic
+ * (csrc/conv3d_tc.cu); mode 1 (or DV3D_CONV3D=ffma) keeps every layer on the fp32 CUDA-core kernels. */
+int dv3d_set_conv3d_mode(int mode);
+int dv3d_get_conv3d_mode(void);
 int dv3d_deconv3d_bn_relu(const float* x, int n, int Cin, int D, int H, int W, const float* weight,
                           const float* scale, const float* shift, int Cout, const float* skip, float* y,
                           void* stream);

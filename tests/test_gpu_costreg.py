@@ -52,6 +52,32 @@ def test_conv3d_bn_relu(ops, n, Cin, Cout, D, H, W, stride):
     np.testing.assert_allclose(got_skip.cpu().numpy(), (ref + skip).numpy(), rtol=0, atol=tol)
 
 
+@pytest.mark.parametrize('n,D,H,W', [
+    (1, 9, 11, 13),        # smaller than one patch column / z segment in every direction
+    (2, 17, 20, 31),       # ragged patches and z segments, two volumes
+    (1, 96, 56, 56),       # BASELINE C2: 480 work items on 148 persistent CTAs
+    (1, 8, 6, 14),         # exactly one interior patch
+    (1, 1, 1, 1),
+])
+def test_first_layer_on_tcgen05(ops, n, D, H, W):
+    """csrc/conv3d_tc.cu (32 -> 8, 3xTF32) against float64, and against the CUDA-core kernel it replaces"""
+    x, w, scale, shift = _case(5, n, 32, 8, D, H, W)
+    ref = F.relu(F.conv3d(x.double(), w.double(), padding=1) * scale.double().view(1, -1, 1, 1, 1)
+                 + shift.double().view(1, -1, 1, 1, 1))
+    assert ops.conv3d_mode() == 'tc'
+    got = ops.conv3d_bn_relu(x.cuda(), w.cuda(), scale.cuda(), shift.cuda(), 1)
+    again = ops.conv3d_bn_relu(x.cuda(), w.cuda(), scale.cuda(), shift.cuda(), 1)
+    ops.set_conv3d_mode('ffma')
+    try:
+        ffma = ops.conv3d_bn_relu(x.cuda(), w.cuda(), scale.cuda(), shift.cuda(), 1)
+    finally:
+        ops.set_conv3d_mode('tc')
+    tol = 4e-6 * max(1.0, float(ref.abs().max()))   # fp32-grade: 3xTF32 products, fp32 accumulation
+    np.testing.assert_allclose(got.cpu().double().numpy(), ref.numpy(), rtol=0, atol=tol)
+    np.testing.assert_allclose(ffma.cpu().double().numpy(), ref.numpy(), rtol=0, atol=tol)
+    assert torch.equal(got, again)                  # deterministic (fixed summation order)
+
+
 @pytest.mark.parametrize('n,Cin,Cout,D,H,W', [
     (1, 64, 32, 12, 7, 7), (1, 32, 16, 24, 14, 14), (1, 16, 8, 48, 28, 28), (2, 16, 8, 5, 6, 7), (1, 24, 16, 4, 4, 4),
 ])
