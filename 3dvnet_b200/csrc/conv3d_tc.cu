@@ -10,9 +10,11 @@
 // of the 6 x 14 interior voxels, summed in a fixed order (deterministic) from a shared-memory copy of T.
 // A CTA slides along z: every input plane is loaded, split into tf32 big + small parts and stored K-major / SWIZZLE_128B
 // once, and serves three output planes from a ring of four slots.  3xTF32: A_big x [W_big; W_small] as one N = 160 MMA
-// plus A_small x W_big (N = 80) per K step of 8; even and odd K steps accumulate into separate TMEM columns, so four
-// independent chains hide the ~190-cycle latency of a dependent tcgen05.mma (tools/microbench/umma_rate.cu).
-// Warps 0-3 produce planes, warps 4-7 drain TMEM / gather / store, warp 8 issues the MMAs.
+// plus A_small x W_big (N = 80) per K step of 8, 240 TMEM columns per output plane, double buffered: the drain / gather /
+// store of plane z runs beside the MMAs of plane z+1.  (Measured, tools/conv3d_phases.py: the 24 MMAs of a plane take
+// ~2300 cycles whether issued as two or as four accumulation chains - they stream 186 KB of operands through the
+// 128 B/clk shared-memory port - so the columns are better spent on the second buffer.)
+// Warps 0-3 produce planes, warps 4-11 drain TMEM / gather / store (two per TMEM lane quarter), warp 12 issues the MMAs.
 #include <stdlib.h>
 
 #include <atomic>
@@ -23,13 +25,15 @@ namespace dv3d {
 
 constexpr int CT_PY = 8, CT_PX = 16;          // input patch (rows x cols) = 128 GEMM rows
 constexpr int CT_IY = CT_PY - 2, CT_IX = CT_PX - 2;   // interior = outputs per patch and plane
-constexpr int CT_ZS = 8;                      // output planes per work item
+constexpr int CT_ZS_MAX = 16;                 // output planes per work item: chosen per launch (launch_conv3d_c32_c8_tc)
 constexpr int CT_NSLOT = 4;                   // ring of input planes
 constexpr int CT_CIN = 32, CT_COUT = 8;
 constexpr int CT_NV = 9 * CT_COUT;            // 72 useful columns
 constexpr int CT_N = 80;                      // padded to a multiple of 16
 constexpr int CT_ACC = 3 * CT_N;              // TMEM columns of one chain pair: [big x big | big x small | small x big]
-constexpr int CT_THREADS = 288;
+constexpr int CT_EPI_WARPS = 8, CT_EPI_THREADS = 32 * CT_EPI_WARPS;
+constexpr int CT_MMA_WARP = 4 + CT_EPI_WARPS;
+constexpr int CT_THREADS = 32 * (CT_MMA_WARP + 1);
 constexpr int CT_STAGE_LD = CT_NV + 1;        // odd pitch: rows of the gather hit different banks
 constexpr uint32_t CT_A_HALF = 128 * 128;     // one [128 x 32] fp32 tile
 constexpr uint32_t CT_A_SLOT = 2 * CT_A_HALF;
@@ -49,8 +53,9 @@ struct Conv3dTcArgs {
     const float* shift;
     float* y;             // [n, 8, D, H, W]
     int n, D, H, W;
-    int npx, npy, nz;
+    int npx, npy, nz, zs;   // patches in x / y, z segments, output planes per segment
     long long n_items;
+    long long* timing;    // profiling aid: 64 clock64 stamps per CTA for its first work item (tools/conv3d_phases.py)
 };
 
 __global__ void __launch_bounds__(CT_THREADS, 1)
@@ -60,8 +65,8 @@ conv3d_c32_c8_tc_kernel(const Conv3dTcArgs a) {
     float* stage = reinterpret_cast<float*>(smem + CT_OFF_STAGE);
     const uint32_t bars = smem_u32(smem + CT_OFF_BAR);
     const uint32_t bar_full = bars, bar_empty = bars + 8 * CT_NSLOT, bar_acc_full = bars + 16 * CT_NSLOT,
-                   bar_acc_empty = bar_acc_full + 8;
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + CT_OFF_BAR + 16 * CT_NSLOT + 16);
+                   bar_acc_empty = bar_acc_full + 16;   // two TMEM buffers each
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + CT_OFF_BAR + 16 * CT_NSLOT + 32);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     // ---- weights -> K-major tf32 big / small images (constant input: before the dependency wait)
@@ -83,17 +88,21 @@ conv3d_c32_c8_tc_kernel(const Conv3dTcArgs a) {
             mbar_init(bar_full + 8 * s, 4);     // one elected arrive per producer warp
             mbar_init(bar_empty + 8 * s, 1);    // tcgen05.commit
         }
-        mbar_init(bar_acc_full, 1);
-        mbar_init(bar_acc_empty, 128);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(bar_acc_full + 8 * b, 1);
+            mbar_init(bar_acc_empty + 8 * b, CT_EPI_THREADS);
+        }
         fence_mbar_init();
     }
-    if (warp == 8) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), 512);
+    if (warp == CT_MMA_WARP) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), 512);
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     pdl_wait();
+    long long* stamp = a.timing ? a.timing + 64 * blockIdx.x : nullptr;
+    if (stamp && tid == 0) stamp[0] = clock64();
 
     const long long vol = (long long)a.D * a.H * a.W, plane = (long long)a.H * a.W;
     int n_my = 0;   // items this CTA has started (plane / output counters follow from it)
@@ -101,13 +110,14 @@ conv3d_c32_c8_tc_kernel(const Conv3dTcArgs a) {
     for (long long item = blockIdx.x; item < a.n_items; item += gridDim.x, ++n_my) {
         const int px = (int)(item % a.npx), py = (int)((item / a.npx) % a.npy);
         const int zs = (int)((item / ((long long)a.npx * a.npy)) % a.nz), nb = (int)(item / ((long long)a.npx * a.npy * a.nz));
-        const int z0 = zs * CT_ZS, Y0 = py * CT_IY - 1, X0 = px * CT_IX - 1;
-        const int pc0 = n_my * (CT_ZS + 2), oc0 = n_my * CT_ZS;   // running plane / output-plane counters of this CTA
+        const int ZS = a.zs;
+        const int z0 = zs * ZS, Y0 = py * CT_IY - 1, X0 = px * CT_IX - 1;
+        const int pc0 = n_my * (ZS + 2), oc0 = n_my * ZS;   // running plane / output-plane counters of this CTA
 
         if (warp < 4) {
             // ---------------------------------------------------------------- producers: one input plane per step
             const int rx = lane & 15, half = lane >> 4, gx = X0 + rx;
-            for (int p = 0; p < CT_ZS + 2; ++p) {
+            for (int p = 0; p < ZS + 2; ++p) {
                 const int pc = pc0 + p, slot = pc % CT_NSLOT;
                 const int gz = z0 - 1 + p;
                 float v[2][16];
@@ -141,18 +151,20 @@ conv3d_c32_c8_tc_kernel(const Conv3dTcArgs a) {
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_full + 8 * slot);
             }
-        } else if (warp == 8) {
+        } else if (warp == CT_MMA_WARP) {
             // ---------------------------------------------------------------- MMA issue
             const uint32_t idesc_pair = umma_idesc_tf32(128, 2 * CT_N), idesc = umma_idesc_tf32(128, CT_N);
-            for (int zi = 0; zi < CT_ZS; ++zi) {
+            for (int zi = 0; zi < ZS; ++zi) {
                 for (int p = (zi == 0 ? 0 : 2); p < 3; ++p) {   // planes zi .. zi+2; the older two were waited for before
                     const int pc = pc0 + zi + p;
                     mbar_wait(bar_full + 8 * (pc % CT_NSLOT), (pc / CT_NSLOT) & 1);
                 }
-                const int oc = oc0 + zi;
-                mbar_wait(bar_acc_empty, (oc & 1) ^ 1);
+                const int oc = oc0 + zi, buf = oc & 1;
+                mbar_wait(bar_acc_empty + 8 * buf, ((oc >> 1) & 1) ^ 1);
                 tc_fence_after();
                 if (elect_one()) {
+                    if (stamp && n_my == 0 && zi < 8) stamp[1 + zi * 5] = clock64();
+                    const uint32_t d = tmem_base + buf * CT_ACC;
 #pragma unroll
                     for (int kz = 0; kz < 3; ++kz) {
                         const int pc = pc0 + zi + kz;
@@ -161,53 +173,49 @@ conv3d_c32_c8_tc_kernel(const Conv3dTcArgs a) {
 #pragma unroll
                         for (int kk = 0; kk < CT_CIN / 8; ++kk) {
                             const uint32_t ko = kk * 32;   // 8 tf32 = 32 bytes inside the swizzle row
-                            const uint32_t d = tmem_base + (kk & 1) * CT_ACC;
-                            const uint32_t acc = (kz > 0 || kk >= 2) ? 1u : 0u;
+                            const uint32_t acc = (kz | kk) ? 1u : 0u;
                             umma_tf32(d, umma_desc_sw128(a_big + ko), umma_desc_sw128(b_big + ko), idesc_pair, acc);
                             umma_tf32(d + 2 * CT_N, umma_desc_sw128(a_small + ko), umma_desc_sw128(b_big + ko), idesc, acc);
                         }
                     }
                     umma_commit(bar_empty + 8 * ((pc0 + zi) % CT_NSLOT));   // plane zi is not read again
-                    if (zi == CT_ZS - 1) {
+                    if (zi == ZS - 1) {
                         umma_commit(bar_empty + 8 * ((pc0 + zi + 1) % CT_NSLOT));
                         umma_commit(bar_empty + 8 * ((pc0 + zi + 2) % CT_NSLOT));
                     }
-                    umma_commit(bar_acc_full);
+                    umma_commit(bar_acc_full + 8 * buf);
+                    if (stamp && n_my == 0 && zi < 8) stamp[2 + zi * 5] = clock64();
                 }
                 __syncwarp();
             }
         } else {
             // ---------------------------------------------------------------- epilogue: TMEM -> T in smem -> gather -> y
-            const int q = warp & 3, et = tid - 128;   // TMEM lane quarter of this warp; epilogue thread 0..127
+            const int q = warp & 3, hw = (warp - 4) >> 2, et = tid - 128;   // TMEM lane quarter, column half, thread 0..255
             const int r = q * 32 + lane;
-            for (int zi = 0; zi < CT_ZS; ++zi) {
-                const int oc = oc0 + zi, gz = z0 + zi;
-                mbar_wait(bar_acc_full, oc & 1);
+            for (int zi = 0; zi < ZS; ++zi) {
+                const int oc = oc0 + zi, buf = oc & 1, gz = z0 + zi;
+                mbar_wait(bar_acc_full + 8 * buf, (oc >> 1) & 1);
                 tc_fence_after();
-                const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+                if (stamp && n_my == 0 && et == 0 && zi < 8) stamp[3 + zi * 5] = clock64();
+                const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + buf * CT_ACC;
+                // this warp's column blocks of T: 0..2 or 3..4 (16 columns each; 72..79 are padding)
+                for (int b = hw ? 3 : 0; b < (hw ? 5 : 3); ++b) {
+                    uint32_t u[3][16];
 #pragma unroll
-                for (int b = 0; b < CT_N / 16; ++b) {
-                    uint32_t u[6][16];
-#pragma unroll
-                    for (int c = 0; c < 2; ++c)
-#pragma unroll
-                        for (int t = 0; t < 3; ++t) tmem_ld16_nowait(trow + c * CT_ACC + t * CT_N + b * 16, u[c * 3 + t]);
+                    for (int t = 0; t < 3; ++t) tmem_ld16_nowait(trow + t * CT_N + b * 16, u[t]);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        if (b * 16 + i < CT_NV) {
-                            // correction terms first, then the two big x big chains
-                            const float corr = (__uint_as_float(u[1][i]) + __uint_as_float(u[4][i])) +
-                                               (__uint_as_float(u[2][i]) + __uint_as_float(u[5][i]));
-                            stage[r * CT_STAGE_LD + b * 16 + i] = (__uint_as_float(u[0][i]) + __uint_as_float(u[3][i])) + corr;
-                        }
-                    }
+                    for (int i = 0; i < 16; ++i)
+                        if (b * 16 + i < CT_NV)   // the two correction terms first
+                            stage[r * CT_STAGE_LD + b * 16 + i] =
+                                __uint_as_float(u[0][i]) + (__uint_as_float(u[1][i]) + __uint_as_float(u[2][i]));
                 }
                 tc_fence_before();
-                mbar_arrive(bar_acc_empty);                      // TMEM is free: the next plane's MMAs may start
-                asm volatile("bar.sync 1, 128;" ::: "memory");   // T complete
+                mbar_arrive(bar_acc_empty + 8 * buf);            // this TMEM buffer is free for the plane after next
+                if (stamp && n_my == 0 && et == 0 && zi < 8) stamp[4 + zi * 5] = clock64();
+                asm volatile("bar.sync 1, %0;" ::"n"(CT_EPI_THREADS) : "memory");   // T complete
                 if (gz < a.D) {
-                    for (int idx = et; idx < CT_IY * CT_IX * CT_COUT; idx += 128) {
+                    for (int idx = et; idx < CT_IY * CT_IX * CT_COUT; idx += CT_EPI_THREADS) {
                         const int ix = idx % CT_IX, iy = (idx / CT_IX) % CT_IY, co = idx / (CT_IX * CT_IY);
                         const int gy = py * CT_IY + iy, gx = px * CT_IX + ix;
                         if (gy >= a.H || gx >= a.W) continue;
@@ -221,17 +229,19 @@ conv3d_c32_c8_tc_kernel(const Conv3dTcArgs a) {
                         a.y[((long long)nb * CT_COUT + co) * vol + (long long)gz * plane + (long long)gy * a.W + gx] = v;
                     }
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");   // T consumed: the next plane may overwrite it
+                asm volatile("bar.sync 1, %0;" ::"n"(CT_EPI_THREADS) : "memory");   // T consumed: the next plane may overwrite it
+                if (stamp && n_my == 0 && et == 0 && zi < 8) stamp[5 + zi * 5] = clock64();
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) tmem_dealloc(tmem_base, 512);
+    if (warp == CT_MMA_WARP) tmem_dealloc(tmem_base, 512);
 }
 
 // 0: tcgen05 kernel when the layer has its shape (default), 1: always the CUDA-core kernels (verification / A-B)
 static std::atomic<int> g_conv3d_mode{-1};
+static std::atomic<long long*> g_conv3d_timing{nullptr};
 
 int conv3d_tc_mode() {
     int m = g_conv3d_mode.load();
@@ -248,8 +258,19 @@ int launch_conv3d_c32_c8_tc(const float* x, int n, int D, int H, int W, const fl
     Conv3dTcArgs a = {};
     a.x = x, a.weight = weight, a.scale = scale, a.shift = shift, a.y = y;
     a.n = n, a.D = D, a.H = H, a.W = W;
-    a.npx = cdiv(W, CT_IX), a.npy = cdiv(H, CT_IY), a.nz = cdiv(D, CT_ZS);
-    a.n_items = (long long)n * a.nz * a.npy * a.npx;
+    a.npx = cdiv(W, CT_IX), a.npy = cdiv(H, CT_IY);
+    // output planes per work item: the fewest plane steps on the busiest CTA, counting the two extra input planes
+    // every item loads and a prologue of about one plane step per item
+    const long long patches = (long long)n * a.npy * a.npx;
+    long long best_cost = -1;
+    for (int zs = 2; zs <= CT_ZS_MAX && zs <= (D > 2 ? D : 2); ++zs) {
+        const long long items = patches * cdiv(D, zs), rounds = (items + kNumSMs - 1) / kNumSMs;
+        const long long cost = rounds * (4 * zs + 3);   // in quarter plane steps
+        if (best_cost < 0 || cost < best_cost) best_cost = cost, a.zs = zs;
+    }
+    a.nz = cdiv(D, a.zs);
+    a.n_items = patches * a.nz;
+    a.timing = g_conv3d_timing.load();
     static std::atomic<unsigned long long> attr{0};
     DV3D_FUNC_SMEM_ONCE(attr, (conv3d_c32_c8_tc_kernel), (int)CT_SMEM);
     const int grid = (int)(a.n_items < kNumSMs ? a.n_items : kNumSMs);
@@ -266,3 +287,7 @@ extern "C" int dv3d_set_conv3d_mode(int mode) {
     return DV3D_OK;
 }
 extern "C" int dv3d_get_conv3d_mode(void) { return dv3d::conv3d_tc_mode(); }
+extern "C" int dv3d_conv3d_set_timing_buffer(void* device_buffer) {
+    dv3d::g_conv3d_timing.store((long long*)device_buffer);
+    return DV3D_OK;
+}

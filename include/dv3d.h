@@ -128,6 +128,8 @@ int dv3d_conv3d_bn_relu(const float* x, int n, int Cin, int D, int H, int W, con
  * (csrc/conv3d_tc.cu); mode 1 (or DV3D_CONV3D=ffma) keeps every layer on the fp32 CUDA-core kernels. */
 int dv3d_set_conv3d_mode(int mode);
 int dv3d_get_conv3d_mode(void);
+/* profiling aid (tools/conv3d_phases.py): 64 int64 clock stamps per CTA (148 CTAs at most) of the next launches, or NULL */
+int dv3d_conv3d_set_timing_buffer(void* device_buffer);
 int dv3d_deconv3d_bn_relu(const float* x, int n, int Cin, int D, int H, int W, const float* weight,
                           const float* scale, const float* shift, int Cout, const float* skip, float* y,
                           void* stream);
