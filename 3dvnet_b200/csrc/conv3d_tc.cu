@@ -34,14 +34,14 @@ constexpr int CT_ACC = 3 * CT_N;              // TMEM columns of one chain pair:
 constexpr int CT_EPI_WARPS = 8, CT_EPI_THREADS = 32 * CT_EPI_WARPS;
 constexpr int CT_MMA_WARP = 4 + CT_EPI_WARPS;
 constexpr int CT_THREADS = 32 * (CT_MMA_WARP + 1);
-constexpr int CT_STAGE_LD = CT_NV + 1;        // odd pitch: rows of the gather hit different banks
+constexpr int CT_STAGE_LD = 128;              // T is kept column-major [72][128]: lanes = consecutive rows both ways
 constexpr uint32_t CT_A_HALF = 128 * 128;     // one [128 x 32] fp32 tile
 constexpr uint32_t CT_A_SLOT = 2 * CT_A_HALF;
 constexpr uint32_t CT_B_HALF = CT_N * 128;
 constexpr uint32_t CT_B_DZ = 2 * CT_B_HALF;
 constexpr uint32_t CT_OFF_B = CT_NSLOT * CT_A_SLOT;
 constexpr uint32_t CT_OFF_STAGE = CT_OFF_B + 3 * CT_B_DZ;
-constexpr uint32_t CT_OFF_BAR = CT_OFF_STAGE + 128 * CT_STAGE_LD * 4;
+constexpr uint32_t CT_OFF_BAR = CT_OFF_STAGE + CT_NV * CT_STAGE_LD * 4;
 constexpr uint32_t CT_SMEM = CT_OFF_BAR + 128 + 1024;   // + alignment slack
 static_assert(CT_SMEM <= 232448, "shared memory budget");
 static_assert(2 * CT_ACC <= 512, "TMEM budget");
@@ -207,7 +207,7 @@ conv3d_c32_c8_tc_kernel(const Conv3dTcArgs a) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i)
                         if (b * 16 + i < CT_NV)   // the two correction terms first
-                            stage[r * CT_STAGE_LD + b * 16 + i] =
+                            stage[(b * 16 + i) * CT_STAGE_LD + r] =
                                 __uint_as_float(u[0][i]) + (__uint_as_float(u[1][i]) + __uint_as_float(u[2][i]));
                 }
                 tc_fence_before();
@@ -215,16 +215,18 @@ conv3d_c32_c8_tc_kernel(const Conv3dTcArgs a) {
                 if (stamp && n_my == 0 && et == 0 && zi < 8) stamp[4 + zi * 5] = clock64();
                 asm volatile("bar.sync 1, %0;" ::"n"(CT_EPI_THREADS) : "memory");   // T complete
                 if (gz < a.D) {
-                    for (int idx = et; idx < CT_IY * CT_IX * CT_COUT; idx += CT_EPI_THREADS) {
-                        const int ix = idx % CT_IX, iy = (idx / CT_IX) % CT_IY, co = idx / (CT_IX * CT_IY);
+                    // 16 lanes per output row (14 active): a warp reads two patch rows, whose T rows are 16 apart -
+                    // consecutive lanes hit consecutive banks and the two halves never collide
+                    for (int slot = et; slot < 16 * CT_IY * CT_COUT; slot += CT_EPI_THREADS) {
+                        const int ix = slot & 15, iy = (slot >> 4) % CT_IY, co = (slot >> 4) / CT_IY;
                         const int gy = py * CT_IY + iy, gx = px * CT_IX + ix;
-                        if (gy >= a.H || gx >= a.W) continue;
+                        if (ix >= CT_IX || gy >= a.H || gx >= a.W) continue;
                         float s = 0.f;
 #pragma unroll
                         for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
                             for (int kx = 0; kx < 3; ++kx)
-                                s += stage[((iy + ky) * CT_PX + ix + kx) * CT_STAGE_LD + (ky * 3 + kx) * CT_COUT + co];
+                                s += stage[((ky * 3 + kx) * CT_COUT + co) * CT_STAGE_LD + (iy + ky) * CT_PX + ix + kx];
                         const float v = fmaxf(fmaf(s, __ldg(a.scale + co), __ldg(a.shift + co)), 0.f);
                         a.y[((long long)nb * CT_COUT + co) * vol + (long long)gz * plane + (long long)gy * a.W + gx] = v;
                     }
