@@ -1,10 +1,10 @@
 #!/bin/bash
-# Regenerates profiles/sass_{gemm_tc,decoder_fused,planesweep}.txt from the objects of the last build:
+# Regenerates profiles/sass_{gemm_tc,decoder_fused,planesweep,conv3d_tc}.txt from the objects of the last build:
 # mnemonic counts of the tensor / copy / barrier / reduction instructions, then those instructions per kernel.
 #   python 3dvnet_b200/build.py && bash tools/sass_listing.sh
 cd "$(dirname "$0")/.."
 PAT='UTCHMMA|UTCBAR|UTCATOMSWS|LDTM|STTM|UBLKCP|UTMALDG|ACQBULK|SYNCS|ELECT|REDUX|REDG|RED\.|ATOMG'
-for k in gemm_tc decoder_fused planesweep; do
+for k in gemm_tc decoder_fused planesweep conv3d_tc; do
     o=3dvnet_b200/build/$k.o
     [ -f "$o" ] || { echo "missing $o"; exit 1; }
     out=profiles/sass_$k.txt
