@@ -26,6 +26,8 @@
 //   sparsity        kernel-map slices with no live row in the tile are skipped by producers and
 //                   issuer alike (flags computed from the staged row table).
 #include "gemm.cuh"
+#include <stdlib.h>
+
 #include "tc.cuh"
 
 namespace dv3d {
@@ -45,6 +47,7 @@ __host__ __device__ constexpr size_t tc_smem_bytes(int N) {
 }
 
 static int g_gemm_precision = 1;  // 1 = 3xTF32, 2 = TF32
+static int g_pair_ws = -1;         // pair-major GEMM: 1 = weight-stationary kernel (default), 0 = the general kernels (DV3D_PAIR_WS=0)
 static int g_gemm_persistent = 0;  // 0 = automatic (more tiles than SMs), 1 = whenever possible, -1 = never (tests / A-B runs)
 // profiling aid (tools/gemm_phases.py): 8 clock64 stamps per CTA of every launch, or nullptr
 __device__ long long* g_gemm_stamps = nullptr;
@@ -597,7 +600,8 @@ template <int BN>
 __host__ __device__ constexpr int tcp_stages() { return BN == 128 ? 2 : 3; }
 template <int BN>
 __host__ __device__ constexpr size_t tcp_smem_bytes() {
-    return 1024 + (size_t)tcp_stages<BN>() * tc_stage_bytes(BN) + (size_t)TC_BM * (BN + 4) * sizeof(float) + 512;
+    return 1024 + (size_t)tcp_stages<BN>() * tc_stage_bytes(BN) + (size_t)TC_BM * (BN + 4) * sizeof(float) + 512 +
+           2 * TC_PRODUCERS * 4 * sizeof(int);   // + two buffers of row numbers (4 per producer thread)
 }
 
 template <int BN>
@@ -611,6 +615,7 @@ gather_gemm_tc_persistent_kernel(const __grid_constant__ GemmDesc d, int precisi
     float* s_tile = reinterpret_cast<float*>(smem + PS * STAGE);
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_tile + TC_BM * TILE_LD);   // full[PS] empty[PS] accum tmem_free
     uint32_t* s_misc = reinterpret_cast<uint32_t*>(s_bar + 2 * PS + 2);
+    int* s_rows = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(s_bar) + 512);   // [2][TC_PRODUCERS][4]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t bar_full = smem_u32(s_bar), bar_empty = smem_u32(s_bar + PS), bar_accum = smem_u32(s_bar + 2 * PS),
                    bar_free = smem_u32(s_bar + 2 * PS + 1);
@@ -689,30 +694,55 @@ gather_gemm_tc_persistent_kernel(const __grid_constant__ GemmDesc d, int precisi
         const int pj = tid & 7, r0 = tid >> 3;   // 16-byte unit of the 128-byte chunk row; rows r0 + 32 i
         const float* src[4];
         float4 buf[TC_PREFETCH][4];
-        auto request_tile = [&](long long tile) {   // row numbers of the tile, then its first chunks
+        // Two requests run ahead of the tile being stored: the ROW NUMBERS of the tile after next and the first chunks of
+        // the next tile (whose row numbers arrived a tile ago).  Measured at 13.7 k pair tiles (tools/
+        // gemm_persistent_phases.py): issued together, the dependent pair (row number -> row address -> chunk load)
+        // stalled every producer thread for 8.3 k of the 20.2 k cycles of a tile period.
+        // The row numbers travel global -> shared memory by cp.async (no register, nothing that could stall behind the
+        // load): with 168 registers per thread the compiler kept them on the stack, and its store of a freshly loaded
+        // value stalled the in-order warp for a full memory round trip, twice per tile.
+        auto request_rows = [&](long long tile, int which) {
             const long long m0 = tile * TC_BM;
+            int* mine = s_rows + ((size_t)which * TC_PRODUCERS + tid) * 4;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const long long m = m0 + r0 + 32 * i;
-                long long rr = -1;
-                if (m < d.M) {
-                    rr = sl.idx ? (long long)__ldg(sl.idx + m * sl.idx_stride) : m + sl.shift;
-                    if (!sl.idx && rr >= d.n_src_rows) rr = -1;
+                if (sl.idx && m < d.M) {
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(mine + i)), "l"(sl.idx + m * sl.idx_stride)
+                                 : "memory");
+                } else {
+                    const long long rr = m + sl.shift;
+                    mine[i] = (!sl.idx && m < d.M && rr >= 0 && rr < d.n_src_rows) ? (int)rr : -1;
                 }
-                src[i] = rr >= 0 ? sl.src + (size_t)rr * sl.ld + pj * 4 : nullptr;
             }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        auto request_chunks = [&](int which) {   // first chunks of the tile whose row numbers were requested a tile ago
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            const int4 rows = *reinterpret_cast<const int4*>(s_rows + ((size_t)which * TC_PRODUCERS + tid) * 4);
+            const int rr[4] = {rows.x, rows.y, rows.z, rows.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) src[i] = rr[i] >= 0 ? sl.src + (size_t)(unsigned)rr[i] * sl.ld + pj * 4 : nullptr;
 #pragma unroll
             for (int p = 0; p < TC_PREFETCH; ++p)
                 if (p < nk) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
-                        buf[p][i] = src[i] ? __ldg(reinterpret_cast<const float4*>(src[i] + p * TC_KC)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        buf[p][i] = src[i] ? __ldcg(reinterpret_cast<const float4*>(src[i] + p * TC_KC)) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
         };
-        if ((long long)blockIdx.x < n_tiles) request_tile(blockIdx.x);
+        if ((long long)blockIdx.x < n_tiles) {
+            request_rows(blockIdx.x, 0);
+            request_chunks(0);
+            if ((long long)blockIdx.x + gridDim.x < n_tiles) request_rows((long long)blockIdx.x + gridDim.x, 1);
+        }
+        // profiling aid (tools/gemm_phases.py --persistent): the phases of this CTA's 8th tile (steady state)
+        long long* const stamps = g_gemm_stamps ? g_gemm_stamps + (size_t)blockIdx.x * 12 : nullptr;
         int j = 0;
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
             const long long m0 = tile * TC_BM;
+            long long* const stamp = (stamps && tid == 0 && (j == 7 || j == 8)) ? stamps + (j - 7) * 6 : nullptr;
+            if (stamp) stamp[0] = clock64();
             for (int it0 = 0; it0 < nk; it0 += TC_PREFETCH) {
 #pragma unroll
                 for (int p = 0; p < TC_PREFETCH; ++p) {
@@ -743,17 +773,23 @@ gather_gemm_tc_persistent_kernel(const __grid_constant__ GemmDesc d, int precisi
                         if (it + TC_PREFETCH < nk) {
 #pragma unroll
                             for (int i = 0; i < 4; ++i)
-                                buf[p][i] = src[i] ? __ldg(reinterpret_cast<const float4*>(src[i] + (it + TC_PREFETCH) * TC_KC))
+                                buf[p][i] = src[i] ? __ldcg(reinterpret_cast<const float4*>(src[i] + (it + TC_PREFETCH) * TC_KC))
                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
                         }
                     }
                 }
             }
             // the next tile's rows and first chunks travel while this tile finishes
-            if (tile + gridDim.x < n_tiles) request_tile(tile + gridDim.x);
+            if (stamp) stamp[1] = clock64();   // chunks stored
+            if (tile + gridDim.x < n_tiles) {
+                request_chunks((j + 1) & 1);
+                if (tile + 2 * (long long)gridDim.x < n_tiles) request_rows(tile + 2 * (long long)gridDim.x, j & 1);
+            }
+            if (stamp) stamp[2] = clock64();   // next tile requested
 
             mbar_wait(bar_accum, (uint32_t)j & 1u);
             tc_fence_after();
+            if (stamp) stamp[3] = clock64();   // accumulator complete
             // every warp is done reading the previous tile from s_tile
             asm volatile("bar.sync 1, %0;" ::"n"(TC_PRODUCERS) : "memory");
             {
@@ -784,12 +820,267 @@ gather_gemm_tc_persistent_kernel(const __grid_constant__ GemmDesc d, int precisi
             tc_fence_before();
             asm volatile("bar.sync 1, %0;" ::"n"(TC_PRODUCERS) : "memory");
             if (tid == 0) mbar_arrive(bar_free);   // TMEM may be overwritten by the next tile's first MMA
+            if (stamp) stamp[4] = clock64();   // tile in shared memory
             tile_epilogue<BN, TC_PRODUCERS>(d, s_tile, m0, tid, epi, nullptr, 1, nullptr);
+            if (stamp) stamp[5] = clock64();   // rows stored
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 8) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+static bool pair_ws_enabled() {
+    if (g_pair_ws < 0) {
+        const char* e = getenv("DV3D_PAIR_WS");
+        g_pair_ws = (e && e[0] == '0') ? 0 : 1;
+    }
+    return g_pair_ws != 0;
+}
+
+// ------------------------------------------------------------------ pair-major GEMM, weight stationary
+// The pair-major sparse convolution (sparse_pairs.cu) is a plain GEMM per 128-pair tile: gathered rows [128, Cin] x the
+// weight block of the tile's kernel offset [Cin, Cout] -> partial rows P.  Tiles are sorted by offset, so a CTA that takes
+// a CONTIGUOUS range of tiles changes its weight block once or twice per launch: the whole block (big + small parts,
+// up to 128 KB) stays in shared memory and only the gathered rows stream through the stage ring.  Measured on the
+// level-1 layers of the 64-view scene (13.7 k tiles, tools/gemm_persistent_phases.py): with the weights streamed per K
+// chunk through a two-stage ring, the third and fourth chunk of every tile waited for a weight copy that could only
+// be issued once its stage was free - 128 KB of weights per 64 KB of rows, 15.3 k cycles per tile for 3.1 k of MMA.
+// The accumulator goes TMEM -> registers -> global (the rows of P are contiguous), no shared-memory tile.
+template <int BN, int NK>
+__host__ __device__ constexpr size_t pair_ws_smem_bytes() {
+    return 1024 + 2 * (size_t)(2 * TC_A_BYTES) + (size_t)NK * 2 * BN * 128 + 512 + 2 * TC_PRODUCERS * 4 * sizeof(int);
+}
+
+template <int BN, int NK>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+pair_gemm_ws_kernel(const __grid_constant__ GemmDesc d, int precision) {
+    constexpr int PS = 2;
+    constexpr int A_STAGE = 2 * TC_A_BYTES, B_CHUNK = 2 * BN * 128;
+    constexpr uint32_t TMEM_COLS = BN == 128 ? 512 : 256;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* s_w = smem + PS * A_STAGE;
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_w + NK * B_CHUNK);   // full[PS] empty[PS] accum free wfull[NK]
+    uint32_t* s_misc = reinterpret_cast<uint32_t*>(s_bar + 2 * PS + 2 + NK);
+    volatile int* s_done = reinterpret_cast<volatile int*>(s_misc + 2);      // tiles whose MMAs have completed
+    int* s_rows = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(s_bar) + 512);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t bar_full = smem_u32(s_bar), bar_empty = smem_u32(s_bar + PS), bar_accum = smem_u32(s_bar + 2 * PS),
+                   bar_free = smem_u32(s_bar + 2 * PS + 1), bar_w = smem_u32(s_bar + 2 * PS + 2);
+    const GemmSlice& sl = d.slice[0];
+    const long long n_tiles = (d.M + TC_BM - 1) / TC_BM;
+    const long long t0 = n_tiles * blockIdx.x / gridDim.x, t1 = n_tiles * (blockIdx.x + 1) / gridDim.x;
+    const float* __restrict__ Wp = d.Wp;
+
+    if (tid == 0) {
+        for (int s = 0; s < PS; ++s) {
+            mbar_init(bar_full + 8 * s, TC_PRODUCERS / 32);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        mbar_init(bar_accum, 1);
+        mbar_init(bar_free, 1);
+        for (int k = 0; k < NK; ++k) mbar_init(bar_w + 8 * k, 1);
+        *s_done = 0;
+        fence_mbar_init();
+    }
+    if (warp == 8) tmem_alloc(smem_u32(s_misc), TMEM_COLS);
+    pdl_wait();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = s_misc[0];
+
+    if (warp == 8) {
+        // ===================== MMA issuer
+        constexpr uint32_t idesc = umma_idesc_tf32(TC_BM, BN), idesc_pair = umma_idesc_tf32(TC_BM, 2 * BN);
+        int cur = -1, n_w = 0, j = 0;
+        for (long long tile = t0; tile < t1; ++tile, ++j) {
+            const int ws = __ldg(d.tile_wslice + tile);
+            const bool changed = ws != cur;
+            if (changed) cur = ws, ++n_w;
+            if (j > 0) {   // the previous tile has left TMEM
+                mbar_wait(bar_free, (uint32_t)(j - 1) & 1u);
+                tc_fence_after();
+            }
+            for (int it = 0; it < NK; ++it) {
+                const int g = j * NK + it, st = g % PS;
+                if (changed) mbar_wait(bar_w + 8 * it, (uint32_t)(n_w - 1) & 1u);
+                mbar_wait(bar_full + 8 * st, (uint32_t)(g / PS) & 1u);
+                tc_fence_after();
+                const uint32_t a_big = smem_u32(smem + st * A_STAGE), a_small = a_big + TC_A_BYTES;
+                const uint32_t b_big = smem_u32(s_w + it * B_CHUNK);
+                if (elect_one()) {
+#pragma unroll
+                    for (int kk = 0; kk < TC_KC / 8; ++kk) {
+                        const uint32_t ko = kk * 32, acc = (it | kk) ? 1u : 0u;
+                        if (precision == 1) {
+                            umma_tf32(tmem_base, umma_desc_sw128(a_big + ko), umma_desc_sw128(b_big + ko), idesc_pair, acc);
+                            umma_tf32(tmem_base + 2 * BN, umma_desc_sw128(a_small + ko), umma_desc_sw128(b_big + ko), idesc, acc);
+                        } else {
+                            umma_tf32(tmem_base, umma_desc_sw128(a_big + ko), umma_desc_sw128(b_big + ko), idesc, acc);
+                        }
+                    }
+                    umma_commit(bar_empty + 8 * st);
+                }
+                __syncwarp();
+            }
+            if (elect_one()) umma_commit(bar_accum);
+            __syncwarp();
+        }
+    } else if (warp == 9) {
+        if (lane == 0) {
+            // ===================== weight block: (re)loaded when the kernel offset changes, once the MMAs that read the
+            // old block have completed (s_done is advanced by the epilogue warps behind their accumulator wait)
+            int cur = -1, j = 0;
+            for (long long tile = t0; tile < t1; ++tile, ++j) {
+                const int ws = __ldg(d.tile_wslice + tile);
+                if (ws == cur) continue;
+                cur = ws;
+                const long long t_start = clock64();
+                while (*s_done < j) {
+                    if (clock64() - t_start > 4000000000ll) __trap();
+                }
+                fence_proxy_async_smem();
+                for (int it = 0; it < NK; ++it) {
+                    mbar_arrive_expect_tx(bar_w + 8 * it, B_CHUNK);
+                    bulk_g2s(smem_u32(s_w + it * B_CHUNK), Wp + ((size_t)ws * NK + it) * (2 * BN * 32), B_CHUNK, bar_w + 8 * it);
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===================== producers + epilogue (warps 0..7)
+        const int pj = tid & 7, r0 = tid >> 3;   // 16-byte unit of the 128-byte chunk row; rows r0 + 32 i
+        float4 buf[NK][4];
+        auto request_rows = [&](long long tile, int which) {   // row numbers by cp.async: see the persistent kernel
+            const long long m0 = tile * TC_BM;
+            int* mine = s_rows + ((size_t)which * TC_PRODUCERS + tid) * 4;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const long long m = m0 + r0 + 32 * i;
+                if (m < d.M)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(mine + i)), "l"(sl.idx + m * sl.idx_stride)
+                                 : "memory");
+                else
+                    mine[i] = -1;
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        auto request_chunks = [&](int which) {   // every chunk of the tile whose row numbers were requested a tile ago
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            const int4 rows = *reinterpret_cast<const int4*>(s_rows + ((size_t)which * TC_PRODUCERS + tid) * 4);
+            const int rr[4] = {rows.x, rows.y, rows.z, rows.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float* src = rr[i] >= 0 ? sl.src + (size_t)(unsigned)rr[i] * sl.ld + pj * 4 : nullptr;
+#pragma unroll
+                for (int p = 0; p < NK; ++p)
+                    buf[p][i] = src ? __ldg(reinterpret_cast<const float4*>(src + p * TC_KC)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        if (t0 < t1) {
+            request_rows(t0, 0);
+            request_chunks(0);
+            if (t0 + 1 < t1) request_rows(t0 + 1, 1);
+        }
+        long long* const stamps = g_gemm_stamps ? g_gemm_stamps + (size_t)blockIdx.x * 12 : nullptr;
+        int j = 0;
+        for (long long tile = t0; tile < t1; ++tile, ++j) {
+            const long long m0 = tile * TC_BM;
+            long long* const stamp = (stamps && tid == 0 && (j == 7 || j == 8)) ? stamps + (j - 7) * 6 : nullptr;
+            if (stamp) stamp[0] = clock64();
+#pragma unroll
+            for (int it = 0; it < NK; ++it) {
+                const int g = j * NK + it, st = g % PS;
+                mbar_wait(bar_empty + 8 * st, ((uint32_t)(g / PS) & 1u) ^ 1u);
+                unsigned char* stage = smem + st * A_STAGE;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float4 a = buf[it][i];
+                    float4 big, small;
+                    split_tf32(a.x, big.x, small.x);
+                    split_tf32(a.y, big.y, small.y);
+                    split_tf32(a.z, big.z, small.z);
+                    split_tf32(a.w, big.w, small.w);
+                    const int r = r0 + 32 * i;
+                    const int off = r * 128 + ((pj ^ (r & 7)) << 4);
+                    *reinterpret_cast<float4*>(stage + off) = big;
+                    *reinterpret_cast<float4*>(stage + TC_A_BYTES + off) = small;
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_full + 8 * st);
+            }
+            // the next tile's chunks and the row numbers of the tile after it travel while this tile finishes
+            if (stamp) stamp[1] = clock64();   // chunks stored
+            if (tile + 1 < t1) {
+                request_chunks((j + 1) & 1);
+                if (tile + 2 < t1) request_rows(tile + 2, j & 1);
+            }
+            if (stamp) stamp[2] = clock64();   // next tile requested
+            mbar_wait(bar_accum, (uint32_t)j & 1u);
+            tc_fence_after();
+            if (tid == 0) *s_done = j + 1;
+            if (stamp) stamp[3] = stamp[4] = clock64();   // accumulator complete (no shared-memory tile in this kernel)
+            {
+                // TMEM -> registers -> the (now idle) stage ring as a [128, BN] tile, 16-byte chunks XOR-swizzled by the row
+                // so that a thread writing its row and a warp reading one row both hit distinct banks ...
+                constexpr int CPR = BN / 4;   // 16-byte chunks per row
+                const int row = (warp & 3) * 32 + lane;
+                const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+                const int c_begin = (warp >> 2) * (BN / 2);
+                unsigned char* srow = smem + (size_t)row * (BN * 4);
+#pragma unroll 1
+                for (int c0 = c_begin; c0 < c_begin + BN / 2; c0 += 16) {
+                    uint32_t ry[16], rz[16], rw[16];
+                    tmem_ld16_nowait(trow + (uint32_t)c0, ry);
+                    if (precision == 1) {
+                        tmem_ld16_nowait(trow + (uint32_t)(BN + c0), rz);
+                        tmem_ld16_nowait(trow + (uint32_t)(2 * BN + c0), rw);
+                    }
+                    tmem_ld_wait();
+                    float y[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) y[i] = __uint_as_float(ry[i]);
+                    if (precision == 1) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) y[i] += __uint_as_float(rz[i]) + __uint_as_float(rw[i]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        *reinterpret_cast<float4*>(srow + ((((c0 >> 2) + i) ^ (row & (CPR - 1))) << 4)) =
+                            make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+                }
+                tc_fence_before();
+                asm volatile("bar.sync 1, %0;" ::"n"(TC_PRODUCERS) : "memory");
+                if (tid == 0) mbar_arrive(bar_free);   // TMEM may be overwritten by the next tile's first MMA
+                // ... and out as whole rows: a warp instruction stores 512 contiguous bytes
+                constexpr int RPI = 32 / CPR;   // rows per warp instruction (1 or 2)
+                const int ch = lane % CPR, sub = lane / CPR;
+#pragma unroll 4
+                for (int rr = warp * RPI + sub; rr < TC_BM; rr += 8 * RPI) {
+                    const float4 v = *reinterpret_cast<const float4*>(smem + (size_t)rr * (BN * 4) + ((ch ^ (rr & (CPR - 1))) << 4));
+                    if (m0 + rr < d.M) *reinterpret_cast<float4*>(d.out + (size_t)(m0 + rr) * d.out_ld + ch * 4) = v;
+                }
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(TC_PRODUCERS) : "memory");   // the ring is free for the next tile's rows
+            if (stamp) stamp[5] = clock64();   // rows stored
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+template <int BN, int NK>
+static int launch_pair_ws(const GemmDesc& d, int tiles, cudaStream_t st) {
+    static std::atomic<unsigned long long> attr{0};
+    constexpr size_t smem_bytes = pair_ws_smem_bytes<BN, NK>();
+    DV3D_FUNC_SMEM_ONCE(attr, (pair_gemm_ws_kernel<BN, NK>), (int)smem_bytes);
+    DV3D_LAUNCH((pair_gemm_ws_kernel<BN, NK>), tiles < kNumSMs ? tiles : kNumSMs, TC_THREADS, smem_bytes, st, d, g_gemm_precision);
+    DV3D_LAUNCHED();
+    return DV3D_OK;
 }
 
 int validate_gather_gemm(const GemmDesc& d, int k_multiple);
@@ -822,8 +1113,17 @@ int launch_gather_gemm_tc(const GemmDesc& d_in, cudaStream_t st) {
         const size_t need = (size_t)tiles * split * TC_BM * d.N * sizeof(float);
         if (d.split_ws_bytes < need) split = 1;  // tiles * split <= 148 partials fit a dv3d_sparse_conv_workspace_bytes buffer
     }
+    // pair-major sparse convolution (plain store of the partial rows): weight-stationary kernel
+    if (d.tile_wslice && d.slice[0].idx && !d.scale && !d.shift && !d.gn_weight && !d.residual && !d.relu_in && !d.relu_out &&
+        !d.zero_row_mod && !d.pool_out && d.n_peers == 0 && pair_ws_enabled()) {
+        const int nk = d.slice[0].K / TC_KC;
+        if (d.N == 128 && nk == 4) return launch_pair_ws<128, 4>(d, tiles, st);
+        if (d.N == 128 && nk == 2) return launch_pair_ws<128, 2>(d, tiles, st);
+        if (d.N == 64 && nk == 4) return launch_pair_ws<64, 4>(d, tiles, st);
+        if (d.N == 64 && nk == 2) return launch_pair_ws<64, 2>(d, tiles, st);
+    }
     // persistent variant: one slice, no kernel map, no K split, more tiles than SMs (or forced for tests)
-    const bool persist_ok = d.n_slices == 1 && !d.kmap && split == 1;
+    const bool persist_ok = d.n_slices == 1 && !d.kmap && split == 1 && d.M + (d.slice[0].shift > 0 ? d.slice[0].shift : 0) < (1ll << 31);
     if (persist_ok && (g_gemm_persistent > 0 || (g_gemm_persistent == 0 && tiles > kNumSMs))) {
         const int grid_p = tiles < kNumSMs ? tiles : kNumSMs;
         if (d.N == 128) {
@@ -879,6 +1179,12 @@ extern "C" int dv3d_get_gemm_precision(void) { return g_gemm_precision; }
 extern "C" int dv3d_set_gemm_persistent(int mode) {
     DV3D_REQUIRE(mode >= -1 && mode <= 1, "set_gemm_persistent: -1 = never, 0 = automatic, 1 = whenever possible; got %d", mode);
     g_gemm_persistent = mode;
+    return DV3D_OK;
+}
+
+extern "C" int dv3d_set_pair_gemm_mode(int weight_stationary) {
+    DV3D_REQUIRE(weight_stationary == 0 || weight_stationary == 1, "set_pair_gemm_mode: 0 or 1");
+    g_pair_ws = weight_stationary;
     return DV3D_OK;
 }
 

@@ -189,6 +189,9 @@ int dv3d_get_gemm_precision(void);
  * Conv2d rows): -1 = never, 0 = automatic (more 128-row tiles than SMs; default), 1 = whenever the launch qualifies.
  * Results are bit-identical in all modes. Process-wide; for tests and A/B measurements. */
 int dv3d_set_gemm_persistent(int mode);
+/* pair-major sparse-convolution GEMM: 1 = weight-stationary kernel (default), 0 = the general gather-GEMM kernels
+ * (A/B measurements; also DV3D_PAIR_WS=0) */
+int dv3d_set_pair_gemm_mode(int weight_stationary);
 /* profiling aid (tools/gemm_phases.py): device buffer of (grid.x * grid.y) * 8 int64 clock stamps written by every
  * tcgen05 gather-GEMM launch on the current device; NULL switches it off */
 int dv3d_gemm_set_timing_buffer(void* device_buffer);

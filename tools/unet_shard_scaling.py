@@ -65,6 +65,8 @@ def main():
                 n = [lv.n for lv in sc.levels]
                 if world == 1:
                     print('voxels per level', n)
+                    print('pair-major tiles (128 pairs each): same', [m.n_tiles for m in sc.same], 'down', [m.n_tiles for m in sc.down],
+                          'up', [m.n_tiles for m in sc.up], 'pairs path', [m.use_pairs for m in sc.same + sc.down + sc.up])
                 x = [torch.randn(n[0], 64, device=dev), torch.randn(n[1], 128, device=dev), torch.randn(n[2], 128, device=dev)]
 
                 def conv(xin, km, mod, gn, level, residual=None):
