@@ -849,13 +849,14 @@ static bool pair_ws_enabled() {
 // The accumulator goes TMEM -> registers -> global (the rows of P are contiguous), no shared-memory tile.
 template <int BN, int NK>
 __host__ __device__ constexpr size_t pair_ws_smem_bytes() {
-    return 1024 + 2 * (size_t)(2 * TC_A_BYTES) + (size_t)NK * 2 * BN * 128 + 512 + 2 * TC_PRODUCERS * 4 * sizeof(int);
+    return 1024 + 3 * (size_t)(2 * TC_A_BYTES) + (size_t)NK * 2 * BN * 128 + 512 + 2 * TC_BM * sizeof(int);
 }
+static_assert(pair_ws_smem_bytes<128, 4>() <= 232448, "shared memory budget of the weight-stationary pair kernel");
 
 template <int BN, int NK>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 pair_gemm_ws_kernel(const __grid_constant__ GemmDesc d, int precision) {
-    constexpr int PS = 2;
+    constexpr int PS = 3;   // three of a tile's four K chunks are stored before the first MMA has to finish
     constexpr int A_STAGE = 2 * TC_A_BYTES, B_CHUNK = 2 * BN * 128;
     constexpr uint32_t TMEM_COLS = BN == 128 ? 512 : 256;
     extern __shared__ unsigned char smem_raw[];
@@ -953,27 +954,32 @@ pair_gemm_ws_kernel(const __grid_constant__ GemmDesc d, int precision) {
         // ===================== producers + epilogue (warps 0..7)
         const int pj = tid & 7, r0 = tid >> 3;   // 16-byte unit of the 128-byte chunk row; rows r0 + 32 i
         float4 buf[NK][4];
-        auto request_rows = [&](long long tile, int which) {   // row numbers by cp.async: see the persistent kernel
-            const long long m0 = tile * TC_BM;
-            int* mine = s_rows + ((size_t)which * TC_PRODUCERS + tid) * 4;
+        // row numbers of a tile by cp.async (see the persistent kernel), one int per row: the first of the 8 threads of a
+        // row fetches it; readers wait for their own copies and meet at a barrier before they read
+        auto request_rows = [&](long long tile, int which) {
+            if (pj == 0) {
+                const long long m0 = tile * TC_BM;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const long long m = m0 + r0 + 32 * i;
-                if (m < d.M)
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(mine + i)), "l"(sl.idx + m * sl.idx_stride)
-                                 : "memory");
-                else
-                    mine[i] = -1;
+                for (int i = 0; i < 4; ++i) {
+                    const int r = r0 + 32 * i;
+                    const long long m = m0 + r;
+                    if (m < d.M)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(s_rows + which * TC_BM + r)),
+                                     "l"(sl.idx + m * sl.idx_stride)
+                                     : "memory");
+                    else
+                        s_rows[which * TC_BM + r] = -1;
+                }
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
         auto request_chunks = [&](int which) {   // every chunk of the tile whose row numbers were requested a tile ago
             asm volatile("cp.async.wait_group 0;" ::: "memory");
-            const int4 rows = *reinterpret_cast<const int4*>(s_rows + ((size_t)which * TC_PRODUCERS + tid) * 4);
-            const int rr[4] = {rows.x, rows.y, rows.z, rows.w};
+            asm volatile("bar.sync 1, %0;" ::"n"(TC_PRODUCERS) : "memory");
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const float* src = rr[i] >= 0 ? sl.src + (size_t)(unsigned)rr[i] * sl.ld + pj * 4 : nullptr;
+                const int rr = s_rows[which * TC_BM + r0 + 32 * i];
+                const float* src = rr >= 0 ? sl.src + (size_t)(unsigned)rr * sl.ld + pj * 4 : nullptr;
 #pragma unroll
                 for (int p = 0; p < NK; ++p)
                     buf[p][i] = src ? __ldg(reinterpret_cast<const float4*>(src + p * TC_KC)) : make_float4(0.f, 0.f, 0.f, 0.f);
