@@ -166,10 +166,46 @@ halo_needs_kernel(HaloMaps hm, int* __restrict__ lo, int* __restrict__ hi) {
 // ... and writes them into every peer's table (first 256 bytes of the heap, behind the barrier flags): entry
 // [level][index of this rank among the destination's peers] = (lo, hi).  The barrier in front of the first layer
 // publishes them.  A producer then stores row g of a level-l output into peer p only when lo <= g < hi.
+// which ranks send this rank rows of a level: those whose row range meets [lo, hi).  The barrier behind a layer then
+// waits for them only (dv3d_symm_barrier_masked): a slow layer on one rank delays its neighbours, not everybody.
+struct RankRows {
+    int b[DV3D_MAX_LEVELS][kMaxPeers + 2];   // rank q owns rows [b[l][q], b[l][q + 1]) of level l
+};
+__global__ void halo_wait_mask_kernel(const int* __restrict__ lo, const int* __restrict__ hi, RankRows rr, int n_levels, int world,
+                                      int rank, int* __restrict__ mask) {
+    pdl_wait();
+    const int l = threadIdx.x;
+    if (l >= n_levels) return;
+    int m = 0;
+    for (int q = 0; q < world; ++q)
+        if (q != rank && lo[l] < hi[l] && lo[l] < rr.b[l][q + 1] && hi[l] > rr.b[l][q]) m |= 1 << q;
+    mask[l] = m;
+}
 constexpr int kHaloTabOff = 64;   // bytes; 3 levels x 7 peers x 2 ints = 168 bytes
 struct PeerPtrs {
     char* p[kMaxPeers];
 };
+// the rank's point rows into every peer's heap in one launch: all NVLink ports at once (seven peer memcpys in a row took
+// ~100 us of copy-engine time per exchange at 8 ranks; the stores of one kernel overlap)
+struct PushSeg {
+    const float4* src;   // local heap
+    size_t off16;        // offset inside the heap, in 16-byte units
+    size_t n16;
+};
+__global__ void __launch_bounds__(256)
+push_rows_kernel(PushSeg a, PushSeg b, PeerPtrs peers, int n_peers) {
+    pdl_wait();
+    const size_t total = a.n16 + b.n16;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const bool first = i < a.n16;
+        const size_t k = first ? i : i - a.n16;
+        const float4 v = first ? a.src[k] : b.src[k];
+        const size_t at = (first ? a.off16 : b.off16) + k;
+#pragma unroll
+        for (int p = 0; p < kMaxPeers; ++p)
+            if (p < n_peers) reinterpret_cast<float4*>(peers.p[p])[at] = v;
+    }
+}
 __global__ void halo_publish_kernel(const int* __restrict__ lo, const int* __restrict__ hi, int n_levels, int rank, int n_peers,
                                     PeerPtrs peers) {
     pdl_wait();
@@ -261,6 +297,7 @@ struct Shard {
 struct Scene {
     Shard* shard;                    // nullptr: single GPU
     const int* halo_tab;             // sharded: [level][peer][lo, hi) rows each peer needs (device, in the heap header)
+    const int* wait_mask;            // sharded: per level, the ranks that send this rank rows (device)
     long long r0[DV3D_MAX_LEVELS], r1[DV3D_MAX_LEVELS];  // this rank's row range per level (whole level when !shard)
     Level lv[DV3D_MAX_LEVELS];
     int n_levels;
@@ -282,6 +319,12 @@ static bool shard_balance() {   // read per call: every rank of a job must see t
     return !(e && e[0] == '0');
 }
 
+// DV3D_SHARD_NEIGHBOUR_WAIT=0: every barrier waits for every rank (A/B measurements)
+static bool shard_neighbour_wait() {
+    const char* e = getenv("DV3D_SHARD_NEIGHBOUR_WAIT");
+    return !(e && e[0] == '0');
+}
+
 // rows of a layer output: the arena, or - sharded scene - the symmetric heap (same offset on every rank, because every
 // rank allocates the same sizes in the same order: the coordinate levels are identical everywhere)
 static float* layer_rows(Scene& sc, Arena& ar, long long n, int C) {
@@ -298,11 +341,13 @@ static float* layer_rows(Scene& sc, Arena& ar, long long n, int C) {
 }
 
 // cross-GPU barrier behind a layer whose output the next layer gathers through a kernel map
-static int layer_barrier(Scene& sc, void* st) {
+// level >= 0: the layer's rows travel by the halo table, wait only for the ranks that send this rank rows of that level
+static int layer_barrier(Scene& sc, void* st, int level = -1) {
     if (!sc.shard) return DV3D_OK;
     Shard& sh = *sc.shard;
     Prof pr(DV3D_STAGE_BARRIER, (cudaStream_t)st);
-    return dv3d_symm_barrier(sh.heap, sh.peer_heaps, sh.n_peers, sh.rank, ++sh.epoch, sh.err_flag, st);
+    const int* mask = (level >= 0 && sc.wait_mask && shard_neighbour_wait()) ? sc.wait_mask + level : nullptr;
+    return dv3d_symm_barrier_masked(sh.heap, sh.peer_heaps, sh.n_peers, sh.rank, ++sh.epoch, sh.err_flag, mask, st);
 }
 
 // One sparse convolution + GroupNorm + ReLU for the rows the kernel map covers (all rows, or this rank's range):
@@ -328,7 +373,7 @@ static int sparse_conv(const dv3d_dense_params_t& p, const float* feat, long lon
                                  sc.split_ws_bytes, o, st));
         if (sc.shard) symm_set_halo(nullptr, 0);
     }
-    return layer_barrier(sc, st);
+    return layer_barrier(sc, st, to_all ? -1 : out_level);
 }
 
 // relu(x + GN2(conv2(relu(GN1(conv1(x))))))  (scenemodeling.py:16-44)
@@ -537,12 +582,14 @@ static int model_scene(const dv3d_net_params_t& net, const float* pts, const flo
     {
         const bool want_plan = net.res_down[0][0][0].Wp != nullptr;
         DV3D_REQUIRE(!sc.shard || want_plan, "hot_path: the row-sharded U-Net needs a tensor-core GEMM mode (packed weights)");
+        RankRows rank_rows = {};         // sharded: every rank's rows of every level (identical on all ranks)
         for (int l = 0; l < nl; ++l) {   // this rank's rows of every level
             const long long n = sc.lv[l].n;
             if (sc.shard) {
                 const long long m = (n + sc.shard->world - 1) / sc.shard->world;
                 sc.r0[l] = std::min((long long)sc.shard->rank * m, n);
                 sc.r1[l] = std::min((long long)(sc.shard->rank + 1) * m, n);
+                for (int q = 0; q <= sc.shard->world; ++q) rank_rows.b[l][q] = (int)std::min((long long)q * m, n);
             } else {
                 sc.r0[l] = 0;
                 sc.r1[l] = n;
@@ -566,6 +613,7 @@ static int model_scene(const dv3d_net_params_t& net, const float* pts, const flo
             for (int l = 1; l < nl; ++l) {
                 sc.r0[l] = host_bounds[l][sc.shard->rank];
                 sc.r1[l] = host_bounds[l][sc.shard->rank + 1];
+                for (int q = 0; q <= world; ++q) rank_rows.b[l][q] = host_bounds[l][q];
                 DV3D_REQUIRE(sc.r0[l] >= 0 && sc.r0[l] <= sc.r1[l] && sc.r1[l] <= sc.lv[l].n, "hot_path_sharded: bad row bounds");
             }
         }
@@ -627,6 +675,12 @@ static int model_scene(const dv3d_net_params_t& net, const float* pts, const flo
             DV3D_LAUNCH((halo_publish_kernel), 1, 32, 0, side->stream, (const int*)lo, (const int*)hi, nl, sh.rank, sh.n_peers, pp);
             DV3D_LAUNCHED();
             sc.halo_tab = reinterpret_cast<const int*>(sh.heap + kHaloTabOff);
+            int* mask = ar.get<int>(DV3D_MAX_LEVELS);
+            ARENA_CHECK(ar);
+            DV3D_LAUNCH((halo_wait_mask_kernel), 1, 32, 0, side->stream, (const int*)lo, (const int*)hi, rank_rows, nl, sh.world, sh.rank,
+                        mask);
+            DV3D_LAUNCHED();
+            sc.wait_mask = mask;
         }
         sc.pair_ws = nullptr;
         sc.pair_ws_bytes = 0;
@@ -678,7 +732,7 @@ static int model_scene(const dv3d_net_params_t& net, const float* pts, const flo
                             net.pointnet[5].b, Cf, 1, F + v0 * Cf, st));
             symm_set_halo(nullptr, 0);
         }
-        TRY(layer_barrier(sc, st));
+        TRY(layer_barrier(sc, st, (nl == 1 && net.n_res[0] == 0) ? -1 : 0));
         x = F;
     }
     for (int b = 0; b < net.n_res[0]; ++b)
@@ -718,7 +772,7 @@ static int model_scene(const dv3d_net_params_t& net, const float* pts, const flo
                                            net.feat_adj[i].a, net.feat_adj[i].b, adj + r0 * Ca, st));
             if (sc.shard) symm_set_halo(nullptr, 0);
         }
-        TRY(layer_barrier(sc, st));
+        TRY(layer_barrier(sc, st, net.n_res[l] == 0 ? -1 : l));
         x = adj;
         // the reversed n_res list: res_up[i] has n_res[nl-2-i] blocks (scenemodeling.py:168-175)
         for (int b = 0; b < net.n_res[l]; ++b)
@@ -1007,12 +1061,17 @@ static int hot_path_impl(const dv3d_net_params_t& net, const float* feats_nhwc, 
                 // past every reader of its copy of the cloud: it has arrived at the last barrier of the previous
                 // scene model, which follows its voxelisation and PointNet in stream order.
                 Prof pr(DV3D_STAGE_EXCHANGE, cs);
-                for (int p = 0; p < sh->n_peers && Np > 0; ++p) {
-                    char* peer = reinterpret_cast<char*>(sh->peer_heaps[p]);
-                    DV3D_CUDA(cudaMemcpyAsync(peer + ((char*)(pts + 3 * row0) - sh->heap), pts + 3 * row0, sizeof(float) * 3 * Np,
-                                              cudaMemcpyDeviceToDevice, cs));
-                    DV3D_CUDA(cudaMemcpyAsync(peer + ((char*)(pfeat + 32 * row0) - sh->heap), pfeat + 32 * row0, sizeof(float) * 32 * Np,
-                                              cudaMemcpyDeviceToDevice, cs));
+                if (Np > 0) {
+                    const float* p_src = pts + 3 * row0;
+                    const float* f_src = pfeat + 32 * row0;
+                    DV3D_REQUIRE((((uintptr_t)p_src | (uintptr_t)f_src) & 15) == 0 && (3 * Np) % 4 == 0,
+                                 "hot_path_sharded: point rows must be 16-byte aligned (h * w a multiple of 4)");
+                    PushSeg a = {reinterpret_cast<const float4*>(p_src), (size_t)((const char*)p_src - sh->heap) / 16, (size_t)(3 * Np) / 4};
+                    PushSeg b = {reinterpret_cast<const float4*>(f_src), (size_t)((const char*)f_src - sh->heap) / 16, (size_t)(32 * Np) / 4};
+                    PeerPtrs pp = {};
+                    for (int p = 0; p < sh->n_peers; ++p) pp.p[p] = reinterpret_cast<char*>(sh->peer_heaps[p]);
+                    DV3D_LAUNCH((push_rows_kernel), 2 * kNumSMs, 256, 0, cs, a, b, pp, sh->n_peers);
+                    DV3D_LAUNCHED();
                 }
                 TRY(dv3d_symm_barrier(sh->heap, sh->peer_heaps, sh->n_peers, sh->rank, ++sh->epoch, sh->err_flag, stream));
                 sh->heap_off = layers_off;

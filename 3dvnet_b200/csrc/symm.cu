@@ -50,7 +50,10 @@ void symm_attach(GemmDesc& d) {
 }
 
 // thread p signals peer p and waits for peer p's signal; flags[j] on a rank is written by rank j only
-__global__ void symm_barrier_kernel(unsigned* local_flags, SymmRegion peers, int rank, unsigned epoch, int* err) {
+// wait_mask (device, optional): bit r set = wait for rank r.  Every peer is always signalled; a rank that only gathers
+// rows of some peers (halo exchange of the row-sharded U-Net) need not wait for the others.
+__global__ void symm_barrier_kernel(unsigned* local_flags, SymmRegion peers, int rank, unsigned epoch, int* err,
+                                    const int* __restrict__ wait_mask) {
     pdl_wait();
     const int p = threadIdx.x;
     if (p >= peers.n_peers) return;
@@ -59,6 +62,7 @@ __global__ void symm_barrier_kernel(unsigned* local_flags, SymmRegion peers, int
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(epoch) : "memory");
     // peer p's slot in MY flags: the host passes the peers in ascending rank order with this rank left out
     const int src_rank = p < rank ? p : p + 1;
+    if (wait_mask && !((__ldg(wait_mask) >> src_rank) & 1)) return;
     const long long t0 = clock64();
     unsigned seen;
     do {
@@ -145,15 +149,20 @@ extern "C" int dv3d_symm_unregister(const void* base) {
     return DV3D_EINVAL;
 }
 
-extern "C" int dv3d_symm_barrier(void* local_flags, void* const* peer_flags, int n_peers, int rank, int epoch,
-                                 int* err_flag, void* stream) {
+extern "C" int dv3d_symm_barrier_masked(void* local_flags, void* const* peer_flags, int n_peers, int rank, int epoch,
+                                        int* err_flag, const int* wait_mask_dev, void* stream) {
     DV3D_REQUIRE(local_flags && peer_flags && err_flag && n_peers >= 1 && n_peers <= kMaxPeers && rank >= 0 && rank <= n_peers,
                  "symm_barrier: bad arguments");
     SymmRegion peers = {};
     peers.n_peers = n_peers;
     for (int p = 0; p < n_peers; ++p) peers.peers[p] = reinterpret_cast<char*>(peer_flags[p]);
     DV3D_LAUNCH((symm_barrier_kernel), 1, 32, 0, (cudaStream_t)stream, reinterpret_cast<unsigned*>(local_flags), peers, rank,
-                (unsigned)epoch, err_flag);
+                (unsigned)epoch, err_flag, wait_mask_dev);
     DV3D_LAUNCHED();
     return DV3D_OK;
+}
+
+extern "C" int dv3d_symm_barrier(void* local_flags, void* const* peer_flags, int n_peers, int rank, int epoch,
+                                 int* err_flag, void* stream) {
+    return dv3d_symm_barrier_masked(local_flags, peer_flags, n_peers, rank, epoch, err_flag, nullptr, stream);
 }

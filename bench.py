@@ -217,7 +217,11 @@ def run_c4(args, rank, world, dev, dist, ops, lm):
         (depth_e, _), ms_e, _, _ = timed(step)
         native_equals_composed = bool(torch.equal(depth_e, depth_c))
         os.environ['DV3D_SHARD_BALANCE'] = '1'      # the default: coarse levels cut by work (csrc/sparse.cu)
+        os.environ['DV3D_SHARD_NEIGHBOUR_WAIT'] = '0'   # every barrier waits for every rank
+        (depth_f, _), ms_f, _, _ = timed(step)
+        os.environ['DV3D_SHARD_NEIGHBOUR_WAIT'] = '1'   # the default: a layer's barrier waits for the ranks that send rows
         (depth, rng), ms, launches, barriers = timed(step)
+        full_equals_neighbour = bool(torch.equal(depth, depth_f))
         # where the step goes: one more (untimed) step with the engine's stage events, on every rank
         ops.engine_profile(True)
         dist.barrier()
@@ -289,6 +293,8 @@ def run_c4(args, rank, world, dev, dist, ops, lm):
                                      'note': 'the same schedule op by op from Python with an NCCL all-gather (round 1)',
                                      'depth_bit_identical_to_native_with_equal_rows': native_equals_composed},
             'native_equal_rows_ms_per_step': float(ms_e.item()) / steps,
+            'native_full_barriers': {'ms_per_step': float(ms_f.item()) / steps, 'depth_bit_identical': full_equals_neighbour,
+                                     'note': 'every layer barrier waits for all ranks instead of the ranks that send rows'},
             'stage_ms_rank0': stage_ms, 'stage_ms_min_max_over_ranks': stage_minmax,
             'stage_note': "'barrier' is part of 'unet'; 'levels' runs on a side stream beside 'pointnet'",
             'exchange_bytes': 2 * refs * PLANE[0] * PLANE[1] * 35 * 4, 'exchanges': 2, 'barriers': barriers,

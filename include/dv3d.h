@@ -528,6 +528,10 @@ int dv3d_symm_register(const void* base, size_t bytes, void* const* peer_bases, 
 int dv3d_symm_unregister(const void* base);
 int dv3d_symm_barrier(void* local_flags, void* const* peer_flags, int n_peers, int rank, int epoch, int* err_flag,
                       void* stream);
+/* as dv3d_symm_barrier, but this rank only waits for the ranks whose bit is set in *wait_mask_dev (a device int,
+ * read when the barrier runs; NULL = all).  Every peer is signalled either way. */
+int dv3d_symm_barrier_masked(void* local_flags, void* const* peer_flags, int n_peers, int rank, int epoch, int* err_flag,
+                             const int* wait_mask_dev, void* stream);
 
 /* BASELINE config C4 from one native call per rank: the hot path of a scene whose reference views are sharded over
  * `world` GPUs (one process each).  This rank computes the cost volumes, depths and PointFlow passes of the
