@@ -213,14 +213,14 @@ def run_c4(args, rank, world, dev, dist, ops, lm):
 
     with torch.no_grad():
         (depth_c, _), ms_c, _, _ = timed(step_composed)
-        os.environ['DV3D_SHARD_BALANCE'] = '0'      # equal row counts on every level, as the composed path shards
-        (depth_e, _), ms_e, _, _ = timed(step)
-        native_equals_composed = bool(torch.equal(depth_e, depth_c))
-        os.environ['DV3D_SHARD_BALANCE'] = '1'      # the default: coarse levels cut by work (csrc/sparse.cu)
+        os.environ['DV3D_SHARD_BALANCE'] = '1'      # coarse levels cut by work (csrc/sparse.cu) instead of equal row counts
+        (depth_b, _), ms_b, _, _ = timed(step)
+        os.environ['DV3D_SHARD_BALANCE'] = '0'      # the default: equal row counts on every level, as the composed path shards
         os.environ['DV3D_SHARD_NEIGHBOUR_WAIT'] = '0'   # every barrier waits for every rank
         (depth_f, _), ms_f, _, _ = timed(step)
         os.environ['DV3D_SHARD_NEIGHBOUR_WAIT'] = '1'   # the default: a layer's barrier waits for the ranks that send rows
         (depth, rng), ms, launches, barriers = timed(step)
+        native_equals_composed = bool(torch.equal(depth, depth_c))
         full_equals_neighbour = bool(torch.equal(depth, depth_f))
         # where the step goes: one more (untimed) step with the engine's stage events, on every rank
         ops.engine_profile(True)
@@ -291,8 +291,8 @@ def run_c4(args, rank, world, dev, dist, ops, lm):
             'sparse_feat_max_rel_err_vs_single_gpu': feat_err,
             'composed_from_python': {'ms_per_step': float(ms_c.item()) / steps,
                                      'note': 'the same schedule op by op from Python with an NCCL all-gather (round 1)',
-                                     'depth_bit_identical_to_native_with_equal_rows': native_equals_composed},
-            'native_equal_rows_ms_per_step': float(ms_e.item()) / steps,
+                                     'depth_bit_identical_to_native': native_equals_composed},
+            'native_work_balanced_rows_ms_per_step': float(ms_b.item()) / steps,
             'native_full_barriers': {'ms_per_step': float(ms_f.item()) / steps, 'depth_bit_identical': full_equals_neighbour,
                                      'note': 'every layer barrier waits for all ranks instead of the ranks that send rows'},
             'stage_ms_rank0': stage_ms, 'stage_ms_min_max_over_ranks': stage_minmax,

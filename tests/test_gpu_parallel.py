@@ -59,11 +59,12 @@ def _worker(rank, world, port, out_dir):
         # the same from ONE native call per rank (dv3d_hot_path_sharded): peer copies of the point rows instead of
         # the NCCL all-gather, twice in a row (the heap is reused behind its barriers)
         heap2 = par.SymmHeap(max(64 << 20, par.native_heap_bytes(net, len(ref_idx), plane)))
-        os.environ['DV3D_SHARD_BALANCE'] = '0'     # equal row counts per rank, as the composed path shards
+        os.environ['DV3D_SHARD_BALANCE'] = '0'     # the default: equal row counts per rank, as the composed path shards
         d_nat, rng_nat = par.hot_path_sharded_native(net, fq, R, t, K, e, b.images_batch.to(dev), cfg, offs, heap2)
         d_nat2, _ = par.hot_path_sharded_native(net, fq, R, t, K, e, b.images_batch.to(dev), cfg, offs, heap2)
-        os.environ['DV3D_SHARD_BALANCE'] = '1'     # the default: coarse levels cut by work
+        os.environ['DV3D_SHARD_BALANCE'] = '1'     # coarse levels cut by work (opt-in)
         d_bal, _ = par.hot_path_sharded_native(net, fq, R, t, K, e, b.images_batch.to(dev), cfg, offs, heap2)
+        os.environ['DV3D_SHARD_BALANCE'] = '0'
         torch.cuda.synchronize()
         heap2.check()
     assert rng_nat == (s0, s1)
@@ -97,7 +98,7 @@ def test_model_scene_sharded_equals_single_gpu(tmp_path):
         assert idx_same == 1 and feat_err < 1e-4, feat_err
         assert rel_sh < 1e-3, rel_sh
         # the native entry with equal row counts runs the same kernels on the same rows as the composed sharded
-        # path: bit-identical depth; with work-balanced rows (default) within the BASELINE tolerance
+        # path: bit-identical depth; with work-balanced rows (opt-in) within the BASELINE tolerance
         assert rel_nat < 1e-3 and nat_same == 1, (rel_nat, nat_same)
 
 
