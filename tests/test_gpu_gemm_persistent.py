@@ -89,3 +89,46 @@ def test_automatic_mode_uses_it_only_beyond_148_tiles(ops):
         never = ops.linear(x, w, b, True, packed=packed)
         ops.lib().call('dv3d_set_gemm_persistent', 0)
         assert torch.equal(auto, never)
+
+
+@pytest.mark.parametrize('n,Cin,Cout,density,mode', [(9000, 128, 128, 0.4, 'tf32x3'), (30000, 64, 64, 0.1, 'tf32x3'),
+                                                    (7000, 64, 128, 0.3, 'tf32x3'), (7000, 128, 64, 0.3, 'tf32x3'),
+                                                    (300, 128, 128, 0.5, 'tf32x3'), (9000, 128, 128, 0.4, 'tf32')])
+def test_weight_stationary_pair_gemm_identical(ops, n, Cin, Cout, density, mode):
+    """the pair-major sparse convolution through pair_gemm_ws_kernel (contiguous tile ranges, resident weight block)
+    and through the general gather-GEMM kernels: same arithmetic, bit-identical rows; all four (Cin, Cout) variants,
+    many offset changes per CTA (n large) and one tile per CTA (n small)"""
+    old = ops.gemm_mode()
+    ops.set_gemm_mode(mode)
+    try:
+        g = torch.Generator().manual_seed(n + Cin)
+        nbr = (torch.arange(n).view(-1, 1) + torch.randint(-500, 500, (n, 27), generator=g)).clamp_(0, n - 1)
+        nbr[torch.rand(n, 27, generator=g) >= density] = -1
+        km = ops.KernelMap(nbr.int().to(DEV)).build_plan()
+        ops.finish_plans([km])
+        km.use_pairs = True
+        feat, W = torch.randn(n, Cin, generator=g).to(DEV), (torch.randn(27, Cin, Cout, generator=g) / (27 * Cin) ** 0.5).to(DEV)
+        pw = ops.pack_weights(W.reshape(-1, Cout).contiguous())
+        gw, gb = torch.randn(Cout, generator=g).to(DEV), torch.randn(Cout, generator=g).to(DEV)
+        res = torch.randn(n, Cout, generator=g).to(DEV) if Cin == Cout else None
+        out = []
+        for ws in (1, 0):
+            ops.lib().call('dv3d_set_pair_gemm_mode', ws)
+            out.append(ops.sparse_conv(feat, km, W, gw, gb, res, True, packed=pw).clone())
+        ops.lib().call('dv3d_set_pair_gemm_mode', 1)
+        assert torch.equal(out[0], out[1])
+        # against float64: conv -> GroupNorm(16 channels per group) -> + residual -> ReLU
+        valid = (nbr >= 0).to(DEV)
+        gathered = feat.double()[nbr.clamp(min=0).to(DEV)] * valid.unsqueeze(-1)                     # [n, 27, Cin]
+        y = torch.einsum('nkc,kcd->nd', gathered, W.double())
+        yg = y.view(n, Cout // 16, 16)
+        yg = (yg - yg.mean(-1, keepdim=True)) / torch.sqrt(yg.var(-1, unbiased=False, keepdim=True) + 1e-5)
+        ref = yg.reshape(n, Cout) * gw.double() + gb.double()
+        if res is not None:
+            ref = ref + res.double()
+        ref = torch.relu(ref)
+        tol = 1e-4 if mode == 'tf32x3' else 3e-2
+        assert (out[0].double() - ref).abs().max().item() <= tol * max(1.0, ref.abs().max().item())
+    finally:
+        ops.lib().call('dv3d_set_pair_gemm_mode', 1)
+        ops.set_gemm_mode(old)
