@@ -458,38 +458,60 @@ def main():
     copy_stream.synchronize()
 
     # Supplementary: SURVEY section 8d's FULL pipeline, end to end through the public API (PL3DVNet.full_pass):
-    # images + cameras uploaded from pinned host memory, backbone + FPN (cuDNN, channels-last, fp32 - TF32
-    # convolutions switched off), the hot path (engine), the three PropagationNets, full-resolution depth read back
+    # images + cameras uploaded from pinned host memory, backbone + FPN (cuDNN, channels-last, fp32 storage, TF32
+    # convolutions allowed - PyTorch's default, what the reference runs with), the hot path (engine), the three
+    # PropagationNets, full-resolution depth read back.  Two steps in flight like `e2e`: uploads on the copy stream,
+    # results awaited one step later.
     full = None
     if world == 1:
-        tf32_was = torch.backends.cudnn.allow_tf32
-        torch.backends.cudnn.allow_tf32 = False
         net_full = full_model(params, dev)
         img_host = synth_images(rank, n_ref + N_SRC).pin_memory()
-        img_dev = torch.empty_like(img_host, device=dev)
-        full_host = torch.empty((n_ref,) + IMG_SIZE, dtype=torch.float32).pin_memory()
-        small = {k: torch.empty_like(v, device=dev) for k, v in host.items() if k != 'feats_quarter'}
+        img_devs = [torch.empty_like(img_host, device=dev) for _ in range(2)]
+        full_hosts = [torch.empty((n_ref,) + IMG_SIZE, dtype=torch.float32).pin_memory() for _ in range(2)]
+        smalls = [{k: torch.empty_like(v, device=dev) for k, v in host.items() if k != 'feats_quarter'} for _ in range(2)]
+        up2, cons2, rb2 = ([torch.cuda.Event(), torch.cuda.Event()] for _ in range(3))
+        st2 = {'i': 0, 'primed': False}
+        for ev_ in cons2 + rb2:
+            ev_.record()
+
+        def upload_full(slot):
+            copy_stream.wait_event(cons2[slot])
+            with torch.cuda.stream(copy_stream):
+                img_devs[slot].copy_(img_host, non_blocking=True)
+                for k in smalls[slot]:
+                    smalls[slot][k].copy_(host[k], non_blocking=True)
+                up2[slot].record(copy_stream)
 
         def step_full():
-            img_dev.copy_(img_host, non_blocking=True)
-            for k in small:
-                small[k].copy_(host[k], non_blocking=True)
-            out = net_full.full_pass(img_dev, small['rotmats'], small['tvecs'], small['K'], edges.clone(),
-                                     small['images_batch'], OFFSETS_LIST)
-            full_host.copy_(out['final'], non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+            i = st2['i']
+            slot = i % 2
+            if not st2['primed']:
+                upload_full(slot)
+                st2['primed'] = True
+            torch.cuda.current_stream().wait_event(up2[slot])
+            upload_full((i + 1) % 2)
+            rb2[slot].synchronize()
+            sm = smalls[slot]
+            out = net_full.full_pass(img_devs[slot], sm['rotmats'], sm['tvecs'], sm['K'], edges.clone(), sm['images_batch'],
+                                     OFFSETS_LIST)
+            cons2[slot].record()
+            full_hosts[slot].copy_(out['final'], non_blocking=True)
+            rb2[slot].record()
+            st2['i'] = i + 1
             return out
 
         for _ in range(3):
             step_full()
         ms_full = timed(step_full, args.steps)
-        torch.backends.cudnn.allow_tf32 = tf32_was
+        copy_stream.synchronize()
         full = {'value': args.steps * n_ref / (ms_full * 1e-3), 'unit': 'ref-views/s', 'ms_per_step': ms_full / args.steps,
-                'h2d_bytes_per_step': int(img_host.numel() * 4 + sum(host[k].numel() * host[k].element_size() for k in small)
+                'h2d_bytes_per_step': int(img_host.numel() * 4 + sum(host[k].numel() * host[k].element_size() for k in smalls[0])
                                           + edges.numel() * 4 + 64),
-                'd2h_bytes_per_step': int(full_host.numel() * 4),
-                'pipeline': 'images -> MnasNet + FPN (torchvision / cuDNN, channels-last, fp32) -> dv3d_hot_path -> '
-                            'PropagationNet x3 (tcgen05 gather-GEMM) -> full-resolution depth (eval-3dvnet.py:58-125)'}
+                'd2h_bytes_per_step': int(full_hosts[0].numel() * 4),
+                'pipeline': 'images -> MnasNet + FPN (torchvision / cuDNN, channels-last, fp32 storage, TF32 convolutions '
+                            'allowed as by PyTorch default) -> dv3d_hot_path -> PropagationNet x3 (tcgen05 gather-GEMM) -> '
+                            'full-resolution depth (eval-3dvnet.py:58-125); two steps in flight: uploads on a copy stream, '
+                            'results awaited one step later'}
         del net_full
 
     # Supplementary: S independent steps in flight (one host thread + CUDA stream each). A single C2
