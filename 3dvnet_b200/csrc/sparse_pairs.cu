@@ -288,7 +288,12 @@ extern "C" int dv3d_sparse_conv_prefers_pairs(long long n_out, long long n_tiles
     // tile-chunks of tensor-core work: pair-major n_tiles vs output-stationary 27 per 128 rows
     // (the pair path adds the reduce pass and a second launch, so it must win clearly)
     const long long dense = 27 * ((n_out + PP_TILE - 1) / PP_TILE);
-    return n_tiles > 0 && 10 * n_tiles <= 6 * dense;
+    if (n_tiles <= 0) return 0;
+    // measured with the weight-stationary pair kernel (tools/sparse_conv_paths.py, 128 channels): at 0.60 of the dense
+    // work the pair path loses on a 54.8 k-row level (324 vs 277 us: its partial rows make a round trip through HBM) but
+    // wins on 6.9 k and 13.7 k rows (46 vs 66, 89 vs 99 us), where the output-stationary kernel cannot fill the SMs
+    if (dense <= 3000) return 10 * n_tiles <= 7 * dense;
+    return 10 * n_tiles <= 6 * dense;
 }
 
 extern "C" size_t dv3d_sparse_conv_pairs_workspace_bytes(long long n_tiles, int Cout) {

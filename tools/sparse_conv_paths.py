@@ -35,7 +35,7 @@ def main():
     print('| voxels | C | density | pair tiles | dense tile-chunks | heuristic | pair-major us | output-stationary us | max diff |')
     print('|---:|---:|---:|---:|---:|---|---:|---:|---:|')
     for n, C, density in ((151635, 128, 0.43), (193602, 64, 0.11), (54803, 128, 0.6), (19000, 128, 0.43), (24000, 64, 0.11),
-                          (3045, 128, 0.10), (2408, 128, 0.38)):
+                          (6850, 128, 0.6), (13700, 128, 0.6), (3045, 128, 0.10), (2408, 128, 0.38)):
         nbr = (torch.arange(n).view(-1, 1) + torch.randint(-3000, 3000, (n, 27), generator=g)).clamp_(0, n - 1)
         nbr[torch.rand(n, 27, generator=g) >= density] = -1
         km = ops.KernelMap(nbr.int().to(dev)).build_plan()
