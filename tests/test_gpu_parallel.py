@@ -102,6 +102,53 @@ def test_model_scene_sharded_equals_single_gpu(tmp_path):
         assert rel_nat < 1e-3 and nat_same == 1, (rel_nat, nat_same)
 
 
+def _worker_one_ref(rank, world, port, out_dir):
+    """more ranks than reference views: rank 1 owns no view but still takes part in the scene model"""
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device('cuda', rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
+    synth = importlib.import_module('3dvnet_b200.synth')
+    lm = importlib.import_module('3dvnet_b200.mv3d.lightningmodel')
+    par = importlib.import_module('3dvnet_b200.parallel')
+    img, plane = (64, 80), (16, 16)
+    cfg = dict(depth_start=0.5, depth_interval=0.3, n_intervals=16, size=plane)
+    b = synth.make_batch(1, 5, img, plane, 32, 2, 2, False, 4)       # 1 reference view + 4 sources
+    net = lm.PL3DVNet(cfg, cfg, 0.3, feat_dim=32, img_size=img)
+    net.load_state_dict(synth.make_params(0), strict=False)
+    net = net.to(dev).eval()
+    fq, R, t, K = b.feats_quarter.to(dev), b.rotmats.to(dev), b.tvecs.to(dev), b.K.to(dev)
+    e, ib = b.ref_src_edges, b.images_batch.to(dev)
+    n_ref = len(torch.unique(e[0]))
+    offs = [[0.3, 0.15]] * 2
+    with torch.no_grad():
+        heap = par.SymmHeap(max(64 << 20, par.native_heap_bytes(net, n_ref, plane)))
+        d_nat, (s0, s1) = par.hot_path_sharded_native(net, fq, R, t, K, e, ib, cfg, offs, heap)
+        torch.cuda.synchronize()
+        heap.check()
+        d_one = net.hot_path(fq, R, t, K, e, ib, cfg, offs)[s0:s1]
+    rel = float(((d_nat - d_one).abs() / (d_one.abs() + 1e-7)).mean()) if s1 > s0 else 0.0
+    np.save(os.path.join(out_dir, 'r%d.npy' % rank), np.array([n_ref, s1 - s0, rel, float(d_nat.shape[0])]))
+    heap.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
+def test_native_sharded_path_with_an_idle_rank(tmp_path):
+    import torch.multiprocessing as mp
+    importlib.import_module('3dvnet_b200.build').build()
+    mp.spawn(_worker_one_ref, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    owned = 0
+    for r in range(2):
+        n_ref, n_loc, rel, rows = np.load(tmp_path / ('r%d.npy' % r))
+        assert n_ref == 1 and rows == n_loc and rel < 1e-3, (n_ref, n_loc, rel)
+        owned += int(n_loc)
+    assert owned == 1
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
 def test_two_devices_in_one_process_agree():
     """kernel attributes (opt-in shared memory) are per device: the same pass on cuda:0 and then cuda:1 of ONE
